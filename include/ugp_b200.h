@@ -1,0 +1,169 @@
+/*
+ * ugp_b200.h — C ABI of libugp_b200.so: the sm_100a kernels behind the
+ * UG-PG-UNet hot path (ProgressiveUNet / PGUNet1..4 training + inference,
+ * UncertaintyGuidedLoss, the trainer step).
+ *
+ * The reference (tridang04022004/UG-PG-UNet) has no native layer: every op
+ * below replaces an ATen/cuDNN call site reached from the reference's
+ * nn.Modules.  Each entry cites the reference line(s) whose arithmetic it
+ * implements.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers
+ *   - activations: NHWC bf16 ("void*"), 16-byte aligned, C % 64 == 0
+ *   - parameters / statistics / logits / losses: fp32
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     allocates nothing, is re-entrant, and never throws
+ *   - return 0 on success, negative on error; ugp_last_error() gives the text
+ *     for the calling thread
+ */
+#ifndef UGP_B200_H_
+#define UGP_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UGP_OK 0
+#define UGP_ERR_INVALID (-1)
+#define UGP_ERR_CUDA (-2)
+#define UGP_ERR_DRIVER (-3)
+
+/* Library / device introspection. */
+const char* ugp_last_error(void);
+int ugp_version(void);                 /* 100 * major + minor */
+int ugp_device_sm_count(void);
+
+/* ---- convolutions (tcgen05 implicit GEMM) -------------------------------
+ * nn.Conv2d(k=3, padding=1) forward and input-gradient, and 1x1 GEMM.
+ * Reference: UG_unet_parts.py:10,13 (DoubleConv convs), :80 (skip concat is
+ * walked as two sources, never materialised).
+ *   D[p, n] = sum_{tap, c} src[p + shift(tap), c] * wpack[tap][n][c]
+ *   y = relu?( (D + bias) * scale + shift )          (null = identity)
+ * src0/src1: NHWC bf16 [B,H,W,c0] / [B,H,W,c1] (c1 = 0 -> single source).
+ * wpack: bf16 [taps][cout][c0+c1]; taps = 9 (3x3) or 1 (1x1).
+ * dst0 gets output channels [0, split_n), dst1 the rest (dst1 = NULL -> all in
+ * dst0); both NHWC bf16.  stats (nullable): fp32 [2][cout], += per-channel sum
+ * and sum of squares of the stored outputs (train-mode BatchNorm2d statistics,
+ * UG_unet_parts.py:11,14).
+ */
+int ugp_conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1,
+                       int B, int H, int W, int taps, const void* wpack,
+                       int cout, void* dst0, void* dst1, int split_n,
+                       const float* bias, const float* scale, const float* shift,
+                       int relu, float* stats, void* stream);
+
+/* Weight gradient of the same convolution (autograd of UG_unet_parts.py:10,13):
+ *   dw_packed[tap][ci][co] += sum_p src[p + shift(tap), ci] * dz[p, co]
+ * dw_packed: fp32 [taps][c0+c1][cout], accumulated (caller zeroes). */
+int ugp_conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
+                        const void* dz, int cout, int B, int H, int W, int taps,
+                        float* dw_packed, void* stream);
+
+/* fp32 OIHW master weights -> bf16 GEMM operands.  wf: forward pack
+ * [9][Cout][Cin]; wd (nullable): input-gradient pack [9][Cin][Cout] with the
+ * taps rotated by 180 degrees.  For the first layer (Cin % 64 != 0, 9*Cin <=
+ * 64) wf is [Cout][64] in im2col order k = (r*3+s)*Cin + ci and wd is unused. */
+int ugp_pack_weights(const float* w_oihw, int Cout, int Cin, void* wf, void* wd,
+                     void* stream);
+/* Packed fp32 gradient -> OIHW fp32 (.grad layout of nn.Conv2d.weight). */
+int ugp_unpack_wgrad(const float* dw_packed, int Cout, int Cin, float* grad_oihw,
+                     int accumulate, void* stream);
+
+/* First-layer input packing: fp32 NCHW [B,Cin,Hin,Win] -> bf16 [B,H,W,64]
+ * 3x3 neighbourhoods (zero padding), with the bilinear align_corners=True
+ * resize of uncertainty_guided_trainer.py:208 / UG_unet.py:36-41 folded in
+ * when (Hin,Win) != (H,W). */
+int ugp_im2col_first(const float* x, int B, int Cin, int Hin, int Win, int H,
+                     int W, void* out, void* stream);
+
+/* ---- BatchNorm2d / ReLU / MaxPool2d / bilinear x2 ------------------------ */
+/* Train-mode statistics -> scale/shift, running-stat update (eps, momentum as
+ * nn.BatchNorm2d: biased var to normalise, unbiased into running_var,
+ * num_batches_tracked += 1).  stats is consumed and zeroed. */
+int ugp_bn_finalize(float* stats, int C, long long count, const float* gamma,
+                    const float* beta, float eps, float momentum,
+                    float* running_mean, float* running_var,
+                    long long* num_batches_tracked, float* scale, float* shift,
+                    float* save_mean, float* save_rstd, void* stream);
+/* Eval mode: scale/shift from the running statistics. */
+int ugp_bn_eval_coeffs(int C, const float* gamma, const float* beta,
+                       const float* running_mean, const float* running_var,
+                       float eps, float* scale, float* shift, void* stream);
+/* a = relu(z*scale + shift) (UG_unet_parts.py:11-12); pooled (nullable) also
+ * receives MaxPool2d(2)(a) (UG_unet_parts.py:49). */
+int ugp_bn_relu_apply(const void* z, const float* scale, const float* shift,
+                      int B, int H, int W, int C, void* a, void* pooled,
+                      void* stream);
+/* Backward of conv-output -> BN(train) -> ReLU (-> MaxPool2d(2)):
+ *   g = (dA + unpool(dP)) * [a > 0]; dz = BN backward of g; sums = [sum g,
+ *   sum g*xhat] (= dbeta, dgamma); dbias += sum dz.  dA or dP may be NULL. */
+int ugp_bn_relu_bwd(const void* z, const void* dA, const void* dP,
+                    const float* scale, const float* shift, const float* mean,
+                    const float* rstd, const float* gamma, int B, int H, int W,
+                    int C, float* sums, float* dbias, void* dz, void* stream);
+/* Stand-alone MaxPool2d(2) with PyTorch index convention (int32 plane-local
+ * h*W+w, first maximum wins); indices nullable. */
+int ugp_maxpool2x2(const void* x, int B, int H, int W, int C, void* out,
+                   int* indices, void* stream);
+int ugp_maxpool2x2_bwd(const void* x, const void* dout, int B, int H, int W,
+                       int C, void* dx, void* stream);
+/* F.interpolate(scale_factor=2, mode='bilinear', align_corners=True)
+ * (UG_unet_parts.py:78) and its adjoint. */
+int ugp_upsample2x(const void* x, int B, int h, int w, int C, void* out,
+                   void* stream);
+int ugp_upsample2x_bwd(const void* dout, int B, int h, int w, int C, void* dx,
+                       void* stream);
+
+/* ---- logit head ---------------------------------------------------------- */
+/* OutConv 1x1 (UG_unet_parts.py:84-91): x NHWC bf16 [B,hw,C] -> fp32 NCHW
+ * [B,nc,hw]; C in {64,128,256}, nc <= 8. */
+int ugp_outconv_fwd(const void* x, const float* w, const float* bias, int B,
+                    int hw, int C, int nc, float* out, void* stream);
+int ugp_outconv_bwd(const void* x, const float* w, const float* dl, int B, int hw,
+                    int C, int nc, int accumulate, void* dx, float* dw, float* db,
+                    void* stream);
+/* logits = sum_s bilinear_up(maps[s]) (UG_unet.py:294-303); maps ordered
+ * coarse -> fine, sizes[s] = side of map s, the last one has side R. */
+int ugp_head_combine_fwd(const float* const* maps, const int* sizes, int n,
+                         int planes, int R, float* logits, void* stream);
+int ugp_head_combine_bwd(const float* dlogits, int planes, int R, int size,
+                         float* dl, void* stream);
+
+/* ---- uncertainty + loss -------------------------------------------------- */
+/* A = 1 - 2*|up(sigmoid(z_prev)) - 0.5| (UG_unet.py:44-57). */
+int ugp_uncertainty_margin(const float* zprev, int planes, int h, int w, int H,
+                           int W, float* A, void* stream);
+/* u_b = H(softmax(z_b)) / ln K (Herlev/train_herlev.py:253-257). */
+int ugp_softmax_entropy(const float* logits, int B, int K, float* u, void* stream);
+/* BCEWithLogitsLoss(pos_weight, 'none') * (1 + alpha*A) summed, with every
+ * metric of the trainer step (UG_unet.py:61-94;
+ * uncertainty_guided_trainer.py:64-65,90-123,177-181) and dlogits =
+ * grad_scale * d(sum l*w)/dz in one pass.  out: double[5 + 3*B] =
+ * {sum l*w, sum l, sum A, sum A^2, #(pred != t), per image {sum pred*t,
+ * sum pred, sum t}}.  A and dlogits nullable. */
+int ugp_bce_uncertainty_loss(const float* z, const float* t, const float* A,
+                             float alpha, float pos_weight, int B,
+                             long long per_image, float grad_scale, float* dlogits,
+                             double* out, void* stream);
+/* mean(CE_i * (1 + alpha*u_i)) pieces (Herlev/train_herlev.py:274-281):
+ * out: double[3] = {sum CE*w, sum CE, #correct}. */
+int ugp_ce_weighted_loss(const float* logits, const long long* labels,
+                         const float* u, float alpha, int B, int K,
+                         float grad_scale, float* dlogits, double* out,
+                         void* stream);
+
+/* ---- optimiser ----------------------------------------------------------- */
+/* torch.optim.RMSprop step (uncertainty_guided_trainer.py:84-88; alpha,
+ * eps, weight_decay, momentum 0, not centered) over a flat fp32 buffer:
+ *   g = grad*grad_scale + wd*p; v = alpha*v + (1-alpha)*g*g;
+ *   p -= lr * g / (sqrt(v) + eps)
+ */
+int ugp_rmsprop_step(float* param, const float* grad, float* square_avg,
+                     long long n, float lr, float alpha, float eps,
+                     float weight_decay, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGP_B200_H_ */

@@ -1,0 +1,82 @@
+"""ctypes binding of libugp_b200.so (the C ABI in include/ugp_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, the
+caller gets an exception.  `lib()` builds the library on first use when nvcc is
+available (the GPU box receives the prebuilt .so with the repo snapshot).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libugp_b200.so"
+
+_p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argtypes; every function returns int (0 = ok) unless noted
+SIGNATURES = {
+    "ugp_conv_gemm_bf16": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p, _p],
+    "ugp_conv_wgrad_bf16": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p],
+    "ugp_pack_weights": [_p, _i, _i, _p, _p, _p],
+    "ugp_unpack_wgrad": [_p, _i, _i, _p, _i, _p],
+    "ugp_im2col_first": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
+    "ugp_bn_finalize": [_p, _i, _ll, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    "ugp_bn_eval_coeffs": [_i, _p, _p, _p, _p, _f, _p, _p, _p],
+    "ugp_bn_relu_apply": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p],
+    "ugp_bn_relu_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "ugp_maxpool2x2": [_p, _i, _i, _i, _i, _p, _p, _p],
+    "ugp_maxpool2x2_bwd": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "ugp_upsample2x": [_p, _i, _i, _i, _i, _p, _p],
+    "ugp_upsample2x_bwd": [_p, _i, _i, _i, _i, _p, _p],
+    "ugp_outconv_fwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "ugp_outconv_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "ugp_head_combine_fwd": [_p, _p, _i, _i, _i, _p, _p],
+    "ugp_head_combine_bwd": [_p, _i, _i, _i, _p, _p],
+    "ugp_uncertainty_margin": [_p, _i, _i, _i, _i, _i, _p, _p],
+    "ugp_softmax_entropy": [_p, _i, _i, _p, _p],
+    "ugp_bce_uncertainty_loss": [_p, _p, _p, _f, _f, _i, _ll, _f, _p, _p, _p],
+    "ugp_ce_weighted_loss": [_p, _p, _p, _f, _i, _i, _f, _p, _p, _p],
+    "ugp_rmsprop_step": [_p, _p, _p, _ll, _f, _f, _f, _f, _f, _p],
+}
+INFO_FUNCS = ("ugp_last_error", "ugp_version", "ugp_device_sm_count")
+EXPORTED = tuple(SIGNATURES) + INFO_FUNCS
+
+_lib = None
+
+
+class UgpError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        from . import build as _build
+
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc and no prebuilt library: fail loudly
+            raise UgpError(
+                f"{LIB_PATH} is missing and could not be built ({e}). "
+                "Run `python -m ug_pg_unet_b200.build` where nvcc is available."
+            ) from e
+    handle = C.CDLL(str(LIB_PATH))
+    for name, args in SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    handle.ugp_last_error.restype = C.c_char_p
+    handle.ugp_last_error.argtypes = []
+    handle.ugp_version.restype = C.c_int
+    handle.ugp_device_sm_count.restype = C.c_int
+    _lib = handle
+    return handle
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ugp_last_error().decode("utf-8", "replace")
+        raise UgpError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,73 @@
+"""Builds libugp_b200.so in-tree with nvcc for sm_100a.
+
+The shared library is the product's only native artefact; it is git-ignored
+but travels to the GPU box with the repo snapshot.  `python -m
+ug_pg_unet_b200.build` (or `__graft_entry__.build()`) rebuilds it when any
+source is newer than the library.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libugp_b200.so"
+SOURCES = ["tmap.cu", "conv_gemm.cu", "conv_wgrad.cu", "elementwise.cu", "head_loss.cu",
+           "optim.cu", "capi.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libugp_b200.so cannot be built")
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    lib_m = LIB_PATH.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "ugp_common.cuh",
+                                         PKG_DIR.parent / "include" / "ugp_b200.h"]
+    return any(d.stat().st_mtime > lib_m for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = _nvcc()
+    obj_dir = PKG_DIR / "build"
+    obj_dir.mkdir(exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def compile_one(src: str) -> Path:
+        obj = obj_dir / (src + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

@@ -1,0 +1,155 @@
+// extern "C" surface of libugp_b200.so (declared in include/ugp_b200.h).
+// Thin forwarding only: argument validation lives with each kernel launcher.
+#include "../../include/ugp_b200.h"
+
+#include "ugp_common.cuh"
+
+namespace ugp {
+const char* last_error();
+
+int conv_gemm_bf16(const void*, int, const void*, int, int, int, int, int, const void*, int,
+                   void*, void*, int, const float*, const float*, const float*, int, float*,
+                   cudaStream_t);
+int conv_wgrad_bf16(const void*, int, const void*, int, const void*, int, int, int, int, int,
+                    float*, cudaStream_t);
+int im2col_first(const float*, int, int, int, int, int, int, void*, cudaStream_t);
+int bn_finalize(float*, int, long long, const float*, const float*, float, float, float*,
+                float*, long long*, float*, float*, float*, float*, cudaStream_t);
+int bn_eval_coeffs(int, const float*, const float*, const float*, const float*, float, float*,
+                   float*, cudaStream_t);
+int bn_relu_apply(const void*, const float*, const float*, int, int, int, int, void*, void*,
+                  cudaStream_t);
+int maxpool2x2(const void*, int, int, int, int, void*, int*, cudaStream_t);
+int maxpool2x2_bwd(const void*, const void*, int, int, int, int, void*, cudaStream_t);
+int upsample2x(const void*, int, int, int, int, void*, cudaStream_t);
+int upsample2x_bwd(const void*, int, int, int, int, void*, cudaStream_t);
+int bn_relu_bwd(const void*, const void*, const void*, const float*, const float*, const float*,
+                const float*, const float*, int, int, int, int, float*, float*, void*,
+                cudaStream_t);
+int pack_weights(const float*, int, int, void*, void*, cudaStream_t);
+int unpack_wgrad(const float*, int, int, float*, int, cudaStream_t);
+int outconv_fwd(const void*, const float*, const float*, int, int, int, int, float*,
+                cudaStream_t);
+int outconv_bwd(const void*, const float*, const float*, int, int, int, int, int, void*, float*,
+                float*, cudaStream_t);
+int head_combine_fwd(const float* const*, const int*, int, int, int, float*, cudaStream_t);
+int head_combine_bwd(const float*, int, int, int, float*, cudaStream_t);
+int uncertainty_margin(const float*, int, int, int, int, int, float*, cudaStream_t);
+int softmax_entropy(const float*, int, int, float*, cudaStream_t);
+int bce_uncertainty_loss(const float*, const float*, const float*, float, float, int, long long,
+                         float, float*, double*, cudaStream_t);
+int ce_weighted_loss(const float*, const long long*, const float*, float, int, int, float,
+                     float*, double*, cudaStream_t);
+int rmsprop_step(float*, const float*, float*, long long, float, float, float, float, float,
+                 cudaStream_t);
+}  // namespace ugp
+
+#define S(stream) static_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+const char* ugp_last_error(void) { return ugp::last_error(); }
+int ugp_version(void) { return 100; }
+int ugp_device_sm_count(void) { return ugp::device_sm_count(); }
+
+int ugp_conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
+                       int taps, const void* wpack, int cout, void* dst0, void* dst1,
+                       int split_n, const float* bias, const float* scale, const float* shift,
+                       int relu, float* stats, void* stream) {
+  return ugp::conv_gemm_bf16(src0, c0, src1, c1, B, H, W, taps, wpack, cout, dst0, dst1, split_n,
+                             bias, scale, shift, relu, stats, S(stream));
+}
+int ugp_conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1, const void* dz,
+                        int cout, int B, int H, int W, int taps, float* dw_packed,
+                        void* stream) {
+  return ugp::conv_wgrad_bf16(src0, c0, src1, c1, dz, cout, B, H, W, taps, dw_packed, S(stream));
+}
+int ugp_pack_weights(const float* w, int Cout, int Cin, void* wf, void* wd, void* stream) {
+  return ugp::pack_weights(w, Cout, Cin, wf, wd, S(stream));
+}
+int ugp_unpack_wgrad(const float* dwp, int Cout, int Cin, float* grad, int accumulate,
+                     void* stream) {
+  return ugp::unpack_wgrad(dwp, Cout, Cin, grad, accumulate, S(stream));
+}
+int ugp_im2col_first(const float* x, int B, int Cin, int Hin, int Win, int H, int W, void* out,
+                     void* stream) {
+  return ugp::im2col_first(x, B, Cin, Hin, Win, H, W, out, S(stream));
+}
+int ugp_bn_finalize(float* stats, int C, long long count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var,
+                    long long* nbt, float* scale, float* shift, float* save_mean,
+                    float* save_rstd, void* stream) {
+  return ugp::bn_finalize(stats, C, count, gamma, beta, eps, momentum, running_mean, running_var,
+                          nbt, scale, shift, save_mean, save_rstd, S(stream));
+}
+int ugp_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* rm,
+                       const float* rv, float eps, float* scale, float* shift, void* stream) {
+  return ugp::bn_eval_coeffs(C, gamma, beta, rm, rv, eps, scale, shift, S(stream));
+}
+int ugp_bn_relu_apply(const void* z, const float* scale, const float* shift, int B, int H, int W,
+                      int C, void* a, void* pooled, void* stream) {
+  return ugp::bn_relu_apply(z, scale, shift, B, H, W, C, a, pooled, S(stream));
+}
+int ugp_bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scale,
+                    const float* shift, const float* mean, const float* rstd, const float* gamma,
+                    int B, int H, int W, int C, float* sums, float* dbias, void* dz,
+                    void* stream) {
+  return ugp::bn_relu_bwd(z, dA, dP, scale, shift, mean, rstd, gamma, B, H, W, C, sums, dbias, dz,
+                          S(stream));
+}
+int ugp_maxpool2x2(const void* x, int B, int H, int W, int C, void* out, int* indices,
+                   void* stream) {
+  return ugp::maxpool2x2(x, B, H, W, C, out, indices, S(stream));
+}
+int ugp_maxpool2x2_bwd(const void* x, const void* dout, int B, int H, int W, int C, void* dx,
+                       void* stream) {
+  return ugp::maxpool2x2_bwd(x, dout, B, H, W, C, dx, S(stream));
+}
+int ugp_upsample2x(const void* x, int B, int h, int w, int C, void* out, void* stream) {
+  return ugp::upsample2x(x, B, h, w, C, out, S(stream));
+}
+int ugp_upsample2x_bwd(const void* dout, int B, int h, int w, int C, void* dx, void* stream) {
+  return ugp::upsample2x_bwd(dout, B, h, w, C, dx, S(stream));
+}
+int ugp_outconv_fwd(const void* x, const float* w, const float* bias, int B, int hw, int C, int nc,
+                    float* out, void* stream) {
+  return ugp::outconv_fwd(x, w, bias, B, hw, C, nc, out, S(stream));
+}
+int ugp_outconv_bwd(const void* x, const float* w, const float* dl, int B, int hw, int C, int nc,
+                    int accumulate, void* dx, float* dw, float* db, void* stream) {
+  return ugp::outconv_bwd(x, w, dl, B, hw, C, nc, accumulate, dx, dw, db, S(stream));
+}
+int ugp_head_combine_fwd(const float* const* maps, const int* sizes, int n, int planes, int R,
+                         float* logits, void* stream) {
+  return ugp::head_combine_fwd(maps, sizes, n, planes, R, logits, S(stream));
+}
+int ugp_head_combine_bwd(const float* dlogits, int planes, int R, int size, float* dl,
+                         void* stream) {
+  return ugp::head_combine_bwd(dlogits, planes, R, size, dl, S(stream));
+}
+int ugp_uncertainty_margin(const float* zprev, int planes, int h, int w, int H, int W, float* A,
+                           void* stream) {
+  return ugp::uncertainty_margin(zprev, planes, h, w, H, W, A, S(stream));
+}
+int ugp_softmax_entropy(const float* logits, int B, int K, float* u, void* stream) {
+  return ugp::softmax_entropy(logits, B, K, u, S(stream));
+}
+int ugp_bce_uncertainty_loss(const float* z, const float* t, const float* A, float alpha,
+                             float pos_weight, int B, long long per_image, float grad_scale,
+                             float* dlogits, double* out, void* stream) {
+  return ugp::bce_uncertainty_loss(z, t, A, alpha, pos_weight, B, per_image, grad_scale, dlogits,
+                                   out, S(stream));
+}
+int ugp_ce_weighted_loss(const float* logits, const long long* labels, const float* u, float alpha,
+                         int B, int K, float grad_scale, float* dlogits, double* out,
+                         void* stream) {
+  return ugp::ce_weighted_loss(logits, labels, u, alpha, B, K, grad_scale, dlogits, out,
+                               S(stream));
+}
+int ugp_rmsprop_step(float* param, const float* grad, float* square_avg, long long n, float lr,
+                     float alpha, float eps, float weight_decay, float grad_scale, void* stream) {
+  return ugp::rmsprop_step(param, grad, square_avg, n, lr, alpha, eps, weight_decay, grad_scale,
+                           S(stream));
+}
+
+}  // extern "C"

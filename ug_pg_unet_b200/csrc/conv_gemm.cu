@@ -1,0 +1,385 @@
+// 3x3 (pad 1) / 1x1 convolution as an implicit GEMM on tcgen05 tensor cores.
+//
+// Replaces the ATen/cuDNN call sites nn.Conv2d forward and its input-gradient
+// (reference: UG_unet_parts.py:10,13 and their autograd), see SURVEY.md K1/K2.
+//
+//   D[m, n] = sum_{tap, c} A[pixel(m) + shift(tap), c] * Wp[tap][n][c]
+//
+//   * A: NHWC bf16 activations, read by TMA as 4-D boxes (64 ch x BW x BH x 1).
+//     The tap shift is applied to the TMA coordinates; out-of-image pixels are
+//     zero-filled by the TMA unit, so there is no im2col and no padding copy.
+//     Up to two sources are walked back to back in K (the skip-concat of
+//     UG_unet_parts.py:80 is never materialised).
+//   * Wp: packed bf16 weights [tap][Cout][Cin] (K-major), TMA 2-D boxes.
+//   * D accumulates in TMEM (fp32), two accumulator stages so the epilogue of
+//     tile i overlaps the main loop of tile i+1.
+//   * Epilogue: +bias, optional per-channel affine (eval-mode BatchNorm fold)
+//     and ReLU, bf16 convert, swizzled smem staging, TMA store; per-channel
+//     sum / sum-of-squares of the stored (bf16-rounded) values for train-mode
+//     BatchNorm statistics (UG_unet_parts.py:11,14).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer and TMEM
+// owner, warps 2..5 = epilogue (one TMEM lane quarter each). Persistent CTAs,
+// static round-robin over (m_tile, n_tile).
+#include "ugp_common.cuh"
+
+namespace ugp {
+
+struct ConvGemmParams {
+  int taps;
+  int chunks0, chunks1;
+  int H, W, BH, BW;
+  int tiles_x, tiles_y;
+  int m_tiles, n_tiles;
+  int cout;
+  int split_n;
+  int relu;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  float* stats;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = 128 B rows
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kOutChunkBytes = kBlockM * 64 * 2;    // 16 KB (64 output channels)
+constexpr int kMaxCout = 1024;
+
+template <int kN>
+struct ConvCfg {
+  static constexpr int kStages = (kN == 256) ? 3 : (kN == 128 ? 5 : 6);
+  static constexpr int kBTileBytes = kN * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kTmemCols = 2 * kN;  // 128 / 256 / 512: powers of two
+  // dynamic smem: stages + 2 staging buffers + stats/bias/scale/shift + barriers
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kOutChunkBytes +
+                                    5 * kMaxCout * 4 + 256 + 1024;
+};
+
+template <int kN>
+__global__ void __launch_bounds__(192, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
+                 const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmO0,
+                 const __grid_constant__ CUtensorMap tmO1,
+                 const ConvGemmParams p) {
+  using Cfg = ConvCfg<kN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + kStages * kATileBytes;
+  uint8_t* sOut = sB + kStages * Cfg::kBTileBytes;
+  float* sStats = reinterpret_cast<float*>(sOut + 2 * kOutChunkBytes);  // [2][kMaxCout]
+  float* sBias = sStats + 2 * kMaxCout;
+  float* sScale = sBias + kMaxCout;
+  float* sShift = sScale + kMaxCout;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + kMaxCout);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = p.taps * (p.chunks0 + p.chunks1);
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmO0);
+    tma_prefetch_desc(&tmO1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp_idx >= 2) {
+    const int et = threadIdx.x - 64;
+    for (int i = et; i < p.cout; i += 128) {
+      sStats[i] = 0.f;
+      sStats[kMaxCout + i] = 0.f;
+      sBias[i] = p.bias ? p.bias[i] : 0.f;
+      sScale[i] = p.scale ? p.scale[i] : 1.f;
+      sShift[i] = p.shift ? p.shift[i] : 0.f;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int chunks = p.chunks0 + p.chunks1;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const int tx = m_tile % p.tiles_x;
+        const int t2 = m_tile / p.tiles_x;
+        const int ty = t2 % p.tiles_y;
+        const int b = t2 / p.tiles_y;
+        const int x0 = tx * p.BW, y0 = ty * p.BH;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+          const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+          const int wrow = tap * p.cout + n_tile * kN;
+          for (int c = 0; c < chunks; ++c) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            uint8_t* a_dst = sA + stage * kATileBytes;
+            if (c < p.chunks0)
+              tma_load_4d(&tmA0, &full_bar[stage], a_dst, c * kBlockK, x0 + dx,
+                          y0 + dy, b);
+            else
+              tma_load_4d(&tmA1, &full_bar[stage], a_dst,
+                          (c - p.chunks0) * kBlockK, x0 + dx, y0 + dy, b);
+            tma_load_2d(&tmW, &full_bar[stage], sB + stage * Cfg::kBTileBytes,
+                        c * kBlockK, wrow);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + as * kN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint64_t a_desc =
+              umma_desc_sw128(smem_u32(sA + stage * kATileBytes), 16, 1024);
+          const uint64_t b_desc =
+              umma_desc_sw128(smem_u32(sB + stage * Cfg::kBTileBytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 B per K=16 step inside the 128 B swizzle row
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int et = threadIdx.x - 64;   // 0..127
+    const int q = warp_idx & 3;        // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;     // row of the 128-row tile
+    const bool do_stats = p.stats != nullptr;
+    uint32_t chunk_counter = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int cc = 0; cc < kN / 64; ++cc, ++chunk_counter) {
+        uint32_t v[64];
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kN + cc * 64;
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_32x32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        if (cc == kN / 64 - 1) {
+          tc_fence_before_sync();
+          mbar_arrive(&tempty_bar[as]);
+        }
+        const int n_base = n_tile * kN + cc * 64;
+        uint32_t packed[32];
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          const float4 bi = *reinterpret_cast<const float4*>(sBias + n_base + j);
+          const float4 sc = *reinterpret_cast<const float4*>(sScale + n_base + j);
+          const float4 sh = *reinterpret_cast<const float4*>(sShift + n_base + j);
+          float f0 = (__uint_as_float(v[j + 0]) + bi.x) * sc.x + sh.x;
+          float f1 = (__uint_as_float(v[j + 1]) + bi.y) * sc.y + sh.y;
+          float f2 = (__uint_as_float(v[j + 2]) + bi.z) * sc.z + sh.z;
+          float f3 = (__uint_as_float(v[j + 3]) + bi.w) * sc.w + sh.w;
+          if (p.relu) {
+            f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f);
+            f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
+          }
+          packed[j / 2] = pack_bf16x2(f0, f1);
+          packed[j / 2 + 1] = pack_bf16x2(f2, f3);
+        }
+        uint8_t* buf = sOut + (chunk_counter & 1) * kOutChunkBytes;
+        // the TMA store that last read this staging buffer must be done
+        if (et == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        uint8_t* rowp = buf + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 val = make_uint4(packed[4 * j], packed[4 * j + 1],
+                                 packed[4 * j + 2], packed[4 * j + 3]);
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = val;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (et == 0) {
+          if (n_base < p.split_n)
+            tma_store_2d(&tmO0, buf, n_base, m_tile * kBlockM);
+          else
+            tma_store_2d(&tmO1, buf, n_base - p.split_n, m_tile * kBlockM);
+          tma_store_commit();
+        }
+        if (do_stats) {
+          // column sums over the bf16-rounded tile: 2 threads per column
+          const int col = et & 63;
+          const int r0 = (et >> 6) * 64;
+          const uint8_t* colp = buf + ((col & 7) << 1);
+          const int chunk = col >> 3;
+          float s = 0.f, s2 = 0.f;
+#pragma unroll 8
+          for (int r = r0; r < r0 + 64; ++r) {
+            const unsigned short h = *reinterpret_cast<const unsigned short*>(
+                colp + r * 128 + ((chunk ^ (r & 7)) << 4));
+            const float f = __uint_as_float(static_cast<uint32_t>(h) << 16);
+            s += f;
+            s2 = fmaf(f, f, s2);
+          }
+          atomicAdd(&sStats[n_base + col], s);
+          atomicAdd(&sStats[kMaxCout + n_base + col], s2);
+        }
+      }
+    }
+    if (et == 0) tma_store_wait_all();
+    if (do_stats) {
+      named_bar_sync(1, 128);
+      for (int i = et; i < p.cout; i += 128) {
+        atomicAdd(p.stats + i, sStats[i]);
+        atomicAdd(p.stats + p.cout + i, sStats[kMaxCout + i]);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int kN>
+static int launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1,
+                       const CUtensorMap& tmW, const CUtensorMap& tmO0,
+                       const CUtensorMap& tmO1, const ConvGemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = ConvCfg<kN>;
+  static bool configured = false;
+  if (!configured) {
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<kN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  conv_gemm_kernel<kN><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA0, tmA1, tmW,
+                                                               tmO0, tmO1, p);
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
+}
+
+// Picks the 128-pixel box (BW x BH) for an H x W image.
+static bool pick_box(int H, int W, int pixels, int* BW, int* BH) {
+  int bw = W < pixels ? W : pixels;
+  if (W % bw != 0) return false;
+  int bh = pixels / bw;
+  if (bw * bh != pixels || H % bh != 0) return false;
+  *BW = bw;
+  *BH = bh;
+  return true;
+}
+
+int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
+                   int H, int W, int taps, const void* wpack, int cout,
+                   void* dst0, void* dst1, int split_n, const float* bias,
+                   const float* scale, const float* shift, int relu,
+                   float* stats, cudaStream_t stream) {
+  UGP_REQUIRE(src0 && wpack && dst0, "conv_gemm: null pointer");
+  UGP_REQUIRE(taps == 9 || taps == 1, "conv_gemm: taps must be 9 or 1 (got %d)", taps);
+  UGP_REQUIRE(c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
+              "conv_gemm: source channels must be multiples of 64 (got %d, %d)", c0, c1);
+  UGP_REQUIRE(c1 == 0 || src1, "conv_gemm: second source missing");
+  UGP_REQUIRE(cout % 64 == 0 && cout <= kMaxCout, "conv_gemm: cout %d unsupported", cout);
+  if (dst1 == nullptr) split_n = cout;
+  UGP_REQUIRE(split_n > 0 && split_n <= cout && split_n % 64 == 0,
+              "conv_gemm: bad split_n %d", split_n);
+  int BW, BH;
+  UGP_REQUIRE(pick_box(H, W, kBlockM, &BW, &BH),
+              "conv_gemm: unsupported spatial size %dx%d (need W in {16,32,64,128} or a "
+              "multiple of 128, and H a multiple of 128/min(W,128))", H, W);
+  int kn = 256;
+  while (kn > 64 && (cout % kn != 0 || split_n % kn != 0 || (cout - split_n) % kn != 0)) kn >>= 1;
+
+  ConvGemmParams p;
+  p.taps = taps;
+  p.chunks0 = c0 / 64;
+  p.chunks1 = c1 / 64;
+  p.H = H; p.W = W; p.BH = BH; p.BW = BW;
+  p.tiles_x = W / BW;
+  p.tiles_y = H / BH;
+  p.m_tiles = B * p.tiles_x * p.tiles_y;
+  p.n_tiles = cout / kn;
+  p.cout = cout;
+  p.split_n = split_n;
+  p.relu = relu;
+  p.bias = bias; p.scale = scale; p.shift = shift; p.stats = stats;
+
+  CUtensorMap tmA0, tmA1, tmW, tmO0, tmO1;
+  int rc;
+  if ((rc = make_tmap_nhwc_bf16(&tmA0, src0, B, H, W, c0, 64, BW, BH))) return rc;
+  if (c1 > 0) {
+    if ((rc = make_tmap_nhwc_bf16(&tmA1, src1, B, H, W, c1, 64, BW, BH))) return rc;
+  } else {
+    tmA1 = tmA0;
+  }
+  if ((rc = make_tmap_2d_bf16(&tmW, wpack, (long long)taps * cout, c0 + c1, 64, kn))) return rc;
+  const long long M = (long long)B * H * W;
+  if ((rc = make_tmap_2d_bf16(&tmO0, dst0, M, split_n, 64, kBlockM))) return rc;
+  if (split_n < cout) {
+    if ((rc = make_tmap_2d_bf16(&tmO1, dst1, M, cout - split_n, 64, kBlockM))) return rc;
+  } else {
+    tmO1 = tmO0;
+  }
+  switch (kn) {
+    case 256: return launch_conv<256>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
+    case 128: return launch_conv<128>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
+    default:  return launch_conv<64>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
+  }
+}
+
+}  // namespace ugp

@@ -1,0 +1,265 @@
+// Weight gradient of the 3x3 (pad 1) / 1x1 convolution on tcgen05 tensor cores.
+//
+// Replaces the autograd weight-gradient of nn.Conv2d (reference call sites
+// UG_unet_parts.py:10,13):
+//
+//   dWp[tap][ci][co] += sum_{pixels p} X[p + shift(tap), ci] * dZ[p, co]
+//
+// GEMM view: M = (tap, ci), N = co, K = pixels.  Both operands are NHWC bf16
+// activations whose contiguous dimension (channels) is the GEMM M / N
+// dimension, so both UMMA operands are MN-major: a TMA box of 64 channels x 64
+// pixels lands in smem as 64 K-rows of 128 B (SWIZZLE_128B), which is exactly
+// the canonical MN-major layout (8-row K groups 1024 B apart = SBO, 64-channel
+// blocks one box apart = LBO).
+//
+// An M tile is two 64-channel boxes; each box is (tap, 64-channel chunk), so
+// for Cin = 64 one tile covers two taps.  K (pixels) is split across CTAs and
+// partial tiles are reduced with vector fp32 atomics into the packed fp32
+// gradient [tap][Cin][Cout] (Cout contiguous).
+#include "ugp_common.cuh"
+
+namespace ugp {
+
+struct WgradParams {
+  int taps;
+  int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
+  int H, W, BHp, BWp;     // 64-pixel K box
+  int boxes;              // taps * (chunks0 + chunks1)
+  int n_tiles;
+  int cout;
+  int kchunks_total;      // B*H*W / 64
+  int kchunks_per_split;
+  float* dw;              // [boxes*64][cout] fp32, accumulated
+};
+
+constexpr int kWgBoxBytes = 64 * 64 * 2;  // 64 pixels x 64 channels bf16 = 8 KB
+constexpr int kWgStages = 4;
+
+template <int kN>
+struct WgradCfg {
+  static constexpr int kABytes = 2 * kWgBoxBytes;
+  static constexpr int kBBytes = (kN / 64) * kWgBoxBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kWgStages * kStageBytes + 256 + 1024;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b,
+                                           float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr),
+               "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+template <int kN>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
+                  const __grid_constant__ CUtensorMap tmX1,
+                  const __grid_constant__ CUtensorMap tmDZ,
+                  const WgradParams p) {
+  using Cfg = WgradCfg<kN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + kWgStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kWgStages * Cfg::kBBytes);
+  uint64_t* empty_bar = full_bar + kWgStages;
+  uint64_t* done_bar = empty_bar + kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tile = blockIdx.x / p.n_tiles;
+  const int n_tile = blockIdx.x - m_tile * p.n_tiles;
+  const int kc_begin = blockIdx.y * p.kchunks_per_split;
+  int kc_end = kc_begin + p.kchunks_per_split;
+  if (kc_end > p.kchunks_total) kc_end = p.kchunks_total;
+  const int n_k = kc_end - kc_begin;   // host guarantees > 0
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX0);
+    tma_prefetch_desc(&tmX1);
+    tma_prefetch_desc(&tmDZ);
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) tmem_alloc(tmem_slot, kN);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int chunks = p.chunks0 + p.chunks1;
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      // the two boxes of this M tile; an odd box count repeats the last box
+      int box[2], bdx[2], bdy[2], bch[2];
+      for (int i = 0; i < 2; ++i) {
+        int id = m_tile * 2 + i;
+        if (id >= p.boxes) id = p.boxes - 1;
+        box[i] = id;
+        const int tap = id / chunks;
+        bch[i] = id - tap * chunks;
+        bdy[i] = (p.taps == 9) ? tap / 3 - 1 : 0;
+        bdx[i] = (p.taps == 9) ? tap % 3 - 1 : 0;
+      }
+      (void)box;
+      const int hw = p.H * p.W;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        const int p0 = kc * 64;
+        const int b = p0 / hw;
+        const int rem = p0 - b * hw;
+        const int y0 = rem / p.W;
+        const int x0 = rem - y0 * p.W;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        uint8_t* a_dst = sA + stage * Cfg::kABytes;
+        for (int i = 0; i < 2; ++i) {
+          if (bch[i] < p.chunks0)
+            tma_load_4d(&tmX0, &full_bar[stage], a_dst + i * kWgBoxBytes,
+                        bch[i] * 64, x0 + bdx[i], y0 + bdy[i], b);
+          else
+            tma_load_4d(&tmX1, &full_bar[stage], a_dst + i * kWgBoxBytes,
+                        (bch[i] - p.chunks0) * 64, x0 + bdx[i], y0 + bdy[i], b);
+        }
+        uint8_t* b_dst = sB + stage * Cfg::kBBytes;
+        for (int j = 0; j < kN / 64; ++j)
+          tma_load_4d(&tmDZ, &full_bar[stage], b_dst + j * kWgBoxBytes,
+                      n_tile * kN + j * 64, x0, y0, b);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp_idx == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, kN, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < n_k; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
+        const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // 16 pixels (K) per MMA = 16 rows of 128 B
+          const uint64_t a_desc = umma_desc_sw128(a_addr + k * 2048, kWgBoxBytes, 1024);
+          const uint64_t b_desc = umma_desc_sw128(b_addr + k * 2048, kWgBoxBytes, 1024);
+          umma_bf16(tmem_base, a_desc, b_desc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (i == n_k - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    const int q = warp_idx & 3;
+    const int row = q * 32 + lane;
+    const int box_id = m_tile * 2 + (row >> 6);
+    mbar_wait(done_bar, 0);
+    tc_fence_after_sync();
+    float* dst = p.dw + (static_cast<size_t>(box_id) * 64 + (row & 63)) * p.cout +
+                 n_tile * kN;
+    const bool live = box_id < p.boxes;
+#pragma unroll 1
+    for (int c = 0; c < kN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          red_add_v4(dst + c * 32 + j, __uint_as_float(v[j]),
+                     __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                     __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kN);
+  }
+}
+
+template <int kN>
+static int launch_wgrad(const CUtensorMap& tmX0, const CUtensorMap& tmX1,
+                        const CUtensorMap& tmDZ, const WgradParams& p, int m_tiles,
+                        int splits, cudaStream_t stream) {
+  using Cfg = WgradCfg<kN>;
+  static bool configured = false;
+  if (!configured) {
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<kN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid(m_tiles * p.n_tiles, splits);
+  conv_wgrad_kernel<kN><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmX0, tmX1, tmDZ, p);
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
+}
+
+int conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
+                    const void* dz, int cout, int B, int H, int W, int taps,
+                    float* dw_packed, cudaStream_t stream) {
+  UGP_REQUIRE(src0 && dz && dw_packed, "conv_wgrad: null pointer");
+  UGP_REQUIRE(taps == 9 || taps == 1, "conv_wgrad: taps must be 9 or 1");
+  UGP_REQUIRE(c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
+              "conv_wgrad: source channels must be multiples of 64");
+  UGP_REQUIRE(cout % 64 == 0 && cout <= 512, "conv_wgrad: cout %d unsupported", cout);
+  int BWp = W < 64 ? W : 64;
+  int BHp = 64 / BWp;
+  UGP_REQUIRE(W % BWp == 0 && BWp * BHp == 64 && H % BHp == 0,
+              "conv_wgrad: unsupported spatial size %dx%d", H, W);
+  int kn = 256;
+  while (kn > 64 && cout % kn != 0) kn >>= 1;
+
+  WgradParams p;
+  p.taps = taps;
+  p.chunks0 = c0 / 64;
+  p.chunks1 = c1 / 64;
+  p.H = H; p.W = W; p.BHp = BHp; p.BWp = BWp;
+  p.boxes = taps * (p.chunks0 + p.chunks1);
+  p.n_tiles = cout / kn;
+  p.cout = cout;
+  p.kchunks_total = (int)(((long long)B * H * W) / 64);
+  p.dw = dw_packed;
+  const int m_tiles = (p.boxes + 1) / 2;
+  const int items = m_tiles * p.n_tiles;
+  int splits = (2 * device_sm_count() + items - 1) / items;
+  if (splits < 1) splits = 1;
+  // keep at least 4 K chunks (256 pixels) per split
+  int max_splits = p.kchunks_total / 4;
+  if (max_splits < 1) max_splits = 1;
+  if (splits > max_splits) splits = max_splits;
+  p.kchunks_per_split = (p.kchunks_total + splits - 1) / splits;
+  splits = (p.kchunks_total + p.kchunks_per_split - 1) / p.kchunks_per_split;
+
+  CUtensorMap tmX0, tmX1, tmDZ;
+  int rc;
+  if ((rc = make_tmap_nhwc_bf16(&tmX0, src0, B, H, W, c0, 64, BWp, BHp))) return rc;
+  if (c1 > 0) {
+    if ((rc = make_tmap_nhwc_bf16(&tmX1, src1, B, H, W, c1, 64, BWp, BHp))) return rc;
+  } else {
+    tmX1 = tmX0;
+  }
+  if ((rc = make_tmap_nhwc_bf16(&tmDZ, dz, B, H, W, cout, 64, BWp, BHp))) return rc;
+  switch (kn) {
+    case 256: return launch_wgrad<256>(tmX0, tmX1, tmDZ, p, m_tiles, splits, stream);
+    case 128: return launch_wgrad<128>(tmX0, tmX1, tmDZ, p, m_tiles, splits, stream);
+    default:  return launch_wgrad<64>(tmX0, tmX1, tmDZ, p, m_tiles, splits, stream);
+  }
+}
+
+}  // namespace ugp

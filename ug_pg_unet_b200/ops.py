@@ -1,0 +1,302 @@
+"""Tensor-level wrappers over the C ABI (include/ugp_b200.h).
+
+PyTorch is used for device memory and streams only: every function here takes
+CUDA tensors, hands raw device pointers to libugp_b200.so on the current
+stream and returns torch tensors that own the results.  Activations are NHWC
+bf16 tensors of shape [B, H, W, C] (contiguous).  Nothing here falls back to
+torch math: a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import ctypes as C
+import torch
+
+from ._lib import check, lib
+
+bf16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the sm_100a path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def _opt(t, dtype, name):
+    return None if t is None else _req(t, dtype, name)
+
+
+# ----------------------------------------------------------------------------- convolutions
+def conv_gemm(src0: torch.Tensor, src1: Optional[torch.Tensor], wpack: torch.Tensor, taps: int,
+              cout: int, *, bias=None, scale=None, shift=None, relu: bool = False, stats=None,
+              split_n: Optional[int] = None, out0=None, out1=None):
+    """D = conv(src0 ++ src1, wpack) (+bias, *scale+shift, relu); see ugp_conv_gemm_bf16."""
+    _req(src0, bf16, "src0")
+    B, H, W, c0 = src0.shape
+    c1 = 0
+    if src1 is not None:
+        _req(src1, bf16, "src1")
+        assert src1.shape[:3] == src0.shape[:3]
+        c1 = src1.shape[3]
+    _req(wpack, bf16, "wpack")
+    assert wpack.numel() == taps * cout * (c0 + c1), (wpack.shape, taps, cout, c0, c1)
+    if split_n is None or split_n >= cout:
+        split_n = cout
+        if out0 is None:
+            out0 = torch.empty((B, H, W, cout), dtype=bf16, device=src0.device)
+    else:
+        if out0 is None:
+            out0 = torch.empty((B, H, W, split_n), dtype=bf16, device=src0.device)
+        if out1 is None:
+            out1 = torch.empty((B, H, W, cout - split_n), dtype=bf16, device=src0.device)
+    _req(out0, bf16, "out0")
+    if out1 is not None:
+        _req(out1, bf16, "out1")
+    rc = lib().ugp_conv_gemm_bf16(_ptr(src0), c0, _ptr(src1), c1, B, H, W, taps, _ptr(wpack), cout,
+                                  _ptr(out0), _ptr(out1), split_n,
+                                  _ptr(_opt(bias, torch.float32, "bias")),
+                                  _ptr(_opt(scale, torch.float32, "scale")),
+                                  _ptr(_opt(shift, torch.float32, "shift")), int(relu),
+                                  _ptr(_opt(stats, torch.float32, "stats")), _stream())
+    check(rc, "ugp_conv_gemm_bf16")
+    return (out0, out1) if out1 is not None else out0
+
+
+def conv_wgrad(src0, src1, dz, taps: int, dw_packed: torch.Tensor):
+    """dw_packed[tap][ci][co] += sum_p src[p+shift, ci] * dz[p, co]."""
+    _req(src0, bf16, "src0")
+    _req(dz, bf16, "dz")
+    _req(dw_packed, torch.float32, "dw_packed")
+    B, H, W, c0 = src0.shape
+    c1 = 0
+    if src1 is not None:
+        _req(src1, bf16, "src1")
+        c1 = src1.shape[3]
+    cout = dz.shape[3]
+    assert dz.shape[:3] == src0.shape[:3]
+    assert dw_packed.numel() == taps * (c0 + c1) * cout
+    assert dw_packed.data_ptr() % 16 == 0
+    rc = lib().ugp_conv_wgrad_bf16(_ptr(src0), c0, _ptr(src1), c1, _ptr(dz), cout, B, H, W, taps,
+                                   _ptr(dw_packed), _stream())
+    check(rc, "ugp_conv_wgrad_bf16")
+    return dw_packed
+
+
+def pack_weights(w: torch.Tensor, need_dgrad: bool = True, wf=None, wd=None):
+    """fp32 OIHW -> (forward pack, input-gradient pack) bf16; see ugp_pack_weights."""
+    _req(w, torch.float32, "weight")
+    cout, cin = w.shape[0], w.shape[1]
+    first = cin % 64 != 0
+    if wf is None:
+        wf = torch.empty((1, cout, 64) if first else (9, cout, cin), dtype=bf16, device=w.device)
+    if first or not need_dgrad:
+        wd = None
+    elif wd is None:
+        wd = torch.empty((9, cin, cout), dtype=bf16, device=w.device)
+    check(lib().ugp_pack_weights(_ptr(w), cout, cin, _ptr(wf), _ptr(wd), _stream()), "ugp_pack_weights")
+    return wf, wd
+
+
+def unpack_wgrad(dw_packed, cout: int, cin: int, grad=None, accumulate: bool = False):
+    _req(dw_packed, torch.float32, "dw_packed")
+    if grad is None:
+        grad = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dw_packed.device)
+        accumulate = False
+    _req(grad, torch.float32, "grad")
+    check(lib().ugp_unpack_wgrad(_ptr(dw_packed), cout, cin, _ptr(grad), int(accumulate), _stream()),
+          "ugp_unpack_wgrad")
+    return grad
+
+
+def im2col_first(x: torch.Tensor, H: Optional[int] = None, W: Optional[int] = None):
+    """fp32 NCHW image -> bf16 [B,H,W,64] 3x3 neighbourhoods (optional bilinear resize)."""
+    _req(x, torch.float32, "x")
+    B, cin, Hin, Win = x.shape
+    H = Hin if H is None else H
+    W = Win if W is None else W
+    out = torch.empty((B, H, W, 64), dtype=bf16, device=x.device)
+    check(lib().ugp_im2col_first(_ptr(x), B, cin, Hin, Win, H, W, _ptr(out), _stream()), "ugp_im2col_first")
+    return out
+
+
+# ----------------------------------------------------------------------------- BN / pool / upsample
+def bn_finalize(stats, count: int, gamma, beta, eps: float, momentum: float, running_mean,
+                running_var, num_batches_tracked, scale, shift, save_mean, save_rstd):
+    Cn = gamma.numel()
+    check(lib().ugp_bn_finalize(_ptr(_req(stats, torch.float32, "stats")), Cn, count, _ptr(gamma),
+                                _ptr(beta), eps, momentum, _ptr(running_mean), _ptr(running_var),
+                                _ptr(num_batches_tracked), _ptr(scale), _ptr(shift), _ptr(save_mean),
+                                _ptr(save_rstd), _stream()), "ugp_bn_finalize")
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps: float, scale, shift):
+    check(lib().ugp_bn_eval_coeffs(gamma.numel(), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                                   _ptr(running_var), eps, _ptr(scale), _ptr(shift), _stream()),
+          "ugp_bn_eval_coeffs")
+
+
+def bn_relu_apply(z, scale, shift, pool: bool = False, out=None, pooled=None):
+    _req(z, bf16, "z")
+    B, H, W, Cn = z.shape
+    if out is None:
+        out = torch.empty_like(z)
+    if pool and pooled is None:
+        pooled = torch.empty((B, H // 2, W // 2, Cn), dtype=bf16, device=z.device)
+    check(lib().ugp_bn_relu_apply(_ptr(z), _ptr(scale), _ptr(shift), B, H, W, Cn, _ptr(out),
+                                  _ptr(pooled) if pool else None, _stream()), "ugp_bn_relu_apply")
+    return (out, pooled) if pool else out
+
+
+def bn_relu_bwd(z, dA, dP, scale, shift, mean, rstd, gamma, sums, dbias, dz=None):
+    _req(z, bf16, "z")
+    B, H, W, Cn = z.shape
+    if dz is None:
+        dz = torch.empty_like(z)
+    check(lib().ugp_bn_relu_bwd(_ptr(z), _ptr(_opt(dA, bf16, "dA")), _ptr(_opt(dP, bf16, "dP")),
+                                _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _ptr(gamma), B, H,
+                                W, Cn, _ptr(_req(sums, torch.float32, "sums")),
+                                _ptr(_opt(dbias, torch.float32, "dbias")), _ptr(dz), _stream()),
+          "ugp_bn_relu_bwd")
+    return dz
+
+
+def maxpool2x2(x, return_indices: bool = False):
+    _req(x, bf16, "x")
+    B, H, W, Cn = x.shape
+    out = torch.empty((B, H // 2, W // 2, Cn), dtype=bf16, device=x.device)
+    idx = torch.empty((B, H // 2, W // 2, Cn), dtype=torch.int32, device=x.device) if return_indices else None
+    check(lib().ugp_maxpool2x2(_ptr(x), B, H, W, Cn, _ptr(out), _ptr(idx), _stream()), "ugp_maxpool2x2")
+    return (out, idx) if return_indices else out
+
+
+def maxpool2x2_bwd(x, dout):
+    _req(x, bf16, "x")
+    _req(dout, bf16, "dout")
+    B, H, W, Cn = x.shape
+    dx = torch.empty_like(x)
+    check(lib().ugp_maxpool2x2_bwd(_ptr(x), _ptr(dout), B, H, W, Cn, _ptr(dx), _stream()), "ugp_maxpool2x2_bwd")
+    return dx
+
+
+def upsample2x(x):
+    _req(x, bf16, "x")
+    B, h, w, Cn = x.shape
+    out = torch.empty((B, 2 * h, 2 * w, Cn), dtype=bf16, device=x.device)
+    check(lib().ugp_upsample2x(_ptr(x), B, h, w, Cn, _ptr(out), _stream()), "ugp_upsample2x")
+    return out
+
+
+def upsample2x_bwd(dout):
+    _req(dout, bf16, "dout")
+    B, H, W, Cn = dout.shape
+    dx = torch.empty((B, H // 2, W // 2, Cn), dtype=bf16, device=dout.device)
+    check(lib().ugp_upsample2x_bwd(_ptr(dout), B, H // 2, W // 2, Cn, _ptr(dx), _stream()), "ugp_upsample2x_bwd")
+    return dx
+
+
+# ----------------------------------------------------------------------------- head / loss
+def outconv_fwd(x, w, bias):
+    """x NHWC bf16 [B,h,w,C], w fp32 [nc,C(,1,1)] -> fp32 NCHW [B,nc,h,w]."""
+    _req(x, bf16, "x")
+    B, h, wd, Cn = x.shape
+    nc = w.shape[0]
+    out = torch.empty((B, nc, h, wd), dtype=torch.float32, device=x.device)
+    check(lib().ugp_outconv_fwd(_ptr(x), _ptr(_req(w, torch.float32, "w")), _ptr(bias), B, h * wd, Cn, nc,
+                                _ptr(out), _stream()), "ugp_outconv_fwd")
+    return out
+
+
+def outconv_bwd(x, w, dl, dx, accumulate: bool, dw, db):
+    _req(x, bf16, "x")
+    _req(dl, torch.float32, "dl")
+    B, h, wd, Cn = x.shape
+    nc = w.shape[0]
+    check(lib().ugp_outconv_bwd(_ptr(x), _ptr(w), _ptr(dl), B, h * wd, Cn, nc, int(accumulate),
+                                _ptr(_req(dx, bf16, "dx")), _ptr(_req(dw, torch.float32, "dw")),
+                                _ptr(_req(db, torch.float32, "db")), _stream()), "ugp_outconv_bwd")
+    return dx
+
+
+def head_combine_fwd(maps: Sequence[torch.Tensor]):
+    """logits = sum of the maps, each bilinearly upsampled (align_corners) to the last one's size."""
+    n = len(maps)
+    B, nc, R, _ = maps[-1].shape
+    logits = torch.empty_like(maps[-1])
+    ptrs = (C.c_void_p * n)(*[_req(m, torch.float32, "map").data_ptr() for m in maps])
+    sizes = (C.c_int * n)(*[m.shape[-1] for m in maps])
+    check(lib().ugp_head_combine_fwd(ptrs, sizes, n, B * nc, R, _ptr(logits), _stream()), "ugp_head_combine_fwd")
+    return logits
+
+
+def head_combine_bwd(dlogits, size: int):
+    _req(dlogits, torch.float32, "dlogits")
+    B, nc, R, _ = dlogits.shape
+    dl = torch.empty((B, nc, size, size), dtype=torch.float32, device=dlogits.device)
+    check(lib().ugp_head_combine_bwd(_ptr(dlogits), B * nc, R, size, _ptr(dl), _stream()), "ugp_head_combine_bwd")
+    return dl
+
+
+def uncertainty_margin(zprev, H: int, W: int):
+    _req(zprev, torch.float32, "zprev")
+    B, nc, h, w = zprev.shape
+    A = torch.empty((B, nc, H, W), dtype=torch.float32, device=zprev.device)
+    check(lib().ugp_uncertainty_margin(_ptr(zprev), B * nc, h, w, H, W, _ptr(A), _stream()), "ugp_uncertainty_margin")
+    return A
+
+
+def softmax_entropy(logits):
+    _req(logits, torch.float32, "logits")
+    B, K = logits.shape
+    u = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    check(lib().ugp_softmax_entropy(_ptr(logits), B, K, _ptr(u), _stream()), "ugp_softmax_entropy")
+    return u
+
+
+def bce_uncertainty_loss(z, t, A, alpha: float, pos_weight: float, want_grad: bool, grad_scale: float):
+    """Returns (out double[5+3B], dlogits or None); see ugp_bce_uncertainty_loss."""
+    _req(z, torch.float32, "logits")
+    _req(t, torch.float32, "target")
+    if t.shape != z.shape:
+        raise ValueError(f"Target size ({tuple(t.shape)}) must be the same as input size ({tuple(z.shape)})")
+    B = z.shape[0]
+    per_image = z.numel() // B
+    out = torch.empty((5 + 3 * B,), dtype=torch.float64, device=z.device)
+    dlogits = torch.empty_like(z) if want_grad else None
+    check(lib().ugp_bce_uncertainty_loss(_ptr(z), _ptr(t), _ptr(_opt(A, torch.float32, "uncertainty")),
+                                         alpha, pos_weight, B, per_image, grad_scale, _ptr(dlogits),
+                                         _ptr(out), _stream()), "ugp_bce_uncertainty_loss")
+    return out, dlogits
+
+
+def ce_weighted_loss(logits, labels, u, alpha: float, want_grad: bool, grad_scale: float):
+    _req(logits, torch.float32, "logits")
+    _req(labels, torch.int64, "labels")
+    B, K = logits.shape
+    out = torch.empty((3,), dtype=torch.float64, device=logits.device)
+    dlogits = torch.empty_like(logits) if want_grad else None
+    check(lib().ugp_ce_weighted_loss(_ptr(logits), _ptr(labels), _ptr(_opt(u, torch.float32, "u")), alpha, B, K,
+                                     grad_scale, _ptr(dlogits), _ptr(out), _stream()), "ugp_ce_weighted_loss")
+    return out, dlogits
+
+
+def rmsprop_step(param, grad, square_avg, lr: float, alpha: float = 0.99, eps: float = 1e-8,
+                 weight_decay: float = 0.0, grad_scale: float = 1.0):
+    _req(param, torch.float32, "param")
+    _req(grad, torch.float32, "grad")
+    _req(square_avg, torch.float32, "square_avg")
+    check(lib().ugp_rmsprop_step(_ptr(param), _ptr(grad), _ptr(square_avg), param.numel(), lr, alpha, eps,
+                                 weight_decay, grad_scale, _stream()), "ugp_rmsprop_step")
