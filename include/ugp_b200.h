@@ -96,8 +96,9 @@ int ugp_bn_relu_apply(const void* z, const float* scale, const float* shift,
                       int B, int H, int W, int C, void* a, void* pooled,
                       void* stream);
 /* Backward of conv-output -> BN(train) -> ReLU (-> MaxPool2d(2)):
- *   g = (dA + unpool(dP)) * [a > 0]; dz = BN backward of g; sums = [sum g,
- *   sum g*xhat] (= dbeta, dgamma); dbias += sum dz.  dA or dP may be NULL. */
+ *   g = (dA + unpool(dP)) * [a > 0]; dz = BN backward of g; sums = [sum g*xhat,
+ *   sum g] (= dgamma, dbeta: the grads of BatchNorm2d.weight, .bias);
+ *   dbias += sum dz.  dA or dP may be NULL. */
 int ugp_bn_relu_bwd(const void* z, const void* dA, const void* dP,
                     const float* scale, const float* shift, const float* mean,
                     const float* rstd, const float* gamma, int B, int H, int W,

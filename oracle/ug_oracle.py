@@ -1,0 +1,264 @@
+"""CPU oracle for the UG-PG-UNet hot path — TEST INFRASTRUCTURE ONLY.
+
+A functional fp32 restatement, in plain torch-on-CPU ops, of the reference's
+algorithm for the path this repository accelerates.  It is the checker for
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / reference
+arm; nothing under `ug_pg_unet_b200/` imports it and the product path never
+routes through it.
+
+Pinning: `tests/golden/*.pt` were produced by importing the UNMODIFIED
+reference (`/root/reference`, PyTorch modules) in the build container with
+`tools/make_goldens.py`; `tests/test_oracle_golden.py` checks every function
+here against those vectors.  The reference itself ships no tests or golden
+vectors, so these reference-generated fixtures are the pin.
+
+Every function cites the reference lines it restates (paths relative to the
+reference repository root).
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+StateDict = Dict[str, Tensor]
+
+STAGE_RESOLUTION = {1: 32, 2: 64, 3: 128, 4: 256}   # uncertainty_guided_trainer.py:42-47
+_UP_OUT = [256, 128, 64, 64]                          # UG_unet.py:184,204-205,236-238,274-277
+
+
+# --------------------------------------------------------------------------- architecture
+def encoder_widths(stage: int) -> List[int]:
+    """Channel widths inc -> ... -> down4 (UG_unet.py:182-183, 200-202, 230-233, 267-271)."""
+    return {1: [512, 512], 2: [256, 512, 512], 3: [128, 256, 512, 512], 4: [64, 128, 256, 512, 512]}[stage]
+
+
+def down_names(stage: int) -> List[str]:
+    return [f"down{k}" for k in range(5 - (stage), 5)]      # stage 1: down4; stage 4: down1..down4
+
+
+def block_specs(stage: int, in_channels: int) -> List[Tuple[str, int, int]]:
+    """(state_dict prefix of the DoubleConv, Cin, Cout) in forward order."""
+    enc = encoder_widths(stage)
+    specs = [("inc.conv", in_channels, enc[0])]
+    for i, name in enumerate(down_names(stage)):
+        specs.append((f"{name}.mpconv.1", enc[i], enc[i + 1]))
+    prev = enc[-1]
+    for j in range(1, stage + 1):
+        skip = enc[stage - j]
+        specs.append((f"up{j}.conv", skip + prev, _UP_OUT[j - 1]))
+        prev = _UP_OUT[j - 1]
+    return specs
+
+
+def head_names(stage: int) -> List[str]:
+    return ["outc"] if stage == 1 else [f"outc{j}" for j in range(1, stage + 1)]   # UG_unet.py:185,206-207
+
+
+def state_dict_shapes(stage: int, in_channels: int, num_classes: int) -> Dict[str, Tuple[int, ...]]:
+    """Every key/shape of PGUNet{stage}.state_dict() (UG_unet_parts.py:9-16,88)."""
+    shapes: Dict[str, Tuple[int, ...]] = {}
+    for prefix, cin, cout in block_specs(stage, in_channels):
+        for conv_i, bn_i, ci in ((0, 1, cin), (3, 4, cout)):
+            shapes[f"{prefix}.conv_op.{conv_i}.weight"] = (cout, ci, 3, 3)
+            shapes[f"{prefix}.conv_op.{conv_i}.bias"] = (cout,)
+            shapes[f"{prefix}.conv_op.{bn_i}.weight"] = (cout,)
+            shapes[f"{prefix}.conv_op.{bn_i}.bias"] = (cout,)
+            shapes[f"{prefix}.conv_op.{bn_i}.running_mean"] = (cout,)
+            shapes[f"{prefix}.conv_op.{bn_i}.running_var"] = (cout,)
+            shapes[f"{prefix}.conv_op.{bn_i}.num_batches_tracked"] = ()
+    for j, name in enumerate(head_names(stage)):
+        c = _UP_OUT[stage - 1] if stage == 1 else _UP_OUT[j]
+        shapes[f"{name}.conv.weight"] = (num_classes, c, 1, 1)
+        shapes[f"{name}.conv.bias"] = (num_classes,)
+    return shapes
+
+
+def seeded_state_dict(stage: int, in_channels: int, num_classes: int, seed: int = 0) -> StateDict:
+    """Deterministic weights that depend only on (key, shape, seed) — identical wherever they are
+    regenerated (golden generator, tests, bench), with no dependence on module construction order."""
+    sd: StateDict = {}
+    for key, shape in state_dict_shapes(stage, in_channels, num_classes).items():
+        g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) % (2 ** 31))
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.zeros((), dtype=torch.int64)
+        elif key.endswith("running_mean"):
+            sd[key] = torch.randn(shape, generator=g) * 0.1
+        elif key.endswith("running_var"):
+            sd[key] = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * math.sqrt(3.0 / fan_in) * 1.4
+        elif ".conv_op.1." in key or ".conv_op.4." in key:
+            sd[key] = torch.rand(shape, generator=g) * 0.5 + 0.75 if key.endswith("weight") \
+                else torch.randn(shape, generator=g) * 0.1
+        else:   # conv / outconv biases
+            sd[key] = torch.randn(shape, generator=g) * 0.05
+    return sd
+
+
+# --------------------------------------------------------------------------- blocks
+def double_conv(x: Tensor, sd: StateDict, prefix: str, training: bool, bn_out: Optional[StateDict] = None,
+                momentum: float = 0.1, eps: float = 1e-5) -> Tensor:
+    """(Conv3x3 pad1 + bias -> BatchNorm2d -> ReLU) x 2 — UG_unet_parts.py:5-19.
+    In training mode batch statistics normalise (biased variance) and, when `bn_out` is given,
+    the updated running statistics (unbiased variance, momentum 0.1) are written there."""
+    for conv_i, bn_i in ((0, 1), (3, 4)):
+        x = F.conv2d(x, sd[f"{prefix}.conv_op.{conv_i}.weight"], sd[f"{prefix}.conv_op.{conv_i}.bias"], padding=1)
+        rm = sd[f"{prefix}.conv_op.{bn_i}.running_mean"].clone()
+        rv = sd[f"{prefix}.conv_op.{bn_i}.running_var"].clone()
+        x = F.batch_norm(x, rm, rv, sd[f"{prefix}.conv_op.{bn_i}.weight"], sd[f"{prefix}.conv_op.{bn_i}.bias"],
+                         training=training, momentum=momentum, eps=eps)
+        if training and bn_out is not None:
+            bn_out[f"{prefix}.conv_op.{bn_i}.running_mean"] = rm
+            bn_out[f"{prefix}.conv_op.{bn_i}.running_var"] = rv
+            bn_out[f"{prefix}.conv_op.{bn_i}.num_batches_tracked"] = sd[f"{prefix}.conv_op.{bn_i}.num_batches_tracked"] + 1
+        x = F.relu(x)
+    return x
+
+
+def up_block(x_low: Tensor, x_skip: Tensor, sd: StateDict, prefix: str, training: bool, bn_out=None) -> Tensor:
+    """bilinear x2 (align_corners=True) -> cat([skip, up]) -> DoubleConv — UG_unet_parts.py:70-81."""
+    up = F.interpolate(x_low, scale_factor=2, mode="bilinear", align_corners=True)
+    return double_conv(torch.cat([x_skip, up], dim=1), sd, prefix, training, bn_out)
+
+
+def pgunet_forward(sd: StateDict, x: Tensor, stage: int, training: bool = True, bn_out: Optional[StateDict] = None,
+                   return_features: bool = False):
+    """PGUNet{stage}.forward — UG_unet.py:188-193, 209-223, 242-260, 282-304."""
+    feats = [double_conv(x, sd, "inc.conv", training, bn_out)]                       # InConv, UG_unet_parts.py:21-28
+    for name in down_names(stage):                                                    # Down, UG_unet_parts.py:44-54
+        feats.append(double_conv(F.max_pool2d(feats[-1], 2), sd, f"{name}.mpconv.1", training, bn_out))
+    dec = []
+    cur = feats[-1]
+    for j in range(1, stage + 1):
+        cur = up_block(cur, feats[stage - j], sd, f"up{j}.conv", training, bn_out)
+        dec.append(cur)
+    logits = None
+    for j, name in enumerate(head_names(stage)):                                      # OutConv, UG_unet_parts.py:84-91
+        d = dec[-1] if stage == 1 else dec[j]
+        l = F.conv2d(d, sd[f"{name}.conv.weight"], sd[f"{name}.conv.bias"])
+        factor = x.shape[-1] // l.shape[-1]
+        if factor > 1:                                                                # UG_unet.py:218,254-255,299-301
+            l = F.interpolate(l, scale_factor=factor, mode="bilinear", align_corners=True)
+        logits = l if logits is None else logits + l
+    if return_features:
+        return logits, feats, dec
+    return logits
+
+
+# --------------------------------------------------------------------------- uncertainty + loss
+def uncertainty_map(x: Tensor, sd_prev: StateDict, prev_stage: int, cur_res: int) -> Tensor:
+    """A = 1 - 2|up(sigmoid(M_prev(down(x)))) - 0.5|, previous model in eval mode — UG_unet.py:19-59."""
+    prev_res = STAGE_RESOLUTION[prev_stage]
+    with torch.no_grad():
+        xp = F.interpolate(x, size=(prev_res, prev_res), mode="bilinear", align_corners=True)
+        p = torch.sigmoid(pgunet_forward(sd_prev, xp, prev_stage, training=False))
+        p = F.interpolate(p, size=(cur_res, cur_res), mode="bilinear", align_corners=True)
+        return 1.0 - 2.0 * torch.abs(p - 0.5)
+
+
+def bce_with_logits(z: Tensor, y: Tensor, pos_weight: float) -> Tensor:
+    """BCEWithLogitsLoss(pos_weight, reduction='none') closed form —
+    uncertainty_guided_trainer.py:64-65: l = (1-y) z + (1+(pw-1) y) softplus(-z)."""
+    return (1 - y) * z + (1 + (pos_weight - 1) * y) * (torch.log1p(torch.exp(-z.abs())) + torch.clamp(-z, min=0))
+
+
+def weighted_loss(z: Tensor, y: Tensor, A: Optional[Tensor], alpha: float, pos_weight: float = 5.0):
+    """final = mean(l * (1 + alpha A)) (or mean(l) at stage 1), base = mean(l) — UG_unet.py:61-94."""
+    pl = bce_with_logits(z, y, pos_weight)
+    final = pl.mean() if A is None else (pl * (1.0 + alpha * A).detach()).mean()
+    return final, pl.mean()
+
+
+def dice_coefficient(pred: Tensor, target: Tensor, smooth: float = 1.0) -> Tensor:
+    """uncertainty_guided_trainer.py:90-107."""
+    p = pred.reshape(pred.shape[0], -1).float()
+    t = target.reshape(target.shape[0], -1).float()
+    return ((2.0 * (p * t).sum(1) + smooth) / (p.sum(1) + t.sum(1) + smooth)).mean()
+
+
+def predictions(z: Tensor) -> Tensor:
+    """sigmoid(z) > 0.5 — uncertainty_guided_trainer.py:109-113."""
+    return (torch.sigmoid(z) > 0.5).float().squeeze(1)
+
+
+def accuracy(pred: Tensor, target: Tensor) -> float:
+    """uncertainty_guided_trainer.py:115-123."""
+    return 1.0 - pred.ne(target).sum().item() / pred.numel()
+
+
+def softmax_entropy_uncertainty(logits: Tensor) -> Tensor:
+    """u = H(softmax(z)) / ln K per sample — Herlev/train_herlev.py:253-257."""
+    p = F.softmax(logits, dim=1)
+    return -(p * torch.log(p + 1e-8)).sum(1) / math.log(logits.shape[1])
+
+
+def weighted_cross_entropy(logits: Tensor, labels: Tensor, u: Optional[Tensor], alpha: float) -> Tensor:
+    """mean(CE_i * (1 + alpha u_i)) — Herlev/train_herlev.py:274-281."""
+    ce = F.cross_entropy(logits, labels, reduction="none")
+    return ce.mean() if u is None else (ce * (1.0 + alpha * u).detach()).mean()
+
+
+# --------------------------------------------------------------------------- trainer step
+def train_step(sd: StateDict, x: Tensor, y: Tensor, stage: int, sd_prev: Optional[StateDict] = None,
+               alpha: float = 1.0, pos_weight: float = 5.0):
+    """One `uncertainty_guided_forward_pass` + backward — uncertainty_guided_trainer.py:143-184,214-217.
+    Returns a dict with logits, losses, metrics, gradients per state_dict key and updated BN buffers."""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
+              and not k.endswith(("running_mean", "running_var"))}
+    full = dict(sd)
+    full.update(params)
+    bn_out: StateDict = {}
+    logits = pgunet_forward(full, x, stage, training=True, bn_out=bn_out)
+    A = None
+    if stage > 1:
+        assert sd_prev is not None
+        A = uncertainty_map(x, sd_prev, stage - 1, STAGE_RESOLUTION[stage])
+    final, base = weighted_loss(logits, y, A, alpha, pos_weight)
+    final.backward()
+    out = {
+        "logits": logits.detach(), "final_loss": final.item(), "base_loss": base.item(),
+        "uncertainty": A, "grads": {k: p.grad for k, p in params.items()}, "bn": bn_out,
+        "uncertainty_weight_mean": 0.0 if A is None else A.mean().item(),
+        "uncertainty_weight_std": 0.0 if A is None else A.std().item(),     # unbiased, as torch.std
+    }
+    if logits.shape[1] == 1:
+        pred = predictions(logits.detach())
+        out["dice"] = dice_coefficient(pred, y.squeeze(1)).item()
+        out["accuracy"] = accuracy(pred, y.squeeze(1))
+    return out
+
+
+def rmsprop_step(p: Tensor, g: Tensor, v: Tensor, lr: float, alpha: float = 0.99, eps: float = 1e-8,
+                 weight_decay: float = 1e-4) -> None:
+    """torch.optim.RMSprop as configured at uncertainty_guided_trainer.py:84-88 (in place)."""
+    g = g + weight_decay * p
+    v.mul_(alpha).addcmul_(g, g, value=1 - alpha)
+    p.addcdiv_(g, v.sqrt().add_(eps), value=-lr)
+
+
+def transfer_weights(prev: StateDict, cur: StateDict) -> Tuple[StateDict, List[str]]:
+    """Same-key copy with leading-slice partial copy on shape mismatch — UG_unet.py:345-411."""
+    new = {k: v.clone() for k, v in cur.items()}
+    copied = []
+    for k, pv in prev.items():
+        if k not in cur:
+            continue
+        cv = cur[k]
+        if pv.shape == cv.shape:
+            new[k] = pv.clone()
+        elif pv.ndim == cv.ndim and pv.ndim in (1, 2, 4):
+            sl = tuple(slice(0, min(a, b)) for a, b in zip(pv.shape[:2], cv.shape[:2])) if pv.ndim > 1 \
+                else (slice(0, min(pv.shape[0], cv.shape[0])),)
+            t = cv.clone()
+            t[sl] = pv[sl]
+            new[k] = t
+        else:
+            continue
+        copied.append(k)
+    return new, copied

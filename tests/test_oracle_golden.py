@@ -1,0 +1,98 @@
+"""Pins the CPU oracle (oracle/ug_oracle.py) against vectors produced by the unmodified reference
+(tools/make_goldens.py).  CPU only."""
+import os
+
+import pytest
+import torch
+
+import ug_oracle as O
+
+CASES = ["trainer_stage1_nc1", "trainer_stage1_nc2_config1", "trainer_stage2_nc1", "trainer_stage3_nc1",
+         "trainer_stage4_nc1"]
+
+
+def _check_sample(t, s, rtol, atol=0.0):
+    f = t.flatten()
+    if "full" in s:
+        torch.testing.assert_close(f, s["full"], rtol=rtol, atol=atol)
+    else:
+        assert f.numel() == s["numel"]
+        torch.testing.assert_close(f[s["idx"]], s["vals"], rtol=rtol, atol=atol)
+        assert abs(f.double().norm().item() - s["norm"]) <= rtol * s["norm"] + atol
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_step_matches_reference(golden_dir, name):
+    fx = torch.load(os.path.join(golden_dir, name + ".pt"))
+    stage, nc = fx["stage"], fx["nc"]
+    if stage == 4 and os.environ.get("UGP_FAST_TESTS"):
+        pytest.skip("fast mode")
+    sd = O.seeded_state_dict(stage, 3, nc, seed=stage)
+    sd_prev = O.seeded_state_dict(stage - 1, 3, nc, seed=stage - 1) if stage > 1 else None
+    out = O.train_step(sd, fx["x"], fx["y"].float(), stage, sd_prev)
+    torch.testing.assert_close(out["logits"], fx["logits"], rtol=1e-4, atol=1e-4)
+    assert abs(out["final_loss"] - fx["final_loss"]) < 1e-5
+    assert abs(out["base_loss"] - fx["base_loss"]) < 1e-5
+    assert abs(out["uncertainty_weight_mean"] - fx["uncertainty_weight_mean"]) < 1e-6
+    assert abs(out["uncertainty_weight_std"] - fx["uncertainty_weight_std"]) < 1e-6
+    if "uncertainty" in fx:
+        torch.testing.assert_close(out["uncertainty"], fx["uncertainty"].float(), rtol=0, atol=1e-3)
+    if nc == 1:
+        assert abs(out["dice"] - fx["dice"]) < 1e-6
+        assert abs(out["accuracy"] - fx["accuracy"]) < 1e-7
+    gmax = max(g.abs().max().item() for g in out["grads"].values())
+    for k, s in fx["grads"].items():
+        _check_sample(out["grads"][k], s, rtol=2e-3, atol=2e-5 * gmax)
+    for k, v in fx["bn"].items():
+        torch.testing.assert_close(out["bn"][k], v, rtol=1e-5, atol=1e-6)
+    # optimiser step (RMSprop lr from the stage config, wd 1e-4)
+    lr = {1: 3e-4}.get(stage, 1e-4)
+    for k, s in fx["after_step"].items():
+        p = sd[k].clone()
+        O.rmsprop_step(p, out["grads"][k], torch.zeros_like(p), lr)
+        # a conv bias in front of train-mode BN has a pure rounding-noise gradient, and the first
+        # RMSprop step is lr * 10 * sign(g): its sign is arbitrary there
+        noise = k.endswith(("conv_op.0.bias", "conv_op.3.bias"))
+        _check_sample(p, s, rtol=1e-4, atol=21 * lr if noise else 2e-5)
+
+
+def test_primitives(golden_dir):
+    import torch.nn.functional as F
+
+    fx = torch.load(os.path.join(golden_dir, "primitives.pt"))
+    pooled, idx = F.max_pool2d(fx["pool_x"], 2, return_indices=True)
+    assert torch.equal(pooled, fx["pool_out"]) and torch.equal(idx, fx["pool_idx"])
+    assert idx[0, 0, 0, 0].item() == 0 and idx[0, 1, 0, 0].item() == 1      # first max wins
+    torch.testing.assert_close(O.bce_with_logits(fx["bce_z"], fx["bce_y"], 5.0), fx["bce_out"], rtol=1e-6, atol=1e-6)
+    A = O.uncertainty_map(fx["unc_x"], O.seeded_state_dict(1, 3, 1, seed=1), 1, 64)
+    torch.testing.assert_close(A, fx["unc_A"], rtol=1e-5, atol=1e-6)
+    assert float(A.min()) >= 0.0 and float(A.max()) <= 1.0
+    moved, copied = O.transfer_weights(O.seeded_state_dict(1, 3, 1, seed=1), O.seeded_state_dict(2, 3, 1, seed=2))
+    assert len(copied) == 42
+    for k, s in fx["transfer_1_to_2"].items():
+        _check_sample(moved[k], s, rtol=0, atol=0)
+
+
+def test_loss_affine_in_alpha():
+    """final(alpha) = base + alpha * mean(l*A): demo_uncertainty_guided.py:155-201."""
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(2, 1, 16, 16, generator=g)
+    y = torch.randint(0, 2, (2, 1, 16, 16), generator=g).float()
+    A = torch.rand(2, 1, 16, 16, generator=g)
+    f0, b0 = O.weighted_loss(z, y, A, 0.0)
+    f1, _ = O.weighted_loss(z, y, A, 1.0)
+    f2, _ = O.weighted_loss(z, y, A, 2.0)
+    assert abs(f0.item() - b0.item()) < 1e-7
+    assert abs((f2 - f1).item() - (f1 - f0).item()) < 1e-6
+    fs1, bs1 = O.weighted_loss(z, y, None, 1.0)
+    assert abs(fs1.item() - bs1.item()) < 1e-7
+
+
+def test_state_dict_tables():
+    counts = {1: 10048769, 2: 12551042, 3: 13175491, 4: 13395780}
+    for stage, n in counts.items():
+        shapes = O.state_dict_shapes(stage, 3, 1)
+        params = sum(int(torch.tensor(s).prod()) if len(s) else 1 for k, s in shapes.items()
+                     if not k.endswith(("running_mean", "running_var", "num_batches_tracked")))
+        assert params == n
+    assert len(O.state_dict_shapes(4, 3, 1)) == 134

@@ -1,0 +1,140 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    python tools/make_goldens.py
+
+Weights come from oracle.ug_oracle.seeded_state_dict (a pure function of key/shape/seed), loaded
+into the reference's own nn.Modules with load_state_dict(strict=True) — which also proves the
+key/shape table of the oracle matches the reference.  Each fixture stores the inputs and the
+reference's outputs (logits, losses, metrics, uncertainty map, BN buffers after the step, and
+gradients: full tensors for small parameters, a strided sample + norm for the big conv weights) so
+the files stay small.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, "/root/reference")
+
+import torch
+import torch.nn.functional as F
+
+import ug_oracle as O
+
+with contextlib.redirect_stdout(io.StringIO()):
+    import UG_unet as REF
+    import uncertainty_guided_trainer as REFT
+
+OUT = os.path.join(ROOT, "tests", "golden")
+SAMPLE = 4096
+
+
+def sample(t: torch.Tensor):
+    f = t.flatten()
+    if f.numel() <= SAMPLE:
+        return {"full": f.clone()}
+    idx = torch.linspace(0, f.numel() - 1, SAMPLE).long()
+    return {"idx": idx, "vals": f[idx].clone(), "norm": f.double().norm().item(), "numel": f.numel()}
+
+
+def trainer_case(stage: int, B: int, nc: int, seed: int):
+    torch.manual_seed(seed)
+    R = O.STAGE_RESOLUTION[stage]
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = torch.randn(B, 3, R, R, generator=g)
+    y = torch.randint(0, 2, (B, nc, R, R), generator=g).float()
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = REFT.UncertaintyGuidedProgressiveTrainer(3, nc, device="cpu", uncertainty_alpha=1.0)
+    tr.models[stage].load_state_dict(O.seeded_state_dict(stage, 3, nc, seed=stage), strict=True)
+    if stage > 1:
+        tr.models[stage - 1].load_state_dict(O.seeded_state_dict(stage - 1, 3, nc, seed=stage - 1), strict=True)
+    tr.current_stage = stage
+    tr.current_model = tr.models[stage]
+    tr.setup_optimizer(stage)
+    tr.current_model.train()
+    if stage > 1:
+        tr.models[stage - 1].eval()
+    tr.optimizer.zero_grad()
+    final_loss, metrics = tr.uncertainty_guided_forward_pass(x, y, stage)
+    final_loss.backward()
+    fx = {
+        "stage": stage, "B": B, "nc": nc, "x": x, "y": y.to(torch.uint8),
+        "logits": metrics["output"].detach().clone(),
+        "final_loss": metrics["final_loss"], "base_loss": metrics["base_loss"],
+        "uncertainty_weight_mean": metrics["uncertainty_weight_mean"],
+        "uncertainty_weight_std": metrics["uncertainty_weight_std"],
+        "grads": {k: sample(p.grad) for k, p in tr.current_model.named_parameters()},
+        "bn": {k: v.clone() for k, v in tr.current_model.state_dict().items()
+               if k.endswith(("running_mean", "running_var", "num_batches_tracked"))},
+    }
+    if stage > 1:
+        A = tr.uncertainty_loss.generate_uncertainty_map(x, tr.models[stage - 1], O.STAGE_RESOLUTION[stage - 1], R)
+        fx["uncertainty"] = A.to(torch.float16)
+    if nc == 1:
+        pred = tr.get_predictions(metrics["output"].detach())
+        fx["dice"] = tr.dice_coefficient(pred.float(), y.squeeze(1)).item()
+        fx["accuracy"] = float(tr.calculate_accuracy(pred, y.squeeze(1).long()))
+    # one optimiser step, then a sample of the updated weights
+    tr.optimizer.step()
+    fx["after_step"] = {k: sample(p.detach()) for k, p in tr.current_model.named_parameters()}
+    # eval-mode logits with the post-step weights / buffers
+    tr.current_model.eval()
+    with torch.no_grad():
+        fx["eval_logits"] = tr.current_model(x).clone()
+    return fx
+
+
+def primitive_case():
+    """Primitive semantics the kernels must reproduce."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 8, 8, 8, generator=g)
+    x[0, 0, :2, :2] = 0.0                        # all-equal window -> index of the first element
+    x[0, 1, :2, :2] = torch.tensor([[1.0, 3.0], [3.0, 2.0]])
+    pooled, idx = F.max_pool2d(x, 2, return_indices=True)
+    up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    z = torch.randn(2, 1, 8, 8, generator=g) * 3
+    y = torch.randint(0, 2, (2, 1, 8, 8), generator=g).float()
+    crit = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([5.0]), reduction="none")
+    prev1 = REF.PGUNet1(3, 1)
+    prev1.load_state_dict(O.seeded_state_dict(1, 3, 1, seed=1))
+    cur = torch.randn(2, 3, 64, 64, generator=g)
+    A = REF.UncertaintyGuidedLoss("cpu").generate_uncertainty_map(cur, prev1, 32, 64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        pu = REF.ProgressiveUNet(3, 1)
+        sd1 = O.seeded_state_dict(1, 3, 1, seed=1)
+        sd2 = O.seeded_state_dict(2, 3, 1, seed=2)
+        moved = pu.transfer_weights(sd1, sd2, 2)
+    return {
+        "pool_x": x, "pool_out": pooled, "pool_idx": idx, "up_out": up,
+        "bce_z": z, "bce_y": y, "bce_out": crit(z, y),
+        "unc_x": cur, "unc_A": A,
+        "transfer_1_to_2": {k: sample(v) for k, v in moved.items() if v.is_floating_point()},
+    }
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    cases = {
+        "trainer_stage1_nc1": (1, 2, 1, 11),
+        "trainer_stage1_nc2_config1": (1, 4, 2, 12),     # BASELINE.json configs[0] shape, smaller batch
+        "trainer_stage2_nc1": (2, 2, 1, 13),
+        "trainer_stage3_nc1": (3, 1, 1, 14),
+        "trainer_stage4_nc1": (4, 1, 1, 15),
+    }
+    for name, (stage, B, nc, seed) in cases.items():
+        fx = trainer_case(stage, B, nc, seed)
+        path = os.path.join(OUT, name + ".pt")
+        torch.save(fx, path)
+        print(f"{name}: final_loss={fx['final_loss']:.6f} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    torch.save(primitive_case(), os.path.join(OUT, "primitives.pt"))
+    print("primitives.pt written")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,22 @@
+"""ug_pg_unet_b200 — the UG-PG-UNet hot path on hand-written sm_100a kernels.
+
+Public surface (mirrors the reference's UG_unet_parts.py / UG_unet.py /
+uncertainty_guided_trainer.py):
+
+    DoubleConv, InConv, Down, Up, OutConv
+    PGUNet1..4, ProgressiveUNet, UncertaintyGuidedLoss
+    UncertaintyGuidedProgressiveTrainer
+
+Everything executes through libugp_b200.so (C ABI in include/ugp_b200.h);
+there is no CPU or library fallback.
+"""
+from .unet_parts import DoubleConv, Down, InConv, OutConv, Up
+from .unet import (PGUNet1, PGUNet2, PGUNet3, PGUNet4, ProgressiveUNet, STAGE_MODELS,
+                   UncertaintyGuidedLoss, transfer_state)
+from .trainer import UncertaintyGuidedProgressiveTrainer
+
+__all__ = [
+    "DoubleConv", "InConv", "Down", "Up", "OutConv",
+    "PGUNet1", "PGUNet2", "PGUNet3", "PGUNet4", "ProgressiveUNet", "STAGE_MODELS",
+    "UncertaintyGuidedLoss", "transfer_state", "UncertaintyGuidedProgressiveTrainer",
+]

@@ -372,8 +372,9 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, in
 // ----------------------------------------------------------------------------
 // BatchNorm(train) + ReLU (+ max-pool) backward.
 //   g  = (dA + unpool(dP)) * [a > 0]          a = relu(z*scale+shift)
-//   pass 1: sums[0][c] = sum g, sums[1][c] = sum g*xhat   (xhat = (z-mean)*rstd)
-//   pass 2: dz = gamma*rstd * (g - sums0/n - xhat*sums1/n); dbias += sum dz
+//   pass 1: sums[0][c] = sum g*xhat (= dgamma), sums[1][c] = sum g (= dbeta)
+//           (xhat = (z-mean)*rstd; the order matches BatchNorm2d's weight, bias)
+//   pass 2: dz = gamma*rstd * (g - sums1/n - xhat*sums0/n); dbias += sum dz
 // Thread = 2x2 window x 8 channels (so the pool arg-max can be recomputed).
 // ----------------------------------------------------------------------------
 struct BnBwdArgs {
@@ -385,7 +386,7 @@ struct BnBwdArgs {
   const float* mean;
   const float* rstd;
   const float* gamma;
-  float* sums;               // [2][C]
+  float* sums;               // [2][C]: dgamma, dbeta
   float* dbias;              // [C] or null (pass 2)
   __nv_bfloat16* dz;         // pass 2 output
   int B, H, W, C;
@@ -417,8 +418,8 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_kernel(const BnBwdArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       k0[j] = __ldg(a.gamma + c0 + j) * rs[j];
-      k1[j] = __ldg(a.sums + c0 + j) * a.inv_count;
-      k2[j] = __ldg(a.sums + a.C + c0 + j) * a.inv_count;
+      k1[j] = __ldg(a.sums + a.C + c0 + j) * a.inv_count;   // mean of g
+      k2[j] = __ldg(a.sums + c0 + j) * a.inv_count;         // mean of g*xhat
     }
   }
   float acc0[8], acc1[8];
@@ -501,8 +502,8 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_kernel(const BnBwdArgs a) {
       if (!kApply) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          atomicAdd(a.sums + c0 + j, acc0[j]);
-          atomicAdd(a.sums + a.C + c0 + j, acc1[j]);
+          atomicAdd(a.sums + c0 + j, acc1[j]);
+          atomicAdd(a.sums + a.C + c0 + j, acc0[j]);
         }
       } else {
 #pragma unroll

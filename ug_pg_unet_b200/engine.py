@@ -1,0 +1,283 @@
+"""Autograd glue between the nn.Module surface and the C-ABI kernels.
+
+The unit of work is Conv3x3(+bias) -> BatchNorm2d -> ReLU ("CBR"), the building
+block of the reference's DoubleConv (UG_unet_parts.py:5-19).  Forward keeps the
+raw conv output z (bf16) and the per-channel BN coefficients; backward
+recomputes the activation from z, so the ReLU mask / max-pool arg-max never
+need to be stored.
+
+Activations travel as NHWC bf16 tensors [B, H, W, C].
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+bf16 = torch.bfloat16
+
+
+class PackedWeights:
+    """bf16 GEMM operands of one nn.Conv2d weight, refreshed when the fp32 master changes
+    (optimizer.step / load_state_dict / .to(device) all bump `_version` or the storage)."""
+
+    def __init__(self, conv: nn.Conv2d, need_dgrad: bool):
+        self.conv = conv
+        self.need_dgrad = need_dgrad
+        self.key = None
+        self.wf = None
+        self.wd = None
+
+    def get(self):
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version, w.device)
+        if key != self.key:
+            self.wf, self.wd = ops.pack_weights(w.detach(), self.need_dgrad)
+            self.key = key
+        return self.wf, self.wd
+
+
+class CBRSaved:
+    __slots__ = ("srcs", "z", "coef", "taps", "pooled")
+
+    def __init__(self, srcs, z, coef, taps, pooled):
+        self.srcs = srcs      # list of 1-2 NHWC bf16 inputs of the conv
+        self.z = z            # raw conv output (+bias), bf16
+        self.coef = coef      # fp32 [4, C]: scale, shift, mean, rstd
+        self.taps = taps
+        self.pooled = pooled  # whether a fused 2x2 max-pool output was emitted
+
+
+def cbr_forward(srcs: Sequence[torch.Tensor], taps: int, conv: nn.Conv2d, bn: nn.BatchNorm2d,
+                packs: PackedWeights, emit_pool: bool, save: bool):
+    """One Conv -> BN -> ReLU unit.  Returns (a, pooled or None, CBRSaved or None)."""
+    src0 = srcs[0]
+    src1 = srcs[1] if len(srcs) > 1 else None
+    B, H, W, _ = src0.shape
+    cout = conv.out_channels
+    wf, _ = packs.get()
+    dev = src0.device
+    bias = conv.bias.detach() if conv.bias is not None else None
+    if bn.training:
+        stats = torch.zeros((2, cout), dtype=torch.float32, device=dev)
+        z = ops.conv_gemm(src0, src1, wf, taps, cout, bias=bias, stats=stats)
+        coef = torch.empty((4, cout), dtype=torch.float32, device=dev)
+        momentum = 0.0 if bn.momentum is None else float(bn.momentum)
+        track = bn.track_running_stats and bn.running_mean is not None
+        if track and bn.momentum is None:   # cumulative moving average
+            momentum = 1.0 / float(int(bn.num_batches_tracked) + 1)
+        ops.bn_finalize(stats, B * H * W, bn.weight.detach(), bn.bias.detach(), float(bn.eps), momentum,
+                        bn.running_mean if track else None, bn.running_var if track else None,
+                        bn.num_batches_tracked if track else None, coef[0], coef[1], coef[2], coef[3])
+        if emit_pool:
+            a, p = ops.bn_relu_apply(z, coef[0], coef[1], pool=True)
+        else:
+            a, p = ops.bn_relu_apply(z, coef[0], coef[1]), None
+        saved = CBRSaved(list(srcs), z, coef, taps, emit_pool) if save else None
+        return a, p, saved
+    # eval: BatchNorm folds into the conv epilogue (running statistics)
+    coef = torch.empty((2, cout), dtype=torch.float32, device=dev)
+    ops.bn_eval_coeffs(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, float(bn.eps),
+                       coef[0], coef[1])
+    a = ops.conv_gemm(src0, src1, wf, taps, cout, bias=bias, scale=coef[0], shift=coef[1], relu=True)
+    p = ops.maxpool2x2(a) if emit_pool else None
+    return a, p, None   # nothing saved: backward through eval-mode BatchNorm is not supported
+
+
+def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch.Tensor], conv: nn.Conv2d,
+                 bn: nn.BatchNorm2d, packs: PackedWeights, need_dgrad: bool):
+    """Backward of one unit.  Returns (d_srcs list or None, (dW, dbias, dgamma, dbeta))."""
+    src0 = saved.srcs[0]
+    src1 = saved.srcs[1] if len(saved.srcs) > 1 else None
+    cout = conv.out_channels
+    cin = conv.in_channels
+    dev = src0.device
+    coef = saved.coef
+    small = torch.zeros((3, cout), dtype=torch.float32, device=dev)   # dgamma, dbeta, dbias
+    dz = ops.bn_relu_bwd(saved.z, dA, dP, coef[0], coef[1], coef[2], coef[3], bn.weight.detach(),
+                         small[:2], small[2])
+    kdim = sum(s.shape[3] for s in saved.srcs)
+    dwp = torch.zeros((saved.taps * kdim * cout,), dtype=torch.float32, device=dev)
+    ops.conv_wgrad(src0, src1, dz, saved.taps, dwp)
+    dW = ops.unpack_wgrad(dwp, cout, cin)
+    d_srcs = None
+    if need_dgrad:
+        _, wd = packs.get()
+        if src1 is None:
+            d_srcs = [ops.conv_gemm(dz, None, wd, 9, kdim)]
+        else:
+            d0, d1 = ops.conv_gemm(dz, None, wd, 9, kdim, split_n=src0.shape[3])
+            d_srcs = [d0, d1]
+    return d_srcs, (dW, small[2], small[0], small[1])
+
+
+# ----------------------------------------------------------------------------- layout helpers
+def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW tensor (any float dtype / strides) -> contiguous NHWC bf16."""
+    return x.permute(0, 2, 3, 1).to(bf16).contiguous()
+
+
+def nhwc_as_nchw(x: torch.Tensor) -> torch.Tensor:
+    """NHWC tensor -> logical NCHW view (channels_last strides, no copy)."""
+    return x.permute(0, 3, 1, 2)
+
+
+def is_fast_act(x: torch.Tensor) -> bool:
+    """bf16, logical NCHW with channels_last strides: the zero-copy inter-block format."""
+    return x.dtype == bf16 and x.dim() == 4 and x.permute(0, 2, 3, 1).is_contiguous()
+
+
+# ----------------------------------------------------------------------------- DoubleConv function
+class DoubleConvFn(torch.autograd.Function):
+    """(optional pre-op) -> CBR -> CBR as one autograd node.
+
+    kind: 'plain'  x NHWC bf16
+          'first'  x fp32 NCHW image, first conv runs through im2col (9*Cin <= 64)
+          'pool'   MaxPool2d(2) then DoubleConv  (Down, UG_unet_parts.py:44-54)
+          'up'     bilinear x2 of x, concat [skip, up], DoubleConv (Up, UG_unet_parts.py:70-81)
+    emit_pool: also return MaxPool2d(2) of the output (fused into the BN/ReLU pass).
+    """
+
+    @staticmethod
+    def forward(ctx, mod, kind: str, emit_pool: bool, x, skip, *params):
+        conv1, bn1, conv2, bn2 = mod.conv_op[0], mod.conv_op[1], mod.conv_op[3], mod.conv_op[4]
+        need_grad = any(ctx.needs_input_grad)
+        pre = None
+        if kind == "first":
+            srcs, taps = [ops.im2col_first(x)], 1
+        elif kind == "pool":
+            pre = x
+            srcs, taps = [ops.maxpool2x2(x)], 9
+        elif kind == "up":
+            srcs, taps = [skip, ops.upsample2x(x)], 9
+        else:
+            srcs, taps = [x], 9
+        a1, _, s1 = cbr_forward(srcs, taps, conv1, bn1, mod._packs[0], False, need_grad)
+        a2, p2, s2 = cbr_forward([a1], 9, conv2, bn2, mod._packs[1], emit_pool, need_grad)
+        ctx.mod, ctx.kind, ctx.emit_pool = mod, kind, emit_pool
+        ctx.s1, ctx.s2, ctx.pre = s1, s2, pre
+        ctx.x_needs_grad = kind != "first" and ctx.needs_input_grad[3]
+        ctx.skip_needs_grad = skip is not None and ctx.needs_input_grad[4]
+        if emit_pool:
+            return a2, p2
+        return a2
+
+    @staticmethod
+    def backward(ctx, dA, dP=None):
+        mod = ctx.mod
+        conv1, bn1, conv2, bn2 = mod.conv_op[0], mod.conv_op[1], mod.conv_op[3], mod.conv_op[4]
+        if ctx.s1 is None or ctx.s2 is None:
+            raise RuntimeError("ug_pg_unet_b200: backward through eval-mode BatchNorm is not supported; "
+                               "call .train() before a training step or run inference under torch.no_grad()")
+        dA = dA.contiguous() if dA is not None else None
+        dP = dP.contiguous() if dP is not None else None
+        d1, g2 = cbr_backward(ctx.s2, dA, dP, conv2, bn2, mod._packs[1], True)
+        need_in = ctx.x_needs_grad or ctx.skip_needs_grad
+        d0, g1 = cbr_backward(ctx.s1, d1[0], None, conv1, bn1, mod._packs[0], need_in)
+        dx = dskip = None
+        if need_in:
+            if ctx.kind == "pool":
+                dx = ops.maxpool2x2_bwd(ctx.pre, d0[0])
+            elif ctx.kind == "up":
+                dskip = d0[0]
+                dx = ops.upsample2x_bwd(d0[1])
+            else:
+                dx = d0[0]
+        ctx.s1 = ctx.s2 = ctx.pre = None
+        # params order: conv1.weight, conv1.bias, bn1.weight, bn1.bias, conv2.weight, ...
+        return (None, None, None, dx, dskip, g1[0], g1[1], g1[2], g1[3], g2[0], g2[1], g2[2], g2[3])
+
+
+def double_conv_params(mod) -> Tuple[torch.Tensor, ...]:
+    c1, b1, c2, b2 = mod.conv_op[0], mod.conv_op[1], mod.conv_op[3], mod.conv_op[4]
+    return (c1.weight, c1.bias, b1.weight, b1.bias, c2.weight, c2.bias, b2.weight, b2.bias)
+
+
+def run_double_conv(mod, kind: str, x, skip=None, emit_pool: bool = False):
+    return DoubleConvFn.apply(mod, kind, emit_pool, x, skip, *double_conv_params(mod))
+
+
+# ----------------------------------------------------------------------------- OutConv / head
+class OutConvFn(torch.autograd.Function):
+    """1x1 conv C -> num_classes on an NHWC bf16 activation; fp32 NCHW logits out
+    (OutConv, UG_unet_parts.py:84-91)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        w2 = weight.detach().reshape(weight.shape[0], -1).contiguous()
+        out = ops.outconv_fwd(x, w2, bias.detach())
+        ctx.save_for_backward(x, weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, dl):
+        x, weight = ctx.saved_tensors
+        nc = weight.shape[0]
+        w2 = weight.detach().reshape(nc, -1).contiguous()
+        dx = torch.empty_like(x)
+        g = torch.zeros((nc * w2.shape[1] + nc,), dtype=torch.float32, device=x.device)
+        dw, db = g[: nc * w2.shape[1]].view(nc, -1), g[nc * w2.shape[1]:]
+        ops.outconv_bwd(x, w2, dl.contiguous(), dx, False, dw, db)
+        return dx, dw.view_as(weight), db
+
+
+class HeadCombineFn(torch.autograd.Function):
+    """logits = sum_s bilinear_up(map_s), coarse -> fine (UG_unet.py:294-303)."""
+
+    @staticmethod
+    def forward(ctx, *maps):
+        ctx.sizes = [m.shape[-1] for m in maps]
+        return ops.head_combine_fwd([m.contiguous() for m in maps])
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        dlogits = dlogits.contiguous()
+        return tuple(ops.head_combine_bwd(dlogits, s) for s in ctx.sizes)
+
+
+# ----------------------------------------------------------------------------- losses
+class BCEUncertaintyLossFn(torch.autograd.Function):
+    """mean(BCEWithLogits(pos_weight)(z, t) * (1 + alpha*A)) with dlogits produced in the same pass;
+    `metrics` (float64 [5+3B] device tensor, see ugp_bce_uncertainty_loss) rides along."""
+
+    @staticmethod
+    def forward(ctx, z, t, A, alpha: float, pos_weight: float):
+        zc = z.detach().contiguous()
+        n = zc.numel()
+        want = ctx.needs_input_grad[0]
+        out, dlogits = ops.bce_uncertainty_loss(zc, t.contiguous(), None if A is None else A.contiguous(),
+                                                alpha, pos_weight, want, 1.0 / n)
+        ctx.dlogits = dlogits
+        loss = (out[0] / n).float()
+        ctx.mark_non_differentiable(out)
+        return loss, out
+
+    @staticmethod
+    def backward(ctx, gloss, _gout):
+        d = ctx.dlogits
+        ctx.dlogits = None
+        if d is None:
+            return None, None, None, None, None
+        return d * gloss, None, None, None, None
+
+
+class CEWeightedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, u, alpha: float):
+        lc = logits.detach().contiguous()
+        B = lc.shape[0]
+        want = ctx.needs_input_grad[0]
+        out, dl = ops.ce_weighted_loss(lc, labels.contiguous(), None if u is None else u.contiguous(), alpha,
+                                       want, 1.0 / B)
+        ctx.dl = dl
+        ctx.mark_non_differentiable(out)
+        return (out[0] / B).float(), out
+
+    @staticmethod
+    def backward(ctx, gloss, _gout):
+        d = ctx.dl
+        ctx.dl = None
+        return (None if d is None else d * gloss), None, None, None

@@ -1,0 +1,153 @@
+"""Data-parallel gradient exchange for the trainer step (new functionality: the
+reference is single-process).
+
+One process per GPU; the batch is sharded by rank; gradients are averaged with
+NCCL all-reduce over NVLink/NVSwitch.  Parameters are grouped into a few flat
+buckets in REVERSE forward order (the order backward produces them); a
+bucket's all-reduce is launched on a side stream from the
+post-accumulate-grad hook of its last parameter, so it overlaps the remaining
+dgrad/wgrad kernels.  `wait()` joins the side stream before the optimiser.
+
+BatchNorm statistics stay rank-local (what DistributedDataParallel gives the
+reference); buffers are broadcast from rank 0 at construction.
+Works with the `gloo` backend on CPU tensors too (used by the world_size-2
+tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(t: torch.Tensor, rank: int, world_size: int) -> torch.Tensor:
+    """Equal contiguous shards along dim 0 (the loss is a per-shard mean, so shards must be equal:
+    UG_unet.py:92)."""
+    if t.shape[0] % world_size != 0:
+        raise ValueError(f"global batch {t.shape[0]} is not divisible by world_size {world_size}")
+    n = t.shape[0] // world_size
+    return t[rank * n:(rank + 1) * n]
+
+
+class _Bucket:
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = params
+        self.numel = sum(p.numel() for p in params)
+        self.flat: Optional[torch.Tensor] = None
+        self.pending = 0
+        self.work = None
+
+
+class GradBucketReducer:
+    """Bucketed, overlapped gradient averaging across ranks."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], bucket_mb: float = 16.0,
+                 process_group=None, overlap: bool = True):
+        self.group = process_group
+        self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.overlap = overlap
+        ps = [p for p in params if p.requires_grad]
+        # reverse forward order = the order gradients become ready
+        ps = list(reversed(ps))
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        self.buckets: List[_Bucket] = []
+        cur: List[torch.nn.Parameter] = []
+        size = 0
+        for p in ps:
+            cur.append(p)
+            size += p.numel()
+            if size >= cap:
+                self.buckets.append(_Bucket(cur))
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(_Bucket(cur))
+        self._owner = {}
+        self._hooks = []
+        self._stream = None
+        for b in self.buckets:
+            for p in b.params:
+                self._owner[p] = b
+                if overlap and self.world_size > 1:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
+        self.reset()
+
+    def reset(self):
+        for b in self.buckets:
+            b.pending = len(b.params)
+            b.work = None
+
+    # -- hook path (during backward) --
+    def _on_grad_ready(self, p):
+        b = self._owner[p]
+        b.pending -= 1
+        if b.pending == 0:
+            self._launch(b)
+
+    def _launch(self, b: _Bucket):
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b.params]
+        dev = grads[0].device
+        if dev.type == "cuda":
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=dev, priority=-1)
+            self._stream.wait_stream(torch.cuda.current_stream(dev))
+            ctx = torch.cuda.stream(self._stream)
+        else:
+            ctx = _null()
+        with ctx:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            if dev.type == "cuda":
+                for g in grads:
+                    g.record_stream(self._stream)
+            b.work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            b.flat = flat
+
+    # -- after backward --
+    def wait(self):
+        """Finish every bucket and write the averaged gradients back into `.grad`."""
+        if self.world_size == 1:
+            self.reset()
+            return
+        for b in self.buckets:
+            if b.work is None:          # hooks disabled, or a parameter got no gradient this step
+                self._launch(b)
+        inv = 1.0 / self.world_size
+        for b in self.buckets:
+            dev = b.flat.device
+            ctx = torch.cuda.stream(self._stream) if dev.type == "cuda" else _null()
+            with ctx:
+                b.work.wait()
+                off = 0
+                for p in b.params:
+                    n = p.numel()
+                    g = b.flat[off:off + n].view_as(p)
+                    if p.grad is None:
+                        p.grad = g * inv
+                    else:
+                        torch.mul(g, inv, out=p.grad)
+                    off += n
+        if self._stream is not None:
+            torch.cuda.current_stream().wait_stream(self._stream)
+        self.reset()
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+class _null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+def broadcast_module_state(module: torch.nn.Module, src: int = 0, process_group=None) -> None:
+    """Make every rank start from rank `src`'s parameters and buffers."""
+    if not dist.is_initialized() or dist.get_world_size(process_group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src=src, group=process_group)

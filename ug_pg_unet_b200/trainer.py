@@ -1,0 +1,307 @@
+"""Drop-in `UncertaintyGuidedProgressiveTrainer` on the sm_100a kernels.
+
+Mirrors the public surface of the reference's
+`uncertainty_guided_trainer.py::UncertaintyGuidedProgressiveTrainer` (:25-524):
+constructor, `stage_configs`, `models`, `current_model`, `current_stage`,
+`base_criterion`, `optimizer`, `uncertainty_loss`, `uncertainty_alpha`, `history`,
+`setup_optimizer`, `dice_coefficient`, `get_predictions`, `calculate_accuracy`,
+`transfer_weights`, `uncertainty_guided_forward_pass`, `train_epoch`,
+`validate_epoch`, `train_progressive`, `load_stage_weights` — so subclasses such
+as `AugMoNuSegTrainer` (MoNuSegImprove/train_aug_monuseg.py:36-121) keep working.
+
+What changes underneath: the models are the kernel-backed PGUNet1..4, the
+loss + all step metrics come out of one fused kernel as a single device tensor
+(one host read-back per log interval instead of six syncs per step, SURVEY.md
+§3.1), and the step can be sharded across ranks (`world_size` > 1) with bucketed
+NCCL gradient all-reduce overlapped with backward.  Plotting / analysis dumps are
+out of scope (reporting only).
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from pathlib import Path
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+import torch.optim as optim
+
+from .parallel import GradBucketReducer, broadcast_module_state
+from .unet import PGUNet1, PGUNet2, PGUNet3, PGUNet4, UncertaintyGuidedLoss, transfer_state
+
+
+class UncertaintyGuidedProgressiveTrainer:
+    def __init__(self, in_channels=3, num_classes=1, device="cuda", uncertainty_alpha=1.0,
+                 distributed: Optional[bool] = None, bucket_mb: float = 16.0, log_interval: int = 10):
+        self.device = device
+        self.in_channels = in_channels
+        self.num_classes = num_classes
+        self.uncertainty_alpha = uncertainty_alpha
+        self.log_interval = log_interval
+        self.bucket_mb = bucket_mb
+
+        # reference uncertainty_guided_trainer.py:42-47
+        self.stage_configs = {
+            1: {"resolution": 32, "epochs_per_stage": 40, "lr": 3e-4},
+            2: {"resolution": 64, "epochs_per_stage": 40, "lr": 1e-4},
+            3: {"resolution": 128, "epochs_per_stage": 40, "lr": 1e-4},
+            4: {"resolution": 256, "epochs_per_stage": 40, "lr": 1e-4},
+        }
+        self.models = {
+            1: PGUNet1(in_channels, num_classes).to(device),
+            2: PGUNet2(in_channels, num_classes).to(device),
+            3: PGUNet3(in_channels, num_classes).to(device),
+            4: PGUNet4(in_channels, num_classes).to(device),
+        }
+        self.distributed = dist.is_initialized() and dist.get_world_size() > 1 if distributed is None else distributed
+        self.world_size = dist.get_world_size() if self.distributed else 1
+        self.rank = dist.get_rank() if self.distributed else 0
+        if self.distributed:
+            for m in self.models.values():
+                broadcast_module_state(m)
+        self._reducer = None
+
+        self.current_stage = 1
+        self.current_model = self.models[1]
+        self.uncertainty_loss = UncertaintyGuidedLoss(device)
+
+        pos_weight = torch.tensor([5.0]).to(device)                       # :64
+        self.base_criterion = nn.BCEWithLogitsLoss(pos_weight=pos_weight, reduction="none")
+        self.optimizer = None
+        self.setup_optimizer(1)
+
+        self.history = {
+            "train_loss": [], "val_loss": [], "train_dice": [], "val_dice": [],
+            "uncertainty_weights_mean": [], "uncertainty_weights_std": [], "base_loss": [],
+            "stage_transitions": [],
+        }
+
+    # ------------------------------------------------------------------ optimiser / weights
+    def setup_optimizer(self, stage):
+        """RMSprop(lr, weight_decay=1e-4) on the current model — reference :81-88."""
+        lr = self.stage_configs[stage]["lr"]
+        self.optimizer = optim.RMSprop(self.current_model.parameters(), lr=lr, weight_decay=1e-4)
+        if self._reducer is not None:
+            self._reducer.remove()
+            self._reducer = None
+        if self.distributed:
+            self._reducer = GradBucketReducer(list(self.current_model.parameters()), bucket_mb=self.bucket_mb)
+
+    def transfer_weights(self, prev_stage, new_stage):
+        """reference :125-141, without the throw-away 49 M-parameter ProgressiveUNet."""
+        print(f"Transferring weights from stage {prev_stage} to stage {new_stage}")
+        prev_dict = self.models[prev_stage].state_dict()
+        new_dict = self.models[new_stage].state_dict()
+        self.models[new_stage].load_state_dict(transfer_state(prev_dict, new_dict, verbose_stage=new_stage))
+        print(f"Weight transfer completed for stage {new_stage}")
+
+    def load_stage_weights(self, stage, checkpoint_path):
+        checkpoint = torch.load(checkpoint_path, map_location=self.device)
+        sd = checkpoint["model_state_dict"] if isinstance(checkpoint, dict) and "model_state_dict" in checkpoint \
+            else checkpoint
+        self.models[stage].load_state_dict(sd)
+        print(f"Loaded weights for stage {stage} from {checkpoint_path}")
+
+    # ------------------------------------------------------------------ metrics (reference :90-123)
+    def dice_coefficient(self, pred, target, smooth=1):
+        pred = pred.to(target.device).contiguous().float()
+        target = target.contiguous().float()
+        p = pred.view(pred.size(0), -1)
+        t = target.view(target.size(0), -1)
+        inter = (p * t).sum(dim=1)
+        return ((2.0 * inter + smooth) / (p.sum(dim=1) + t.sum(dim=1) + smooth)).mean()
+
+    def get_predictions(self, output_batch):
+        return (output_batch > 0).float().squeeze(1)          # sigmoid(z) > 0.5  <=>  z > 0
+
+    def calculate_accuracy(self, pred, target):
+        pred = pred.to(target.device)
+        assert pred.size() == target.size()
+        return 1 - pred.ne(target).sum().item() / pred.numel()
+
+    # ------------------------------------------------------------------ the step
+    def _forward_loss(self, data, target, stage):
+        """Forward + fused loss.  Returns (final_loss tensor, logits, metrics device tensor or None,
+        base_loss float or None)."""
+        output_current = self.current_model(data)
+        uncertainty_map = None
+        if stage > 1:
+            uncertainty_map = self.uncertainty_loss.generate_uncertainty_map(
+                data, self.models[stage - 1], self.stage_configs[stage - 1]["resolution"],
+                self.stage_configs[stage]["resolution"])
+        self.uncertainty_loss.last_metrics = None
+        ul = self.uncertainty_loss
+        if ul.fused_criterion(self.base_criterion, output_current, uncertainty_map):
+            final_loss, _ = ul.weighted_loss_device(self.base_criterion, output_current, target,
+                                                    uncertainty_map, self.uncertainty_alpha)
+            base = None
+        else:
+            final_loss, base = ul.apply_uncertainty_weighted_loss(
+                self.base_criterion, output_current, target, uncertainty_map, self.uncertainty_alpha)
+        return final_loss, output_current, uncertainty_map, base
+
+    def _metrics_from_device(self, m: torch.Tensor, n_elem: int, batch: int, has_unc: bool):
+        """Turns the fused kernel's accumulators (double[5+3B]) into the reference's step metrics."""
+        v = m.tolist()
+        final, base = v[0] / n_elem, v[1] / n_elem
+        unc_mean = v[2] / n_elem if has_unc else 0.0
+        unc_std = 0.0
+        if has_unc and n_elem > 1:
+            var = max(v[3] - v[2] * v[2] / n_elem, 0.0) / (n_elem - 1)     # torch.std: unbiased
+            unc_std = math.sqrt(var)
+        acc = 1.0 - v[4] / n_elem
+        dice = 0.0
+        for b in range(batch):
+            pt, p, t = v[5 + 3 * b: 8 + 3 * b]
+            dice += (2.0 * pt + 1.0) / (p + t + 1.0)
+        return final, base, dice / batch, acc, unc_mean, unc_std
+
+    def uncertainty_guided_forward_pass(self, data, target, stage):
+        """reference :143-184 — same return value `(final_loss, metrics)`."""
+        final_loss, output_current, unc, base = self._forward_loss(data, target, stage)
+        m = self.uncertainty_loss.last_metrics
+        if m is not None:
+            f, b, _, _, um, us = self._metrics_from_device(m, output_current.numel(), output_current.shape[0],
+                                                            unc is not None)
+            metrics = {"final_loss": f, "base_loss": b, "output": output_current,
+                       "uncertainty_weight_mean": um, "uncertainty_weight_std": us}
+        else:
+            metrics = {"final_loss": final_loss.item(), "base_loss": base, "output": output_current,
+                       "uncertainty_weight_mean": torch.mean(unc).item() if unc is not None else 0.0,
+                       "uncertainty_weight_std": torch.std(unc).item() if unc is not None else 0.0}
+        return final_loss, metrics
+
+    def _resize(self, data, target, resolution):
+        """reference :208-209; identity when the loader already yields the stage resolution."""
+        if data.shape[-2:] != (resolution, resolution):
+            data = F.interpolate(data, size=(resolution, resolution), mode="bilinear", align_corners=True)
+        if target.shape[-2:] != (resolution, resolution):
+            target = F.interpolate(target, size=(resolution, resolution), mode="nearest")
+        return data, target
+
+    def train_step(self, data, target, stage):
+        """One optimisation step on already-resident device tensors; no host synchronisation.
+        Returns the fused-metrics device tensor (see `_metrics_from_device`)."""
+        self.optimizer.zero_grad()
+        final_loss, output_current, unc, _ = self._forward_loss(data, target, stage)
+        final_loss.backward()
+        if self._reducer is not None:
+            self._reducer.wait()
+        self.optimizer.step()
+        return self.uncertainty_loss.last_metrics, output_current, unc
+
+    def _epoch(self, dataloader, stage, train: bool):
+        resolution = self.stage_configs[stage]["resolution"]
+        totals = [0.0] * 6
+        pending = []                      # fused-metric device tensors not yet read back
+        num_batches = 0
+
+        def drain():
+            last = None
+            for item in pending:
+                last = item if isinstance(item, tuple) and len(item) == 6 else \
+                    self._metrics_from_device(*item)
+                for i in range(6):
+                    totals[i] += last[i]
+            pending.clear()
+            return last
+
+        for batch_idx, (data, target) in enumerate(dataloader):
+            data = data.to(self.device, non_blocking=True)
+            target = target.to(self.device, non_blocking=True)
+            data, target = self._resize(data, target, resolution)
+            if train:
+                m, out, unc = self.train_step(data, target, stage)
+            else:
+                final_loss, out, unc, base = self._forward_loss(data, target, stage)
+                m = self.uncertainty_loss.last_metrics
+            if m is not None:
+                pending.append((m, out.numel(), out.shape[0], unc is not None))
+            else:
+                # custom criterion: the reference's own metric arithmetic (:221-234)
+                with torch.no_grad():
+                    fl, mt = self.uncertainty_guided_forward_pass(data, target, stage)
+                    pred = self.get_predictions(out)
+                    tsq = target.squeeze(1)
+                    pending.append((mt["final_loss"], mt["base_loss"],
+                                    self.dice_coefficient(pred.float(), tsq.float()).item(),
+                                    self.calculate_accuracy(pred, tsq.long()),
+                                    mt["uncertainty_weight_mean"], mt["uncertainty_weight_std"]))
+            num_batches += 1
+            if train and self.log_interval and batch_idx % self.log_interval == 0:
+                f, b, d, a, um, _ = drain()
+                info = f", Unc_mean: {um:.4f}" if stage > 1 else ""
+                print(f"Stage {stage}, Batch {batch_idx}, Loss: {f:.4f}, Base_Loss: {b:.4f}, "
+                      f"Dice: {d:.4f}, Acc: {a:.4f}{info}")
+        drain()
+        n = max(num_batches, 1)
+        kind = "training" if train else "validation"
+        print(f"Stage {stage} {kind} epoch completed. Batches processed: {num_batches}")
+        return tuple(t / n for t in totals)
+
+    def train_epoch(self, dataloader, stage):
+        """reference :186-256 — returns (loss, base_loss, dice, accuracy, unc_mean, unc_std) averages."""
+        self.current_model.train()
+        if stage > 1:
+            self.models[stage - 1].eval()
+        return self._epoch(dataloader, stage, train=True)
+
+    def validate_epoch(self, dataloader, stage):
+        """reference :258-314."""
+        self.current_model.eval()
+        if stage > 1:
+            self.models[stage - 1].eval()
+        with torch.no_grad():
+            return self._epoch(dataloader, stage, train=False)
+
+    def train_progressive(self, train_loader, val_loader, max_stages=4, save_dir="./uncertainty_guided_weights"):
+        """reference :316-398 (checkpoint dict layout preserved; plots omitted)."""
+        save_path = Path(save_dir)
+        save_path.mkdir(exist_ok=True)
+        print("Starting Uncertainty-Guided Progressive Growing U-Net Training")
+        print("=" * 60)
+        for stage in range(1, max_stages + 1):
+            res = self.stage_configs[stage]["resolution"]
+            print(f"\nStarting Stage {stage}")
+            print(f"Resolution: {res}x{res}")
+            if stage > 1:
+                print(f"Using uncertainty-guided loss weighting (alpha={self.uncertainty_alpha})")
+                self.transfer_weights(stage - 1, stage)
+            print("-" * 40)
+            self.current_stage = stage
+            self.current_model = self.models[stage]
+            self.setup_optimizer(stage)
+            self.history["stage_transitions"].append(len(self.history["train_loss"]))
+            epochs = self.stage_configs[stage]["epochs_per_stage"]
+            best_val_dice = 0
+            for epoch in range(epochs):
+                start_time = time.time()
+                tr = self.train_epoch(train_loader, stage)
+                va = self.validate_epoch(val_loader, stage)
+                self.history["train_loss"].append(tr[0])
+                self.history["val_loss"].append(va[0])
+                self.history["train_dice"].append(tr[2])
+                self.history["val_dice"].append(va[2])
+                self.history["uncertainty_weights_mean"].append(va[4])
+                self.history["uncertainty_weights_std"].append(va[5])
+                self.history["base_loss"].append(va[1])
+                print(f"Stage {stage}, Epoch {epoch + 1}/{epochs} ({time.time() - start_time:.2f}s)")
+                print(f"Train - Loss: {tr[0]:.4f}, Base: {tr[1]:.4f}, Dice: {tr[2]:.4f}, Acc: {tr[3]:.4f}")
+                print(f"Val   - Loss: {va[0]:.4f}, Base: {va[1]:.4f}, Dice: {va[2]:.4f}, Acc: {va[3]:.4f}")
+                if stage > 1:
+                    print(f"Uncertainty - Mean: {va[4]:.4f}, Std: {va[5]:.4f}")
+                if va[2] > best_val_dice and self.rank == 0:
+                    best_val_dice = va[2]
+                    torch.save({
+                        "stage": stage, "epoch": epoch,
+                        "model_state_dict": self.current_model.state_dict(),
+                        "optimizer_state_dict": self.optimizer.state_dict(),
+                        "val_dice": va[2], "train_dice": tr[2],
+                        "uncertainty_alpha": self.uncertainty_alpha, "history": self.history,
+                    }, save_path / f"ug_pgunet_stage{stage}_best.pth")
+                print("-" * 60)
+        print("Uncertainty-guided progressive training completed!")
