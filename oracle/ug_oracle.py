@@ -101,14 +101,56 @@ def seeded_state_dict(stage: int, in_channels: int, num_classes: int, seed: int 
     return sd
 
 
+# --------------------------------------------------------------------------- bf16 storage emulation
+class _RoundBF16(torch.autograd.Function):
+    """Round-to-bf16 in forward AND backward: models a tensor (and its gradient) being stored in
+    bf16 between kernels while all arithmetic stays fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _q(x: Tensor, bf16_storage: bool) -> Tensor:
+    return _RoundBF16.apply(x) if bf16_storage else x
+
+
+# set by `bf16_storage(True)`: every activation / conv weight is rounded to bf16 where the sm_100a
+# path stores it in bf16 (conv inputs, conv outputs, post-ReLU activations, upsampled tensors and
+# their gradients); arithmetic stays fp32.  Used to separate kernel bugs from precision effects.
+_BF16_STORAGE = False
+
+
+class bf16_storage:
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        global _BF16_STORAGE
+        self.prev, _BF16_STORAGE = _BF16_STORAGE, self.on
+
+    def __exit__(self, *a):
+        global _BF16_STORAGE
+        _BF16_STORAGE = self.prev
+
+
 # --------------------------------------------------------------------------- blocks
 def double_conv(x: Tensor, sd: StateDict, prefix: str, training: bool, bn_out: Optional[StateDict] = None,
                 momentum: float = 0.1, eps: float = 1e-5) -> Tensor:
     """(Conv3x3 pad1 + bias -> BatchNorm2d -> ReLU) x 2 — UG_unet_parts.py:5-19.
     In training mode batch statistics normalise (biased variance) and, when `bn_out` is given,
     the updated running statistics (unbiased variance, momentum 0.1) are written there."""
+    bq = _BF16_STORAGE
+    x = _q(x, bq)
     for conv_i, bn_i in ((0, 1), (3, 4)):
-        x = F.conv2d(x, sd[f"{prefix}.conv_op.{conv_i}.weight"], sd[f"{prefix}.conv_op.{conv_i}.bias"], padding=1)
+        w = sd[f"{prefix}.conv_op.{conv_i}.weight"]
+        x = F.conv2d(x, _q(w, bq), sd[f"{prefix}.conv_op.{conv_i}.bias"], padding=1)
+        if bq and training:
+            x = _q(x, True)        # train: raw conv output stored in bf16; eval: BN+ReLU fused in the epilogue
         rm = sd[f"{prefix}.conv_op.{bn_i}.running_mean"].clone()
         rv = sd[f"{prefix}.conv_op.{bn_i}.running_var"].clone()
         x = F.batch_norm(x, rm, rv, sd[f"{prefix}.conv_op.{bn_i}.weight"], sd[f"{prefix}.conv_op.{bn_i}.bias"],
@@ -117,13 +159,13 @@ def double_conv(x: Tensor, sd: StateDict, prefix: str, training: bool, bn_out: O
             bn_out[f"{prefix}.conv_op.{bn_i}.running_mean"] = rm
             bn_out[f"{prefix}.conv_op.{bn_i}.running_var"] = rv
             bn_out[f"{prefix}.conv_op.{bn_i}.num_batches_tracked"] = sd[f"{prefix}.conv_op.{bn_i}.num_batches_tracked"] + 1
-        x = F.relu(x)
+        x = _q(F.relu(x), bq)
     return x
 
 
 def up_block(x_low: Tensor, x_skip: Tensor, sd: StateDict, prefix: str, training: bool, bn_out=None) -> Tensor:
     """bilinear x2 (align_corners=True) -> cat([skip, up]) -> DoubleConv — UG_unet_parts.py:70-81."""
-    up = F.interpolate(x_low, scale_factor=2, mode="bilinear", align_corners=True)
+    up = _q(F.interpolate(x_low, scale_factor=2, mode="bilinear", align_corners=True), _BF16_STORAGE)
     return double_conv(torch.cat([x_skip, up], dim=1), sd, prefix, training, bn_out)
 
 

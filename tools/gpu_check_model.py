@@ -44,6 +44,8 @@ def check_stage(stage: int, B: int = 2, nc: int = 1):
         prev.load_state_dict(sd_prev)
 
     ref = O.train_step(sd, x, y, stage, sd_prev, alpha=1.0, pos_weight=5.0)
+    with O.bf16_storage(True):
+        emu = O.train_step(sd, x, y, stage, sd_prev, alpha=1.0, pos_weight=5.0)
 
     model.train()
     ugl = U.UncertaintyGuidedLoss(dev)
@@ -102,9 +104,22 @@ def check_stage(stage: int, B: int = 2, nc: int = 1):
         le = model(x)
         refe = O.pgunet_forward({k: v for k, v in model.state_dict().items()}, x, stage, training=False)
     rows.append(("eval logits", rel(le, refe)))
+    # same comparison against the bf16-storage emulation of the oracle (isolates kernel bugs)
+    rows.append(("[emu] logits", rel(logits, emu["logits"])))
+    rows.append(("[emu] final_loss", abs(final.item() - emu["final_loss"])))
+    rows.append(("[emu-vs-fp32 oracle] logits", rel(emu["logits"], ref["logits"])))
+    ge = []
+    for k, p in model.named_parameters():
+        if k.endswith("conv_op.0.bias") or k.endswith("conv_op.3.bias") or p.grad is None:
+            continue
+        ge.append((k, rel(p.grad, emu["grads"][k]), rel(emu["grads"][k], ref["grads"][k])))
+    for k, e1, e2 in ge:
+        if k.endswith(".weight") and ("conv_op.0" in k or "conv_op.3" in k or "outc" in k):
+            rows.append((f"[emu] grad {k}  (emu-vs-fp32: {e2:.2e})", e1))
+    rows.append(("[emu] grad worst", max(e for _, e, _ in ge)))
     print(f"== stage {stage}  B={B} nc={nc} R={R}")
     for name, v in rows:
-        print(f"   {name:55s} {v:.3e}")
+        print(f"   {name:75s} {v:.3e}")
     return rows
 
 

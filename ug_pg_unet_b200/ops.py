@@ -13,9 +13,64 @@ from typing import Optional, Sequence
 import ctypes as C
 import torch
 
-from ._lib import check, lib
+from ._lib import check as _check_rc, lib
 
 bf16 = torch.bfloat16
+
+# ---- instrumentation used by bench.py: kernel-launch counter and per-launch CUDA-event timing ----
+_LAUNCHES = 0
+_PROFILE = None     # list of (name, flops, start_event, end_event) while profiling
+
+
+def _count(n: int = 1) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def reset_launch_count() -> None:
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def start_profile() -> None:
+    global _PROFILE
+    _PROFILE = []
+
+
+def stop_profile():
+    """-> list of (kernel name, algorithmic flops, milliseconds) for every tensor-core launch."""
+    global _PROFILE
+    torch.cuda.synchronize()
+    out = [(n, f, a.elapsed_time(b)) for (n, f, a, b) in (_PROFILE or [])]
+    _PROFILE = None
+    return out
+
+
+class _timed:
+    def __init__(self, name: str, flops: float):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.b.record()
+            _PROFILE.append((self.name, self.flops, self.a, self.b))
+        return False
+
+
+def check(rc: int, what: str) -> None:
+    _check_rc(rc, what)
+    if what not in ("ugp_conv_gemm_bf16", "ugp_conv_wgrad_bf16"):
+        _count(2 if what == "ugp_bn_relu_bwd" else 1)
 
 
 def _stream() -> int:
@@ -66,13 +121,15 @@ def conv_gemm(src0: torch.Tensor, src1: Optional[torch.Tensor], wpack: torch.Ten
     _req(out0, bf16, "out0")
     if out1 is not None:
         _req(out1, bf16, "out1")
-    rc = lib().ugp_conv_gemm_bf16(_ptr(src0), c0, _ptr(src1), c1, B, H, W, taps, _ptr(wpack), cout,
-                                  _ptr(out0), _ptr(out1), split_n,
-                                  _ptr(_opt(bias, torch.float32, "bias")),
-                                  _ptr(_opt(scale, torch.float32, "scale")),
-                                  _ptr(_opt(shift, torch.float32, "shift")), int(relu),
-                                  _ptr(_opt(stats, torch.float32, "stats")), _stream())
+    with _timed("conv_gemm", 2.0 * B * H * W * cout * taps * (c0 + c1)):
+        rc = lib().ugp_conv_gemm_bf16(_ptr(src0), c0, _ptr(src1), c1, B, H, W, taps, _ptr(wpack), cout,
+                                      _ptr(out0), _ptr(out1), split_n,
+                                      _ptr(_opt(bias, torch.float32, "bias")),
+                                      _ptr(_opt(scale, torch.float32, "scale")),
+                                      _ptr(_opt(shift, torch.float32, "shift")), int(relu),
+                                      _ptr(_opt(stats, torch.float32, "stats")), _stream())
     check(rc, "ugp_conv_gemm_bf16")
+    _count()
     return (out0, out1) if out1 is not None else out0
 
 
@@ -90,9 +147,11 @@ def conv_wgrad(src0, src1, dz, taps: int, dw_packed: torch.Tensor):
     assert dz.shape[:3] == src0.shape[:3]
     assert dw_packed.numel() == taps * (c0 + c1) * cout
     assert dw_packed.data_ptr() % 16 == 0
-    rc = lib().ugp_conv_wgrad_bf16(_ptr(src0), c0, _ptr(src1), c1, _ptr(dz), cout, B, H, W, taps,
-                                   _ptr(dw_packed), _stream())
+    with _timed("conv_wgrad", 2.0 * B * H * W * cout * taps * (c0 + c1)):
+        rc = lib().ugp_conv_wgrad_bf16(_ptr(src0), c0, _ptr(src1), c1, _ptr(dz), cout, B, H, W, taps,
+                                       _ptr(dw_packed), _stream())
     check(rc, "ugp_conv_wgrad_bf16")
+    _count()
     return dw_packed
 
 
