@@ -1,0 +1,284 @@
+// Backward of conv-output -> BatchNorm2d(train) -> ReLU (-> MaxPool2d(2)).
+// Reference: autograd of UG_unet_parts.py:11-12,14-15 (+ :49 for the pool).
+//
+//   g    = (dA + unpool(dP)) * [a > 0]            a = relu(z*scale + shift)
+//   pass 1 (reduce):  sums[0][c] = sum g*xhat (= dgamma), sums[1][c] = sum g (= dbeta)
+//   pass 2 (apply):   dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat));  dbias += sum dz
+//
+// HBM-bound: pass 1 reads dA and z, pass 2 reads them again and writes dz (5
+// bf16 units per conv-output element).  The plain variant
+// streams pixels (4 independent 16-byte loads per array in flight per thread);
+// the pooled variant walks 2x2 windows so the max-pool arg-max can be recomputed
+// from z with exactly the forward arithmetic.
+#include "ugp_common.cuh"
+#include "ugp_vec.cuh"
+
+namespace ugp {
+
+struct BnBwdArgs {
+  const __nv_bfloat16* z;
+  const __nv_bfloat16* dA;   // nullable (full-resolution gradient)
+  const __nv_bfloat16* dP;   // nullable (gradient of the 2x2 max-pooled tensor)
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  float* sums;               // [2][C]: dgamma, dbeta
+  float* dbias;              // [C] or null (pass 2)
+  __nv_bfloat16* dz;         // pass 2 output
+  int B, H, W, C;
+  float inv_count;
+};
+
+constexpr int kBnThreads = 256;
+constexpr int kBnUnroll = 4;
+
+// Block reduction over the rows that share a channel group, then one atomic per
+// channel per block.
+template <int kVals>
+__device__ __forceinline__ void block_reduce_channels(float (*red)[kBnThreads][9], const float* acc0,
+                                                      const float* acc1, int cg, int my_cg,
+                                                      int my_row, int rows_per_block, float* out0,
+                                                      float* out1, int c0) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.x][j] = acc0[j];
+    if (kVals > 1) red[1][threadIdx.x][j] = acc1[j];
+  }
+  __syncthreads();
+  if (my_row == 0) {
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a0[j] = acc0[j]; a1[j] = (kVals > 1) ? acc1[j] : 0.f; }
+    for (int r = 1; r < rows_per_block; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0[j] += red[0][r * cg + my_cg][j];
+        if (kVals > 1) a1[j] += red[1][r * cg + my_cg][j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(out0 + c0 + j, a0[j]);
+      if (kVals > 1) atomicAdd(out1 + c0 + j, a1[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// plain variant: no pooled gradient; one pixel x 8 channels per (thread, slot)
+// ---------------------------------------------------------------------------
+template <bool kApply>
+__global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const BnBwdArgs a) {
+  const int cg = a.C >> 3;
+  const int my_cg = threadIdx.x % cg;
+  const int my_row = threadIdx.x / cg;
+  const int rows_per_block = kBnThreads / cg;
+  const int c0 = my_cg * 8;
+  const long long M = static_cast<long long>(a.B) * a.H * a.W;
+
+  float sc[8], sh[8];
+  float k0[8], kz[8], kc[8];   // apply: dz = k0*g + kz*z + kc ; reduce: kz = mean
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(a.scale + c0 + j);
+    sh[j] = __ldg(a.shift + c0 + j);
+    const float mu = __ldg(a.mean + c0 + j);
+    if (kApply) {
+      const float rs = __ldg(a.rstd + c0 + j);
+      const float gr = __ldg(a.gamma + c0 + j) * rs;
+      const float mg = __ldg(a.sums + a.C + c0 + j) * a.inv_count;     // mean g
+      const float mgx = __ldg(a.sums + c0 + j) * a.inv_count;          // mean g*xhat
+      // dz = gr*(g - mg - (z-mu)*rs*mgx)
+      k0[j] = gr;
+      kz[j] = -gr * rs * mgx;
+      kc[j] = -gr * mg - mu * kz[j];
+    } else {
+      kz[j] = mu;
+      k0[j] = 0.f;
+      kc[j] = 0.f;
+    }
+  }
+  float acc0[8], acc1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+
+  const long long stride = static_cast<long long>(gridDim.x) * rows_per_block;
+  for (long long p = static_cast<long long>(blockIdx.x) * rows_per_block + my_row; p < M;
+       p += stride * kBnUnroll) {
+    Vec8 zv[kBnUnroll], gv[kBnUnroll];
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const long long pp = p + u * stride;
+      if (pp < M) {
+        zv[u] = load8(a.z + pp * a.C + c0);
+        gv[u] = load8(a.dA + pp * a.C + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const long long pp = p + u * stride;
+      if (pp < M) {
+        Vec8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = zv[u].v[j];
+          const float g = (fmaf(z, sc[j], sh[j]) > 0.f) ? gv[u].v[j] : 0.f;
+          if (!kApply) {
+            acc0[j] = fmaf(g, z - kz[j], acc0[j]);   // sum g*(z-mean); * rstd at the end
+            acc1[j] += g;
+          } else {
+            const float d = fmaf(k0[j], g, fmaf(kz[j], z, kc[j]));
+            o.v[j] = d;
+            acc0[j] += d;
+          }
+        }
+        if (kApply) store8(a.dz + pp * a.C + c0, o);
+      }
+    }
+  }
+  __shared__ float red[2][kBnThreads][9];
+  if (!kApply) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc0[j] *= __ldg(a.rstd + c0 + j);
+    block_reduce_channels<2>(red, acc0, acc1, cg, my_cg, my_row, rows_per_block, a.sums,
+                             a.sums + a.C, c0);
+  } else if (a.dbias) {
+    block_reduce_channels<1>(red, acc0, acc1, cg, my_cg, my_row, rows_per_block, a.dbias, nullptr, c0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pooled variant: thread = 2x2 window x 8 channels
+// ---------------------------------------------------------------------------
+template <bool kApply>
+__global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_pool_kernel(const BnBwdArgs a) {
+  const int cg = a.C >> 3;
+  const int Ho = a.H >> 1, Wo = a.W >> 1;
+  const long long windows = static_cast<long long>(a.B) * Ho * Wo;
+  const int my_cg = threadIdx.x % cg;
+  const int c0 = my_cg * 8;
+  const int rows_per_block = kBnThreads / cg;
+  const int my_row = threadIdx.x / cg;
+
+  float sc[8], sh[8], k0[8], kz[8], kc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(a.scale + c0 + j);
+    sh[j] = __ldg(a.shift + c0 + j);
+    const float mu = __ldg(a.mean + c0 + j);
+    if (kApply) {
+      const float rs = __ldg(a.rstd + c0 + j);
+      const float gr = __ldg(a.gamma + c0 + j) * rs;
+      const float mg = __ldg(a.sums + a.C + c0 + j) * a.inv_count;
+      const float mgx = __ldg(a.sums + c0 + j) * a.inv_count;
+      k0[j] = gr;
+      kz[j] = -gr * rs * mgx;
+      kc[j] = -gr * mg - mu * kz[j];
+    } else {
+      kz[j] = mu;
+      k0[j] = 0.f;
+      kc[j] = 0.f;
+    }
+  }
+  float acc0[8], acc1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+
+  for (long long win = static_cast<long long>(blockIdx.x) * rows_per_block + my_row;
+       win < windows; win += static_cast<long long>(gridDim.x) * rows_per_block) {
+    const int xo = static_cast<int>(win % Wo);
+    const int yo = static_cast<int>((win / Wo) % Ho);
+    const int b = static_cast<int>(win / (static_cast<long long>(Wo) * Ho));
+    Vec8 zv[4], gv[4];
+    long long pix[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pix[i] = (static_cast<long long>(b) * a.H + (2 * yo + (i >> 1))) * a.W + 2 * xo + (i & 1);
+      zv[i] = load8(a.z + pix[i] * a.C + c0);
+      if (a.dA) gv[i] = load8(a.dA + pix[i] * a.C + c0);
+    }
+    const Vec8 gp = load8(a.dP + win * a.C + c0);
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float best = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float av = round_bf16(bn_relu_val(zv[i].v[j], sc[j], sh[j]));
+        if (i == 0 || av > best) { best = av; arg[j] = i; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Vec8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = zv[i].v[j];
+        float g = a.dA ? gv[i].v[j] : 0.f;
+        if (arg[j] == i) g += gp.v[j];
+        g = (fmaf(z, sc[j], sh[j]) > 0.f) ? g : 0.f;
+        if (!kApply) {
+          acc0[j] = fmaf(g, z - kz[j], acc0[j]);
+          acc1[j] += g;
+        } else {
+          const float d = fmaf(k0[j], g, fmaf(kz[j], z, kc[j]));
+          o.v[j] = d;
+          acc0[j] += d;
+        }
+      }
+      if (kApply) store8(a.dz + pix[i] * a.C + c0, o);
+    }
+  }
+  __shared__ float red[2][kBnThreads][9];
+  if (!kApply) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc0[j] *= __ldg(a.rstd + c0 + j);
+    block_reduce_channels<2>(red, acc0, acc1, cg, my_cg, my_row, rows_per_block, a.sums,
+                             a.sums + a.C, c0);
+  } else if (a.dbias) {
+    block_reduce_channels<1>(red, acc0, acc1, cg, my_cg, my_row, rows_per_block, a.dbias, nullptr, c0);
+  }
+}
+
+int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scale,
+                const float* shift, const float* mean, const float* rstd,
+                const float* gamma, int B, int H, int W, int C, float* sums,
+                float* dbias, void* dz, cudaStream_t stream) {
+  UGP_REQUIRE(z && (dA || dP) && scale && shift && mean && rstd && gamma && sums && dz,
+              "bn_relu_bwd: null pointer");
+  UGP_REQUIRE(C % 64 == 0 && C <= 2048 && kBnThreads % (C / 8) == 0,
+              "bn_relu_bwd: C %d unsupported", C);
+  BnBwdArgs a;
+  a.z = static_cast<const __nv_bfloat16*>(z);
+  a.dA = static_cast<const __nv_bfloat16*>(dA);
+  a.dP = static_cast<const __nv_bfloat16*>(dP);
+  a.scale = scale; a.shift = shift; a.mean = mean; a.rstd = rstd; a.gamma = gamma;
+  a.sums = sums; a.dbias = dbias; a.dz = static_cast<__nv_bfloat16*>(dz);
+  a.B = B; a.H = H; a.W = W; a.C = C;
+  const long long M = static_cast<long long>(B) * H * W;
+  a.inv_count = 1.f / static_cast<float>(M);
+  const int rows_per_block = kBnThreads / (C / 8);
+  UGP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
+  const long long cap = static_cast<long long>(device_sm_count()) * 8;
+  if (dP) {
+    UGP_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_bwd: pooled gradient needs even H, W");
+    long long blocks = (M / 4 + rows_per_block - 1) / rows_per_block;
+    if (blocks > cap) blocks = cap;
+    bn_relu_bwd_pool_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+    UGP_CHECK_CUDA(cudaGetLastError());
+    bn_relu_bwd_pool_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+  } else {
+    long long blocks = (M + rows_per_block * kBnUnroll - 1) / (rows_per_block * kBnUnroll);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    bn_relu_bwd_plain_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+    UGP_CHECK_CUDA(cudaGetLastError());
+    bn_relu_bwd_plain_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+  }
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
+}
+
+}  // namespace ugp

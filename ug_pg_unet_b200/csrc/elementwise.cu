@@ -6,102 +6,9 @@
 // Reference call sites: UG_unet_parts.py:11-15 (BatchNorm2d,
 // ReLU), :49 (MaxPool2d(2)), :78 (F.interpolate x2 bilinear align_corners=True).
 #include "ugp_common.cuh"
+#include "ugp_vec.cuh"
 
 namespace ugp {
-
-// PyTorch's align_corners=True source index: src = dst * (in-1)/(out-1).
-__device__ __forceinline__ void bilinear_src(int dst, int in, int out, int* i0,
-                                             int* i1, float* lambda) {
-  const float scale = (out > 1) ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f;
-  const float src = scale * static_cast<float>(dst);
-  int a = static_cast<int>(src);
-  if (a > in - 1) a = in - 1;
-  *i0 = a;
-  *i1 = a + ((a < in - 1) ? 1 : 0);
-  *lambda = src - static_cast<float>(a);
-}
-
-// The one definition of train/eval BatchNorm + ReLU on a stored bf16 conv
-// output; forward, max-pool and backward all call this so the recomputed
-// activation (and therefore the arg-max / ReLU mask) is bit-identical.
-__device__ __forceinline__ float bn_relu_val(float z, float sc, float sh) {
-  return fmaxf(fmaf(z, sc, sh), 0.f);
-}
-__device__ __forceinline__ float round_bf16(float v) {
-  return __bfloat162float(__float2bfloat16_rn(v));
-}
-
-struct Vec8 {
-  float v[8];
-};
-__device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  Vec8 r;
-  r.v[0] = bf16_lo(u.x); r.v[1] = bf16_hi(u.x);
-  r.v[2] = bf16_lo(u.y); r.v[3] = bf16_hi(u.y);
-  r.v[4] = bf16_lo(u.z); r.v[5] = bf16_hi(u.z);
-  r.v[6] = bf16_lo(u.w); r.v[7] = bf16_hi(u.w);
-  return r;
-}
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
-  uint4 u;
-  u.x = pack_bf16x2(r.v[0], r.v[1]);
-  u.y = pack_bf16x2(r.v[2], r.v[3]);
-  u.z = pack_bf16x2(r.v[4], r.v[5]);
-  u.w = pack_bf16x2(r.v[6], r.v[7]);
-  *reinterpret_cast<uint4*>(p) = u;
-}
-
-// ----------------------------------------------------------------------------
-// First-layer packing: fp32 NCHW image (optionally bilinearly resized,
-// align_corners=True) -> bf16 [B,H,W,64] rows holding the 3x3 neighbourhood,
-// k = (r*3+s)*Cin + ci, zero beyond 9*Cin and outside the image (pad 1).
-// ----------------------------------------------------------------------------
-__global__ void im2col_first_kernel(const float* __restrict__ x, int B, int Cin,
-                                    int Hin, int Win, int H, int W,
-                                    __nv_bfloat16* __restrict__ out) {
-  const long long total = static_cast<long long>(B) * H * W * 8;
-  const bool resize = (Hin != H) || (Win != W);
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-       idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx & 7);
-    const long long pix = idx >> 3;
-    const int xo = static_cast<int>(pix % W);
-    const int yo = static_cast<int>((pix / W) % H);
-    const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-    Vec8 r;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      float val = 0.f;
-      if (k < 9 * Cin) {
-        const int tap = k / Cin;
-        const int ci = k - tap * Cin;
-        const int yy = yo + tap / 3 - 1;
-        const int xx = xo + tap % 3 - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          const float* plane = x + (static_cast<long long>(b) * Cin + ci) * Hin * Win;
-          if (!resize) {
-            val = __ldg(plane + static_cast<long long>(yy) * Win + xx);
-          } else {
-            int y0, y1, x0, x1;
-            float ly, lx;
-            bilinear_src(yy, Hin, H, &y0, &y1, &ly);
-            bilinear_src(xx, Win, W, &x0, &x1, &lx);
-            const float v00 = __ldg(plane + static_cast<long long>(y0) * Win + x0);
-            const float v01 = __ldg(plane + static_cast<long long>(y0) * Win + x1);
-            const float v10 = __ldg(plane + static_cast<long long>(y1) * Win + x0);
-            const float v11 = __ldg(plane + static_cast<long long>(y1) * Win + x1);
-            val = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) +
-                  ly * ((1.f - lx) * v10 + lx * v11);
-          }
-        }
-      }
-      r.v[j] = val;
-    }
-    store8(out + pix * 64 + g * 8, r);
-  }
-}
 
 // ----------------------------------------------------------------------------
 // BatchNorm statistics -> per-channel scale/shift (+ running stats update).
@@ -370,229 +277,9 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, in
 }
 
 // ----------------------------------------------------------------------------
-// BatchNorm(train) + ReLU (+ max-pool) backward.
-//   g  = (dA + unpool(dP)) * [a > 0]          a = relu(z*scale+shift)
-//   pass 1: sums[0][c] = sum g*xhat (= dgamma), sums[1][c] = sum g (= dbeta)
-//           (xhat = (z-mean)*rstd; the order matches BatchNorm2d's weight, bias)
-//   pass 2: dz = gamma*rstd * (g - sums1/n - xhat*sums0/n); dbias += sum dz
-// Thread = 2x2 window x 8 channels (so the pool arg-max can be recomputed).
-// ----------------------------------------------------------------------------
-struct BnBwdArgs {
-  const __nv_bfloat16* z;
-  const __nv_bfloat16* dA;   // nullable (full-resolution gradient)
-  const __nv_bfloat16* dP;   // nullable (gradient of the 2x2 max-pooled tensor)
-  const float* scale;
-  const float* shift;
-  const float* mean;
-  const float* rstd;
-  const float* gamma;
-  float* sums;               // [2][C]: dgamma, dbeta
-  float* dbias;              // [C] or null (pass 2)
-  __nv_bfloat16* dz;         // pass 2 output
-  int B, H, W, C;
-  float inv_count;
-};
-
-template <bool kApply>
-__global__ void __launch_bounds__(256) bn_relu_bwd_kernel(const BnBwdArgs a) {
-  // blockDim.x = 256; thread's channel group is fixed: (threadIdx.x % cg) when
-  // cg divides 256 (C in {64,...,512} -> cg in {8,...,64}).
-  const int cg = a.C >> 3;
-  const int Ho = a.H >> 1, Wo = a.W >> 1;
-  const long long windows = static_cast<long long>(a.B) * Ho * Wo;
-  const int my_cg = threadIdx.x % cg;
-  const int c0 = my_cg * 8;
-  const int rows_per_block = blockDim.x / cg;
-  const int my_row = threadIdx.x / cg;
-
-  float sc[8], sh[8], mu[8], rs[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = __ldg(a.scale + c0 + j);
-    sh[j] = __ldg(a.shift + c0 + j);
-    mu[j] = __ldg(a.mean + c0 + j);
-    rs[j] = __ldg(a.rstd + c0 + j);
-  }
-  float k0[8], k1[8], k2[8];
-  if (kApply) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      k0[j] = __ldg(a.gamma + c0 + j) * rs[j];
-      k1[j] = __ldg(a.sums + a.C + c0 + j) * a.inv_count;   // mean of g
-      k2[j] = __ldg(a.sums + c0 + j) * a.inv_count;         // mean of g*xhat
-    }
-  }
-  float acc0[8], acc1[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-
-  for (long long win = static_cast<long long>(blockIdx.x) * rows_per_block + my_row;
-       win < windows; win += static_cast<long long>(gridDim.x) * rows_per_block) {
-    const int xo = static_cast<int>(win % Wo);
-    const int yo = static_cast<int>((win / Wo) % Ho);
-    const int b = static_cast<int>(win / (static_cast<long long>(Wo) * Ho));
-    Vec8 zv[4];
-    float best[8];
-    int arg[8];
-    long long pix[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      pix[i] = (static_cast<long long>(b) * a.H + (2 * yo + (i >> 1))) * a.W + 2 * xo + (i & 1);
-      zv[i] = load8(a.z + pix[i] * a.C + c0);
-    }
-    Vec8 gp;
-    if (a.dP) {
-      gp = load8(a.dP + win * a.C + c0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float av = round_bf16(bn_relu_val(zv[i].v[j], sc[j], sh[j]));
-          if (i == 0 || av > best[j]) { best[j] = av; arg[j] = i; }
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      Vec8 g;
-      if (a.dA) {
-        g = load8(a.dA + pix[i] * a.C + c0);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
-      }
-      Vec8 o;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float gj = g.v[j];
-        if (a.dP && arg[j] == i) gj += gp.v[j];
-        const float pre = fmaf(zv[i].v[j], sc[j], sh[j]);
-        gj = (pre > 0.f) ? gj : 0.f;
-        const float xhat = (zv[i].v[j] - mu[j]) * rs[j];
-        if (!kApply) {
-          acc0[j] += gj;
-          acc1[j] = fmaf(gj, xhat, acc1[j]);
-        } else {
-          const float d = k0[j] * (gj - k1[j] - xhat * k2[j]);
-          o.v[j] = d;
-          acc0[j] += d;
-        }
-      }
-      if (kApply) store8(a.dz + pix[i] * a.C + c0, o);
-    }
-  }
-
-  // block reduction over the rows sharing a channel group
-  __shared__ float red[2][256][9];
-  if (!kApply || a.dbias) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      red[0][threadIdx.x][j] = acc0[j];
-      red[1][threadIdx.x][j] = acc1[j];
-    }
-    __syncthreads();
-    if (my_row == 0) {
-      for (int r = 1; r < rows_per_block; ++r) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc0[j] += red[0][r * cg + my_cg][j];
-          acc1[j] += red[1][r * cg + my_cg][j];
-        }
-      }
-      if (!kApply) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          atomicAdd(a.sums + c0 + j, acc1[j]);
-          atomicAdd(a.sums + a.C + c0 + j, acc0[j]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(a.dbias + c0 + j, acc0[j]);
-      }
-    }
-  }
-}
-
-// ----------------------------------------------------------------------------
-// Weight packing. fp32 OIHW master weights -> bf16 GEMM operands.
-//   fwd  pack: Wf[tap][co][ci]      (tap = r*3+s)
-//   dgrad pack: Wd[tap][ci][co] = W[co][ci][2-r][2-s]
-//   first layer (9*Cin <= 64): Wf[co][k], k = (r*3+s)*Cin + ci, zero padded to 64
-// ----------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin,
-                                    __nv_bfloat16* __restrict__ wf,
-                                    __nv_bfloat16* __restrict__ wd) {
-  const long long total = static_cast<long long>(Cout) * Cin * 9;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-       idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    // idx enumerates the fwd pack: (tap, co, ci), ci fastest
-    const int ci = static_cast<int>(idx % Cin);
-    const int co = static_cast<int>((idx / Cin) % Cout);
-    const int tap = static_cast<int>(idx / (static_cast<long long>(Cin) * Cout));
-    const float v = w[(static_cast<long long>(co) * Cin + ci) * 9 + tap];
-    const __nv_bfloat16 bv = __float2bfloat16_rn(v);
-    wf[idx] = bv;
-    if (wd) wd[(static_cast<long long>(8 - tap) * Cin + ci) * Cout + co] = bv;
-  }
-}
-
-__global__ void pack_weights_first_kernel(const float* __restrict__ w, int Cout,
-                                          int Cin, __nv_bfloat16* __restrict__ wf) {
-  const int total = Cout * 64;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += gridDim.x * blockDim.x) {
-    const int k = idx & 63;
-    const int co = idx >> 6;
-    float v = 0.f;
-    if (k < 9 * Cin) {
-      const int tap = k / Cin, ci = k - tap * Cin;
-      v = w[(co * Cin + ci) * 9 + tap];
-    }
-    wf[idx] = __float2bfloat16_rn(v);
-  }
-}
-
-// Packed fp32 gradient [tap][Cin][Cout] -> OIHW fp32 (accumulate optional).
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int Cout, int Cin,
-                                    int first_layer, float* __restrict__ grad,
-                                    int accumulate) {
-  const long long total = static_cast<long long>(Cout) * Cin * 9;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-       idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    // idx enumerates OIHW: (co, ci, tap), tap fastest
-    const int tap = static_cast<int>(idx % 9);
-    const int ci = static_cast<int>((idx / 9) % Cin);
-    const int co = static_cast<int>(idx / (9LL * Cin));
-    float v;
-    if (first_layer)
-      v = dwp[static_cast<long long>(tap * Cin + ci) * Cout + co];
-    else
-      v = dwp[(static_cast<long long>(tap) * Cin + ci) * Cout + co];
-    grad[idx] = accumulate ? grad[idx] + v : v;
-  }
-}
-
-// ----------------------------------------------------------------------------
 // host launchers
 // ----------------------------------------------------------------------------
-static inline int grid_for(long long total, int block, int max_blocks_per_sm = 16) {
-  long long g = (total + block - 1) / block;
-  const long long cap = static_cast<long long>(device_sm_count()) * max_blocks_per_sm;
-  if (g > cap) g = cap;
-  if (g < 1) g = 1;
-  return static_cast<int>(g);
-}
 
-int im2col_first(const float* x, int B, int Cin, int Hin, int Win, int H, int W,
-                 void* out, cudaStream_t stream) {
-  UGP_REQUIRE(x && out, "im2col_first: null pointer");
-  UGP_REQUIRE(Cin >= 1 && 9 * Cin <= 64, "im2col_first: Cin %d unsupported (9*Cin must be <= 64)", Cin);
-  const long long total = static_cast<long long>(B) * H * W * 8;
-  im2col_first_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
-      x, B, Cin, Hin, Win, H, W, static_cast<__nv_bfloat16*>(out));
-  UGP_CHECK_CUDA(cudaGetLastError());
-  return UGP_OK;
-}
 
 int bn_finalize(float* stats, int C, long long count, const float* gamma,
                 const float* beta, float eps, float momentum, float* running_mean,
@@ -682,60 +369,7 @@ int upsample2x_bwd(const void* dout, int B, int h, int w, int C, void* dx,
   return UGP_OK;
 }
 
-int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scale,
-                const float* shift, const float* mean, const float* rstd,
-                const float* gamma, int B, int H, int W, int C, float* sums,
-                float* dbias, void* dz, cudaStream_t stream) {
-  UGP_REQUIRE(z && (dA || dP) && scale && shift && mean && rstd && gamma && sums && dz,
-              "bn_relu_bwd: null pointer");
-  UGP_REQUIRE(C % 64 == 0 && C <= 2048 && 256 % (C / 8) == 0,
-              "bn_relu_bwd: C %d unsupported", C);
-  UGP_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_bwd: needs even H, W");
-  BnBwdArgs a;
-  a.z = static_cast<const __nv_bfloat16*>(z);
-  a.dA = static_cast<const __nv_bfloat16*>(dA);
-  a.dP = static_cast<const __nv_bfloat16*>(dP);
-  a.scale = scale; a.shift = shift; a.mean = mean; a.rstd = rstd; a.gamma = gamma;
-  a.sums = sums; a.dbias = dbias; a.dz = static_cast<__nv_bfloat16*>(dz);
-  a.B = B; a.H = H; a.W = W; a.C = C;
-  a.inv_count = 1.f / static_cast<float>(static_cast<long long>(B) * H * W);
-  const long long windows = static_cast<long long>(B) * (H / 2) * (W / 2);
-  const int rows_per_block = 256 / (C / 8);
-  long long blocks = (windows + rows_per_block - 1) / rows_per_block;
-  const long long cap = static_cast<long long>(device_sm_count()) * 8;
-  if (blocks > cap) blocks = cap;
-  UGP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
-  bn_relu_bwd_kernel<false><<<static_cast<int>(blocks), 256, 0, stream>>>(a);
-  UGP_CHECK_CUDA(cudaGetLastError());
-  bn_relu_bwd_kernel<true><<<static_cast<int>(blocks), 256, 0, stream>>>(a);
-  UGP_CHECK_CUDA(cudaGetLastError());
-  return UGP_OK;
-}
 
-int pack_weights(const float* w, int Cout, int Cin, void* wf, void* wd,
-                 cudaStream_t stream) {
-  UGP_REQUIRE(w && wf, "pack_weights: null pointer");
-  if (Cin % 64 == 0) {
-    const long long total = static_cast<long long>(Cout) * Cin * 9;
-    pack_weights_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
-        w, Cout, Cin, static_cast<__nv_bfloat16*>(wf), static_cast<__nv_bfloat16*>(wd));
-  } else {
-    UGP_REQUIRE(9 * Cin <= 64, "pack_weights: Cin %d unsupported", Cin);
-    pack_weights_first_kernel<<<grid_for(Cout * 64, 256), 256, 0, stream>>>(
-        w, Cout, Cin, static_cast<__nv_bfloat16*>(wf));
-  }
-  UGP_CHECK_CUDA(cudaGetLastError());
-  return UGP_OK;
-}
 
-int unpack_wgrad(const float* dwp, int Cout, int Cin, float* grad, int accumulate,
-                 cudaStream_t stream) {
-  UGP_REQUIRE(dwp && grad, "unpack_wgrad: null pointer");
-  const long long total = static_cast<long long>(Cout) * Cin * 9;
-  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
-      dwp, Cout, Cin, Cin % 64 != 0, grad, accumulate);
-  UGP_CHECK_CUDA(cudaGetLastError());
-  return UGP_OK;
-}
 
 }  // namespace ugp

@@ -1,0 +1,107 @@
+// First-layer input packing (replaces the implicit im2col of the 3-channel
+// nn.Conv2d at UG_unet_parts.py:10 inside InConv, and folds in the bilinear
+// align_corners=True resize of uncertainty_guided_trainer.py:208 /
+// UG_unet.py:36-41): fp32 NCHW image -> bf16 [B,H,W,64] rows holding the 3x3
+// neighbourhood, k = (r*3+s)*Cin + ci, zero beyond 9*Cin and outside the image.
+// The 64-wide rows then feed the tcgen05 GEMM as a 1x1 convolution.
+//
+// HBM-bound on the 128 B/pixel output.  One thread = one pixel: neighbours are
+// read through L1 (adjacent threads share them), the row is written as eight
+// 16-byte stores.
+#include "ugp_common.cuh"
+#include "ugp_vec.cuh"
+
+namespace ugp {
+
+template <int kCin, bool kResize>
+__global__ void __launch_bounds__(256)
+im2col_first_kernel(const float* __restrict__ x, int B, int Hin, int Win, int H, int W,
+                    __nv_bfloat16* __restrict__ out) {
+  const long long total = static_cast<long long>(B) * H * W;
+  const long long plane = static_cast<long long>(Hin) * Win;
+  for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xo = static_cast<int>(pix % W);
+    const int yo = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    const float* img = x + static_cast<long long>(b) * kCin * plane;
+    float vals[64];
+#pragma unroll
+    for (int k = 9 * kCin; k < 64; ++k) vals[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = yo + r - 1;
+      int y0 = 0, y1 = 0;
+      float ly = 0.f;
+      if (kResize) bilinear_src(yy < 0 ? 0 : (yy >= H ? H - 1 : yy), Hin, H, &y0, &y1, &ly);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int xx = xo + s - 1;
+        const bool inside = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        int x0 = 0, x1 = 0;
+        float lx = 0.f;
+        if (kResize) bilinear_src(xx < 0 ? 0 : (xx >= W ? W - 1 : xx), Win, W, &x0, &x1, &lx);
+#pragma unroll
+        for (int ci = 0; ci < kCin; ++ci) {
+          float v = 0.f;
+          if (inside) {
+            const float* p = img + ci * plane;
+            if (!kResize) {
+              v = __ldg(p + static_cast<long long>(yy) * Win + xx);
+            } else {
+              const float v00 = __ldg(p + static_cast<long long>(y0) * Win + x0);
+              const float v01 = __ldg(p + static_cast<long long>(y0) * Win + x1);
+              const float v10 = __ldg(p + static_cast<long long>(y1) * Win + x0);
+              const float v11 = __ldg(p + static_cast<long long>(y1) * Win + x1);
+              v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+            }
+          }
+          vals[(r * 3 + s) * kCin + ci] = v;
+        }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * 64);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      uint4 u;
+      u.x = pack_bf16x2(vals[g * 8 + 0], vals[g * 8 + 1]);
+      u.y = pack_bf16x2(vals[g * 8 + 2], vals[g * 8 + 3]);
+      u.z = pack_bf16x2(vals[g * 8 + 4], vals[g * 8 + 5]);
+      u.w = pack_bf16x2(vals[g * 8 + 6], vals[g * 8 + 7]);
+      dst[g] = u;
+    }
+  }
+}
+
+template <int kCin>
+static int launch_im2col(const float* x, int B, int Hin, int Win, int H, int W, void* out,
+                         cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * H * W;
+  const int grid = grid_for(total, 256);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (Hin != H || Win != W)
+    im2col_first_kernel<kCin, true><<<grid, 256, 0, stream>>>(x, B, Hin, Win, H, W, o);
+  else
+    im2col_first_kernel<kCin, false><<<grid, 256, 0, stream>>>(x, B, Hin, Win, H, W, o);
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
+}
+
+int im2col_first(const float* x, int B, int Cin, int Hin, int Win, int H, int W, void* out,
+                 cudaStream_t stream) {
+  UGP_REQUIRE(x && out, "im2col_first: null pointer");
+  switch (Cin) {
+    case 1: return launch_im2col<1>(x, B, Hin, Win, H, W, out, stream);
+    case 2: return launch_im2col<2>(x, B, Hin, Win, H, W, out, stream);
+    case 3: return launch_im2col<3>(x, B, Hin, Win, H, W, out, stream);
+    case 4: return launch_im2col<4>(x, B, Hin, Win, H, W, out, stream);
+    case 5: return launch_im2col<5>(x, B, Hin, Win, H, W, out, stream);
+    case 6: return launch_im2col<6>(x, B, Hin, Win, H, W, out, stream);
+    case 7: return launch_im2col<7>(x, B, Hin, Win, H, W, out, stream);
+    default:
+      UGP_REQUIRE(false, "im2col_first: Cin %d unsupported (1..7: 9*Cin must be <= 64)", Cin);
+  }
+  return UGP_OK;
+}
+
+}  // namespace ugp

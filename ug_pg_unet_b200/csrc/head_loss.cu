@@ -28,16 +28,16 @@ __device__ __forceinline__ void bilinear_src_f(int dst, int in, int out, int* i0
 // 1x1 OutConv forward: x bf16 [M][C] (NHWC) -> l fp32 [B][nc][h*w] (NCHW).
 // C/8 lanes cooperate on one pixel (16-byte loads), shuffle-reduced.
 // ----------------------------------------------------------------------------
-template <int kLanes>   // lanes per pixel = C/8 in {8,16,32}
+template <int kLanes, int kNC>   // lanes per pixel = C/8 in {8,16,32}; kNC = classes rounded up
 __global__ void __launch_bounds__(256)
 outconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                    const float* __restrict__ bias, int nc, long long M, int hw,
                    float* __restrict__ out) {
   constexpr int C = kLanes * 8;
   const int sub = threadIdx.x % kLanes;
-  float wr[kMaxClasses][8];
+  float wr[kNC][8];
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k)
+  for (int k = 0; k < kNC; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) wr[k][j] = (k < nc) ? __ldg(w + k * C + sub * 8 + j) : 0.f;
   const long long gthreads = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -46,22 +46,22 @@ outconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   long long pix = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) / kLanes;
   for (long long it = 0; it < iters; ++it, pix += pix_per_iter) {
     const bool live = pix < M;
-    float acc[kMaxClasses];
+    float acc[kNC];
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
+    for (int k = 0; k < kNC; ++k) acc[k] = 0.f;
     if (live) {
       const uint4 u = *reinterpret_cast<const uint4*>(x + pix * C + sub * 8);
       const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
                            bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
-      for (int k = 0; k < kMaxClasses; ++k)
+      for (int k = 0; k < kNC; ++k)
         if (k < nc) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[k] = fmaf(xv[j], wr[k][j], acc[k]);
         }
     }
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
+    for (int k = 0; k < kNC; ++k)
       if (k < nc) {
 #pragma unroll
         for (int o = kLanes / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
@@ -75,7 +75,7 @@ outconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 
 // 1x1 OutConv backward: dx[p][c] (+)= sum_k dl[k][p]*w[k][c];
 // dw[k][c] += sum_p dl[k][p]*x[p][c]; db[k] += sum_p dl[k][p].
-template <int kLanes>
+template <int kLanes, int kNC>
 __global__ void __launch_bounds__(256)
 outconv_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                    const float* __restrict__ dl, int nc, long long M, int hw,
@@ -83,9 +83,9 @@ outconv_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
                    float* __restrict__ db) {
   constexpr int C = kLanes * 8;
   const int sub = threadIdx.x % kLanes;
-  float wr[kMaxClasses][8], dwr[kMaxClasses][8], dbr[kMaxClasses];
+  float wr[kNC][8], dwr[kNC][8], dbr[kNC];
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
+  for (int k = 0; k < kNC; ++k) {
     dbr[k] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -111,7 +111,7 @@ outconv_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       for (int j = 0; j < 8; ++j) g[j] = 0.f;
     }
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
+    for (int k = 0; k < kNC; ++k)
       if (k < nc) {
         const float d = __ldg(dl + (b * nc + k) * hw + r);
         if (sub == 0) dbr[k] += d;
@@ -127,13 +127,13 @@ outconv_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     *reinterpret_cast<uint4*>(dx + pix * C + sub * 8) = o;
   }
   // block reduction of dw / db through shared memory
-  __shared__ float red[kMaxClasses][C];
-  __shared__ float redb[kMaxClasses];
-  for (int i = threadIdx.x; i < kMaxClasses * C; i += blockDim.x) (&red[0][0])[i] = 0.f;
-  if (threadIdx.x < kMaxClasses) redb[threadIdx.x] = 0.f;
+  __shared__ float red[kNC][C];
+  __shared__ float redb[kNC];
+  for (int i = threadIdx.x; i < kNC * C; i += blockDim.x) (&red[0][0])[i] = 0.f;
+  if (threadIdx.x < kNC) redb[threadIdx.x] = 0.f;
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k)
+  for (int k = 0; k < kNC; ++k)
     if (k < nc) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) atomicAdd(&red[k][sub * 8 + j], dwr[k][j]);
@@ -398,12 +398,13 @@ int outconv_fwd(const void* x, const float* w, const float* bias, int B, int hw,
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   const int lanes = C / 8;
   const int grid = grid_cap((M * lanes + 255) / 256, 8);
-  switch (C) {
-    case 64: outconv_fwd_kernel<8><<<grid, 256, 0, stream>>>(xp, w, bias, nc, M, hw, out); break;
-    case 128: outconv_fwd_kernel<16><<<grid, 256, 0, stream>>>(xp, w, bias, nc, M, hw, out); break;
-    case 256: outconv_fwd_kernel<32><<<grid, 256, 0, stream>>>(xp, w, bias, nc, M, hw, out); break;
-    default: UGP_REQUIRE(false, "outconv_fwd: C %d unsupported (64/128/256)", C);
-  }
+  UGP_REQUIRE(C == 64 || C == 128 || C == 256, "outconv_fwd: C %d unsupported (64/128/256)", C);
+#define UGP_OC_FWD(L, N) outconv_fwd_kernel<L, N><<<grid, 256, 0, stream>>>(xp, w, bias, nc, M, hw, out)
+#define UGP_OC_FWD_C(N) \
+  do { if (C == 64) UGP_OC_FWD(8, N); else if (C == 128) UGP_OC_FWD(16, N); else UGP_OC_FWD(32, N); } while (0)
+  if (nc == 1) UGP_OC_FWD_C(1); else if (nc == 2) UGP_OC_FWD_C(2); else if (nc <= 4) UGP_OC_FWD_C(4); else UGP_OC_FWD_C(8);
+#undef UGP_OC_FWD_C
+#undef UGP_OC_FWD
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
@@ -417,13 +418,15 @@ int outconv_bwd(const void* x, const float* w, const float* dl, int B, int hw, i
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(dx);
   const int lanes = C / 8;
-  const int grid = grid_cap((M * lanes + 255) / 256, 4);
-  switch (C) {
-    case 64: outconv_bwd_kernel<8><<<grid, 256, 0, stream>>>(xp, w, dl, nc, M, hw, accumulate, dxp, dw, db); break;
-    case 128: outconv_bwd_kernel<16><<<grid, 256, 0, stream>>>(xp, w, dl, nc, M, hw, accumulate, dxp, dw, db); break;
-    case 256: outconv_bwd_kernel<32><<<grid, 256, 0, stream>>>(xp, w, dl, nc, M, hw, accumulate, dxp, dw, db); break;
-    default: UGP_REQUIRE(false, "outconv_bwd: C %d unsupported (64/128/256)", C);
-  }
+  const int grid = grid_cap((M * lanes + 255) / 256, 8);
+  UGP_REQUIRE(C == 64 || C == 128 || C == 256, "outconv_bwd: C %d unsupported (64/128/256)", C);
+#define UGP_OC_BWD(L, N) \
+  outconv_bwd_kernel<L, N><<<grid, 256, 0, stream>>>(xp, w, dl, nc, M, hw, accumulate, dxp, dw, db)
+#define UGP_OC_BWD_C(N) \
+  do { if (C == 64) UGP_OC_BWD(8, N); else if (C == 128) UGP_OC_BWD(16, N); else UGP_OC_BWD(32, N); } while (0)
+  if (nc == 1) UGP_OC_BWD_C(1); else if (nc == 2) UGP_OC_BWD_C(2); else if (nc <= 4) UGP_OC_BWD_C(4); else UGP_OC_BWD_C(8);
+#undef UGP_OC_BWD_C
+#undef UGP_OC_BWD
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
