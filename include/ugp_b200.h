@@ -33,6 +33,9 @@ extern "C" {
 const char* ugp_last_error(void);
 int ugp_version(void);                 /* 100 * major + minor */
 int ugp_device_sm_count(void);
+/* Tuning switches (process-wide).  "conv_halo": 0 = per-tap TMA loads for every layer, 1/2 = halo
+ * staging for the wide thin layers (see csrc/conv_halo.cu). */
+int ugp_set_option(const char* name, int value);
 
 /* ---- convolutions (tcgen05 implicit GEMM) -------------------------------
  * nn.Conv2d(k=3, padding=1) forward and input-gradient, and 1x1 GEMM.

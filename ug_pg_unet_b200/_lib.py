@@ -39,7 +39,7 @@ SIGNATURES = {
     "ugp_ce_weighted_loss": [_p, _p, _p, _f, _i, _i, _f, _p, _p, _p],
     "ugp_rmsprop_step": [_p, _p, _p, _ll, _f, _f, _f, _f, _f, _p],
 }
-INFO_FUNCS = ("ugp_last_error", "ugp_version", "ugp_device_sm_count")
+INFO_FUNCS = ("ugp_last_error", "ugp_version", "ugp_device_sm_count", "ugp_set_option")
 EXPORTED = tuple(SIGNATURES) + INFO_FUNCS
 
 _lib = None
@@ -72,8 +72,14 @@ def lib() -> C.CDLL:
     handle.ugp_last_error.argtypes = []
     handle.ugp_version.restype = C.c_int
     handle.ugp_device_sm_count.restype = C.c_int
+    handle.ugp_set_option.restype = C.c_int
+    handle.ugp_set_option.argtypes = [C.c_char_p, C.c_int]
     _lib = handle
     return handle
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().ugp_set_option(name.encode(), int(value)), f"ugp_set_option({name})")
 
 
 def check(rc: int, what: str) -> None:

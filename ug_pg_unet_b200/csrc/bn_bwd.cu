@@ -261,7 +261,9 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
   a.inv_count = 1.f / static_cast<float>(M);
   const int rows_per_block = kBnThreads / (C / 8);
   UGP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
-  const long long cap = static_cast<long long>(device_sm_count()) * 8;
+  // two resident blocks per SM keep ~64 KB of loads in flight per SM; more blocks only add
+  // same-address atomic traffic in the final per-channel reduction
+  const long long cap = static_cast<long long>(device_sm_count()) * 2;
   if (dP) {
     UGP_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_bwd: pooled gradient needs even H, W");
     long long blocks = (M / 4 + rows_per_block - 1) / rows_per_block;

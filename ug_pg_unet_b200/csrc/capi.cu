@@ -6,6 +6,7 @@
 
 namespace ugp {
 const char* last_error();
+int set_option(const char*, int);
 
 int conv_gemm_bf16(const void*, int, const void*, int, int, int, int, int, const void*, int,
                    void*, void*, int, const float*, const float*, const float*, int, float*,
@@ -51,6 +52,7 @@ extern "C" {
 const char* ugp_last_error(void) { return ugp::last_error(); }
 int ugp_version(void) { return 100; }
 int ugp_device_sm_count(void) { return ugp::device_sm_count(); }
+int ugp_set_option(const char* name, int value) { return ugp::set_option(name, value); }
 
 int ugp_conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
                        int taps, const void* wpack, int cout, void* dst0, void* dst1,

@@ -324,6 +324,14 @@ static bool pick_box(int H, int W, int pixels, int* BW, int* BH) {
   return true;
 }
 
+// conv_halo.cu
+bool conv_halo_eligible(int H, int W, int cout, int split_n, int taps);
+int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
+                   const void* wpack, int cout, void* dst0, void* dst1, int split_n,
+                   const float* bias, const float* scale, const float* shift, int relu, float* stats,
+                   int base_offset_mode, cudaStream_t stream);
+extern int g_conv_halo_mode;   // 0 = off, 1 = on (descriptor base_offset), 2 = on (base_offset 0)
+
 int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
                    int H, int W, int taps, const void* wpack, int cout,
                    void* dst0, void* dst1, int split_n, const float* bias,
@@ -338,6 +346,9 @@ int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
   if (dst1 == nullptr) split_n = cout;
   UGP_REQUIRE(split_n > 0 && split_n <= cout && split_n % 64 == 0,
               "conv_gemm: bad split_n %d", split_n);
+  if (g_conv_halo_mode != 0 && conv_halo_eligible(H, W, cout, split_n, taps))
+    return conv_halo_bf16(src0, c0, src1, c1, B, H, W, wpack, cout, dst0, dst1, split_n, bias, scale,
+                          shift, relu, stats, g_conv_halo_mode == 1 ? 1 : 0, stream);
   int BW, BH;
   UGP_REQUIRE(pick_box(H, W, kBlockM, &BW, &BH),
               "conv_gemm: unsupported spatial size %dx%d (need W in {16,32,64,128} or a "

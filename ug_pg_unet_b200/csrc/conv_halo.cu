@@ -1,0 +1,366 @@
+// 3x3 (pad 1) convolution for the wide, thin layers (W a multiple of 128, few
+// channels): the ones whose implicit GEMM is bound by L2 -> SM operand traffic,
+// not by the tensor pipe (UG_unet_parts.py:10,13 at the 256^2 / 128^2 levels:
+// inc, down1, up3, up4 and their input-gradients).
+//
+// Same math and epilogue as conv_gemm.cu, different operand staging:
+//   * a CTA tile is 2 image rows x 128 pixels (two 128 x N accumulators);
+//   * per 64-channel chunk ONE TMA box brings the 4 x 130-pixel halo of the
+//     tile into shared memory (66.5 KB, SWIZZLE_128B).  All nine taps read
+//     their shifted 128-row A operand out of that halo through the UMMA
+//     descriptor start address (+128 B per pixel, +130*128 B per row): the
+//     activation is fetched from L2 once per tile instead of nine times;
+//   * the weight tile of a (chunk, tap) is shared by both accumulators.
+// L2 -> SM bytes per MAC drop ~3x versus the per-tap TMA loads of conv_gemm.cu.
+//
+// Warp roles as in conv_gemm.cu: warp 0 TMA producer, warp 1 MMA issuer / TMEM
+// owner, warps 2..5 epilogue.
+#include "ugp_common.cuh"
+
+namespace ugp {
+
+struct ConvHaloParams {
+  int chunks0, chunks1;
+  int H, W;
+  int tiles_x, tiles_y;      // W/128, H/2
+  int m_tiles, n_tiles;
+  int cout;
+  int split_n;
+  int relu;
+  int base_offset_mode;      // 1: descriptor base_offset = (start >> 7) & 7, 0: leave 0
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  float* stats;
+};
+
+constexpr int kHaloRows = 2;                               // image rows per CTA tile
+constexpr int kHaloW = 130;                                // 128 pixels + 1 halo pixel each side
+constexpr int kHaloBytes = (kHaloRows + 2) * kHaloW * 128;  // 66,560 B = 65 * 1024
+constexpr int kHaloStages = 2;
+constexpr int kHaloMaxCout = 256;
+
+template <int kN>
+struct HaloCfg {
+  static constexpr int kBStages = (kN == 64) ? 6 : 3;
+  static constexpr int kBBytes = kN * 128;
+  static constexpr int kTmemCols = 2 * kHaloRows * kN;     // 256 / 512
+  static constexpr int kSmemBytes = kHaloStages * kHaloBytes + kBStages * kBBytes + 2 * 16384 +
+                                    5 * kHaloMaxCout * 4 + 256 + 1024;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t smem_addr, uint32_t sbo_bytes,
+                                                        int base_offset_mode) {
+  uint64_t d = umma_desc_sw128(smem_addr, 16, sbo_bytes);
+  if (base_offset_mode) d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;
+  return d;
+}
+
+template <int kN>
+__global__ void __launch_bounds__(192, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
+                 const __grid_constant__ CUtensorMap tmO1, const ConvHaloParams p) {
+  using Cfg = HaloCfg<kN>;
+  constexpr int kBStages = Cfg::kBStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sHalo = smem;
+  uint8_t* sB = sHalo + kHaloStages * kHaloBytes;
+  uint8_t* sOut = sB + kBStages * Cfg::kBBytes;
+  float* sStats = reinterpret_cast<float*>(sOut + 2 * 16384);     // [2][kHaloMaxCout]
+  float* sBias = sStats + 2 * kHaloMaxCout;
+  float* sScale = sBias + kHaloMaxCout;
+  float* sShift = sScale + kHaloMaxCout;
+  uint64_t* hfull = reinterpret_cast<uint64_t*>(sShift + kHaloMaxCout);
+  uint64_t* hempty = hfull + kHaloStages;
+  uint64_t* bfull = hempty + kHaloStages;
+  uint64_t* bempty = bfull + kBStages;
+  uint64_t* tfull = bempty + kBStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int chunks = p.chunks0 + p.chunks1;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmO0);
+    tma_prefetch_desc(&tmO1);
+    for (int i = 0; i < kHaloStages; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp_idx >= 2) {
+    const int et = threadIdx.x - 64;
+    for (int i = et; i < p.cout; i += 128) {
+      sStats[i] = 0.f;
+      sStats[kHaloMaxCout + i] = 0.f;
+      sBias[i] = p.bias ? p.bias[i] : 0.f;
+      sScale[i] = p.scale ? p.scale[i] : 1.f;
+      sShift[i] = p.shift ? p.shift[i] : 0.f;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int hs = 0, bs = 0;
+      uint32_t hph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const int tx = m_tile % p.tiles_x;
+        const int t2 = m_tile / p.tiles_x;
+        const int ty = t2 % p.tiles_y;
+        const int b = t2 / p.tiles_y;
+        const int x0 = tx * 128, y0 = ty * kHaloRows;
+        for (int c = 0; c < chunks; ++c) {
+          mbar_wait(&hempty[hs], hph ^ 1);
+          mbar_arrive_expect_tx(&hfull[hs], kHaloBytes);
+          if (c < p.chunks0)
+            tma_load_4d(&tmA0, &hfull[hs], sHalo + hs * kHaloBytes, c * 64, x0 - 1, y0 - 1, b);
+          else
+            tma_load_4d(&tmA1, &hfull[hs], sHalo + hs * kHaloBytes, (c - p.chunks0) * 64, x0 - 1,
+                        y0 - 1, b);
+          if (++hs == kHaloStages) { hs = 0; hph ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&bempty[bs], bph ^ 1);
+            mbar_arrive_expect_tx(&bfull[bs], Cfg::kBBytes);
+            tma_load_2d(&tmW, &bfull[bs], sB + bs * Cfg::kBBytes, c * 64, tap * p.cout + n_tile * kN);
+            if (++bs == kBStages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, kN, 0, 0);
+    int hs = 0, bs = 0;
+    uint32_t hph = 0, bph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + as * (kHaloRows * kN);
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait(&hfull[hs], hph);
+        const uint32_t halo_addr = smem_u32(sHalo + hs * kHaloBytes);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&bfull[bs], bph);
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const int dy = tap / 3, dx = tap % 3;      // halo-relative: +1 already folded in
+            const uint32_t b_addr = smem_u32(sB + bs * Cfg::kBBytes);
+#pragma unroll
+            for (int r = 0; r < kHaloRows; ++r) {
+              const uint32_t a_addr = halo_addr + ((r + dy) * kHaloW + dx) * 128;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t a_desc = umma_desc_sw128_off(a_addr + k * 32, 1024, p.base_offset_mode);
+                const uint64_t b_desc = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+                umma_bf16(d_tmem + r * kN, a_desc, b_desc, idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&bempty[bs]);
+            if (tap == 8) {
+              umma_commit(&hempty[hs]);
+              if (c == chunks - 1) umma_commit(&tfull[as]);
+            }
+          }
+          __syncwarp();
+          if (++bs == kBStages) { bs = 0; bph ^= 1; }
+        }
+        if (++hs == kHaloStages) { hs = 0; hph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int et = threadIdx.x - 64;
+    const int q = warp_idx & 3;
+    const int row = q * 32 + lane;
+    const bool do_stats = p.stats != nullptr;
+    uint32_t chunk_counter = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const int tx = m_tile % p.tiles_x;
+      const int t2 = m_tile / p.tiles_x;
+      const int ty = t2 % p.tiles_y;
+      const int b = t2 / p.tiles_y;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int r = 0; r < kHaloRows; ++r) {
+        const int out_row0 = ((b * p.H + ty * kHaloRows + r) * p.W) + tx * 128;   // pixel index
+#pragma unroll 1
+        for (int cc = 0; cc < kN / 64; ++cc, ++chunk_counter) {
+          uint32_t v[64];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 as * (kHaloRows * kN) + r * kN + cc * 64;
+          tmem_ld_32x32(taddr, v);
+          tmem_ld_32x32(taddr + 32, v + 32);
+          tmem_ld_wait();
+          if (r == kHaloRows - 1 && cc == kN / 64 - 1) {
+            tc_fence_before_sync();
+            mbar_arrive(&tempty[as]);
+          }
+          const int n_base = n_tile * kN + cc * 64;
+          uint32_t packed[32];
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const float4 bi = *reinterpret_cast<const float4*>(sBias + n_base + j);
+            const float4 sc = *reinterpret_cast<const float4*>(sScale + n_base + j);
+            const float4 sh = *reinterpret_cast<const float4*>(sShift + n_base + j);
+            float f0 = (__uint_as_float(v[j + 0]) + bi.x) * sc.x + sh.x;
+            float f1 = (__uint_as_float(v[j + 1]) + bi.y) * sc.y + sh.y;
+            float f2 = (__uint_as_float(v[j + 2]) + bi.z) * sc.z + sh.z;
+            float f3 = (__uint_as_float(v[j + 3]) + bi.w) * sc.w + sh.w;
+            if (p.relu) {
+              f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f);
+              f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
+            }
+            packed[j / 2] = pack_bf16x2(f0, f1);
+            packed[j / 2 + 1] = pack_bf16x2(f2, f3);
+          }
+          uint8_t* buf = sOut + (chunk_counter & 1) * 16384;
+          if (et == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          uint8_t* rowp = buf + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 val = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = val;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (et == 0) {
+            if (n_base < p.split_n)
+              tma_store_2d(&tmO0, buf, n_base, out_row0);
+            else
+              tma_store_2d(&tmO1, buf, n_base - p.split_n, out_row0);
+            tma_store_commit();
+          }
+          if (do_stats) {
+            const int col = et & 63;
+            const int r0 = (et >> 6) * 64;
+            const uint8_t* colp = buf + ((col & 7) << 1);
+            const int chunk = col >> 3;
+            float s = 0.f, s2 = 0.f;
+#pragma unroll 8
+            for (int rr = r0; rr < r0 + 64; ++rr) {
+              const unsigned short h = *reinterpret_cast<const unsigned short*>(
+                  colp + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+              const float f = __uint_as_float(static_cast<uint32_t>(h) << 16);
+              s += f;
+              s2 = fmaf(f, f, s2);
+            }
+            atomicAdd(&sStats[n_base + col], s);
+            atomicAdd(&sStats[kHaloMaxCout + n_base + col], s2);
+          }
+        }
+      }
+    }
+    if (et == 0) tma_store_wait_all();
+    if (do_stats) {
+      named_bar_sync(1, 128);
+      for (int i = et; i < p.cout; i += 128) {
+        atomicAdd(p.stats + i, sStats[i]);
+        atomicAdd(p.stats + p.cout + i, sStats[kHaloMaxCout + i]);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int kN>
+static int launch_halo(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW,
+                       const CUtensorMap& tmO0, const CUtensorMap& tmO1, const ConvHaloParams& p,
+                       cudaStream_t stream) {
+  using Cfg = HaloCfg<kN>;
+  static bool configured = false;
+  if (!configured) {
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  conv_halo_kernel<kN><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
+}
+
+// Returns 1 when the shape is one this kernel covers (the caller then must not run conv_gemm).
+bool conv_halo_eligible(int H, int W, int cout, int split_n, int taps) {
+  if (taps != 9 || W % 128 != 0 || H % kHaloRows != 0 || cout > kHaloMaxCout) return false;
+  int kn = 128;
+  while (kn > 64 && (cout % kn != 0 || split_n % kn != 0 || (cout - split_n) % kn != 0)) kn >>= 1;
+  return cout % kn == 0;
+}
+
+int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
+                   const void* wpack, int cout, void* dst0, void* dst1, int split_n,
+                   const float* bias, const float* scale, const float* shift, int relu, float* stats,
+                   int base_offset_mode, cudaStream_t stream) {
+  if (dst1 == nullptr) split_n = cout;
+  int kn = 128;
+  while (kn > 64 && (cout % kn != 0 || split_n % kn != 0 || (cout - split_n) % kn != 0)) kn >>= 1;
+  ConvHaloParams p;
+  p.chunks0 = c0 / 64;
+  p.chunks1 = c1 / 64;
+  p.H = H; p.W = W;
+  p.tiles_x = W / 128;
+  p.tiles_y = H / kHaloRows;
+  p.m_tiles = B * p.tiles_x * p.tiles_y;
+  p.n_tiles = cout / kn;
+  p.cout = cout;
+  p.split_n = split_n;
+  p.relu = relu;
+  p.base_offset_mode = base_offset_mode;
+  p.bias = bias; p.scale = scale; p.shift = shift; p.stats = stats;
+
+  CUtensorMap tmA0, tmA1, tmW, tmO0, tmO1;
+  int rc;
+  if ((rc = make_tmap_nhwc_bf16(&tmA0, src0, B, H, W, c0, 64, kHaloW, kHaloRows + 2))) return rc;
+  if (c1 > 0) {
+    if ((rc = make_tmap_nhwc_bf16(&tmA1, src1, B, H, W, c1, 64, kHaloW, kHaloRows + 2))) return rc;
+  } else {
+    tmA1 = tmA0;
+  }
+  if ((rc = make_tmap_2d_bf16(&tmW, wpack, 9LL * cout, c0 + c1, 64, kn))) return rc;
+  const long long M = static_cast<long long>(B) * H * W;
+  if ((rc = make_tmap_2d_bf16(&tmO0, dst0, M, split_n, 64, 128))) return rc;
+  if (split_n < cout) {
+    if ((rc = make_tmap_2d_bf16(&tmO1, dst1, M, cout - split_n, 64, 128))) return rc;
+  } else {
+    tmO1 = tmO0;
+  }
+  if (kn == 128) return launch_halo<128>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
+  return launch_halo<64>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
+}
+
+}  // namespace ugp

@@ -85,6 +85,17 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, long long rows,
   return encode(out, ptr, 2, dims, strides, box);
 }
 
+int g_conv_halo_mode = 0;
+
+int set_option(const char* name, int value) {
+  if (strcmp(name, "conv_halo") == 0) {
+    g_conv_halo_mode = value;
+    return UGP_OK;
+  }
+  set_last_error("unknown option '%s'", name);
+  return UGP_ERR_INVALID;
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {
