@@ -50,7 +50,7 @@ def main():
         (1, 256, 256, 64, 0, 128, 64),
     ]
     ok_modes = {}
-    for mode in (1, 2):
+    for mode in (1,):
         all_ok = True
         for (B, H, W, c0, c1, cout, split) in cases:
             x0 = torch.randn(B, H, W, c0, device="cuda", generator=g).bfloat16()

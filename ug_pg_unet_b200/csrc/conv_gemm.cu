@@ -48,13 +48,19 @@ constexpr int kMaxCout = 1024;
 
 template <int kN>
 struct ConvCfg {
-  static constexpr int kStages = (kN == 256) ? 3 : (kN == 128 ? 5 : 6);
+  // A pipeline stage carries kG consecutive K blocks (one 64-channel A box + one B box each)
+  // behind ONE mbarrier: the single MMA-issuing thread pays ~100+ cycles per barrier wait, so a
+  // stage must hold enough tensor work to hide it (N = 256: 4 MMAs x 128 cycles; N = 128: 8 x 64).
+  static constexpr int kG = (kN == 128) ? 2 : 1;
+  static constexpr int kStages = (kN == 256) ? 3 : (kN == 128 ? 3 : 6);
+  static constexpr int kStagingBufs = (kN == 128) ? 1 : 2;
+  static constexpr int kMaxCoutT = (kN == 256) ? kMaxCout : 512;
   static constexpr int kBTileBytes = kN * kBlockK * 2;
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kBlockBytes = kATileBytes + kBTileBytes;   // one K block
   static constexpr int kTmemCols = 2 * kN;  // 128 / 256 / 512: powers of two
-  // dynamic smem: stages + 2 staging buffers + stats/bias/scale/shift + barriers
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kOutChunkBytes +
-                                    5 * kMaxCout * 4 + 256 + 1024;
+  // dynamic smem: stages + staging buffers + stats/bias/scale/shift + barriers
+  static constexpr int kSmemBytes = kStages * kG * kBlockBytes + kStagingBufs * kOutChunkBytes +
+                                    5 * kMaxCoutT * 4 + 256 + 1024;
 };
 
 template <int kN>
@@ -71,14 +77,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = sA + kStages * kATileBytes;
-  uint8_t* sOut = sB + kStages * Cfg::kBTileBytes;
-  float* sStats = reinterpret_cast<float*>(sOut + 2 * kOutChunkBytes);  // [2][kMaxCout]
-  float* sBias = sStats + 2 * kMaxCout;
-  float* sScale = sBias + kMaxCout;
-  float* sShift = sScale + kMaxCout;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + kMaxCout);
+  constexpr int kG = Cfg::kG;
+  constexpr int kMaxC = Cfg::kMaxCoutT;
+  uint8_t* sA = smem;                                   // [stage][g] A boxes
+  uint8_t* sB = sA + kStages * kG * kATileBytes;        // [stage][g] B boxes
+  uint8_t* sOut = sB + kStages * kG * Cfg::kBTileBytes;
+  float* sStats = reinterpret_cast<float*>(sOut + Cfg::kStagingBufs * kOutChunkBytes);  // [2][kMaxC]
+  float* sBias = sStats + 2 * kMaxC;
+  float* sScale = sBias + kMaxC;
+  float* sShift = sScale + kMaxC;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + kMaxC);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -110,7 +118,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int et = threadIdx.x - 64;
     for (int i = et; i < p.cout; i += 128) {
       sStats[i] = 0.f;
-      sStats[kMaxCout + i] = 0.f;
+      sStats[kMaxC + i] = 0.f;
       sBias[i] = p.bias ? p.bias[i] : 0.f;
       sScale[i] = p.scale ? p.scale[i] : 1.f;
       sShift[i] = p.shift ? p.shift[i] : 0.f;
@@ -135,24 +143,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         const int ty = t2 % p.tiles_y;
         const int b = t2 / p.tiles_y;
         const int x0 = tx * p.BW, y0 = ty * p.BH;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-          const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-          const int wrow = tap * p.cout + n_tile * kN;
-          for (int c = 0; c < chunks; ++c) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            uint8_t* a_dst = sA + stage * kATileBytes;
+        for (int kb0 = 0; kb0 < k_blocks; kb0 += kG) {
+          const int g = (k_blocks - kb0 < kG) ? (k_blocks - kb0) : kG;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], g * Cfg::kBlockBytes);
+          for (int i = 0; i < g; ++i) {
+            const int kb = kb0 + i;
+            const int tap = kb / chunks;
+            const int c = kb - tap * chunks;
+            const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+            const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+            uint8_t* a_dst = sA + (stage * kG + i) * kATileBytes;
             if (c < p.chunks0)
-              tma_load_4d(&tmA0, &full_bar[stage], a_dst, c * kBlockK, x0 + dx,
-                          y0 + dy, b);
+              tma_load_4d(&tmA0, &full_bar[stage], a_dst, c * kBlockK, x0 + dx, y0 + dy, b);
             else
-              tma_load_4d(&tmA1, &full_bar[stage], a_dst,
-                          (c - p.chunks0) * kBlockK, x0 + dx, y0 + dy, b);
-            tma_load_2d(&tmW, &full_bar[stage], sB + stage * Cfg::kBTileBytes,
-                        c * kBlockK, wrow);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+              tma_load_4d(&tmA1, &full_bar[stage], a_dst, (c - p.chunks0) * kBlockK, x0 + dx,
+                          y0 + dy, b);
+            tma_load_2d(&tmW, &full_bar[stage], sB + (stage * kG + i) * Cfg::kBTileBytes,
+                        c * kBlockK, tap * p.cout + n_tile * kN);
           }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -168,22 +178,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + as * kN;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb0 = 0; kb0 < k_blocks; kb0 += kG) {
+        const int g = (k_blocks - kb0 < kG) ? (k_blocks - kb0) : kG;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
         if (lane == 0) {
-          const uint64_t a_desc =
-              umma_desc_sw128(smem_u32(sA + stage * kATileBytes), 16, 1024);
-          const uint64_t b_desc =
-              umma_desc_sw128(smem_u32(sB + stage * Cfg::kBTileBytes), 16, 1024);
+          for (int i = 0; i < g; ++i) {
+            const uint64_t a_desc =
+                umma_desc_sw128(smem_u32(sA + (stage * kG + i) * kATileBytes), 16, 1024);
+            const uint64_t b_desc =
+                umma_desc_sw128(smem_u32(sB + (stage * kG + i) * Cfg::kBTileBytes), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 B per K=16 step inside the 128 B swizzle row
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // +32 B per K=16 step inside the 128 B swizzle row
+              umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                        (kb0 + i > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
+          if (kb0 + g >= k_blocks) umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -234,9 +247,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           packed[j / 2] = pack_bf16x2(f0, f1);
           packed[j / 2 + 1] = pack_bf16x2(f2, f3);
         }
-        uint8_t* buf = sOut + (chunk_counter & 1) * kOutChunkBytes;
+        uint8_t* buf = sOut + (chunk_counter % Cfg::kStagingBufs) * kOutChunkBytes;
         // the TMA store that last read this staging buffer must be done
-        if (et == 0) tma_store_wait_read<1>();
+        if (et == 0) tma_store_wait_read<Cfg::kStagingBufs - 1>();
         named_bar_sync(1, 128);
         uint8_t* rowp = buf + row * 128;
 #pragma unroll
@@ -270,7 +283,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             s2 = fmaf(f, f, s2);
           }
           atomicAdd(&sStats[n_base + col], s);
-          atomicAdd(&sStats[kMaxCout + n_base + col], s2);
+          atomicAdd(&sStats[kMaxC + n_base + col], s2);
         }
       }
     }
@@ -279,7 +292,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       named_bar_sync(1, 128);
       for (int i = et; i < p.cout; i += 128) {
         atomicAdd(p.stats + i, sStats[i]);
-        atomicAdd(p.stats + p.cout + i, sStats[kMaxCout + i]);
+        atomicAdd(p.stats + p.cout + i, sStats[kMaxC + i]);
       }
     }
   }
@@ -329,8 +342,8 @@ bool conv_halo_eligible(int H, int W, int cout, int split_n, int taps);
 int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
                    const void* wpack, int cout, void* dst0, void* dst1, int split_n,
                    const float* bias, const float* scale, const float* shift, int relu, float* stats,
-                   int base_offset_mode, cudaStream_t stream);
-extern int g_conv_halo_mode;   // 0 = off, 1 = on (descriptor base_offset), 2 = on (base_offset 0)
+                   cudaStream_t stream);
+extern int g_conv_halo_mode;   // 0 = per-tap loads everywhere, 1 = halo staging for wide thin layers
 
 int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
                    int H, int W, int taps, const void* wpack, int cout,
@@ -348,13 +361,15 @@ int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
               "conv_gemm: bad split_n %d", split_n);
   if (g_conv_halo_mode != 0 && conv_halo_eligible(H, W, cout, split_n, taps))
     return conv_halo_bf16(src0, c0, src1, c1, B, H, W, wpack, cout, dst0, dst1, split_n, bias, scale,
-                          shift, relu, stats, g_conv_halo_mode == 1 ? 1 : 0, stream);
+                          shift, relu, stats, stream);
   int BW, BH;
   UGP_REQUIRE(pick_box(H, W, kBlockM, &BW, &BH),
               "conv_gemm: unsupported spatial size %dx%d (need W in {16,32,64,128} or a "
               "multiple of 128, and H a multiple of 128/min(W,128))", H, W);
   int kn = 256;
   while (kn > 64 && (cout % kn != 0 || split_n % kn != 0 || (cout - split_n) % kn != 0)) kn >>= 1;
+
+  UGP_REQUIRE(kn == 256 || cout <= 512, "conv_gemm: cout %d with a %d-wide tile unsupported", cout, kn);
 
   ConvGemmParams p;
   p.taps = taps;

@@ -27,7 +27,6 @@ struct ConvHaloParams {
   int cout;
   int split_n;
   int relu;
-  int base_offset_mode;      // 1: descriptor base_offset = (start >> 7) & 7, 0: leave 0
   const float* bias;
   const float* scale;
   const float* shift;
@@ -42,19 +41,17 @@ constexpr int kHaloMaxCout = 256;
 
 template <int kN>
 struct HaloCfg {
-  static constexpr int kBStages = (kN == 64) ? 6 : 3;
-  static constexpr int kBBytes = kN * 128;
+  // One mbarrier wait of the single MMA-issuing thread costs ~100+ cycles, so a B slot must carry
+  // enough tensor work to hide it: a slot holds kTapsPerSlot weight tiles (one kernel row of taps
+  // for N = 64: 3 taps x 2 rows x 4 = 24 MMAs of 32 cycles per wait; N = 128: 8 MMAs of 64 cycles).
+  static constexpr int kTapsPerSlot = (kN == 64) ? 3 : 1;
+  static constexpr int kBStages = (kN == 64) ? 2 : 3;
+  static constexpr int kTapBytes = kN * 128;
+  static constexpr int kBBytes = kTapsPerSlot * kTapBytes;
   static constexpr int kTmemCols = 2 * kHaloRows * kN;     // 256 / 512
   static constexpr int kSmemBytes = kHaloStages * kHaloBytes + kBStages * kBBytes + 2 * 16384 +
                                     5 * kHaloMaxCout * 4 + 256 + 1024;
 };
-
-__device__ __forceinline__ uint64_t umma_desc_sw128_off(uint32_t smem_addr, uint32_t sbo_bytes,
-                                                        int base_offset_mode) {
-  uint64_t d = umma_desc_sw128(smem_addr, 16, sbo_bytes);
-  if (base_offset_mode) d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;
-  return d;
-}
 
 template <int kN>
 __global__ void __launch_bounds__(192, 1)
@@ -136,10 +133,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             tma_load_4d(&tmA1, &hfull[hs], sHalo + hs * kHaloBytes, (c - p.chunks0) * 64, x0 - 1,
                         y0 - 1, b);
           if (++hs == kHaloStages) { hs = 0; hph ^= 1; }
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < 9; tap += Cfg::kTapsPerSlot) {
             mbar_wait(&bempty[bs], bph ^ 1);
             mbar_arrive_expect_tx(&bfull[bs], Cfg::kBBytes);
-            tma_load_2d(&tmW, &bfull[bs], sB + bs * Cfg::kBBytes, c * 64, tap * p.cout + n_tile * kN);
+#pragma unroll
+            for (int t = 0; t < Cfg::kTapsPerSlot; ++t)
+              tma_load_2d(&tmW, &bfull[bs], sB + bs * Cfg::kBBytes + t * Cfg::kTapBytes, c * 64,
+                          (tap + t) * p.cout + n_tile * kN);
             if (++bs == kBStages) { bs = 0; bph ^= 1; }
           }
         }
@@ -160,24 +160,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       for (int c = 0; c < chunks; ++c) {
         mbar_wait(&hfull[hs], hph);
         const uint32_t halo_addr = smem_u32(sHalo + hs * kHaloBytes);
-        for (int tap = 0; tap < 9; ++tap) {
+        // descriptor template: start address 0, SBO 1024, SWIZZLE_128B; the shifted A window only
+        // changes the start-address field (absolute-address swizzle, base_offset stays 0)
+        const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);
+        for (int tap = 0; tap < 9; tap += Cfg::kTapsPerSlot) {
           mbar_wait(&bfull[bs], bph);
           tc_fence_after_sync();
           if (lane == 0) {
-            const int dy = tap / 3, dx = tap % 3;      // halo-relative: +1 already folded in
-            const uint32_t b_addr = smem_u32(sB + bs * Cfg::kBBytes);
+            const uint32_t slot_addr = smem_u32(sB + bs * Cfg::kBBytes);
 #pragma unroll
-            for (int r = 0; r < kHaloRows; ++r) {
-              const uint32_t a_addr = halo_addr + ((r + dy) * kHaloW + dx) * 128;
+            for (int t = 0; t < Cfg::kTapsPerSlot; ++t) {
+              const int dy = (tap + t) / 3, dx = (tap + t) % 3;   // halo-relative (+1 folded in)
+              const uint64_t b_desc = desc0 + ((slot_addr + t * Cfg::kTapBytes) >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t a_desc = umma_desc_sw128_off(a_addr + k * 32, 1024, p.base_offset_mode);
-                const uint64_t b_desc = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-                umma_bf16(d_tmem + r * kN, a_desc, b_desc, idesc, (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              for (int r = 0; r < kHaloRows; ++r) {
+                const uint64_t a_desc = desc0 + ((halo_addr + ((r + dy) * kHaloW + dx) * 128) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_tmem + r * kN, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                            (c > 0 || tap + t > 0 || k > 0) ? 1u : 0u);
               }
             }
             umma_commit(&bempty[bs]);
-            if (tap == 8) {
+            if (tap + Cfg::kTapsPerSlot >= 9) {
               umma_commit(&hempty[hs]);
               if (c == chunks - 1) umma_commit(&tfull[as]);
             }
@@ -325,7 +330,7 @@ bool conv_halo_eligible(int H, int W, int cout, int split_n, int taps) {
 int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
                    const void* wpack, int cout, void* dst0, void* dst1, int split_n,
                    const float* bias, const float* scale, const float* shift, int relu, float* stats,
-                   int base_offset_mode, cudaStream_t stream) {
+                   cudaStream_t stream) {
   if (dst1 == nullptr) split_n = cout;
   int kn = 128;
   while (kn > 64 && (cout % kn != 0 || split_n % kn != 0 || (cout - split_n) % kn != 0)) kn >>= 1;
@@ -340,7 +345,6 @@ int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, in
   p.cout = cout;
   p.split_n = split_n;
   p.relu = relu;
-  p.base_offset_mode = base_offset_mode;
   p.bias = bias; p.scale = scale; p.shift = shift; p.stats = stats;
 
   CUtensorMap tmA0, tmA1, tmW, tmO0, tmO1;
