@@ -1,0 +1,112 @@
+// Shared epilogue of the tcgen05 convolution kernels: one 128-row x 64-column
+// accumulator chunk (already in registers) -> +bias, optional affine + ReLU,
+// bf16, swizzled smem staging, TMA store, and per-channel sum / sum-of-squares of
+// the stored values (train-mode BatchNorm statistics, UG_unet_parts.py:11,14).
+// Executed by the 128 epilogue threads (warps 2..5).
+#pragma once
+
+#include "ugp_common.cuh"
+
+namespace ugp {
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_b32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t addr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+struct EpilogueCtx {
+  uint32_t bias_addr;    // smem byte addresses of the per-channel arrays
+  uint32_t scale_addr;
+  uint32_t shift_addr;
+  uint32_t stats_addr;   // [2][stats_stride] floats
+  uint32_t stats_stride; // in floats
+  bool has_bias, has_affine, relu, do_stats;
+};
+
+// v: 64 fp32 accumulator values of this thread's row (columns n_base .. n_base+63).
+// buf_addr: smem byte address of the 16 KB staging buffer (1024-aligned, SWIZZLE_128B rows).
+template <int kStagingBufs>
+__device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint32_t* v, int n_base,
+                                               uint32_t buf_addr, int row, int et,
+                                               const CUtensorMap* tm_out, int out_col, int out_row) {
+  uint32_t packed[32];
+#pragma unroll
+  for (int j = 0; j < 64; j += 4) {
+    float f0 = __uint_as_float(v[j + 0]), f1 = __uint_as_float(v[j + 1]);
+    float f2 = __uint_as_float(v[j + 2]), f3 = __uint_as_float(v[j + 3]);
+    if (e.has_bias) {
+      const float4 bi = ld_shared_f4(e.bias_addr + (n_base + j) * 4);
+      f0 += bi.x; f1 += bi.y; f2 += bi.z; f3 += bi.w;
+    }
+    if (e.has_affine) {
+      const float4 sc = ld_shared_f4(e.scale_addr + (n_base + j) * 4);
+      const float4 sh = ld_shared_f4(e.shift_addr + (n_base + j) * 4);
+      f0 = fmaf(f0, sc.x, sh.x); f1 = fmaf(f1, sc.y, sh.y);
+      f2 = fmaf(f2, sc.z, sh.z); f3 = fmaf(f3, sc.w, sh.w);
+    }
+    if (e.relu) {
+      f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f);
+      f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
+    }
+    packed[j / 2] = pack_bf16x2(f0, f1);
+    packed[j / 2 + 1] = pack_bf16x2(f2, f3);
+  }
+  // the TMA store that last read this staging buffer must be done
+  if (et == 0) tma_store_wait_read<kStagingBufs - 1>();
+  named_bar_sync(1, 128);
+  const uint32_t rowp = buf_addr + row * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    st_shared_v4(rowp + ((j ^ (row & 7)) << 4), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2],
+                 packed[4 * j + 3]);
+  fence_proxy_async_smem();
+  named_bar_sync(2, 128);
+  if (et == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm_out)),
+                 "r"(buf_addr), "r"(out_col), "r"(out_row)
+                 : "memory");
+    tma_store_commit();
+  }
+  if (e.do_stats) {
+    // column sums over the bf16-rounded tile: a thread owns one 32-bit word column (2 channels)
+    // over a quarter of the rows; reads are conflict-free (32 lanes = one 128 B row)
+    const int wcol = et & 31;
+    const int r0 = (et >> 5) * 32;
+    const uint32_t colp = buf_addr + ((wcol & 3) << 2);
+    const int chunk = wcol >> 2;
+    float s0a = 0.f, s1a = 0.f, q0a = 0.f, q1a = 0.f, s0b = 0.f, s1b = 0.f, q0b = 0.f, q1b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {      // r0 is a multiple of 8: (r0 + i) & 7 == i & 7
+      const uint32_t wa = ld_shared_b32(colp + (r0 + i) * 128 + ((chunk ^ (i & 7)) << 4));
+      const uint32_t wb = ld_shared_b32(colp + (r0 + i + 1) * 128 + ((chunk ^ ((i + 1) & 7)) << 4));
+      const float a0 = bf16_lo(wa), a1 = bf16_hi(wa), b0 = bf16_lo(wb), b1 = bf16_hi(wb);
+      s0a += a0; s1a += a1; q0a = fmaf(a0, a0, q0a); q1a = fmaf(a1, a1, q1a);
+      s0b += b0; s1b += b1; q0b = fmaf(b0, b0, q0b); q1b = fmaf(b1, b1, q1b);
+    }
+    const int c = n_base + 2 * wcol;
+    red_shared_add(e.stats_addr + c * 4, s0a + s0b);
+    red_shared_add(e.stats_addr + (c + 1) * 4, s1a + s1b);
+    red_shared_add(e.stats_addr + (e.stats_stride + c) * 4, q0a + q0b);
+    red_shared_add(e.stats_addr + (e.stats_stride + c + 1) * 4, q1a + q1b);
+  }
+}
+
+}  // namespace ugp

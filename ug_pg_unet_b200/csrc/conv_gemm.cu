@@ -22,6 +22,7 @@
 // owner, warps 2..5 = epilogue (one TMEM lane quarter each). Persistent CTAs,
 // static round-robin over (m_tile, n_tile).
 #include "ugp_common.cuh"
+#include "conv_epilogue.cuh"
 
 namespace ugp {
 
@@ -208,6 +209,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int q = warp_idx & 3;        // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;     // row of the 128-row tile
     const bool do_stats = p.stats != nullptr;
+    EpilogueCtx ectx;
+    ectx.bias_addr = smem_u32(sBias);
+    ectx.scale_addr = smem_u32(sScale);
+    ectx.shift_addr = smem_u32(sShift);
+    ectx.stats_addr = smem_u32(sStats);
+    ectx.stats_stride = kMaxC;
+    ectx.has_bias = p.bias != nullptr;
+    ectx.has_affine = p.scale != nullptr;
+    ectx.relu = p.relu != 0;
+    ectx.do_stats = do_stats;
     uint32_t chunk_counter = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -230,61 +241,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           mbar_arrive(&tempty_bar[as]);
         }
         const int n_base = n_tile * kN + cc * 64;
-        uint32_t packed[32];
-#pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          const float4 bi = *reinterpret_cast<const float4*>(sBias + n_base + j);
-          const float4 sc = *reinterpret_cast<const float4*>(sScale + n_base + j);
-          const float4 sh = *reinterpret_cast<const float4*>(sShift + n_base + j);
-          float f0 = (__uint_as_float(v[j + 0]) + bi.x) * sc.x + sh.x;
-          float f1 = (__uint_as_float(v[j + 1]) + bi.y) * sc.y + sh.y;
-          float f2 = (__uint_as_float(v[j + 2]) + bi.z) * sc.z + sh.z;
-          float f3 = (__uint_as_float(v[j + 3]) + bi.w) * sc.w + sh.w;
-          if (p.relu) {
-            f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f);
-            f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
-          }
-          packed[j / 2] = pack_bf16x2(f0, f1);
-          packed[j / 2 + 1] = pack_bf16x2(f2, f3);
-        }
-        uint8_t* buf = sOut + (chunk_counter % Cfg::kStagingBufs) * kOutChunkBytes;
-        // the TMA store that last read this staging buffer must be done
-        if (et == 0) tma_store_wait_read<Cfg::kStagingBufs - 1>();
-        named_bar_sync(1, 128);
-        uint8_t* rowp = buf + row * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 val = make_uint4(packed[4 * j], packed[4 * j + 1],
-                                 packed[4 * j + 2], packed[4 * j + 3]);
-          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = val;
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(2, 128);
-        if (et == 0) {
-          if (n_base < p.split_n)
-            tma_store_2d(&tmO0, buf, n_base, m_tile * kBlockM);
-          else
-            tma_store_2d(&tmO1, buf, n_base - p.split_n, m_tile * kBlockM);
-          tma_store_commit();
-        }
-        if (do_stats) {
-          // column sums over the bf16-rounded tile: 2 threads per column
-          const int col = et & 63;
-          const int r0 = (et >> 6) * 64;
-          const uint8_t* colp = buf + ((col & 7) << 1);
-          const int chunk = col >> 3;
-          float s = 0.f, s2 = 0.f;
-#pragma unroll 8
-          for (int r = r0; r < r0 + 64; ++r) {
-            const unsigned short h = *reinterpret_cast<const unsigned short*>(
-                colp + r * 128 + ((chunk ^ (r & 7)) << 4));
-            const float f = __uint_as_float(static_cast<uint32_t>(h) << 16);
-            s += f;
-            s2 = fmaf(f, f, s2);
-          }
-          atomicAdd(&sStats[n_base + col], s);
-          atomicAdd(&sStats[kMaxC + n_base + col], s2);
-        }
+        const uint32_t buf_addr = smem_u32(sOut) + (chunk_counter % Cfg::kStagingBufs) * kOutChunkBytes;
+        if (n_base < p.split_n)
+          epilogue_chunk<Cfg::kStagingBufs>(ectx, v, n_base, buf_addr, row, et, &tmO0, n_base,
+                                            m_tile * kBlockM);
+        else
+          epilogue_chunk<Cfg::kStagingBufs>(ectx, v, n_base, buf_addr, row, et, &tmO1,
+                                            n_base - p.split_n, m_tile * kBlockM);
       }
     }
     if (et == 0) tma_store_wait_all();

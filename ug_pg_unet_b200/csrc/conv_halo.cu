@@ -16,6 +16,7 @@
 // Warp roles as in conv_gemm.cu: warp 0 TMA producer, warp 1 MMA issuer / TMEM
 // owner, warps 2..5 epilogue.
 #include "ugp_common.cuh"
+#include "conv_epilogue.cuh"
 
 namespace ugp {
 
@@ -27,11 +28,14 @@ struct ConvHaloParams {
   int cout;
   int split_n;
   int relu;
+  int debug;                 // what-if timing only: 1 = skip MMA issue, 2 = skip epilogue body
   const float* bias;
   const float* scale;
   const float* shift;
   float* stats;
 };
+
+extern int g_conv_debug;
 
 constexpr int kHaloRows = 2;                               // image rows per CTA tile
 constexpr int kHaloW = 130;                                // 128 pixels + 1 halo pixel each side
@@ -172,13 +176,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int t = 0; t < Cfg::kTapsPerSlot; ++t) {
               const int dy = (tap + t) / 3, dx = (tap + t) % 3;   // halo-relative (+1 folded in)
               const uint64_t b_desc = desc0 + ((slot_addr + t * Cfg::kTapBytes) >> 4);
+              // alternate the two accumulators MMA by MMA (independent TMEM targets back to back)
 #pragma unroll
-              for (int r = 0; r < kHaloRows; ++r) {
-                const uint64_t a_desc = desc0 + ((halo_addr + ((r + dy) * kHaloW + dx) * 128) >> 4);
+              for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_tmem + r * kN, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                            (c > 0 || tap + t > 0 || k > 0) ? 1u : 0u);
+                for (int r = 0; r < kHaloRows; ++r) {
+                  const uint64_t a_desc = desc0 + ((halo_addr + ((r + dy) * kHaloW + dx) * 128) >> 4);
+                  if (!(p.debug & 1))
+                    umma_bf16(d_tmem + r * kN, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                              (c > 0 || tap + t > 0 || k > 0) ? 1u : 0u);
+                }
               }
             }
             umma_commit(&bempty[bs]);
@@ -199,6 +206,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int q = warp_idx & 3;
     const int row = q * 32 + lane;
     const bool do_stats = p.stats != nullptr;
+    EpilogueCtx ectx;
+    ectx.bias_addr = smem_u32(sBias);
+    ectx.scale_addr = smem_u32(sScale);
+    ectx.shift_addr = smem_u32(sShift);
+    ectx.stats_addr = smem_u32(sStats);
+    ectx.stats_stride = kHaloMaxCout;
+    ectx.has_bias = p.bias != nullptr;
+    ectx.has_affine = p.scale != nullptr;
+    ectx.relu = p.relu != 0;
+    ectx.do_stats = do_stats;
     uint32_t chunk_counter = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -212,6 +229,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after_sync();
+      if (p.debug & 2) {
+        tc_fence_before_sync();
+        mbar_arrive(&tempty[as]);
+        continue;
+      }
 #pragma unroll 1
       for (int r = 0; r < kHaloRows; ++r) {
         const int out_row0 = ((b * p.H + ty * kHaloRows + r) * p.W) + tx * 128;   // pixel index
@@ -228,58 +250,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             mbar_arrive(&tempty[as]);
           }
           const int n_base = n_tile * kN + cc * 64;
-          uint32_t packed[32];
-#pragma unroll
-          for (int j = 0; j < 64; j += 4) {
-            const float4 bi = *reinterpret_cast<const float4*>(sBias + n_base + j);
-            const float4 sc = *reinterpret_cast<const float4*>(sScale + n_base + j);
-            const float4 sh = *reinterpret_cast<const float4*>(sShift + n_base + j);
-            float f0 = (__uint_as_float(v[j + 0]) + bi.x) * sc.x + sh.x;
-            float f1 = (__uint_as_float(v[j + 1]) + bi.y) * sc.y + sh.y;
-            float f2 = (__uint_as_float(v[j + 2]) + bi.z) * sc.z + sh.z;
-            float f3 = (__uint_as_float(v[j + 3]) + bi.w) * sc.w + sh.w;
-            if (p.relu) {
-              f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f);
-              f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
-            }
-            packed[j / 2] = pack_bf16x2(f0, f1);
-            packed[j / 2 + 1] = pack_bf16x2(f2, f3);
-          }
-          uint8_t* buf = sOut + (chunk_counter & 1) * 16384;
-          if (et == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-          uint8_t* rowp = buf + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 val = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = val;
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(2, 128);
-          if (et == 0) {
-            if (n_base < p.split_n)
-              tma_store_2d(&tmO0, buf, n_base, out_row0);
-            else
-              tma_store_2d(&tmO1, buf, n_base - p.split_n, out_row0);
-            tma_store_commit();
-          }
-          if (do_stats) {
-            const int col = et & 63;
-            const int r0 = (et >> 6) * 64;
-            const uint8_t* colp = buf + ((col & 7) << 1);
-            const int chunk = col >> 3;
-            float s = 0.f, s2 = 0.f;
-#pragma unroll 8
-            for (int rr = r0; rr < r0 + 64; ++rr) {
-              const unsigned short h = *reinterpret_cast<const unsigned short*>(
-                  colp + rr * 128 + ((chunk ^ (rr & 7)) << 4));
-              const float f = __uint_as_float(static_cast<uint32_t>(h) << 16);
-              s += f;
-              s2 = fmaf(f, f, s2);
-            }
-            atomicAdd(&sStats[n_base + col], s);
-            atomicAdd(&sStats[kHaloMaxCout + n_base + col], s2);
-          }
+          const uint32_t buf_addr = smem_u32(sOut) + (chunk_counter & 1) * 16384;
+          if (n_base < p.split_n)
+            epilogue_chunk<2>(ectx, v, n_base, buf_addr, row, et, &tmO0, n_base, out_row0);
+          else
+            epilogue_chunk<2>(ectx, v, n_base, buf_addr, row, et, &tmO1, n_base - p.split_n, out_row0);
         }
       }
     }
@@ -345,6 +320,7 @@ int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, in
   p.cout = cout;
   p.split_n = split_n;
   p.relu = relu;
+  p.debug = g_conv_debug;
   p.bias = bias; p.scale = scale; p.shift = shift; p.stats = stats;
 
   CUtensorMap tmA0, tmA1, tmW, tmO0, tmO1;
