@@ -36,13 +36,16 @@ from .unet import PGUNet1, PGUNet2, PGUNet3, PGUNet4, UncertaintyGuidedLoss, tra
 
 class UncertaintyGuidedProgressiveTrainer:
     def __init__(self, in_channels=3, num_classes=1, device="cuda", uncertainty_alpha=1.0,
-                 distributed: Optional[bool] = None, bucket_mb: float = 16.0, log_interval: int = 10):
+                 distributed: Optional[bool] = None, bucket_mb: float = 16.0, log_interval: int = 10,
+                 use_cuda_graph: bool = True):
         self.device = device
         self.in_channels = in_channels
         self.num_classes = num_classes
         self.uncertainty_alpha = uncertainty_alpha
         self.log_interval = log_interval
         self.bucket_mb = bucket_mb
+        self.use_cuda_graph = use_cuda_graph and os.environ.get("UGP_NO_CUDA_GRAPH", "0") != "1"
+        self._graph = None
 
         # reference uncertainty_guided_trainer.py:42-47
         self.stage_configs = {
@@ -84,7 +87,10 @@ class UncertaintyGuidedProgressiveTrainer:
     def setup_optimizer(self, stage):
         """RMSprop(lr, weight_decay=1e-4) on the current model — reference :81-88."""
         lr = self.stage_configs[stage]["lr"]
-        self.optimizer = optim.RMSprop(self.current_model.parameters(), lr=lr, weight_decay=1e-4)
+        on_cuda = next(self.current_model.parameters()).is_cuda
+        self.optimizer = optim.RMSprop(self.current_model.parameters(), lr=lr, weight_decay=1e-4,
+                                       capturable=bool(on_cuda and self.use_cuda_graph))
+        self._graph = None
         if self._reducer is not None:
             self._reducer.remove()
             self._reducer = None
@@ -183,16 +189,48 @@ class UncertaintyGuidedProgressiveTrainer:
             target = F.interpolate(target, size=(resolution, resolution), mode="nearest")
         return data, target
 
-    def train_step(self, data, target, stage):
-        """One optimisation step on already-resident device tensors; no host synchronisation.
-        Returns the fused-metrics device tensor (see `_metrics_from_device`)."""
-        self.optimizer.zero_grad()
+    def _eager_step(self, data, target, stage):
+        self.optimizer.zero_grad(set_to_none=True)
         final_loss, output_current, unc, _ = self._forward_loss(data, target, stage)
         final_loss.backward()
         if self._reducer is not None:
             self._reducer.wait()
         self.optimizer.step()
         return self.uncertainty_loss.last_metrics, output_current, unc
+
+    def train_step(self, data, target, stage):
+        """One optimisation step on already-resident device tensors; no host synchronisation.
+        Returns (fused-metrics device tensor, logits, uncertainty map); see `_metrics_from_device`.
+
+        The step launches ~230 kernels; after a few eager warm-up steps the whole step (forward,
+        uncertainty forward, loss, backward, optimiser) is captured once into a CUDA graph per
+        (stage, shapes) and replayed, so the GPU is not left waiting for the host.  Tensors returned
+        from a replay are static buffers that the next step overwrites (the metrics are cloned)."""
+        crit = self.base_criterion
+        fused = isinstance(crit, nn.BCEWithLogitsLoss) and crit.reduction == "none" and crit.weight is None
+        if not (self.use_cuda_graph and data.is_cuda and self._reducer is None and fused):
+            return self._eager_step(data, target, stage)
+        key = (stage, tuple(data.shape), tuple(target.shape), id(self.current_model), id(self.optimizer),
+               self.current_model.training)
+        g = self._graph
+        if g is None or g["key"] != key:
+            self._graph = g = {"key": key, "warm": 0, "graph": None}
+        if g["graph"] is None:
+            if g["warm"] < 3:
+                g["warm"] += 1
+                return self._eager_step(data, target, stage)
+            g["x"], g["y"] = data.clone(), target.clone()
+            self.optimizer.zero_grad(set_to_none=True)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g["out"] = self._eager_step(g["x"], g["y"], stage)
+            g["graph"] = graph
+        g["x"].copy_(data, non_blocking=True)
+        g["y"].copy_(target, non_blocking=True)
+        g["graph"].replay()
+        m, logits, unc = g["out"]
+        return m.clone(), logits, unc
 
     def _epoch(self, dataloader, stage, train: bool):
         resolution = self.stage_configs[stage]["resolution"]
