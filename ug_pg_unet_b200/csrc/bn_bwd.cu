@@ -32,7 +32,9 @@ struct BnBwdArgs {
 };
 
 constexpr int kBnThreads = 256;
-constexpr int kBnUnroll = 4;
+// independent 16-byte loads per array in flight per thread: 8 in the reduce pass, 4 in the apply
+// pass (which also needs the three per-channel coefficient sets in registers)
+template <bool kApply> struct BnUnroll { static constexpr int v = kApply ? 4 : 8; };
 
 // Block reduction over the rows that share a channel group, then one atomic per
 // channel per block.
@@ -104,16 +106,17 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const 
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
 
+  constexpr int kBnUnroll = BnUnroll<kApply>::v;
   const long long stride = static_cast<long long>(gridDim.x) * rows_per_block;
   for (long long p = static_cast<long long>(blockIdx.x) * rows_per_block + my_row; p < M;
        p += stride * kBnUnroll) {
-    Vec8 zv[kBnUnroll], gv[kBnUnroll];
+    uint4 zr[kBnUnroll], gr[kBnUnroll];     // raw bf16x8 keeps the in-flight footprint small
 #pragma unroll
     for (int u = 0; u < kBnUnroll; ++u) {
       const long long pp = p + u * stride;
       if (pp < M) {
-        zv[u] = load8(a.z + pp * a.C + c0);
-        gv[u] = load8(a.dA + pp * a.C + c0);
+        zr[u] = *reinterpret_cast<const uint4*>(a.z + pp * a.C + c0);
+        gr[u] = *reinterpret_cast<const uint4*>(a.dA + pp * a.C + c0);
       }
     }
 #pragma unroll
@@ -121,10 +124,12 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const 
       const long long pp = p + u * stride;
       if (pp < M) {
         Vec8 o;
+        const Vec8 zv = unpack8(zr[u]);
+        const Vec8 gv = unpack8(gr[u]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float z = zv[u].v[j];
-          const float g = (fmaf(z, sc[j], sh[j]) > 0.f) ? gv[u].v[j] : 0.f;
+          const float z = zv.v[j];
+          const float g = (fmaf(z, sc[j], sh[j]) > 0.f) ? gv.v[j] : 0.f;
           if (!kApply) {
             acc0[j] = fmaf(g, z - kz[j], acc0[j]);   // sum g*(z-mean); * rstd at the end
             acc1[j] += g;
@@ -266,13 +271,16 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
   const long long cap = static_cast<long long>(device_sm_count()) * 2;
   if (dP) {
     UGP_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_bwd: pooled gradient needs even H, W");
-    long long blocks = (M / 4 + rows_per_block - 1) / rows_per_block;
+    long long blocks = (M / 4 + rows_per_block * 4 - 1) / (rows_per_block * 4);
     if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
     bn_relu_bwd_pool_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
     UGP_CHECK_CUDA(cudaGetLastError());
     bn_relu_bwd_pool_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
   } else {
-    long long blocks = (M + rows_per_block * kBnUnroll - 1) / (rows_per_block * kBnUnroll);
+    // at least two trips of kBnUnroll pixels per thread: small tensors get few blocks, which
+    // keeps the per-channel atomic tail short (16 pixels per thread at least)
+    long long blocks = (M + rows_per_block * 16 - 1) / (rows_per_block * 16);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     bn_relu_bwd_plain_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);

@@ -13,9 +13,12 @@
 // blocks one box apart = LBO).
 //
 // An M tile is two 64-channel boxes; each box is (tap, 64-channel chunk), so
-// for Cin = 64 one tile covers two taps.  K (pixels) is split across CTAs and
-// partial tiles are reduced with vector fp32 atomics into the packed fp32
-// gradient [tap][Cin][Cout] (Cout contiguous).
+// for Cin = 64 one tile covers two taps.  A CTA owns up to kT M tiles (kT
+// accumulators of 128 x kN in TMEM, kT * kN <= 512 columns) that all share the
+// dZ tile of each 64-pixel K chunk: the operand bytes pulled from L2 per MMA
+// drop by ~kT/2 versus one tile per CTA, which is what bounds this kernel.
+// K (pixels) is split across CTAs and partial tiles are reduced with vector
+// fp32 atomics into the packed fp32 gradient [tap][Cin][Cout] (Cout contiguous).
 #include "ugp_common.cuh"
 
 namespace ugp {
@@ -25,6 +28,8 @@ struct WgradParams {
   int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
   int H, W, BHp, BWp;     // 64-pixel K box
   int boxes;              // taps * (chunks0 + chunks1)
+  int m_tiles;            // ceil(boxes / 2)
+  int m_groups;           // ceil(m_tiles / kT)
   int n_tiles;
   int cout;
   int kchunks_total;      // B*H*W / 64
@@ -33,14 +38,15 @@ struct WgradParams {
 };
 
 constexpr int kWgBoxBytes = 64 * 64 * 2;  // 64 pixels x 64 channels bf16 = 8 KB
-constexpr int kWgStages = 4;
 
 template <int kN>
 struct WgradCfg {
-  static constexpr int kABytes = 2 * kWgBoxBytes;
+  static constexpr int kT = 512 / kN > 5 ? 5 : 512 / kN;            // 5 / 4 / 2 accumulators
+  static constexpr int kStages = (kN == 256) ? 3 : 2;
+  static constexpr int kABytes = 2 * kT * kWgBoxBytes;
   static constexpr int kBBytes = (kN / 64) * kWgBoxBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kWgStages * kStageBytes + 256 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b,
@@ -57,21 +63,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
                   const __grid_constant__ CUtensorMap tmDZ,
                   const WgradParams p) {
   using Cfg = WgradCfg<kN>;
+  constexpr int kT = Cfg::kT;
+  constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = sA + kWgStages * Cfg::kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kWgStages * Cfg::kBBytes);
-  uint64_t* empty_bar = full_bar + kWgStages;
-  uint64_t* done_bar = empty_bar + kWgStages;
+  uint8_t* sB = sA + kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kStages * Cfg::kBBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* done_bar = empty_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tile = blockIdx.x / p.n_tiles;
-  const int n_tile = blockIdx.x - m_tile * p.n_tiles;
+  const int m_group = blockIdx.x / p.n_tiles;
+  const int n_tile = blockIdx.x - m_group * p.n_tiles;
+  const int tile0 = m_group * kT;                         // first M tile of this CTA
+  const int nt = (p.m_tiles - tile0 < kT) ? (p.m_tiles - tile0) : kT;   // live M tiles
   const int kc_begin = blockIdx.y * p.kchunks_per_split;
   int kc_end = kc_begin + p.kchunks_per_split;
   if (kc_end > p.kchunks_total) kc_end = p.kchunks_total;
@@ -81,14 +91,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
     tma_prefetch_desc(&tmX0);
     tma_prefetch_desc(&tmX1);
     tma_prefetch_desc(&tmDZ);
-    for (int i = 0; i < kWgStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(done_bar, 1);
     fence_mbar_init();
   }
-  if (warp_idx == 1) tmem_alloc(tmem_slot, kN);
+  if (warp_idx == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -98,19 +108,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
 
   if (warp_idx == 0) {
     if (lane == 0) {
-      // the two boxes of this M tile; an odd box count repeats the last box
-      int box[2], bdx[2], bdy[2], bch[2];
-      for (int i = 0; i < 2; ++i) {
-        int id = m_tile * 2 + i;
-        if (id >= p.boxes) id = p.boxes - 1;
-        box[i] = id;
-        const int tap = id / chunks;
-        bch[i] = id - tap * chunks;
-        bdy[i] = (p.taps == 9) ? tap / 3 - 1 : 0;
-        bdx[i] = (p.taps == 9) ? tap % 3 - 1 : 0;
-      }
-      (void)box;
       const int hw = p.H * p.W;
+      const uint32_t stage_bytes = nt * 2 * kWgBoxBytes + Cfg::kBBytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = kc_begin; kc < kc_end; ++kc) {
@@ -120,25 +119,33 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
         const int y0 = rem / p.W;
         const int x0 = rem - y0 * p.W;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
         uint8_t* a_dst = sA + stage * Cfg::kABytes;
-        for (int i = 0; i < 2; ++i) {
-          if (bch[i] < p.chunks0)
-            tma_load_4d(&tmX0, &full_bar[stage], a_dst + i * kWgBoxBytes,
-                        bch[i] * 64, x0 + bdx[i], y0 + bdy[i], b);
+        for (int i = 0; i < 2 * nt; ++i) {
+          // the boxes of this CTA; an odd box count repeats the last box
+          int id = tile0 * 2 + i;
+          if (id >= p.boxes) id = p.boxes - 1;
+          const int tap = id / chunks;
+          const int ch = id - tap * chunks;
+          const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+          const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+          if (ch < p.chunks0)
+            tma_load_4d(&tmX0, &full_bar[stage], a_dst + i * kWgBoxBytes, ch * 64, x0 + dx, y0 + dy, b);
           else
-            tma_load_4d(&tmX1, &full_bar[stage], a_dst + i * kWgBoxBytes,
-                        (bch[i] - p.chunks0) * 64, x0 + bdx[i], y0 + bdy[i], b);
+            tma_load_4d(&tmX1, &full_bar[stage], a_dst + i * kWgBoxBytes, (ch - p.chunks0) * 64,
+                        x0 + dx, y0 + dy, b);
         }
         uint8_t* b_dst = sB + stage * Cfg::kBBytes;
         for (int j = 0; j < kN / 64; ++j)
           tma_load_4d(&tmDZ, &full_bar[stage], b_dst + j * kWgBoxBytes,
                       n_tile * kN + j * 64, x0, y0, b);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp_idx == 1) {
     constexpr uint32_t idesc = umma_idesc_bf16(128, kN, 1, 1);
+    // MN-major SWIZZLE_128B descriptor template: LBO = one box (next 64 channels), SBO = 1024 B
+    const uint64_t desc0 = umma_desc_sw128(0, kWgBoxBytes, 1024);
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < n_k; ++i) {
@@ -147,39 +154,42 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
         const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
+        for (int t = 0; t < nt; ++t) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // 16 pixels (K) per MMA = 16 rows of 128 B
-          const uint64_t a_desc = umma_desc_sw128(a_addr + k * 2048, kWgBoxBytes, 1024);
-          const uint64_t b_desc = umma_desc_sw128(b_addr + k * 2048, kWgBoxBytes, 1024);
-          umma_bf16(tmem_base, a_desc, b_desc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            // 16 pixels (K) per MMA = 16 rows of 128 B
+            const uint64_t a_desc = desc0 + ((a_addr + t * 2 * kWgBoxBytes + k * 2048) >> 4);
+            const uint64_t b_desc = desc0 + ((b_addr + k * 2048) >> 4);
+            umma_bf16(tmem_base + t * kN, a_desc, b_desc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (i == n_k - 1) umma_commit(done_bar);
       }
       __syncwarp();
-      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else {
     const int q = warp_idx & 3;
     const int row = q * 32 + lane;
-    const int box_id = m_tile * 2 + (row >> 6);
     mbar_wait(done_bar, 0);
     tc_fence_after_sync();
-    float* dst = p.dw + (static_cast<size_t>(box_id) * 64 + (row & 63)) * p.cout +
-                 n_tile * kN;
-    const bool live = box_id < p.boxes;
+    for (int t = 0; t < nt; ++t) {
+      const int box_id = (tile0 + t) * 2 + (row >> 6);
+      float* dst = p.dw + (static_cast<size_t>(box_id) * 64 + (row & 63)) * p.cout + n_tile * kN;
+      const bool live = box_id < p.boxes;
 #pragma unroll 1
-    for (int c = 0; c < kN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      if (live) {
+      for (int c = 0; c < kN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * kN + c * 32, v);
+        tmem_ld_wait();
+        if (live) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          red_add_v4(dst + c * 32 + j, __uint_as_float(v[j]),
-                     __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                     __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(dst + c * 32 + j, __uint_as_float(v[j]),
+                       __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                       __uint_as_float(v[j + 3]));
+        }
       }
     }
   }
@@ -188,14 +198,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
   __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kN);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
 template <int kN>
 static int launch_wgrad(const CUtensorMap& tmX0, const CUtensorMap& tmX1,
-                        const CUtensorMap& tmDZ, const WgradParams& p, int m_tiles,
-                        int splits, cudaStream_t stream) {
+                        const CUtensorMap& tmDZ, WgradParams p, cudaStream_t stream) {
   using Cfg = WgradCfg<kN>;
   static bool configured = false;
   if (!configured) {
@@ -204,7 +213,17 @@ static int launch_wgrad(const CUtensorMap& tmX0, const CUtensorMap& tmX1,
                                         Cfg::kSmemBytes));
     configured = true;
   }
-  dim3 grid(m_tiles * p.n_tiles, splits);
+  p.m_groups = (p.m_tiles + Cfg::kT - 1) / Cfg::kT;
+  const int items = p.m_groups * p.n_tiles;
+  int splits = (2 * device_sm_count() + items - 1) / items;
+  if (splits < 1) splits = 1;
+  // keep at least 8 K chunks (512 pixels) per split
+  int max_splits = p.kchunks_total / 8;
+  if (max_splits < 1) max_splits = 1;
+  if (splits > max_splits) splits = max_splits;
+  p.kchunks_per_split = (p.kchunks_total + splits - 1) / splits;
+  splits = (p.kchunks_total + p.kchunks_per_split - 1) / p.kchunks_per_split;
+  dim3 grid(items, splits);
   conv_wgrad_kernel<kN><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmX0, tmX1, tmDZ, p);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
@@ -231,20 +250,13 @@ int conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
   p.chunks1 = c1 / 64;
   p.H = H; p.W = W; p.BHp = BHp; p.BWp = BWp;
   p.boxes = taps * (p.chunks0 + p.chunks1);
+  p.m_tiles = (p.boxes + 1) / 2;
+  p.m_groups = 0;
   p.n_tiles = cout / kn;
   p.cout = cout;
   p.kchunks_total = (int)(((long long)B * H * W) / 64);
+  p.kchunks_per_split = 0;
   p.dw = dw_packed;
-  const int m_tiles = (p.boxes + 1) / 2;
-  const int items = m_tiles * p.n_tiles;
-  int splits = (2 * device_sm_count() + items - 1) / items;
-  if (splits < 1) splits = 1;
-  // keep at least 4 K chunks (256 pixels) per split
-  int max_splits = p.kchunks_total / 4;
-  if (max_splits < 1) max_splits = 1;
-  if (splits > max_splits) splits = max_splits;
-  p.kchunks_per_split = (p.kchunks_total + splits - 1) / splits;
-  splits = (p.kchunks_total + p.kchunks_per_split - 1) / p.kchunks_per_split;
 
   CUtensorMap tmX0, tmX1, tmDZ;
   int rc;
@@ -256,9 +268,9 @@ int conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
   }
   if ((rc = make_tmap_nhwc_bf16(&tmDZ, dz, B, H, W, cout, 64, BWp, BHp))) return rc;
   switch (kn) {
-    case 256: return launch_wgrad<256>(tmX0, tmX1, tmDZ, p, m_tiles, splits, stream);
-    case 128: return launch_wgrad<128>(tmX0, tmX1, tmDZ, p, m_tiles, splits, stream);
-    default:  return launch_wgrad<64>(tmX0, tmX1, tmDZ, p, m_tiles, splits, stream);
+    case 256: return launch_wgrad<256>(tmX0, tmX1, tmDZ, p, stream);
+    case 128: return launch_wgrad<128>(tmX0, tmX1, tmDZ, p, stream);
+    default:  return launch_wgrad<64>(tmX0, tmX1, tmDZ, p, stream);
   }
 }
 

@@ -32,6 +32,14 @@ __device__ __forceinline__ float round_bf16(float v) {
 struct Vec8 {
   float v[8];
 };
+__device__ __forceinline__ Vec8 unpack8(const uint4 u) {
+  Vec8 r;
+  r.v[0] = bf16_lo(u.x); r.v[1] = bf16_hi(u.x);
+  r.v[2] = bf16_lo(u.y); r.v[3] = bf16_hi(u.y);
+  r.v[4] = bf16_lo(u.z); r.v[5] = bf16_hi(u.z);
+  r.v[6] = bf16_lo(u.w); r.v[7] = bf16_hi(u.w);
+  return r;
+}
 __device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   Vec8 r;
