@@ -196,14 +196,12 @@ def run_ours(args):
     sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ops.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         trainer.train_step(x, y, STAGE)
     e1.record()
     sync_all()
-    launches = ops.launch_count()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
 
@@ -234,11 +232,17 @@ def run_ours(args):
     # ---------------- per-kernel roofline (instrumented step, rank 0) ----------------
     peaks = load_peaks()
     roof = None
+    # kernels per step: counted on one eagerly launched step (the CUDA graph replays exactly these)
+    ops.reset_launch_count()
+    if rank != 0:
+        trainer._eager_step(x, y, STAGE)
     if rank == 0:
         ops.start_profile()
-        trainer.train_step(x, y, STAGE)
+        trainer._eager_step(x, y, STAGE)      # same kernels as the captured graph, launched one by one
         torch.cuda.synchronize()
         prof = ops.stop_profile()
+    launches = ops.launch_count() * args.steps
+    if rank == 0:
         conv = [(f, t_ms) for (name, f, t_ms) in prof if name == "conv_gemm"]
         wg = [(f, t_ms) for (name, f, t_ms) in prof if name == "conv_wgrad"]
         tot_f = sum(f for f, _ in conv)

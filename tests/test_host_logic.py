@@ -1,0 +1,158 @@
+"""CPU-only checks of the host side: module surface / state_dict parity with the reference tables,
+weight transfer, trainer metric arithmetic, the no-CPU-fallback contract and the C-ABI exports."""
+import os
+import re
+
+import pytest
+import torch
+
+import ug_oracle as O
+import ug_pg_unet_b200 as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("stage", [1, 2, 3, 4])
+@pytest.mark.parametrize("nc", [1, 2, 7])
+def test_state_dict_keys_and_shapes_match_reference_tables(stage, nc):
+    model = U.STAGE_MODELS[stage](3, nc)
+    sd = model.state_dict()
+    shapes = O.state_dict_shapes(stage, 3, nc)          # pinned against the reference in test_oracle_golden
+    assert list(sd.keys()) == list(shapes.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == shapes[k], k
+    assert sd["inc.conv.conv_op.1.num_batches_tracked"].dtype == torch.int64
+    # reference-format state dicts load strictly, and round-trip through torch.save
+    model.load_state_dict(O.seeded_state_dict(stage, 3, nc, seed=3), strict=True)
+
+
+def test_module_attribute_names():
+    m = U.PGUNet4(3, 1)
+    for name in ("inc", "down1", "down2", "down3", "down4", "up1", "up2", "up3", "up4", "outc1", "outc2", "outc3", "outc4"):
+        assert hasattr(m, name)
+    assert hasattr(U.PGUNet1(3, 1), "outc")
+    assert isinstance(m.down1.mpconv[0], torch.nn.MaxPool2d)
+    assert isinstance(m.inc.conv.conv_op[0], torch.nn.Conv2d) and isinstance(m.inc.conv.conv_op[1], torch.nn.BatchNorm2d)
+    pu = U.ProgressiveUNet(3, 1)
+    assert pu.stage_resolutions == {1: 32, 2: 64, 3: 128, 4: 256} and pu.current_stage == 1
+    assert set(pu.stages) == {1, 2, 3, 4} and pu.stage4 is pu.stages[4]
+
+
+def test_progressive_unet_signatures_and_errors():
+    pu = U.ProgressiveUNet(in_channels=3, out_channels=1, stage=2, task_type="segmentation")   # README form
+    assert pu.current_stage == 2 and pu.get_current_resolution() == 64 and pu.num_classes == 1
+    with pytest.raises(ValueError, match="Stage must be 1, 2, 3, or 4"):
+        pu.set_stage(5)
+    with pytest.raises(TypeError):
+        U.ProgressiveUNet(3)
+    ul = U.UncertaintyGuidedLoss(task_type="segmentation")
+    assert isinstance(ul, torch.nn.Module) and ul.device == "cuda"
+
+
+def test_transfer_weights_matches_reference_semantics(golden_dir):
+    sd1 = O.seeded_state_dict(1, 3, 1, seed=1)
+    sd2 = O.seeded_state_dict(2, 3, 1, seed=2)
+    moved = U.transfer_state(sd1, sd2)
+    ref, copied = O.transfer_weights(sd1, sd2)
+    assert len(copied) == 42
+    for k in ref:
+        assert torch.equal(moved[k], ref[k]), k
+    # partial leading-slice copy: (512,3,3,3) -> first 256 output channels
+    k = "inc.conv.conv_op.0.weight"
+    assert torch.equal(moved[k], sd1[k][:256])
+    fx = torch.load(os.path.join(golden_dir, "primitives.pt"))
+    for key, s in fx["transfer_1_to_2"].items():
+        f = moved[key].flatten()
+        got = f if "full" in s else f[s["idx"]]
+        assert torch.equal(got, s["full"] if "full" in s else s["vals"]), key
+    pu = U.ProgressiveUNet(3, 1)
+    again = pu.transfer_weights(sd1, sd2, 2)
+    assert all(torch.equal(again[k], moved[k]) for k in moved)
+
+
+def test_no_cpu_fallback():
+    m = U.PGUNet1(3, 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(1, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        U.DoubleConv(64, 64)(torch.randn(1, 64, 16, 16))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        U.UncertaintyGuidedLoss("cpu").generate_uncertainty_map(torch.randn(1, 3, 64, 64), m, 32, 64)
+    with pytest.raises(ValueError):
+        U.DoubleConv(96, 64)           # channel counts the kernels do not cover fail loudly at construction
+    with pytest.raises(ValueError):
+        U.OutConv(64, 9)
+
+
+def test_generic_criterion_path_matches_reference_arithmetic():
+    """A loss_fn that is not the fused BCEWithLogitsLoss goes through the reference's own arithmetic
+    (UG_unet.py:78-94); works on CPU tensors because no kernel is involved."""
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(2, 1, 8, 8, generator=g, requires_grad=True)
+    y = torch.randint(0, 2, (2, 1, 8, 8), generator=g).float()
+    A = torch.rand(2, 1, 8, 8, generator=g)
+    ul = U.UncertaintyGuidedLoss("cpu")
+    crit = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([5.0]), reduction="none")
+    final, base = ul.apply_uncertainty_weighted_loss(crit, z, y, A, 0.5)
+    rf, rb = O.weighted_loss(z, y, A, 0.5, 5.0)
+    assert abs(final.item() - rf.item()) < 1e-6 and abs(base - rb.item()) < 1e-6
+    f1, b1 = ul.apply_uncertainty_weighted_loss(crit, z, y, None, 1.0)
+    assert abs(f1.item() - b1) < 1e-6
+
+
+def test_trainer_surface_and_metric_arithmetic():
+    tr = U.UncertaintyGuidedProgressiveTrainer(3, 1, device="cpu", uncertainty_alpha=0.7)
+    assert tr.stage_configs[1] == {"resolution": 32, "epochs_per_stage": 40, "lr": 3e-4}
+    assert tr.stage_configs[4]["lr"] == 1e-4 and set(tr.models) == {1, 2, 3, 4}
+    assert tr.current_model is tr.models[1] and tr.uncertainty_alpha == 0.7
+    assert isinstance(tr.base_criterion, torch.nn.BCEWithLogitsLoss) and float(tr.base_criterion.pos_weight) == 5.0
+    assert isinstance(tr.optimizer, torch.optim.RMSprop)
+    d = tr.optimizer.defaults
+    assert (d["lr"], d["weight_decay"], d["alpha"], d["eps"], d["momentum"], d["centered"]) == (3e-4, 1e-4, 0.99, 1e-8, 0, False)
+    for key in ("train_loss", "val_loss", "train_dice", "val_dice", "uncertainty_weights_mean",
+                "uncertainty_weights_std", "base_loss", "stage_transitions"):
+        assert tr.history[key] == []
+    # fused-kernel accumulators -> reference metrics (uncertainty_guided_trainer.py:90-123,177-181)
+    g = torch.Generator().manual_seed(1)
+    B, n = 3, 3 * 16
+    z = torch.randn(B, 1, 4, 4, generator=g)
+    y = torch.randint(0, 2, (B, 1, 4, 4), generator=g).float()
+    A = torch.rand(B, 1, 4, 4, generator=g)
+    l = O.bce_with_logits(z, y, 5.0)
+    pred = (z > 0).float()
+    acc = [(l * (1 + 0.7 * A)).sum(), l.sum(), A.sum(), (A * A).sum(), pred.ne(y).sum().float()]
+    for b in range(B):
+        acc += [(pred[b] * y[b]).sum(), pred[b].sum(), y[b].sum()]
+    m = torch.stack([a.double() for a in acc])
+    final, base, dice, accuracy, um, us = tr._metrics_from_device(m, n, B, True)
+    assert abs(final - (l * (1 + 0.7 * A)).mean().item()) < 1e-6
+    assert abs(base - l.mean().item()) < 1e-6
+    assert abs(dice - O.dice_coefficient(pred.squeeze(1), y.squeeze(1)).item()) < 1e-6
+    assert abs(accuracy - O.accuracy(pred.squeeze(1), y.squeeze(1))) < 1e-9
+    assert abs(um - A.mean().item()) < 1e-6 and abs(us - A.std().item()) < 1e-5
+    # reference helper methods keep their semantics
+    assert torch.equal(tr.get_predictions(z), O.predictions(z))
+    assert abs(tr.dice_coefficient(pred.squeeze(1), y.squeeze(1)).item() - dice) < 1e-6
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from ug_pg_unet_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "ugp_b200.h")).read()
+    declared = set(re.findall(r"\b(ugp_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)
+    handle = _lib.lib()                      # loads (and builds if nvcc is present); no compute call
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert handle.ugp_version() >= 100
+    assert handle.ugp_set_option(b"no_such_option", 1) < 0
+    assert b"no_such_option" in handle.ugp_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ug_pg_unet_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "ug_oracle" not in src and "import oracle" not in src, fn
