@@ -31,9 +31,17 @@ class PackedWeights:
         self.wf = None
         self.wd = None
 
+    # bumped by whoever changes weights behind autograd's back (a CUDA-graph replay that contains
+    # the optimizer step does not advance `_version`)
+    epoch = 0
+
+    @classmethod
+    def invalidate_all(cls):
+        cls.epoch += 1
+
     def get(self):
         w = self.conv.weight
-        key = (w.data_ptr(), w._version, w.device)
+        key = (w.data_ptr(), w._version, w.device, PackedWeights.epoch)
         if key != self.key:
             self.wf, self.wd = ops.pack_weights(w.detach(), self.need_dgrad)
             self.key = key

@@ -30,6 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 import torch.optim as optim
 
+from .engine import PackedWeights
 from .parallel import GradBucketReducer, broadcast_module_state
 from .unet import PGUNet1, PGUNet2, PGUNet3, PGUNet4, UncertaintyGuidedLoss, transfer_state
 
@@ -229,6 +230,7 @@ class UncertaintyGuidedProgressiveTrainer:
         g["x"].copy_(data, non_blocking=True)
         g["y"].copy_(target, non_blocking=True)
         g["graph"].replay()
+        PackedWeights.invalidate_all()     # the replayed optimizer step changed the fp32 weights
         m, logits, unc = g["out"]
         return m.clone(), logits, unc
 
