@@ -95,10 +95,9 @@ class GradBucketReducer:
         else:
             ctx = _null()
         with ctx:
+            # the side stream forked from the current stream above and is joined again in wait()
+            # before the optimizer runs, so the gradient tensors outlive their use here
             flat = torch.cat([g.reshape(-1) for g in grads])
-            if dev.type == "cuda":
-                for g in grads:
-                    g.record_stream(self._stream)
             b.work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             b.flat = flat
 

@@ -209,7 +209,8 @@ class UncertaintyGuidedProgressiveTrainer:
         from a replay are static buffers that the next step overwrites (the metrics are cloned)."""
         crit = self.base_criterion
         fused = isinstance(crit, nn.BCEWithLogitsLoss) and crit.reduction == "none" and crit.weight is None
-        if not (self.use_cuda_graph and data.is_cuda and self._reducer is None and fused):
+        dp_graph_ok = self._reducer is None or os.environ.get("UGP_DP_CUDA_GRAPH", "1") == "1"
+        if not (self.use_cuda_graph and data.is_cuda and dp_graph_ok and fused):
             return self._eager_step(data, target, stage)
         key = (stage, tuple(data.shape), tuple(target.shape), id(self.current_model), id(self.optimizer),
                self.current_model.training)
