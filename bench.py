@@ -287,7 +287,13 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: communicators referenced by captured CUDA graphs made
+        # destroy_process_group() hang at exit on this stack.  Everything is flushed and all ranks
+        # have passed the final barrier, so a hard exit is safe.
+        sync_all()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

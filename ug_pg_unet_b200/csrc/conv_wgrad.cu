@@ -23,6 +23,8 @@
 
 namespace ugp {
 
+extern int g_conv_debug;
+
 struct WgradParams {
   int taps;
   int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
@@ -35,6 +37,7 @@ struct WgradParams {
   int kchunks_total;      // B*H*W / 64
   int kchunks_per_split;
   float* dw;              // [boxes*64][cout] fp32, accumulated
+  int debug;              // what-if timing only: 1 = skip MMA issue, 2 = skip the reduction stores
 };
 
 constexpr int kWgBoxBytes = 64 * 64 * 2;  // 64 pixels x 64 channels bf16 = 8 KB
@@ -160,7 +163,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
             // 16 pixels (K) per MMA = 16 rows of 128 B
             const uint64_t a_desc = desc0 + ((a_addr + t * 2 * kWgBoxBytes + k * 2048) >> 4);
             const uint64_t b_desc = desc0 + ((b_addr + k * 2048) >> 4);
-            umma_bf16(tmem_base + t * kN, a_desc, b_desc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if (!(p.debug & 1))
+              umma_bf16(tmem_base + t * kN, a_desc, b_desc, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -183,7 +187,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * kN + c * 32, v);
         tmem_ld_wait();
-        if (live) {
+        if (live && !(p.debug & 2)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             red_add_v4(dst + c * 32 + j, __uint_as_float(v[j]),
@@ -229,6 +233,12 @@ static int launch_wgrad(const CUtensorMap& tmX0, const CUtensorMap& tmX1,
   return UGP_OK;
 }
 
+// conv_wgrad_halo.cu
+bool conv_wgrad_halo_eligible(int H, int W, int cout, int taps);
+int conv_wgrad_halo_bf16(const void* src0, int c0, const void* src1, int c1, const void* dz, int cout,
+                         int B, int H, int W, float* dw_packed, cudaStream_t stream);
+extern int g_wgrad_halo_mode;
+
 int conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
                     const void* dz, int cout, int B, int H, int W, int taps,
                     float* dw_packed, cudaStream_t stream) {
@@ -237,6 +247,8 @@ int conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
   UGP_REQUIRE(c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
               "conv_wgrad: source channels must be multiples of 64");
   UGP_REQUIRE(cout % 64 == 0 && cout <= 512, "conv_wgrad: cout %d unsupported", cout);
+  if (g_wgrad_halo_mode != 0 && conv_wgrad_halo_eligible(H, W, cout, taps))
+    return conv_wgrad_halo_bf16(src0, c0, src1, c1, dz, cout, B, H, W, dw_packed, stream);
   int BWp = W < 64 ? W : 64;
   int BHp = 64 / BWp;
   UGP_REQUIRE(W % BWp == 0 && BWp * BHp == 64 && H % BHp == 0,
@@ -257,6 +269,7 @@ int conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
   p.kchunks_total = (int)(((long long)B * H * W) / 64);
   p.kchunks_per_split = 0;
   p.dw = dw_packed;
+  p.debug = g_conv_debug;
 
   CUtensorMap tmX0, tmX1, tmDZ;
   int rc;
