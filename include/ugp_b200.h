@@ -69,8 +69,9 @@ int ugp_conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
  * 64) wf is [Cout][64] in im2col order k = (r*3+s)*Cin + ci and wd is unused. */
 int ugp_pack_weights(const float* w_oihw, int Cout, int Cin, void* wf, void* wd,
                      void* stream);
-/* Packed fp32 gradient -> OIHW fp32 (.grad layout of nn.Conv2d.weight). */
-int ugp_unpack_wgrad(const float* dw_packed, int Cout, int Cin, float* grad_oihw,
+/* Packed fp32 gradient -> OIHW fp32 (.grad layout of nn.Conv2d.weight).  dw_packed is ZEROED after it
+ * has been read, so a persistent accumulation buffer is ready for the next ugp_conv_wgrad_bf16. */
+int ugp_unpack_wgrad(float* dw_packed, int Cout, int Cin, float* grad_oihw,
                      int accumulate, void* stream);
 
 /* First-layer input packing: fp32 NCHW [B,Cin,Hin,Win] -> bf16 [B,H,W,64]
@@ -101,7 +102,7 @@ int ugp_bn_relu_apply(const void* z, const float* scale, const float* shift,
 /* Backward of conv-output -> BN(train) -> ReLU (-> MaxPool2d(2)):
  *   g = (dA + unpool(dP)) * [a > 0]; dz = BN backward of g; sums = [sum g*xhat,
  *   sum g] (= dgamma, dbeta: the grads of BatchNorm2d.weight, .bias);
- *   dbias += sum dz.  dA or dP may be NULL. */
+ *   dbias = sum dz (overwritten).  dA or dP may be NULL. */
 int ugp_bn_relu_bwd(const void* z, const void* dA, const void* dP,
                     const float* scale, const float* shift, const float* mean,
                     const float* rstd, const float* gamma, int B, int H, int W,
@@ -166,6 +167,12 @@ int ugp_ce_weighted_loss(const float* logits, const long long* labels,
 int ugp_rmsprop_step(float* param, const float* grad, float* square_avg,
                      long long n, float lr, float alpha, float eps,
                      float weight_decay, float grad_scale, void* stream);
+
+/* The same update for n_tensors separate tensors in ONE launch (host arrays of device pointers and
+ * element counts; at most 96 tensors per launch, more are chunked). */
+int ugp_rmsprop_multi(float* const* params, const float* const* grads, float* const* square_avgs,
+                      const long long* sizes, int n_tensors, float lr, float alpha, float eps,
+                      float weight_decay, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -104,8 +104,12 @@ def test_trainer_step_against_reference_goldens(dev, golden_dir, name):
 
     floor = rel(emu["logits"], fx["logits"])
     assert rel(logits, fx["logits"]) <= 1.5 * floor + 2e-3, (rel(logits, fx["logits"]), floor)
-    assert abs(final.item() - fx["final_loss"]) <= 1e-3 * abs(fx["final_loss"]) + 1e-4
-    assert abs(base - fx["base_loss"]) <= 1e-3 * abs(fx["base_loss"]) + 1e-4
+    # loss: 1e-3 relative, or the bf16-storage floor of the oracle itself where that is larger
+    # (stage 4, batch 1: the emulated oracle is already ~1.3e-3 away from the fp32 reference)
+    lfloor = abs(emu["final_loss"] - fx["final_loss"])
+    bfloor = abs(emu["base_loss"] - fx["base_loss"])
+    assert abs(final.item() - fx["final_loss"]) <= max(1e-3 * abs(fx["final_loss"]), 1.5 * lfloor) + 1e-4
+    assert abs(base - fx["base_loss"]) <= max(1e-3 * abs(fx["base_loss"]), 1.5 * bfloor) + 1e-4
     # predicted mask: bit-exact wherever the reference logit is not within bf16 noise of zero
     zr = fx["logits"]
     safe = zr.abs() > 0.05 * zr.abs().max()
@@ -300,3 +304,31 @@ def test_full_size_properties_stage4_batch16(dev):
     lhs = ops.conv_gemm(s, None, wf, 9, 64).float()
     rhs = ops.conv_gemm(x1, None, wf, 9, 64).float() + ops.conv_gemm(x2, None, wf, 9, 64).float()
     assert rel(lhs, rhs) < 8e-3
+
+
+def test_fused_rmsprop_matches_torch_rmsprop(dev):
+    """One-launch RMSprop vs torch.optim.RMSprop with the reference's configuration
+    (uncertainty_guided_trainer.py:84-88), including state_dict interchange."""
+    from ug_pg_unet_b200.optim import FusedRMSprop
+
+    torch.manual_seed(0)
+    shapes = [(64, 3, 3, 3), (64,), (128, 64, 3, 3), (1, 64, 1, 1), (1,), (7,)]
+    pa = [torch.randn(s, device=dev, requires_grad=True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = FusedRMSprop(pa, lr=1e-4, weight_decay=1e-4)
+    ob = torch.optim.RMSprop(pb, lr=1e-4, weight_decay=1e-4)
+    assert isinstance(oa, torch.optim.RMSprop)
+    for step in range(4):
+        for x, y in zip(pa, pb):
+            g = torch.randn_like(x)
+            x.grad, y.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+    for x, y in zip(pa, pb):
+        torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-7)
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["param_groups"][0]["lr"] == sb["param_groups"][0]["lr"]
+    for k in sb["state"]:
+        torch.testing.assert_close(sa["state"][k]["square_avg"], sb["state"][k]["square_avg"], rtol=1e-6, atol=1e-9)
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 4.0
+    ob.load_state_dict(sa)          # checkpoints interchange

@@ -3,7 +3,7 @@
 //
 //   g    = (dA + unpool(dP)) * [a > 0]            a = relu(z*scale + shift)
 //   pass 1 (reduce):  sums[0][c] = sum g*xhat (= dgamma), sums[1][c] = sum g (= dbeta)
-//   pass 2 (apply):   dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat));  dbias += sum dz
+//   pass 2 (apply):   dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat));  dbias = sum dz
 //
 // HBM-bound: pass 1 reads dA and z, pass 2 reads them again and writes dz (5
 // bf16 units per conv-output element).  The plain variant
@@ -266,6 +266,7 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
   a.inv_count = 1.f / static_cast<float>(M);
   const int rows_per_block = kBnThreads / (C / 8);
   UGP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
+  if (dbias) UGP_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, stream));
   // two resident blocks per SM keep ~64 KB of loads in flight per SM; more blocks only add
   // same-address atomic traffic in the final per-channel reduction
   const long long cap = static_cast<long long>(device_sm_count()) * 2;

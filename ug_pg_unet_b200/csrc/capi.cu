@@ -28,7 +28,7 @@ int bn_relu_bwd(const void*, const void*, const void*, const float*, const float
                 const float*, const float*, int, int, int, int, float*, float*, void*,
                 cudaStream_t);
 int pack_weights(const float*, int, int, void*, void*, cudaStream_t);
-int unpack_wgrad(const float*, int, int, float*, int, cudaStream_t);
+int unpack_wgrad(float*, int, int, float*, int, cudaStream_t);
 int outconv_fwd(const void*, const float*, const float*, int, int, int, int, float*,
                 cudaStream_t);
 int outconv_bwd(const void*, const float*, const float*, int, int, int, int, int, void*, float*,
@@ -43,6 +43,8 @@ int ce_weighted_loss(const float*, const long long*, const float*, float, int, i
                      float*, double*, cudaStream_t);
 int rmsprop_step(float*, const float*, float*, long long, float, float, float, float, float,
                  cudaStream_t);
+int rmsprop_multi(float* const*, const float* const*, float* const*, const long long*, int, float,
+                  float, float, float, float, cudaStream_t);
 }  // namespace ugp
 
 #define S(stream) static_cast<cudaStream_t>(stream)
@@ -69,7 +71,7 @@ int ugp_conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1, cons
 int ugp_pack_weights(const float* w, int Cout, int Cin, void* wf, void* wd, void* stream) {
   return ugp::pack_weights(w, Cout, Cin, wf, wd, S(stream));
 }
-int ugp_unpack_wgrad(const float* dwp, int Cout, int Cin, float* grad, int accumulate,
+int ugp_unpack_wgrad(float* dwp, int Cout, int Cin, float* grad, int accumulate,
                      void* stream) {
   return ugp::unpack_wgrad(dwp, Cout, Cin, grad, accumulate, S(stream));
 }
@@ -152,6 +154,13 @@ int ugp_rmsprop_step(float* param, const float* grad, float* square_avg, long lo
                      float alpha, float eps, float weight_decay, float grad_scale, void* stream) {
   return ugp::rmsprop_step(param, grad, square_avg, n, lr, alpha, eps, weight_decay, grad_scale,
                            S(stream));
+}
+
+int ugp_rmsprop_multi(float* const* params, const float* const* grads, float* const* square_avgs,
+                      const long long* sizes, int n_tensors, float lr, float alpha, float eps,
+                      float weight_decay, float grad_scale, void* stream) {
+  return ugp::rmsprop_multi(params, grads, square_avgs, sizes, n_tensors, lr, alpha, eps, weight_decay,
+                            grad_scale, S(stream));
 }
 
 }  // extern "C"

@@ -56,3 +56,64 @@ int rmsprop_step(float* param, const float* grad, float* square_avg, long long n
 }
 
 }  // namespace ugp
+
+// ---------------------------------------------------------------------------
+// Multi-tensor variant: one launch updates up to kRmsMaxTensors parameter
+// tensors (pointer table passed by value in the kernel parameters), replacing
+// the ~10 foreach kernels of torch.optim.RMSprop over the model's 80 tensors.
+// ---------------------------------------------------------------------------
+namespace ugp {
+
+constexpr int kRmsMaxTensors = 96;
+
+struct RmsTable {
+  float* p[kRmsMaxTensors];
+  const float* g[kRmsMaxTensors];
+  float* v[kRmsMaxTensors];
+  int n[kRmsMaxTensors];
+};
+
+__global__ void __launch_bounds__(256)
+rmsprop_multi_kernel(const __grid_constant__ RmsTable t, float lr, float alpha, float eps, float wd,
+                     float gscale) {
+  const int k = blockIdx.y;
+  float* __restrict__ p = t.p[k];
+  const float* __restrict__ g = t.g[k];
+  float* __restrict__ v = t.v[k];
+  const int n = t.n[k];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    const float gr = fmaf(wd, pv, g[i] * gscale);
+    const float vn = alpha * v[i] + (1.f - alpha) * gr * gr;
+    v[i] = vn;
+    p[i] = pv - lr * gr / (sqrtf(vn) + eps);
+  }
+}
+
+int rmsprop_multi(float* const* params, const float* const* grads, float* const* avgs,
+                  const long long* sizes, int n_tensors, float lr, float alpha, float eps,
+                  float weight_decay, float grad_scale, cudaStream_t stream) {
+  UGP_REQUIRE(params && grads && avgs && sizes && n_tensors > 0, "rmsprop_multi: bad arguments");
+  for (int base = 0; base < n_tensors; base += kRmsMaxTensors) {
+    const int cnt = (n_tensors - base < kRmsMaxTensors) ? (n_tensors - base) : kRmsMaxTensors;
+    RmsTable t;
+    long long biggest = 0;
+    for (int i = 0; i < cnt; ++i) {
+      UGP_REQUIRE(sizes[base + i] > 0 && sizes[base + i] < (1LL << 31), "rmsprop_multi: bad size");
+      t.p[i] = params[base + i];
+      t.g[i] = grads[base + i];
+      t.v[i] = avgs[base + i];
+      t.n[i] = static_cast<int>(sizes[base + i]);
+      if (sizes[base + i] > biggest) biggest = sizes[base + i];
+    }
+    int gx = static_cast<int>((biggest + 256 * 8 - 1) / (256 * 8));
+    if (gx > 64) gx = 64;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, cnt);
+    rmsprop_multi_kernel<<<grid, 256, 0, stream>>>(t, lr, alpha, eps, weight_decay, grad_scale);
+    UGP_CHECK_CUDA(cudaGetLastError());
+  }
+  return UGP_OK;
+}
+
+}  // namespace ugp

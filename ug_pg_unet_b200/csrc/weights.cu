@@ -4,40 +4,42 @@
 //   dgrad pack: Wd[tap][ci][co] = W[co][ci][2-r][2-s]
 //   first layer (9*Cin <= 64): Wf[co][k], k = (r*3+s)*Cin + ci, zero padded to 64
 // and back for the packed fp32 weight gradient dWp[tap][ci][co] -> OIHW.
-// Tiled through shared memory so both the fp32 side (36-byte tap runs) and the
-// packed side are accessed in contiguous segments.
+// Small tiles (8 co x 32 ci x 9 taps) through shared memory: the fp32 side is read / written as
+// 288-float runs, and even the 64 x 64 layers get 16 blocks (these kernels are latency-, not
+// bandwidth-bound: 53.6 MB of parameters in total).
 #include "ugp_common.cuh"
 #include "ugp_vec.cuh"
 
 namespace ugp {
 
-constexpr int kWT = 32;                 // tile of 32 co x 32 ci x 9 taps
-constexpr int kWRow = kWT * 9 + 1;      // padded smem row (conflict-free transposed reads)
+constexpr int kWCo = 8;                  // output channels per block
+constexpr int kWCi = 32;                 // input channels per block
+constexpr int kWRow = kWCi * 9 + 1;      // padded smem row (conflict-free transposed reads)
 
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin,
                     __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
-  __shared__ float tile[kWT][kWRow];
-  const int co0 = blockIdx.y * kWT, ci0 = blockIdx.x * kWT;
-  for (int i = threadIdx.x; i < kWT * kWT * 9; i += blockDim.x) {
-    const int r = i / (kWT * 9), c = i - r * (kWT * 9);
+  __shared__ float tile[kWCo][kWRow];
+  const int co0 = blockIdx.y * kWCo, ci0 = blockIdx.x * kWCi;
+  for (int i = threadIdx.x; i < kWCo * kWCi * 9; i += blockDim.x) {
+    const int r = i / (kWCi * 9), c = i - r * (kWCi * 9);
     tile[r][c] = w[(static_cast<long long>(co0 + r) * Cin + ci0) * 9 + c];
   }
   __syncthreads();
   // forward pack: rows (tap, co), 32 ci contiguous
-  for (int i = threadIdx.x; i < 9 * kWT * (kWT / 2); i += blockDim.x) {
-    const int cp = i % (kWT / 2);
-    const int r = (i / (kWT / 2)) % kWT;
-    const int tap = i / ((kWT / 2) * kWT);
+  for (int i = threadIdx.x; i < 9 * kWCo * (kWCi / 2); i += blockDim.x) {
+    const int cp = i % (kWCi / 2);
+    const int r = (i / (kWCi / 2)) % kWCo;
+    const int tap = i / ((kWCi / 2) * kWCo);
     const uint32_t v = pack_bf16x2(tile[r][(2 * cp) * 9 + tap], tile[r][(2 * cp + 1) * 9 + tap]);
     *reinterpret_cast<uint32_t*>(wf + (static_cast<long long>(tap) * Cout + co0 + r) * Cin + ci0 + 2 * cp) = v;
   }
   if (wd) {
-    // dgrad pack: rows (8 - tap, ci), 32 co contiguous
-    for (int i = threadIdx.x; i < 9 * kWT * (kWT / 2); i += blockDim.x) {
-      const int rp = i % (kWT / 2);
-      const int c = (i / (kWT / 2)) % kWT;
-      const int tap = i / ((kWT / 2) * kWT);
+    // dgrad pack: rows (8 - tap, ci), 8 co contiguous
+    for (int i = threadIdx.x; i < 9 * kWCi * (kWCo / 2); i += blockDim.x) {
+      const int rp = i % (kWCo / 2);
+      const int c = (i / (kWCo / 2)) % kWCi;
+      const int tap = i / ((kWCo / 2) * kWCi);
       const uint32_t v = pack_bf16x2(tile[2 * rp][c * 9 + tap], tile[2 * rp + 1][c * 9 + tap]);
       *reinterpret_cast<uint32_t*>(wd + (static_cast<long long>(8 - tap) * Cin + ci0 + c) * Cout + co0 + 2 * rp) = v;
     }
@@ -59,35 +61,40 @@ __global__ void pack_weights_first_kernel(const float* __restrict__ w, int Cout,
   }
 }
 
-// dWp[tap][ci][co] (co contiguous) -> grad[co][ci][tap]
+// dWp[tap][ci][co] (co contiguous) -> grad[co][ci][tap]; dWp is zeroed after it is read so the
+// next step's wgrad can accumulate into it again without a separate fill.
 __global__ void __launch_bounds__(256)
-unpack_wgrad_kernel(const float* __restrict__ dwp, int Cout, int Cin, float* __restrict__ grad,
+unpack_wgrad_kernel(float* __restrict__ dwp, int Cout, int Cin, float* __restrict__ grad,
                     int accumulate) {
-  __shared__ float tile[kWT][kWRow];          // [co][ci*9 + tap]
-  const int co0 = blockIdx.y * kWT, ci0 = blockIdx.x * kWT;
-  for (int i = threadIdx.x; i < 9 * kWT * kWT; i += blockDim.x) {
-    const int r = i % kWT;                     // co (contiguous in dWp)
-    const int c = (i / kWT) % kWT;             // ci
-    const int tap = i / (kWT * kWT);
-    tile[r][c * 9 + tap] = dwp[(static_cast<long long>(tap) * Cin + ci0 + c) * Cout + co0 + r];
+  __shared__ float tile[kWCo][kWRow];          // [co][ci*9 + tap]
+  const int co0 = blockIdx.y * kWCo, ci0 = blockIdx.x * kWCi;
+  for (int i = threadIdx.x; i < 9 * kWCi * kWCo; i += blockDim.x) {
+    const int r = i % kWCo;                     // co (contiguous in dWp)
+    const int c = (i / kWCo) % kWCi;            // ci
+    const int tap = i / (kWCo * kWCi);
+    float* src = dwp + (static_cast<long long>(tap) * Cin + ci0 + c) * Cout + co0 + r;
+    tile[r][c * 9 + tap] = *src;
+    *src = 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kWT * kWT * 9; i += blockDim.x) {
-    const int r = i / (kWT * 9), c = i - r * (kWT * 9);
+  for (int i = threadIdx.x; i < kWCo * kWCi * 9; i += blockDim.x) {
+    const int r = i / (kWCi * 9), c = i - r * (kWCi * 9);
     float* dst = grad + (static_cast<long long>(co0 + r) * Cin + ci0) * 9 + c;
     *dst = accumulate ? *dst + tile[r][c] : tile[r][c];
   }
 }
 
 // first layer: dWp[k][co] with k = tap*Cin + ci -> grad[co][ci][tap]
-__global__ void unpack_wgrad_first_kernel(const float* __restrict__ dwp, int Cout, int Cin,
+__global__ void unpack_wgrad_first_kernel(float* __restrict__ dwp, int Cout, int Cin,
                                           float* __restrict__ grad, int accumulate) {
   const int total = Cout * Cin * 9;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int tap = idx % 9;
     const int ci = (idx / 9) % Cin;
     const int co = idx / (9 * Cin);
-    const float v = dwp[(tap * Cin + ci) * Cout + co];
+    float* src = dwp + (tap * Cin + ci) * Cout + co;
+    const float v = *src;
+    *src = 0.f;
     grad[idx] = accumulate ? grad[idx] + v : v;
   }
 }
@@ -95,8 +102,8 @@ __global__ void unpack_wgrad_first_kernel(const float* __restrict__ dwp, int Cou
 int pack_weights(const float* w, int Cout, int Cin, void* wf, void* wd, cudaStream_t stream) {
   UGP_REQUIRE(w && wf, "pack_weights: null pointer");
   if (Cin % 64 == 0) {
-    UGP_REQUIRE(Cout % kWT == 0, "pack_weights: Cout %d must be a multiple of %d", Cout, kWT);
-    dim3 grid(Cin / kWT, Cout / kWT);
+    UGP_REQUIRE(Cout % kWCo == 0, "pack_weights: Cout %d must be a multiple of %d", Cout, kWCo);
+    dim3 grid(Cin / kWCi, Cout / kWCo);
     pack_weights_kernel<<<grid, 256, 0, stream>>>(w, Cout, Cin, static_cast<__nv_bfloat16*>(wf),
                                                   static_cast<__nv_bfloat16*>(wd));
   } else {
@@ -108,12 +115,11 @@ int pack_weights(const float* w, int Cout, int Cin, void* wf, void* wd, cudaStre
   return UGP_OK;
 }
 
-int unpack_wgrad(const float* dwp, int Cout, int Cin, float* grad, int accumulate,
-                 cudaStream_t stream) {
+int unpack_wgrad(float* dwp, int Cout, int Cin, float* grad, int accumulate, cudaStream_t stream) {
   UGP_REQUIRE(dwp && grad, "unpack_wgrad: null pointer");
   if (Cin % 64 == 0) {
-    UGP_REQUIRE(Cout % kWT == 0, "unpack_wgrad: Cout %d must be a multiple of %d", Cout, kWT);
-    dim3 grid(Cin / kWT, Cout / kWT);
+    UGP_REQUIRE(Cout % kWCo == 0, "unpack_wgrad: Cout %d must be a multiple of %d", Cout, kWCo);
+    dim3 grid(Cin / kWCi, Cout / kWCo);
     unpack_wgrad_kernel<<<grid, 256, 0, stream>>>(dwp, Cout, Cin, grad, accumulate);
   } else {
     unpack_wgrad_first_kernel<<<grid_for(static_cast<long long>(Cout) * Cin * 9, 256), 256, 0, stream>>>(

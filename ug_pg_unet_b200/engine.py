@@ -30,6 +30,18 @@ class PackedWeights:
         self.key = None
         self.wf = None
         self.wd = None
+        self._stats = None   # persistent fp32 [2, C] BN statistics accumulator (bn_finalize re-zeroes it)
+        self._dwp = None     # persistent packed fp32 weight-gradient accumulator (unpack_wgrad re-zeroes it)
+
+    def stats_buffer(self, cout: int, device) -> torch.Tensor:
+        if self._stats is None or self._stats.device != device or self._stats.shape[1] != cout:
+            self._stats = torch.zeros((2, cout), dtype=torch.float32, device=device)
+        return self._stats
+
+    def dwp_buffer(self, numel: int, device) -> torch.Tensor:
+        if self._dwp is None or self._dwp.device != device or self._dwp.numel() != numel:
+            self._dwp = torch.zeros((numel,), dtype=torch.float32, device=device)
+        return self._dwp
 
     # bumped by whoever changes weights behind autograd's back (a CUDA-graph replay that contains
     # the optimizer step does not advance `_version`)
@@ -70,7 +82,7 @@ def cbr_forward(srcs: Sequence[torch.Tensor], taps: int, conv: nn.Conv2d, bn: nn
     dev = src0.device
     bias = conv.bias.detach() if conv.bias is not None else None
     if bn.training:
-        stats = torch.zeros((2, cout), dtype=torch.float32, device=dev)
+        stats = packs.stats_buffer(cout, dev)
         z = ops.conv_gemm(src0, src1, wf, taps, cout, bias=bias, stats=stats)
         coef = torch.empty((4, cout), dtype=torch.float32, device=dev)
         momentum = 0.0 if bn.momentum is None else float(bn.momentum)
@@ -104,11 +116,11 @@ def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch
     cin = conv.in_channels
     dev = src0.device
     coef = saved.coef
-    small = torch.zeros((3, cout), dtype=torch.float32, device=dev)   # dgamma, dbeta, dbias
+    small = torch.empty((3, cout), dtype=torch.float32, device=dev)   # dgamma, dbeta, dbias (kernel-zeroed)
     dz = ops.bn_relu_bwd(saved.z, dA, dP, coef[0], coef[1], coef[2], coef[3], bn.weight.detach(),
                          small[:2], small[2])
     kdim = sum(s.shape[3] for s in saved.srcs)
-    dwp = torch.zeros((saved.taps * kdim * cout,), dtype=torch.float32, device=dev)
+    dwp = packs.dwp_buffer(saved.taps * kdim * cout, dev)
     ops.conv_wgrad(src0, src1, dz, saved.taps, dwp)
     dW = ops.unpack_wgrad(dwp, cout, cin)
     d_srcs = None

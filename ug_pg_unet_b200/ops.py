@@ -359,3 +359,17 @@ def rmsprop_step(param, grad, square_avg, lr: float, alpha: float = 0.99, eps: f
     _req(square_avg, torch.float32, "square_avg")
     check(lib().ugp_rmsprop_step(_ptr(param), _ptr(grad), _ptr(square_avg), param.numel(), lr, alpha, eps,
                                  weight_decay, grad_scale, _stream()), "ugp_rmsprop_step")
+
+
+def rmsprop_multi(params, grads, square_avgs, lr: float, alpha: float, eps: float, weight_decay: float,
+                  grad_scale: float = 1.0):
+    """One launch of the RMSprop update over a list of tensors (see ugp_rmsprop_multi)."""
+    n = len(params)
+    for t in list(params) + list(grads) + list(square_avgs):
+        _req(t, torch.float32, "rmsprop tensor")
+    P = (C.c_void_p * n)(*[t.data_ptr() for t in params])
+    G = (C.c_void_p * n)(*[t.data_ptr() for t in grads])
+    V = (C.c_void_p * n)(*[t.data_ptr() for t in square_avgs])
+    S = (C.c_longlong * n)(*[t.numel() for t in params])
+    check(lib().ugp_rmsprop_multi(P, G, V, S, n, lr, alpha, eps, weight_decay, grad_scale, _stream()),
+          "ugp_rmsprop_multi")

@@ -31,6 +31,7 @@ import torch.nn.functional as F
 import torch.optim as optim
 
 from .engine import PackedWeights
+from .optim import FusedRMSprop
 from .parallel import GradBucketReducer, broadcast_module_state
 from .unet import PGUNet1, PGUNet2, PGUNet3, PGUNet4, UncertaintyGuidedLoss, transfer_state
 
@@ -89,8 +90,10 @@ class UncertaintyGuidedProgressiveTrainer:
         """RMSprop(lr, weight_decay=1e-4) on the current model — reference :81-88."""
         lr = self.stage_configs[stage]["lr"]
         on_cuda = next(self.current_model.parameters()).is_cuda
-        self.optimizer = optim.RMSprop(self.current_model.parameters(), lr=lr, weight_decay=1e-4,
-                                       capturable=bool(on_cuda and self.use_cuda_graph))
+        # same hyper-parameters and state_dict layout as the reference's optim.RMSprop; on CUDA the
+        # update of all 80 tensors is one kernel launch (FusedRMSprop subclasses optim.RMSprop)
+        opt_cls = FusedRMSprop if on_cuda else optim.RMSprop
+        self.optimizer = opt_cls(self.current_model.parameters(), lr=lr, weight_decay=1e-4)
         self._graph = None
         if self._reducer is not None:
             self._reducer.remove()
@@ -232,6 +235,8 @@ class UncertaintyGuidedProgressiveTrainer:
         g["y"].copy_(target, non_blocking=True)
         g["graph"].replay()
         PackedWeights.invalidate_all()     # the replayed optimizer step changed the fp32 weights
+        if isinstance(self.optimizer, FusedRMSprop):
+            self.optimizer.note_replayed_steps(1)
         m, logits, unc = g["out"]
         return m.clone(), logits, unc
 
