@@ -329,6 +329,6 @@ def test_fused_rmsprop_matches_torch_rmsprop(dev):
     sa, sb = oa.state_dict(), ob.state_dict()
     assert sa["param_groups"][0]["lr"] == sb["param_groups"][0]["lr"]
     for k in sb["state"]:
-        torch.testing.assert_close(sa["state"][k]["square_avg"], sb["state"][k]["square_avg"], rtol=1e-6, atol=1e-9)
+        torch.testing.assert_close(sa["state"][k]["square_avg"], sb["state"][k]["square_avg"], rtol=1e-5, atol=1e-8)
         assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 4.0
     ob.load_state_dict(sa)          # checkpoints interchange
