@@ -15,6 +15,8 @@ namespace ugp {
 constexpr int kWCo = 8;                  // output channels per block
 constexpr int kWCi = 32;                 // input channels per block
 constexpr int kWRow = kWCi * 9 + 1;      // padded smem row (conflict-free transposed reads)
+constexpr int kUCo = 32;                 // unpack: output channels per block (contiguous in dWp)
+constexpr int kUCi = 8;                  // unpack: input channels per block
 
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin,
@@ -66,19 +68,21 @@ __global__ void pack_weights_first_kernel(const float* __restrict__ w, int Cout,
 __global__ void __launch_bounds__(256)
 unpack_wgrad_kernel(float* __restrict__ dwp, int Cout, int Cin, float* __restrict__ grad,
                     int accumulate) {
-  __shared__ float tile[kWCo][kWRow];          // [co][ci*9 + tap]
-  const int co0 = blockIdx.y * kWCo, ci0 = blockIdx.x * kWCi;
-  for (int i = threadIdx.x; i < 9 * kWCi * kWCo; i += blockDim.x) {
-    const int r = i % kWCo;                     // co (contiguous in dWp)
-    const int c = (i / kWCo) % kWCi;            // ci
-    const int tap = i / (kWCo * kWCi);
+  // tile of 32 co x 8 ci x 9 taps: 128-byte runs along co on the packed side, 288-byte runs along
+  // (ci, tap) on the OIHW side
+  __shared__ float tile[kUCo][kUCi * 9 + 1];   // [co][ci*9 + tap]
+  const int co0 = blockIdx.y * kUCo, ci0 = blockIdx.x * kUCi;
+  for (int i = threadIdx.x; i < 9 * kUCi * kUCo; i += blockDim.x) {
+    const int r = i % kUCo;                     // co (contiguous in dWp)
+    const int c = (i / kUCo) % kUCi;            // ci
+    const int tap = i / (kUCo * kUCi);
     float* src = dwp + (static_cast<long long>(tap) * Cin + ci0 + c) * Cout + co0 + r;
     tile[r][c * 9 + tap] = *src;
     *src = 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kWCo * kWCi * 9; i += blockDim.x) {
-    const int r = i / (kWCi * 9), c = i - r * (kWCi * 9);
+  for (int i = threadIdx.x; i < kUCo * kUCi * 9; i += blockDim.x) {
+    const int r = i / (kUCi * 9), c = i - r * (kUCi * 9);
     float* dst = grad + (static_cast<long long>(co0 + r) * Cin + ci0) * 9 + c;
     *dst = accumulate ? *dst + tile[r][c] : tile[r][c];
   }
@@ -118,8 +122,8 @@ int pack_weights(const float* w, int Cout, int Cin, void* wf, void* wd, cudaStre
 int unpack_wgrad(float* dwp, int Cout, int Cin, float* grad, int accumulate, cudaStream_t stream) {
   UGP_REQUIRE(dwp && grad, "unpack_wgrad: null pointer");
   if (Cin % 64 == 0) {
-    UGP_REQUIRE(Cout % kWCo == 0, "unpack_wgrad: Cout %d must be a multiple of %d", Cout, kWCo);
-    dim3 grid(Cin / kWCi, Cout / kWCo);
+    UGP_REQUIRE(Cout % kUCo == 0, "unpack_wgrad: Cout %d must be a multiple of %d", Cout, kUCo);
+    dim3 grid(Cin / kUCi, Cout / kUCo);
     unpack_wgrad_kernel<<<grid, 256, 0, stream>>>(dwp, Cout, Cin, grad, accumulate);
   } else {
     unpack_wgrad_first_kernel<<<grid_for(static_cast<long long>(Cout) * Cin * 9, 256), 256, 0, stream>>>(
