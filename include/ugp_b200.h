@@ -174,6 +174,18 @@ int ugp_rmsprop_multi(float* const* params, const float* const* grads, float* co
                       const long long* sizes, int n_tensors, float lr, float alpha, float eps,
                       float weight_decay, float grad_scale, void* stream);
 
+/* RMSprop for the 3x3 convolution weights straight from the PACKED gradient that
+ * ugp_conv_wgrad_bf16 accumulates (replaces ugp_unpack_wgrad + optimizer.step() of
+ * uncertainty_guided_trainer.py:231 + ugp_pack_weights for the next forward).  Per tensor i:
+ *   g = dw_packed[i]*grad_scale + wd*w[i]; v = alpha*v + (1-alpha)*g*g; w -= lr*g/(sqrt(v)+eps)
+ * w / square_avgs: fp32 OIHW [cout][cin][3][3]; dw_packed: fp32 [9][cin][cout], ZEROED on return;
+ * wf / wd: the bf16 operand packs of ugp_pack_weights, rewritten from the new weights (wd[i] may be
+ * null).  cout, cin multiples of 32.  One launch per 40 tensors. */
+int ugp_rmsprop_conv_packed(float* const* w, float* const* square_avgs, float* const* dw_packed,
+                            void* const* wf, void* const* wd, const int* cout, const int* cin,
+                            int n_tensors, float lr, float alpha, float eps, float weight_decay,
+                            float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,8 @@ int rmsprop_step(float*, const float*, float*, long long, float, float, float, f
                  cudaStream_t);
 int rmsprop_multi(float* const*, const float* const*, float* const*, const long long*, int, float,
                   float, float, float, float, cudaStream_t);
+int rmsprop_conv_packed(float* const*, float* const*, float* const*, void* const*, void* const*,
+                        const int*, const int*, int, float, float, float, float, float, cudaStream_t);
 }  // namespace ugp
 
 #define S(stream) static_cast<cudaStream_t>(stream)
@@ -163,4 +165,11 @@ int ugp_rmsprop_multi(float* const* params, const float* const* grads, float* co
                             grad_scale, S(stream));
 }
 
+int ugp_rmsprop_conv_packed(float* const* w, float* const* square_avgs, float* const* dw_packed,
+                            void* const* wf, void* const* wd, const int* cout, const int* cin,
+                            int n_tensors, float lr, float alpha, float eps, float weight_decay,
+                            float grad_scale, void* stream) {
+  return ugp::rmsprop_conv_packed(w, square_avgs, dw_packed, wf, wd, cout, cin, n_tensors, lr, alpha,
+                                  eps, weight_decay, grad_scale, S(stream));
+}
 }  // extern "C"

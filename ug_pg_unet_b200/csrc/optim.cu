@@ -117,3 +117,171 @@ int rmsprop_multi(float* const* params, const float* const* grads, float* const*
 }
 
 }  // namespace ugp
+
+// ---------------------------------------------------------------------------
+// Convolution weights: RMSprop straight from the PACKED fp32 weight gradient.
+//
+// conv_wgrad leaves dWp[tap][ci][co] (what the tensor-core kernel reduces into);
+// the forward / input-gradient kernels read bf16 packs Wf[tap][co][ci] and
+// Wd[8-tap][ci][co]; the master weights and the optimiser state stay fp32 OIHW
+// (state_dict layout of nn.Conv2d / torch.optim.RMSprop).  One launch over all
+// 3x3 layers does, per 32co x 32ci x 9 tile staged through shared memory:
+//   g = dWp*gscale + wd*w ; v = alpha*v + (1-alpha)*g^2 ; w -= lr*g/(sqrt(v)+eps)
+//   Wf, Wd <- bf16(w) ; dWp <- 0
+// replacing unpack_wgrad + rmsprop + pack_weights (3 passes, 2 transposes).
+// ---------------------------------------------------------------------------
+namespace ugp {
+
+extern int g_conv_debug;
+constexpr int kCoTile = 32, kCiTile = 32;
+constexpr int kCoRow = kCiTile * 9 + 1;      // 289 floats: conflict-free for all three access patterns
+constexpr int kConvOptMaxItems = 40;
+
+struct ConvOptItem {
+  float* w;              // [Cout][Cin][3][3]
+  float* v;              // square_avg, same layout
+  float* dwp;            // [9][Cin][Cout]
+  __nv_bfloat16* wf;     // [9][Cout][Cin]
+  __nv_bfloat16* wd;     // [9][Cin][Cout], taps rotated; may be null
+  int cout, cin;
+  int tile_begin;        // first global tile index of this tensor
+  int ci_tiles;
+};
+struct ConvOptTable {
+  ConvOptItem it[kConvOptMaxItems];
+  int n;
+};
+
+__global__ void __launch_bounds__(256)
+rmsprop_conv_packed_kernel(const __grid_constant__ ConvOptTable t, float lr, float alpha, float eps,
+                           float wd_coef, float gscale, int dbg) {
+  extern __shared__ float tile[];             // [32][289]
+  int k = 0;
+  while (k + 1 < t.n && static_cast<int>(blockIdx.x) >= t.it[k + 1].tile_begin) ++k;
+  const ConvOptItem& it = t.it[k];
+  const int local = blockIdx.x - it.tile_begin;
+  const int co0 = (local / it.ci_tiles) * kCoTile;
+  const int ci0 = (local % it.ci_tiles) * kCiTile;
+  const int Cout = it.cout, Cin = it.cin;
+
+  // packed gradient -> tile[co][ci*9 + tap]; dWp is left zeroed for the next accumulation.
+  // Loads are issued in batches of 6 before their dependent stores (the zeroing store may alias the
+  // next load as far as the compiler knows, which would serialise one load per DRAM round trip).
+  constexpr int kB1 = 6;
+  for (int base = threadIdx.x; base < 9 * kCiTile * kCoTile; base += 256 * kB1) {
+    float x[kB1];
+    float* src[kB1];
+#pragma unroll
+    for (int u = 0; u < kB1; ++u) {
+      const int i = base + u * 256;
+      const int r = i % kCoTile;
+      const int c = (i / kCoTile) % kCiTile;
+      const int tap = i / (kCoTile * kCiTile);
+      src[u] = it.dwp + (static_cast<long long>(tap) * Cin + ci0 + c) * Cout + co0 + r;
+      x[u] = (dbg & 4) ? 0.f : __ldcs(src[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kB1; ++u) {
+      const int i = base + u * 256;
+      const int r = i % kCoTile;
+      const int c = (i / kCoTile) % kCiTile;
+      const int tap = i / (kCoTile * kCiTile);
+      tile[r * kCoRow + c * 9 + tap] = x[u];
+      if (!(dbg & 4)) __stcs(src[u], 0.f);
+    }
+  }
+  __syncthreads();
+  // update in OIHW order (288-float runs per output channel, float4 accesses); the tile then holds
+  // the new weights.  2304 float4 per tile = 9 per thread, in batches of 3.
+  constexpr int kB2 = 3;
+  if (!(dbg & 8))
+  for (int base = threadIdx.x; base < kCoTile * kCiTile * 9 / 4; base += 256 * kB2) {
+    float4 pw[kB2], pv[kB2];
+#pragma unroll
+    for (int u = 0; u < kB2; ++u) {
+      const int i = base + u * 256;
+      const int r = i / (kCiTile * 9 / 4), j = (i - r * (kCiTile * 9 / 4)) * 4;
+      const long long off = (static_cast<long long>(co0 + r) * Cin + ci0) * 9 + j;
+      pw[u] = *reinterpret_cast<const float4*>(it.w + off);
+      pv[u] = *reinterpret_cast<const float4*>(it.v + off);
+    }
+#pragma unroll
+    for (int u = 0; u < kB2; ++u) {
+      const int i = base + u * 256;
+      const int r = i / (kCiTile * 9 / 4), j = (i - r * (kCiTile * 9 / 4)) * 4;
+      const long long off = (static_cast<long long>(co0 + r) * Cin + ci0) * 9 + j;
+      float w4[4] = {pw[u].x, pw[u].y, pw[u].z, pw[u].w};
+      float v4[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float gr = fmaf(wd_coef, w4[e], tile[r * kCoRow + j + e] * gscale);
+        v4[e] = alpha * v4[e] + (1.f - alpha) * gr * gr;
+        w4[e] = w4[e] - lr * gr / (sqrtf(v4[e]) + eps);
+        tile[r * kCoRow + j + e] = w4[e];
+      }
+      *reinterpret_cast<float4*>(it.v + off) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+      *reinterpret_cast<float4*>(it.w + off) = make_float4(w4[0], w4[1], w4[2], w4[3]);
+    }
+  }
+  __syncthreads();
+  if (dbg & 16) return;
+  // forward pack: rows (tap, co), 32 ci contiguous
+  for (int i = threadIdx.x; i < 9 * kCoTile * (kCiTile / 2); i += 256) {
+    const int cp = i % (kCiTile / 2);
+    const int r = (i / (kCiTile / 2)) % kCoTile;
+    const int tap = i / ((kCiTile / 2) * kCoTile);
+    const uint32_t pk = pack_bf16x2(tile[r * kCoRow + (2 * cp) * 9 + tap], tile[r * kCoRow + (2 * cp + 1) * 9 + tap]);
+    *reinterpret_cast<uint32_t*>(it.wf + (static_cast<long long>(tap) * Cout + co0 + r) * Cin + ci0 + 2 * cp) = pk;
+  }
+  if (it.wd) {
+    // input-gradient pack: rows (8 - tap, ci), 32 co contiguous
+    for (int i = threadIdx.x; i < 9 * kCiTile * (kCoTile / 2); i += 256) {
+      const int rp = i % (kCoTile / 2);
+      const int c = (i / (kCoTile / 2)) % kCiTile;
+      const int tap = i / ((kCoTile / 2) * kCiTile);
+      const uint32_t pk = pack_bf16x2(tile[(2 * rp) * kCoRow + c * 9 + tap], tile[(2 * rp + 1) * kCoRow + c * 9 + tap]);
+      *reinterpret_cast<uint32_t*>(it.wd + (static_cast<long long>(8 - tap) * Cin + ci0 + c) * Cout + co0 + 2 * rp) = pk;
+    }
+  }
+}
+
+int rmsprop_conv_packed(float* const* w, float* const* v, float* const* dwp, void* const* wf,
+                        void* const* wd, const int* cout, const int* cin, int n_tensors, float lr,
+                        float alpha, float eps, float weight_decay, float grad_scale,
+                        cudaStream_t stream) {
+  UGP_REQUIRE(w && v && dwp && wf && wd && cout && cin && n_tensors > 0, "rmsprop_conv_packed: bad arguments");
+  constexpr int kSmem = kCoTile * kCoRow * 4;
+  static bool configured = false;
+  if (!configured) {
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(rmsprop_conv_packed_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  for (int base = 0; base < n_tensors; base += kConvOptMaxItems) {
+    const int cnt = (n_tensors - base < kConvOptMaxItems) ? (n_tensors - base) : kConvOptMaxItems;
+    ConvOptTable t;
+    int tiles = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const int co = cout[base + i], ci = cin[base + i];
+      UGP_REQUIRE(co > 0 && ci > 0 && co % kCoTile == 0 && ci % kCiTile == 0,
+                  "rmsprop_conv_packed: Cout %d / Cin %d must be multiples of 32", co, ci);
+      UGP_REQUIRE(w[base + i] && v[base + i] && dwp[base + i] && wf[base + i],
+                  "rmsprop_conv_packed: null tensor pointer");
+      ConvOptItem& it = t.it[i];
+      it.w = w[base + i]; it.v = v[base + i]; it.dwp = dwp[base + i];
+      it.wf = static_cast<__nv_bfloat16*>(wf[base + i]);
+      it.wd = static_cast<__nv_bfloat16*>(wd[base + i]);
+      it.cout = co; it.cin = ci;
+      it.tile_begin = tiles;
+      it.ci_tiles = ci / kCiTile;
+      tiles += (co / kCoTile) * it.ci_tiles;
+    }
+    t.n = cnt;
+    rmsprop_conv_packed_kernel<<<tiles, 256, kSmem, stream>>>(t, lr, alpha, eps, weight_decay, grad_scale,
+                                                              g_conv_debug);
+    UGP_CHECK_CUDA(cudaGetLastError());
+  }
+  return UGP_OK;
+}
+
+}  // namespace ugp

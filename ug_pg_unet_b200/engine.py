@@ -22,7 +22,14 @@ bf16 = torch.bfloat16
 
 class PackedWeights:
     """bf16 GEMM operands of one nn.Conv2d weight, refreshed when the fp32 master changes
-    (optimizer.step / load_state_dict / .to(device) all bump `_version` or the storage)."""
+    (optimizer.step / load_state_dict / .to(device) all bump `_version` or the storage), plus the
+    persistent per-layer accumulators (BN statistics, packed fp32 weight gradient).
+
+    Deferred weight gradients: with `defer = True` (set by `enable_deferred_wgrad`, used by the
+    trainer together with `FusedRMSprop`) backward leaves the weight gradient in the PACKED layout
+    the tensor-core kernel reduces into and returns no `.grad` for the conv weight; the optimiser
+    kernel consumes the packed gradient, rewrites these bf16 packs and zeroes the accumulator.  The
+    default (`defer = False`) materialises the OIHW `.grad` like the reference's autograd."""
 
     def __init__(self, conv: nn.Conv2d, need_dgrad: bool):
         self.conv = conv
@@ -31,7 +38,10 @@ class PackedWeights:
         self.wf = None
         self.wd = None
         self._stats = None   # persistent fp32 [2, C] BN statistics accumulator (bn_finalize re-zeroes it)
-        self._dwp = None     # persistent packed fp32 weight-gradient accumulator (unpack_wgrad re-zeroes it)
+        self._dwp = None     # persistent packed fp32 weight-gradient accumulator (its consumer re-zeroes it)
+        self.defer = False
+        self.grad_pending = False      # a backward accumulated into _dwp since the last optimiser step
+        self.on_grad_ready = None      # data-parallel reducer callback, called after the wgrad launch
 
     def stats_buffer(self, cout: int, device) -> torch.Tensor:
         if self._stats is None or self._stats.device != device or self._stats.shape[1] != cout:
@@ -43,21 +53,83 @@ class PackedWeights:
             self._dwp = torch.zeros((numel,), dtype=torch.float32, device=device)
         return self._dwp
 
+    def assign_dwp(self, buf: Optional[torch.Tensor]) -> None:
+        """Use `buf` (a zeroed slice of a flat gradient arena) as the packed-gradient accumulator."""
+        self._dwp = buf
+
+    def can_defer(self) -> bool:
+        w = self.conv.weight
+        return w.is_cuda and w.shape[1] % 64 == 0 and w.shape[0] % 32 == 0 and tuple(w.shape[2:]) == (3, 3)
+
     # bumped by whoever changes weights behind autograd's back (a CUDA-graph replay that contains
-    # the optimizer step does not advance `_version`)
+    # the optimizer step, or FusedRMSprop's kernels, do not advance `_version`)
     epoch = 0
 
     @classmethod
     def invalidate_all(cls):
         cls.epoch += 1
 
-    def get(self):
+    def _current_key(self):
         w = self.conv.weight
-        key = (w.data_ptr(), w._version, w.device, PackedWeights.epoch)
+        return (w.data_ptr(), w._version, w.device, PackedWeights.epoch)
+
+    def invalidate(self) -> None:
+        self.key = None
+
+    def mark_fresh(self) -> None:
+        """The packs were just rewritten from the current weights (by the optimiser kernel)."""
+        if self.wf is not None:
+            self.key = self._current_key()
+
+    def get(self):
+        key = self._current_key()
         if key != self.key:
-            self.wf, self.wd = ops.pack_weights(w.detach(), self.need_dgrad)
+            w = self.conv.weight
+            same = self.wf is not None and self.wf.device == w.device and self.wf.numel() == \
+                (w.shape[0] * 64 if w.shape[1] % 64 else w.numel())
+            # refresh IN PLACE when possible: captured CUDA graphs hold these addresses
+            self.wf, self.wd = ops.pack_weights(w.detach(), self.need_dgrad, wf=self.wf if same else None,
+                                                wd=self.wd if same else None)
             self.key = key
         return self.wf, self.wd
+
+
+def conv_packs(model: nn.Module) -> List[PackedWeights]:
+    """All PackedWeights of `model` in forward (registration) order."""
+    out: List[PackedWeights] = []
+    for m in model.modules():
+        pk = getattr(m, "_packs", None)
+        if pk is not None:
+            out.extend(pk)
+    return out
+
+
+def enable_deferred_wgrad(model: nn.Module, enable: bool = True):
+    """Switches every eligible 3x3 conv of `model` to deferred (packed) weight gradients and lays
+    their accumulators out in ONE flat fp32 arena, in reverse forward order = the order backward
+    fills them, so a data-parallel bucket is a contiguous arena range.
+
+    Returns (packs in arena order, arena tensor) — ([], None) when disabled / nothing eligible."""
+    packs = [pk for pk in conv_packs(model)]
+    if not enable:
+        for pk in packs:
+            if pk.defer:
+                pk.defer, pk.grad_pending, pk.on_grad_ready = False, False, None
+                pk.assign_dwp(None)
+        return [], None
+    elig = [pk for pk in reversed(packs) if pk.can_defer()]
+    if not elig:
+        return [], None
+    dev = elig[0].conv.weight.device
+    total = sum(pk.conv.weight.numel() for pk in elig)
+    arena = torch.zeros((total,), dtype=torch.float32, device=dev)
+    off = 0
+    for pk in elig:
+        n = pk.conv.weight.numel()
+        pk.assign_dwp(arena[off:off + n])
+        pk.defer, pk.grad_pending = True, False
+        off += n
+    return elig, arena
 
 
 class CBRSaved:
@@ -122,7 +194,13 @@ def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch
     kdim = sum(s.shape[3] for s in saved.srcs)
     dwp = packs.dwp_buffer(saved.taps * kdim * cout, dev)
     ops.conv_wgrad(src0, src1, dz, saved.taps, dwp)
-    dW = ops.unpack_wgrad(dwp, cout, cin)
+    if packs.defer:
+        dW = None                      # stays packed in the arena; FusedRMSprop consumes it
+        packs.grad_pending = True
+        if packs.on_grad_ready is not None:
+            packs.on_grad_ready(packs)
+    else:
+        dW = ops.unpack_wgrad(dwp, cout, cin)
     d_srcs = None
     if need_dgrad:
         _, wd = packs.get()

@@ -373,3 +373,26 @@ def rmsprop_multi(params, grads, square_avgs, lr: float, alpha: float, eps: floa
     S = (C.c_longlong * n)(*[t.numel() for t in params])
     check(lib().ugp_rmsprop_multi(P, G, V, S, n, lr, alpha, eps, weight_decay, grad_scale, _stream()),
           "ugp_rmsprop_multi")
+
+
+def rmsprop_conv_packed(weights, square_avgs, dw_packed, wfs, wds, lr: float, alpha: float, eps: float,
+                        weight_decay: float, grad_scale: float = 1.0):
+    """RMSprop on 3x3 conv weights straight from the packed gradients; rewrites the bf16 operand
+    packs and zeroes the gradients (see ugp_rmsprop_conv_packed).  `wds` entries may be None."""
+    n = len(weights)
+    for w, v, g, wf in zip(weights, square_avgs, dw_packed, wfs):
+        _req(w, torch.float32, "weight")
+        _req(v, torch.float32, "square_avg")
+        _req(g, torch.float32, "dw_packed")
+        _req(wf, bf16, "wf")
+        assert w.dim() == 4 and w.shape[2:] == (3, 3) and v.shape == w.shape
+        assert g.numel() == w.numel() and wf.numel() == w.numel()
+    Wp = (C.c_void_p * n)(*[t.data_ptr() for t in weights])
+    Vp = (C.c_void_p * n)(*[t.data_ptr() for t in square_avgs])
+    Gp = (C.c_void_p * n)(*[t.data_ptr() for t in dw_packed])
+    Fp = (C.c_void_p * n)(*[t.data_ptr() for t in wfs])
+    Dp = (C.c_void_p * n)(*[None if t is None else _req(t, bf16, "wd").data_ptr() for t in wds])
+    co = (C.c_int * n)(*[w.shape[0] for w in weights])
+    ci = (C.c_int * n)(*[w.shape[1] for w in weights])
+    check(lib().ugp_rmsprop_conv_packed(Wp, Vp, Gp, Fp, Dp, co, ci, n, lr, alpha, eps, weight_decay, grad_scale,
+                                        _stream()), "ugp_rmsprop_conv_packed")

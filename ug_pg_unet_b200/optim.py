@@ -14,16 +14,42 @@ from . import ops
 
 
 class FusedRMSprop(torch.optim.RMSprop):
-    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, weight_decay=0, momentum=0, centered=False, **kw):
+    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, weight_decay=0, momentum=0, centered=False,
+                 conv_packs=None, **kw):
+        """`conv_packs`: the `engine.PackedWeights` of the model's convolutions.  Those with deferred
+        weight gradients (left in the packed layout by backward, see `engine.enable_deferred_wgrad`)
+        get their update, the refresh of the bf16 operand packs and the zeroing of the gradient
+        accumulator in one kernel launch; all other parameters take the multi-tensor kernel from
+        their `.grad`, and the operand packs of non-deferred convolutions are marked stale."""
         kw.pop("capturable", None)
         kw.pop("foreach", None)
         super().__init__(params, lr=lr, alpha=alpha, eps=eps, weight_decay=weight_decay, momentum=momentum,
                          centered=centered, **kw)
         self._replayed_steps = 0
+        self._targeted = conv_packs is not None
+        self._packs = {id(pk.conv.weight): pk for pk in (conv_packs or [])}
+        self.deferred_grad_scale = 1.0      # 1/world_size when the packed gradients were sum-all-reduced
 
     def note_replayed_steps(self, n: int = 1) -> None:
-        """A CUDA-graph replay ran `step()`'s kernel without running this Python code."""
+        """A CUDA-graph replay ran `step()`'s kernels without running this Python code."""
         self._replayed_steps += n
+        self._invalidate_packs(())
+
+    def _invalidate_packs(self, rewritten) -> None:
+        """The kernels write parameters without advancing autograd's version counters: bf16 operand
+        caches of the updated convolutions are stale, except those the packed kernel has rewritten."""
+        from .engine import PackedWeights
+
+        if not self._targeted:
+            PackedWeights.invalidate_all()
+            return
+        fresh = {id(pk) for pk in rewritten}
+        for pk in self._packs.values():
+            if id(pk) in fresh:
+                pk.grad_pending = False
+                pk.mark_fresh()
+            elif not pk.defer:
+                pk.invalidate()
 
     def state_dict(self):
         if self._replayed_steps:
@@ -39,11 +65,30 @@ class FusedRMSprop(torch.optim.RMSprop):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        rewritten = []
         for group in self.param_groups:
             if group["momentum"] != 0 or group["centered"] or group.get("maximize", False):
+                if any(pk.defer for pk in self._packs.values()):
+                    raise RuntimeError("FusedRMSprop: deferred conv gradients need momentum=0, centered=False")
                 return super().step()
             ps, gs, vs = [], [], []
+            dw, dv, dg, dwf, dwd, dpk = [], [], [], [], [], []
             for p in group["params"]:
+                pk = self._packs.get(id(p))
+                if pk is not None and pk.defer and pk.grad_pending and p.grad is None:
+                    st = self.state[p]
+                    if len(st) == 0:
+                        st["step"] = torch.zeros((), dtype=torch.float32)
+                        st["square_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["step"] += 1
+                    wf, wd = pk.get()
+                    dw.append(p.data)
+                    dv.append(st["square_avg"])
+                    dg.append(pk._dwp)
+                    dwf.append(wf)
+                    dwd.append(wd)
+                    dpk.append(pk)
+                    continue
                 if p.grad is None:
                     continue
                 if not p.is_cuda or p.grad.is_sparse:
@@ -59,4 +104,10 @@ class FusedRMSprop(torch.optim.RMSprop):
             if ps:
                 ops.rmsprop_multi(ps, gs, vs, float(group["lr"]), float(group["alpha"]), float(group["eps"]),
                                   float(group["weight_decay"]))
+            if dw:
+                ops.rmsprop_conv_packed(dw, dv, dg, dwf, dwd, float(group["lr"]), float(group["alpha"]),
+                                        float(group["eps"]), float(group["weight_decay"]),
+                                        float(self.deferred_grad_scale))
+                rewritten.extend(dpk)
+        self._invalidate_packs(rewritten)
         return loss

@@ -39,15 +39,29 @@ class _Bucket:
         self.work = None
 
 
+class _ArenaBucket:
+    """A contiguous range of the packed weight-gradient arena (engine.enable_deferred_wgrad): reduced
+    in place, no flatten / copy-back; the 1/world_size factor is applied by the optimiser kernel."""
+
+    def __init__(self, packs, flat: torch.Tensor):
+        self.packs = packs
+        self.flat = flat
+        self.pending = 0
+        self.work = None
+
+
 class GradBucketReducer:
     """Bucketed, overlapped gradient averaging across ranks."""
 
     def __init__(self, params: Sequence[torch.nn.Parameter], bucket_mb: float = 16.0,
-                 process_group=None, overlap: bool = True):
+                 process_group=None, overlap: bool = True, conv_packs=None, arena: Optional[torch.Tensor] = None):
+        """`conv_packs` / `arena`: the deferred convolutions and their flat packed-gradient arena, in
+        arena order; their weights are skipped in `params` (they get no `.grad`)."""
         self.group = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.overlap = overlap
-        ps = [p for p in params if p.requires_grad]
+        deferred = {id(pk.conv.weight) for pk in (conv_packs or [])}
+        ps = [p for p in params if p.requires_grad and id(p) not in deferred]
         # reverse forward order = the order gradients become ready
         ps = list(reversed(ps))
         cap = int(bucket_mb * 1024 * 1024 / 4)
@@ -65,6 +79,25 @@ class GradBucketReducer:
         self._owner = {}
         self._hooks = []
         self._stream = None
+        self.arena_buckets: List[_ArenaBucket] = []
+        self._packs = list(conv_packs or [])
+        if self._packs:
+            cur_p, start, off = [], 0, 0
+            for pk in self._packs:
+                n = pk.conv.weight.numel()
+                assert pk._dwp is not None and pk._dwp.data_ptr() == arena.data_ptr() + 4 * off, \
+                    "conv_packs must be given in arena order"
+                cur_p.append(pk)
+                off += n
+                if off - start >= cap:
+                    self.arena_buckets.append(_ArenaBucket(cur_p, arena[start:off]))
+                    cur_p, start = [], off
+            if cur_p:
+                self.arena_buckets.append(_ArenaBucket(cur_p, arena[start:off]))
+            for ab in self.arena_buckets:
+                for pk in ab.packs:
+                    self._owner[id(pk)] = ab
+                    pk.on_grad_ready = self._on_pack_ready if (overlap and self.world_size > 1) else None
         for b in self.buckets:
             for p in b.params:
                 self._owner[p] = b
@@ -76,6 +109,27 @@ class GradBucketReducer:
         for b in self.buckets:
             b.pending = len(b.params)
             b.work = None
+        for ab in self.arena_buckets:
+            ab.pending = len(ab.packs)
+            ab.work = None
+
+    def _side_stream_ctx(self, dev):
+        if dev.type != "cuda":
+            return _null()
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev, priority=-1)
+        self._stream.wait_stream(torch.cuda.current_stream(dev))
+        return torch.cuda.stream(self._stream)
+
+    def _on_pack_ready(self, pk):
+        ab = self._owner[id(pk)]
+        ab.pending -= 1
+        if ab.pending == 0:
+            self._launch_arena(ab)
+
+    def _launch_arena(self, ab: _ArenaBucket):
+        with self._side_stream_ctx(ab.flat.device):
+            ab.work = dist.all_reduce(ab.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     # -- hook path (during backward) --
     def _on_grad_ready(self, p):
@@ -107,9 +161,16 @@ class GradBucketReducer:
         if self.world_size == 1:
             self.reset()
             return
+        for ab in self.arena_buckets:
+            if ab.work is None:
+                self._launch_arena(ab)
         for b in self.buckets:
             if b.work is None:          # hooks disabled, or a parameter got no gradient this step
                 self._launch(b)
+        for ab in self.arena_buckets:
+            ctx = torch.cuda.stream(self._stream) if ab.flat.is_cuda else _null()
+            with ctx:
+                ab.work.wait()
         inv = 1.0 / self.world_size
         for b in self.buckets:
             dev = b.flat.device
@@ -133,6 +194,8 @@ class GradBucketReducer:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        for pk in self._packs:
+            pk.on_grad_ready = None
 
 
 class _null:

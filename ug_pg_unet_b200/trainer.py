@@ -30,7 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 import torch.optim as optim
 
-from .engine import PackedWeights
+from .engine import PackedWeights, conv_packs, enable_deferred_wgrad
 from .optim import FusedRMSprop
 from .parallel import GradBucketReducer, broadcast_module_state
 from .unet import PGUNet1, PGUNet2, PGUNet3, PGUNet4, UncertaintyGuidedLoss, transfer_state
@@ -47,7 +47,9 @@ class UncertaintyGuidedProgressiveTrainer:
         self.log_interval = log_interval
         self.bucket_mb = bucket_mb
         self.use_cuda_graph = use_cuda_graph and os.environ.get("UGP_NO_CUDA_GRAPH", "0") != "1"
+        self.defer_conv_grads = os.environ.get("UGP_NO_DEFERRED_WGRAD", "0") != "1"
         self._graph = None
+        self._grad_arena = None
 
         # reference uncertainty_guided_trainer.py:42-47
         self.stage_configs = {
@@ -92,14 +94,26 @@ class UncertaintyGuidedProgressiveTrainer:
         on_cuda = next(self.current_model.parameters()).is_cuda
         # same hyper-parameters and state_dict layout as the reference's optim.RMSprop; on CUDA the
         # update of all 80 tensors is one kernel launch (FusedRMSprop subclasses optim.RMSprop)
-        opt_cls = FusedRMSprop if on_cuda else optim.RMSprop
-        self.optimizer = opt_cls(self.current_model.parameters(), lr=lr, weight_decay=1e-4)
         self._graph = None
         if self._reducer is not None:
             self._reducer.remove()
             self._reducer = None
+        # 3x3 conv weight gradients stay in the packed layout the wgrad kernel reduces into (one flat
+        # arena); FusedRMSprop consumes them there and rewrites the bf16 operand packs in the same
+        # launch.  Only the model being trained defers; every other stage model is restored.
+        for m in self.models.values():
+            enable_deferred_wgrad(m, False)
+        packs, arena = enable_deferred_wgrad(self.current_model, on_cuda and self.defer_conv_grads)
+        self._grad_arena = arena
+        if on_cuda:
+            self.optimizer = FusedRMSprop(self.current_model.parameters(), lr=lr, weight_decay=1e-4,
+                                          conv_packs=conv_packs(self.current_model))
+            self.optimizer.deferred_grad_scale = 1.0 / self.world_size
+        else:
+            self.optimizer = optim.RMSprop(self.current_model.parameters(), lr=lr, weight_decay=1e-4)
         if self.distributed:
-            self._reducer = GradBucketReducer(list(self.current_model.parameters()), bucket_mb=self.bucket_mb)
+            self._reducer = GradBucketReducer(list(self.current_model.parameters()), bucket_mb=self.bucket_mb,
+                                              conv_packs=packs, arena=arena)
 
     def transfer_weights(self, prev_stage, new_stage):
         """reference :125-141, without the throw-away 49 M-parameter ProgressiveUNet."""
@@ -231,12 +245,15 @@ class UncertaintyGuidedProgressiveTrainer:
             with torch.cuda.graph(graph):
                 g["out"] = self._eager_step(g["x"], g["y"], stage)
             g["graph"] = graph
+            g["counted"] = True            # the capture pass already advanced the optimiser's step counters
         g["x"].copy_(data, non_blocking=True)
         g["y"].copy_(target, non_blocking=True)
         g["graph"].replay()
-        PackedWeights.invalidate_all()     # the replayed optimizer step changed the fp32 weights
+        # the replayed optimizer step changed the fp32 weights behind autograd's version counters
         if isinstance(self.optimizer, FusedRMSprop):
-            self.optimizer.note_replayed_steps(1)
+            self.optimizer.note_replayed_steps(0 if g.pop("counted", False) else 1)
+        else:
+            PackedWeights.invalidate_all()
         m, logits, unc = g["out"]
         return m.clone(), logits, unc
 
