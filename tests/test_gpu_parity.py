@@ -410,7 +410,7 @@ def test_deferred_packed_gradients_train_like_materialised_gradients(dev):
     # gradient elements makes the trajectories drift apart slowly: tight early, looser later
     for losses, _ in runs[1:]:
         for i, (a, b) in enumerate(zip(losses, base)):
-            assert abs(a - b) <= (5e-3 if i < 3 else 0.15) * abs(b), (i, losses, base)
+            assert abs(a - b) <= (1.5e-2 if i < 3 else 0.15) * abs(b), (i, losses, base)
         assert losses[-1] < 0.9 * losses[0], losses
     for _, w in runs[1:]:
         assert rel(w, runs[0][1]) < 0.1

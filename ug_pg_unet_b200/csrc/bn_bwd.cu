@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const 
 // pooled variant: thread = 2x2 window x 8 channels
 // ---------------------------------------------------------------------------
 template <bool kApply>
-__global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_pool_kernel(const BnBwdArgs a) {
+__global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_pool_kernel(const BnBwdArgs a) {
   const int cg = a.C >> 3;
   const int Ho = a.H >> 1, Wo = a.W >> 1;
   const long long windows = static_cast<long long>(a.B) * Ho * Wo;
@@ -194,46 +194,68 @@ __global__ void __launch_bounds__(kBnThreads) bn_relu_bwd_pool_kernel(const BnBw
   for (long long win = static_cast<long long>(blockIdx.x) * rows_per_block + my_row;
        win < windows; win += static_cast<long long>(gridDim.x) * rows_per_block) {
     const int xo = static_cast<int>(win % Wo);
-    const int yo = static_cast<int>((win / Wo) % Ho);
-    const int b = static_cast<int>(win / (static_cast<long long>(Wo) * Ho));
-    Vec8 zv[4], gv[4];
+    const long long t2 = win / Wo;
+    const int yo = static_cast<int>(t2 % Ho);
+    const int b = static_cast<int>(t2 / Ho);
+    // raw bf16x8 words stay packed until they are consumed (register footprint: 2 blocks / SM)
+    uint32_t zr[4][4], gr[4][4], pr[4];
     long long pix[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       pix[i] = (static_cast<long long>(b) * a.H + (2 * yo + (i >> 1))) * a.W + 2 * xo + (i & 1);
-      zv[i] = load8(a.z + pix[i] * a.C + c0);
-      if (a.dA) gv[i] = load8(a.dA + pix[i] * a.C + c0);
-    }
-    const Vec8 gp = load8(a.dP + win * a.C + c0);
-    int arg[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float best = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float av = round_bf16(bn_relu_val(zv[i].v[j], sc[j], sh[j]));
-        if (i == 0 || av > best) { best = av; arg[j] = i; }
+      const uint4 zq = *reinterpret_cast<const uint4*>(a.z + pix[i] * a.C + c0);
+      zr[i][0] = zq.x; zr[i][1] = zq.y; zr[i][2] = zq.z; zr[i][3] = zq.w;
+      if (a.dA) {
+        const uint4 gq = *reinterpret_cast<const uint4*>(a.dA + pix[i] * a.C + c0);
+        gr[i][0] = gq.x; gr[i][1] = gq.y; gr[i][2] = gq.z; gr[i][3] = gq.w;
+      } else {
+        gr[i][0] = gr[i][1] = gr[i][2] = gr[i][3] = 0u;
       }
     }
+    {
+      const uint4 pq = *reinterpret_cast<const uint4*>(a.dP + win * a.C + c0);
+      pr[0] = pq.x; pr[1] = pq.y; pr[2] = pq.z; pr[3] = pq.w;
+    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      Vec8 o;
+    for (int w = 0; w < 4; ++w) {
+      float dlo[4], dhi[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = zv[i].v[j];
-        float g = a.dA ? gv[i].v[j] : 0.f;
-        if (arg[j] == i) g += gp.v[j];
-        g = (fmaf(z, sc[j], sh[j]) > 0.f) ? g : 0.f;
-        if (!kApply) {
-          acc0[j] = fmaf(g, z - kz[j], acc0[j]);
-          acc1[j] += g;
-        } else {
-          const float d = fmaf(k0[j], g, fmaf(kz[j], z, kc[j]));
-          o.v[j] = d;
-          acc0[j] += d;
+      for (int hh = 0; hh < 2; ++hh) {
+        const int j = 2 * w + hh;
+        float zf[4];
+        int arg = 0;
+        float best = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          zf[i] = hh ? bf16_hi(zr[i][w]) : bf16_lo(zr[i][w]);
+          const float av = round_bf16(bn_relu_val(zf[i], sc[j], sh[j]));
+          if (i == 0 || av > best) { best = av; arg = i; }     // first max wins (MaxPool2d)
+        }
+        const float gpv = hh ? bf16_hi(pr[w]) : bf16_lo(pr[w]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float g = hh ? bf16_hi(gr[i][w]) : bf16_lo(gr[i][w]);
+          if (arg == i) g += gpv;
+          g = (fmaf(zf[i], sc[j], sh[j]) > 0.f) ? g : 0.f;
+          if (!kApply) {
+            acc0[j] = fmaf(g, zf[i] - kz[j], acc0[j]);
+            acc1[j] += g;
+          } else {
+            const float d = fmaf(k0[j], g, fmaf(kz[j], zf[i], kc[j]));
+            if (hh) dhi[i] = d; else dlo[i] = d;
+            acc0[j] += d;
+          }
         }
       }
-      if (kApply) store8(a.dz + pix[i] * a.C + c0, o);
+      if (kApply) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gr[i][w] = pack_bf16x2(dlo[i], dhi[i]);
+      }
+    }
+    if (kApply) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(a.dz + pix[i] * a.C + c0) = make_uint4(gr[i][0], gr[i][1], gr[i][2], gr[i][3]);
     }
   }
   __shared__ float red[2][kBnThreads][9];

@@ -187,92 +187,94 @@ __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x,
 }
 
 // ----------------------------------------------------------------------------
-// Bilinear x2 upsample (align_corners=True) on NHWC bf16 and its adjoint.
+// Bilinear x2 upsample (align_corners=True) on NHWC bf16 and its adjoint
+// (F.interpolate / nn.Upsample at UG_unet_parts.py:76-79 and UG_unet.py:296-301).
 // ----------------------------------------------------------------------------
-__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int B, int h,
-                                  int w, int C, __nv_bfloat16* __restrict__ out) {
+// One block per output row (b, Y): the row interpolation is block-uniform, index math is 32-bit,
+// and the two source rows are re-read by neighbouring X through L1.
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int B, int h, int w, int C,
+                  __nv_bfloat16* __restrict__ out) {
   const int cg = C >> 3;
   const int H = 2 * h, W = 2 * w;
-  const long long total = static_cast<long long>(B) * H * W * cg;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-       idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(idx % cg) * 8;
-    const long long op = idx / cg;
-    const int X = static_cast<int>(op % W);
-    const int Y = static_cast<int>((op / W) % H);
-    const int b = static_cast<int>(op / (static_cast<long long>(W) * H));
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bilinear_src(Y, h, H, &y0, &y1, &ly);
+  const int row = blockIdx.x;
+  const int b = row / H, Y = row - b * H;
+  int y0, y1;
+  float ly;
+  bilinear_src(Y, h, H, &y0, &y1, &ly);
+  const __nv_bfloat16* r0 = x + (static_cast<long long>(b) * h + y0) * w * C;
+  const __nv_bfloat16* r1 = x + (static_cast<long long>(b) * h + y1) * w * C;
+  __nv_bfloat16* o = out + static_cast<long long>(row) * W * C;
+  const int items = W * cg;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int X = i / cg;
+    const int c0 = (i - X * cg) * 8;
+    int x0, x1;
+    float lx;
     bilinear_src(X, w, W, &x0, &x1, &lx);
-    const __nv_bfloat16* base = x + static_cast<long long>(b) * h * w * C + c0;
-    const Vec8 v00 = load8(base + (static_cast<long long>(y0) * w + x0) * C);
-    const Vec8 v01 = load8(base + (static_cast<long long>(y0) * w + x1) * C);
-    const Vec8 v10 = load8(base + (static_cast<long long>(y1) * w + x0) * C);
-    const Vec8 v11 = load8(base + (static_cast<long long>(y1) * w + x1) * C);
-    Vec8 o;
+    const Vec8 v00 = load8(r0 + x0 * C + c0);
+    const Vec8 v01 = load8(r0 + x1 * C + c0);
+    const Vec8 v10 = load8(r1 + x0 * C + c0);
+    const Vec8 v11 = load8(r1 + x1 * C + c0);
+    Vec8 ov;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      o.v[j] = (1.f - ly) * ((1.f - lx) * v00.v[j] + lx * v01.v[j]) +
-               ly * ((1.f - lx) * v10.v[j] + lx * v11.v[j]);
-    store8(out + op * C + c0, o);
+      ov.v[j] = (1.f - ly) * ((1.f - lx) * v00.v[j] + lx * v01.v[j]) +
+                ly * ((1.f - lx) * v10.v[j] + lx * v11.v[j]);
+    store8(o + static_cast<long long>(i) * 8, ov);
   }
 }
 
-// Adjoint in gather form (deterministic, no atomics): every low-res pixel sums
-// the contributions of the (at most 5x5) high-res pixels that read it.
-__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int B,
-                                      int h, int w, int C,
-                                      __nv_bfloat16* __restrict__ dx) {
+// weight of high-res index I = 2*i - 2 + k (k = 0..4) on low-res index i; 0 outside the image
+__device__ __forceinline__ float up2_adjoint_weight(int I, int i, int n_lo, int n_hi) {
+  if (I < 0 || I >= n_hi) return 0.f;
+  int i0, i1;
+  float l;
+  bilinear_src(I, n_lo, n_hi, &i0, &i1, &l);
+  float wgt = 0.f;
+  if (i0 == i) wgt += 1.f - l;
+  if (i1 == i) wgt += l;
+  return wgt;
+}
+
+// Adjoint in gather form (deterministic, no atomics): every low-res pixel sums the contributions of
+// the (at most 5x5, typically 4x4) high-res pixels that read it.  One block per low-res row.
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int B, int h, int w, int C,
+                      __nv_bfloat16* __restrict__ dx) {
   const int cg = C >> 3;
   const int H = 2 * h, W = 2 * w;
-  const long long total = static_cast<long long>(B) * h * w * cg;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-       idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(idx % cg) * 8;
-    const long long ip = idx / cg;
-    const int x = static_cast<int>(ip % w);
-    const int y = static_cast<int>((ip / w) % h);
-    const int b = static_cast<int>(ip / (static_cast<long long>(w) * h));
-    float wy[5], wx[5];
+  const int row = blockIdx.x;
+  const int b = row / h, y = row - b * h;
+  float wy[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const int Y = 2 * y - 2 + i;
-      float wgt = 0.f;
-      if (Y >= 0 && Y < H) {
-        int i0, i1; float l;
-        bilinear_src(Y, h, H, &i0, &i1, &l);
-        if (i0 == y) wgt += 1.f - l;
-        if (i1 == y) wgt += l;
-      }
-      wy[i] = wgt;
-      const int X = 2 * x - 2 + i;
-      wgt = 0.f;
-      if (X >= 0 && X < W) {
-        int i0, i1; float l;
-        bilinear_src(X, w, W, &i0, &i1, &l);
-        if (i0 == x) wgt += 1.f - l;
-        if (i1 == x) wgt += l;
-      }
-      wx[i] = wgt;
-    }
+  for (int i = 0; i < 5; ++i) wy[i] = up2_adjoint_weight(2 * y - 2 + i, y, h, H);
+  const __nv_bfloat16* base = dout + static_cast<long long>(b) * H * W * C;
+  __nv_bfloat16* o = dx + static_cast<long long>(row) * w * C;
+  const int items = w * cg;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int x = it / cg;
+    const int c0 = (it - x * cg) * 8;
+    float wx[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) wx[k] = up2_adjoint_weight(2 * x - 2 + k, x, w, W);
     Vec8 acc;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
-    const __nv_bfloat16* base = dout + static_cast<long long>(b) * H * W * C + c0;
+#pragma unroll
     for (int i = 0; i < 5; ++i) {
       if (wy[i] == 0.f) continue;
-      const int Y = 2 * y - 2 + i;
+      const __nv_bfloat16* rp = base + static_cast<long long>(2 * y - 2 + i) * W * C + c0;
+#pragma unroll
       for (int k = 0; k < 5; ++k) {
         if (wx[k] == 0.f) continue;
-        const int X = 2 * x - 2 + k;
-        const Vec8 g = load8(base + (static_cast<long long>(Y) * W + X) * C);
+        const Vec8 g = load8(rp + (2 * x - 2 + k) * C);
         const float wgt = wy[i] * wx[k];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(wgt, g.v[j], acc.v[j]);
       }
     }
-    store8(dx + ip * C + c0, acc);
+    store8(o + static_cast<long long>(it) * 8, acc);
   }
 }
 
@@ -351,8 +353,10 @@ int maxpool2x2_bwd(const void* x, const void* dout, int B, int H, int W, int C, 
 int upsample2x(const void* x, int B, int h, int w, int C, void* out, cudaStream_t stream) {
   UGP_REQUIRE(x && out, "upsample2x: null pointer");
   UGP_REQUIRE(C % 8 == 0, "upsample2x: C must be a multiple of 8");
-  const long long total = static_cast<long long>(B) * 4 * h * w * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+  UGP_REQUIRE(B > 0 && h > 0 && w > 0 && static_cast<long long>(B) * 2 * h < (1LL << 31) &&
+                  static_cast<long long>(2 * w) * C < (1LL << 28),
+              "upsample2x: shape out of range");
+  upsample2x_kernel<<<B * 2 * h, 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x), B, h, w, C, static_cast<__nv_bfloat16*>(out));
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
@@ -362,8 +366,10 @@ int upsample2x_bwd(const void* dout, int B, int h, int w, int C, void* dx,
                    cudaStream_t stream) {
   UGP_REQUIRE(dout && dx, "upsample2x_bwd: null pointer");
   UGP_REQUIRE(C % 8 == 0, "upsample2x_bwd: C must be a multiple of 8");
-  const long long total = static_cast<long long>(B) * h * w * (C / 8);
-  upsample2x_bwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+  UGP_REQUIRE(B > 0 && h > 0 && w > 0 && static_cast<long long>(B) * h < (1LL << 31) &&
+                  static_cast<long long>(2 * w) * C < (1LL << 28),
+              "upsample2x_bwd: shape out of range");
+  upsample2x_bwd_kernel<<<B * h, 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(dout), B, h, w, C, static_cast<__nv_bfloat16*>(dx));
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
