@@ -23,29 +23,9 @@
 // static round-robin over (m_tile, n_tile).
 #include "ugp_common.cuh"
 #include "conv_epilogue.cuh"
+#include "conv_gemm.cuh"
 
 namespace ugp {
-
-struct ConvGemmParams {
-  int taps;
-  int chunks0, chunks1;
-  int H, W, BH, BW;
-  int tiles_x, tiles_y;
-  int m_tiles, n_tiles;
-  int cout;
-  int split_n;
-  int relu;
-  const float* bias;
-  const float* scale;
-  const float* shift;
-  float* stats;
-};
-
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                       // bf16 elements = 128 B rows
-constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kOutChunkBytes = kBlockM * 64 * 2;    // 16 KB (64 output channels)
-constexpr int kMaxCout = 1024;
 
 template <int kN>
 struct ConvCfg {
@@ -308,6 +288,12 @@ int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, in
                    cudaStream_t stream);
 extern int g_conv_halo_mode;   // 0 = per-tap loads everywhere, 1 = halo staging for wide thin layers
 
+// conv_pair.cu
+bool conv_pair_eligible(int m_tiles, int cout, int split_n);
+int launch_conv_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW,
+                     const CUtensorMap& tmO0, const CUtensorMap& tmO1, const ConvGemmParams& p,
+                     cudaStream_t stream);
+
 int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
                    int H, int W, int taps, const void* wpack, int cout,
                    void* dst0, void* dst1, int split_n, const float* bias,
@@ -356,7 +342,9 @@ int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
   } else {
     tmA1 = tmA0;
   }
-  if ((rc = make_tmap_2d_bf16(&tmW, wpack, (long long)taps * cout, c0 + c1, 64, kn))) return rc;
+  // CTA pairs (cta_group::2) for the 256-wide tiles: each CTA stages half of the weight tile
+  const bool pair = kn == 256 && conv_pair_eligible(p.m_tiles, cout, split_n);
+  if ((rc = make_tmap_2d_bf16(&tmW, wpack, (long long)taps * cout, c0 + c1, 64, pair ? 128 : kn))) return rc;
   const long long M = (long long)B * H * W;
   if ((rc = make_tmap_2d_bf16(&tmO0, dst0, M, split_n, 64, kBlockM))) return rc;
   if (split_n < cout) {
@@ -364,6 +352,7 @@ int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
   } else {
     tmO1 = tmO0;
   }
+  if (pair) return launch_conv_pair(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
   switch (kn) {
     case 256: return launch_conv<256>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
     case 128: return launch_conv<128>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
