@@ -62,6 +62,66 @@ def _worker(rank, world, port, overlap, out_dir):
         dist.destroy_process_group()
 
 
+class _FakePack:
+    """Stand-in for engine.PackedWeights with a deferred (packed) gradient slice in a flat arena."""
+
+    def __init__(self, conv, buf):
+        self.conv, self._dwp, self.on_grad_ready = conv, buf, None
+
+
+def _arena_worker(rank, world, port, overlap, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = _model(seed=5)
+        convs = [m for m in model if isinstance(m, torch.nn.Conv2d)]
+        deferred = list(reversed(convs[:2]))                 # arena order = reverse forward order
+        arena = torch.zeros(sum(c.weight.numel() for c in deferred))
+        packs, off = [], 0
+        for c in deferred:
+            n = c.weight.numel()
+            packs.append(_FakePack(c, arena[off:off + n]))
+            off += n
+        reducer = GradBucketReducer(list(model.parameters()), bucket_mb=0.0005, overlap=overlap,
+                                    conv_packs=packs, arena=arena)
+        assert len(reducer.arena_buckets) == 2
+        # deferred weights are not in the `.grad` buckets
+        in_buckets = {id(p) for b in reducer.buckets for p in b.params}
+        assert all(id(c.weight) not in in_buckets for c in deferred)
+        for step in range(2):
+            # "backward": rank-dependent packed gradients land in the arena layer by layer
+            for i, pk in enumerate(packs):
+                pk._dwp.copy_(torch.full_like(pk._dwp, float((rank + 1) * (i + 1) + step)))
+                if pk.on_grad_ready is not None:
+                    pk.on_grad_ready(pk)
+            for p in model.parameters():
+                if id(p) not in {id(c.weight) for c in deferred}:
+                    p.grad = torch.full_like(p, float(rank + 1))
+            if overlap:
+                assert all(ab.work is not None for ab in reducer.arena_buckets)   # launched from the hooks
+            reducer.wait()
+            # arena holds the SUM (the optimiser kernel applies 1/world); `.grad`s hold the mean
+            for i, pk in enumerate(packs):
+                want = sum((r + 1) * (i + 1) + step for r in range(world))
+                assert torch.all(pk._dwp == float(want)), (i, pk._dwp[:4], want)
+            for p in model.parameters():
+                if p.grad is not None:
+                    assert torch.allclose(p.grad, torch.full_like(p, sum(range(1, world + 1)) / world))
+        reducer.remove()
+        assert all(pk.on_grad_ready is None for pk in packs)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_packed_gradient_arena_buckets_world2(tmp_path, overlap):
+    port = _free_port()
+    mp.spawn(_arena_worker, args=(2, port, overlap, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
 @pytest.mark.parametrize("overlap", [True, False])
 def test_bucketed_gradient_averaging_world2(tmp_path, overlap):
     port = _free_port()
