@@ -158,6 +158,12 @@ int ugp_ce_weighted_loss(const float* logits, const long long* labels,
                          float grad_scale, float* dlogits, double* out,
                          void* stream);
 
+/* nn.AdaptiveAvgPool2d(1) + Flatten on an NHWC bf16 feature map [B][HW][C] -> fp32 [B][C] (the
+ * Herlev classifier head input, Herlev/train_herlev.py:66-68), and its adjoint
+ * dx[b][p][c] = dy[b][c] / HW (bf16).  C multiple of 64 (fwd) / 8 (bwd). */
+int ugp_global_avg_pool(const void* x, int B, int HW, int C, float* out, void* stream);
+int ugp_global_avg_pool_bwd(const float* dy, int B, int HW, int C, void* dx, void* stream);
+
 /* ---- optimiser ----------------------------------------------------------- */
 /* torch.optim.RMSprop step (uncertainty_guided_trainer.py:84-88; alpha,
  * eps, weight_decay, momentum 0, not centered) over a flat fp32 buffer:

@@ -246,6 +246,68 @@ def weighted_cross_entropy(logits: Tensor, labels: Tensor, u: Optional[Tensor], 
     return ce.mean() if u is None else (ce * (1.0 + alpha * u).detach()).mean()
 
 
+# --------------------------------------------------------------------------- Herlev variant
+def seeded_herlev_state_dict(stage: int, num_classes: int, seed: int = 0) -> StateDict:
+    """`HerlevClassificationModel(stage, num_classes).state_dict()` layout (Herlev/train_herlev.py:47,
+    66-77): `unet.*` = PGUNet{stage}(3, 1), `classifier.{3,6,9}.{weight,bias}` = the three Linear layers."""
+    sd = {"unet." + k: v for k, v in seeded_state_dict(stage, 3, 1, seed).items()}
+    for idx, (fo, fi) in ((3, (512, 512)), (6, (256, 512)), (9, (num_classes, 256))):
+        for kind, shape in (("weight", (fo, fi)), ("bias", (fo,))):
+            key = f"classifier.{idx}.{kind}"
+            g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) % (2 ** 31))
+            bound = 1.0 / math.sqrt(fi)
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    return sd
+
+
+def herlev_forward(sd: StateDict, x: Tensor, stage: int, training: bool = True,
+                   bn_out: Optional[StateDict] = None) -> Tensor:
+    """HerlevClassificationModel.forward with the Dropout layers inactive — encoder blocks up to
+    `down3` (Herlev/train_herlev.py:83-102), AdaptiveAvgPool2d(1)+Flatten, Linear-ReLU-Linear-ReLU-
+    Linear (:66-77)."""
+    usd = {k[5:]: v for k, v in sd.items() if k.startswith("unet.")}
+    ubn: Optional[StateDict] = {} if bn_out is not None else None
+    f = double_conv(x, usd, "inc.conv", training, ubn)
+    for name in down_names(stage)[: stage - 1]:
+        f = double_conv(F.max_pool2d(f, 2), usd, f"{name}.mpconv.1", training, ubn)
+    if bn_out is not None:
+        bn_out.update({"unet." + k: v for k, v in ubn.items()})
+    h = f.mean(dim=(2, 3))
+    h = F.relu(F.linear(h, sd["classifier.3.weight"], sd["classifier.3.bias"]))
+    h = F.relu(F.linear(h, sd["classifier.6.weight"], sd["classifier.6.bias"]))
+    return F.linear(h, sd["classifier.9.weight"], sd["classifier.9.bias"])
+
+
+def herlev_train_step(sd: StateDict, x: Tensor, y: Tensor, stage: int, sd_prev: Optional[StateDict] = None,
+                      alpha: float = 1.0):
+    """HerlevTrainer.uncertainty_guided_forward_pass + backward for num_classes > 2, no class weights —
+    Herlev/train_herlev.py:219-296 (previous stage in eval mode on the bilinearly down-sized input)."""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
+              and not k.endswith(("running_mean", "running_var"))}
+    full = dict(sd)
+    full.update(params)
+    bn_out: StateDict = {}
+    logits = herlev_forward(full, x, stage, training=True, bn_out=bn_out)
+    u = None
+    if stage > 1:
+        assert sd_prev is not None
+        pr = STAGE_RESOLUTION[stage - 1]
+        with torch.no_grad():
+            xp = F.interpolate(x, size=(pr, pr), mode="bilinear", align_corners=True)
+            u = softmax_entropy_uncertainty(herlev_forward(sd_prev, xp, stage - 1, training=False))
+    base = F.cross_entropy(logits, y)
+    final = weighted_cross_entropy(logits, y, u, alpha)
+    final.backward()
+    w = None if u is None else 1.0 + alpha * u
+    return {
+        "logits": logits.detach(), "final_loss": final.item(), "base_loss": base.item(), "u": u,
+        "grads": {k: p.grad for k, p in params.items()}, "bn": bn_out,
+        "correct": int((logits.argmax(1) == y).sum()),
+        "uncertainty_weight_mean": 0.0 if w is None else w.mean().item(),
+        "uncertainty_weight_std": 0.0 if w is None else w.std().item(),
+    }
+
+
 # --------------------------------------------------------------------------- trainer step
 def train_step(sd: StateDict, x: Tensor, y: Tensor, stage: int, sd_prev: Optional[StateDict] = None,
                alpha: float = 1.0, pos_weight: float = 5.0):

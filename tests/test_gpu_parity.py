@@ -414,3 +414,72 @@ def test_deferred_packed_gradients_train_like_materialised_gradients(dev):
         assert losses[-1] < 0.9 * losses[0], losses
     for _, w in runs[1:]:
         assert rel(w, runs[0][1]) < 0.1
+
+
+@pytest.mark.parametrize("name", ["herlev_stage1_k7", "herlev_stage2_k7"])
+def test_herlev_step_against_reference_goldens(dev, golden_dir, name):
+    """HerlevTrainer step (encoder on tcgen05, GAP / entropy / weighted-CE kernels) vs the fixture the
+    unmodified Herlev/train_herlev.py produced; classifier Dropout inactive on both sides."""
+    import contextlib
+    import io
+    import ug_oracle as O
+    import ug_pg_unet_b200.herlev as H
+
+    fx = torch.load(os.path.join(golden_dir, name + ".pt"))
+    stage, K = fx["stage"], fx["K"]
+    sd = O.seeded_herlev_state_dict(stage, K, seed=stage)
+    sd_prev = O.seeded_herlev_state_dict(stage - 1, K, seed=stage - 1) if stage > 1 else None
+    ref = O.herlev_train_step(sd, fx["x"], fx["y"], stage, sd_prev)
+    with O.bf16_storage(True):
+        emu = O.herlev_train_step(sd, fx["x"], fx["y"], stage, sd_prev)
+    cfg = {"device": dev, "epochs_per_stage": 1, "num_classes": K, "uncertainty_alpha": 1.0, "log_interval": 0}
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = H.HerlevTrainer(cfg)
+    tr.models[stage].load_state_dict(sd)
+    if stage > 1:
+        tr.models[stage - 1].load_state_dict(sd_prev)
+        tr.models[stage - 1].eval()
+    model = tr.models[stage]
+    model.train()
+    for m in model.classifier:
+        if isinstance(m, torch.nn.Dropout):
+            m.eval()
+    x, y = fx["x"].to(dev), fx["y"].to(dev)
+    final, metrics = tr.uncertainty_guided_forward_pass(x, y, stage)
+    final.backward()
+    torch.cuda.synchronize()
+    floor = rel(emu["logits"], fx["logits"])
+    assert rel(metrics["output"], fx["logits"]) <= 1.5 * floor + 2e-3, (rel(metrics["output"], fx["logits"]), floor)
+    lfloor = abs(emu["final_loss"] - fx["final_loss"])
+    assert abs(metrics["final_loss"] - fx["final_loss"]) <= max(1e-3 * abs(fx["final_loss"]), 1.5 * lfloor) + 1e-4
+    assert abs(metrics["base_loss"] - fx["base_loss"]) <= max(1e-3 * abs(fx["base_loss"]), 1.5 * lfloor) + 1e-4
+    assert abs(metrics["uncertainty_weight_mean"] - fx["uncertainty_weight_mean"]) < 5e-3
+    assert abs(metrics["uncertainty_weight_std"] - fx["uncertainty_weight_std"]) < 5e-3
+    for k, p in model.named_parameters():
+        if k in fx["no_grad_keys"]:
+            assert p.grad is None, k
+            continue
+        if k.endswith(("conv_op.0.bias", "conv_op.3.bias")):
+            continue
+        fl = rel(emu["grads"][k], ref["grads"][k])
+        assert rel(p.grad, ref["grads"][k]) <= 1.5 * fl + 2e-2, (k, rel(p.grad, ref["grads"][k]), fl)
+    # feature extractor exposed the way Herlev/train_herlev.py:83-102 returns it, and one optimiser step
+    feats = model._extract_features(x)
+    assert feats.shape == (fx["B"], 512, 32, 32) and feats.dtype == torch.float32
+    tr.setup_optimizer_scheduler(stage)
+    w0 = model.classifier[9].weight.detach().clone()
+    m5 = tr.train_step(x, y, stage)
+    assert m5.shape == (5,) and not torch.equal(w0, model.classifier[9].weight.detach())
+
+
+def test_global_avg_pool_kernels(dev):
+    from ug_pg_unet_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(3, 16, 16, 128, device=dev, generator=g).bfloat16()
+    out = ops.global_avg_pool(x)
+    torch.testing.assert_close(out, x.float().mean(dim=(1, 2)), rtol=1e-5, atol=1e-6)
+    dy = torch.randn(3, 128, device=dev, generator=g)
+    dx = ops.global_avg_pool_bwd(dy, 16, 16)
+    want = (dy / 256.0).bfloat16()[:, None, None, :].expand(3, 16, 16, 128)
+    assert torch.equal(dx, want)

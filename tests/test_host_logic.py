@@ -156,3 +156,27 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "ug_oracle" not in src and "import oracle" not in src, fn
+
+
+def test_herlev_model_surface_matches_reference_tables():
+    """HerlevClassificationModel: state_dict keys/shapes, attribute names, encoder parameter set."""
+    import ug_oracle as O
+    import ug_pg_unet_b200.herlev as H
+
+    for stage in (1, 2, 3, 4):
+        m = H.HerlevClassificationModel(stage, 7)
+        sd = m.state_dict()
+        want = O.seeded_herlev_state_dict(stage, 7)
+        assert set(sd) == set(want)
+        for k, v in want.items():
+            assert tuple(sd[k].shape) == tuple(v.shape), k
+        m.load_state_dict(want, strict=True)
+        assert isinstance(m.classifier[0], torch.nn.AdaptiveAvgPool2d) and isinstance(m.classifier[9], torch.nn.Linear)
+        enc = {id(p) for p in m.encoder_parameters()}
+        names = {k.split(".")[1] for k, p in m.named_parameters() if id(p) in enc}
+        assert names == {"inc", *[f"down{i}" for i in range(5 - stage, 4)]}, (stage, names)
+    with pytest.raises(ValueError):
+        H.HerlevClassificationModel(5, 7)
+    m = H.HerlevClassificationModel(1, 7)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 32, 32))

@@ -96,3 +96,30 @@ def test_state_dict_tables():
                      if not k.endswith(("running_mean", "running_var", "num_batches_tracked")))
         assert params == n
     assert len(O.state_dict_shapes(4, 3, 1)) == 134
+
+
+@pytest.mark.parametrize("name", ["herlev_stage1_k7", "herlev_stage2_k7"])
+def test_herlev_step_matches_reference(golden_dir, name):
+    """oracle.herlev_train_step vs the unmodified Herlev/train_herlev.py step (classifier Dropout inactive)."""
+    fx = torch.load(os.path.join(golden_dir, name + ".pt"))
+    stage, K = fx["stage"], fx["K"]
+    sd = O.seeded_herlev_state_dict(stage, K, seed=stage)
+    sd_prev = O.seeded_herlev_state_dict(stage - 1, K, seed=stage - 1) if stage > 1 else None
+    out = O.herlev_train_step(sd, fx["x"], fx["y"], stage, sd_prev)
+    torch.testing.assert_close(out["logits"], fx["logits"], rtol=1e-4, atol=1e-5)
+    assert abs(out["final_loss"] - fx["final_loss"]) < 1e-5
+    assert abs(out["base_loss"] - fx["base_loss"]) < 1e-5
+    assert abs(out["uncertainty_weight_mean"] - fx["uncertainty_weight_mean"]) < 1e-6
+    assert abs(out["uncertainty_weight_std"] - fx["uncertainty_weight_std"]) < 1e-6
+    assert out["correct"] == fx["correct"]
+    gmax = max(g.abs().max().item() for g in out["grads"].values() if g is not None)
+    for k, s in fx["grads"].items():
+        _check_sample(out["grads"][k], s, rtol=2e-3, atol=2e-5 * gmax)
+    # decoder / heads / down4 never run in the classification model: no gradient (SURVEY.md §8e)
+    for k in fx["no_grad_keys"]:
+        assert out["grads"][k] is None, k
+    for k, v in fx["bn"].items():
+        if k in out["bn"]:
+            torch.testing.assert_close(out["bn"][k], v, rtol=1e-5, atol=1e-6)
+        else:                                      # untouched blocks keep their buffers
+            torch.testing.assert_close(sd[k], v, rtol=0, atol=0)

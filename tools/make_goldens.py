@@ -118,8 +118,55 @@ def primitive_case():
     }
 
 
+def herlev_case(stage: int, B: int, K: int, seed: int):
+    """One `HerlevTrainer.uncertainty_guided_forward_pass` + backward of the UNMODIFIED reference
+    (Herlev/train_herlev.py) with the classifier's Dropout layers switched to eval (they draw from the
+    global RNG; everything else is as in train_epoch)."""
+    sys.path.insert(0, "/root/reference/Herlev")
+    with contextlib.redirect_stdout(io.StringIO()):
+        import train_herlev as REFH
+    R = O.STAGE_RESOLUTION[stage]
+    g = torch.Generator().manual_seed(2000 + seed)
+    x = torch.randn(B, 3, R, R, generator=g)
+    y = torch.randint(0, K, (B,), generator=g)
+    cfg = {"device": "cpu", "epochs_per_stage": 1, "num_classes": K, "uncertainty_alpha": 1.0}
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = REFH.HerlevTrainer(cfg)
+    tr.models[stage].load_state_dict(O.seeded_herlev_state_dict(stage, K, seed=stage), strict=True)
+    if stage > 1:
+        tr.models[stage - 1].load_state_dict(O.seeded_herlev_state_dict(stage - 1, K, seed=stage - 1), strict=True)
+        tr.models[stage - 1].eval()
+    model = tr.models[stage]
+    model.train()
+    for m in model.classifier:
+        if isinstance(m, torch.nn.Dropout):
+            m.eval()
+    final_loss, metrics = tr.uncertainty_guided_forward_pass(x, y, stage)
+    final_loss.backward()
+    return {
+        "stage": stage, "B": B, "K": K, "x": x, "y": y,
+        "logits": metrics["output"].detach().clone(),
+        "final_loss": metrics["final_loss"], "base_loss": metrics["base_loss"],
+        "uncertainty_weight_mean": metrics["uncertainty_weight_mean"],
+        "uncertainty_weight_std": metrics["uncertainty_weight_std"],
+        "correct": int((metrics["output"].argmax(1) == y).sum()),
+        "grads": {k: sample(p.grad) for k, p in model.named_parameters() if p.grad is not None},
+        "no_grad_keys": [k for k, p in model.named_parameters() if p.grad is None],
+        "bn": {k: v.clone() for k, v in model.state_dict().items()
+               if k.endswith(("running_mean", "running_var", "num_batches_tracked"))},
+    }
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    for name, (stage, B, K, seed) in {"herlev_stage1_k7": (1, 4, 7, 21), "herlev_stage2_k7": (2, 4, 7, 22)}.items():
+        fx = herlev_case(stage, B, K, seed)
+        path = os.path.join(OUT, name + ".pt")
+        torch.save(fx, path)
+        print(f"{name}: final_loss={fx['final_loss']:.6f} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    if "--herlev-only" in sys.argv:
+        return
     cases = {
         "trainer_stage1_nc1": (1, 2, 1, 11),
         "trainer_stage1_nc2_config1": (1, 4, 2, 12),     # BASELINE.json configs[0] shape, smaller batch

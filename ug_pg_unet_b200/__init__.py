@@ -6,6 +6,7 @@ uncertainty_guided_trainer.py):
     DoubleConv, InConv, Down, Up, OutConv
     PGUNet1..4, ProgressiveUNet, UncertaintyGuidedLoss
     UncertaintyGuidedProgressiveTrainer
+    HerlevClassificationModel, HerlevTrainer          (Herlev/train_herlev.py)
 
 Everything executes through libugp_b200.so (C ABI in include/ugp_b200.h);
 there is no CPU or library fallback.
@@ -14,9 +15,11 @@ from .unet_parts import DoubleConv, Down, InConv, OutConv, Up
 from .unet import (PGUNet1, PGUNet2, PGUNet3, PGUNet4, ProgressiveUNet, STAGE_MODELS,
                    UncertaintyGuidedLoss, transfer_state)
 from .trainer import UncertaintyGuidedProgressiveTrainer
+from .herlev import HerlevClassificationModel, HerlevTrainer
 
 __all__ = [
     "DoubleConv", "InConv", "Down", "Up", "OutConv",
     "PGUNet1", "PGUNet2", "PGUNet3", "PGUNet4", "ProgressiveUNet", "STAGE_MODELS",
     "UncertaintyGuidedLoss", "transfer_state", "UncertaintyGuidedProgressiveTrainer",
+    "HerlevClassificationModel", "HerlevTrainer",
 ]

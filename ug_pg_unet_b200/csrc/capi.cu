@@ -45,6 +45,8 @@ int rmsprop_step(float*, const float*, float*, long long, float, float, float, f
                  cudaStream_t);
 int rmsprop_multi(float* const*, const float* const*, float* const*, const long long*, int, float,
                   float, float, float, float, cudaStream_t);
+int global_avg_pool(const void*, int, int, int, float*, cudaStream_t);
+int global_avg_pool_bwd(const float*, int, int, int, void*, cudaStream_t);
 int rmsprop_conv_packed(float* const*, float* const*, float* const*, void* const*, void* const*,
                         const int*, const int*, int, float, float, float, float, float, cudaStream_t);
 }  // namespace ugp
@@ -171,5 +173,11 @@ int ugp_rmsprop_conv_packed(float* const* w, float* const* square_avgs, float* c
                             float grad_scale, void* stream) {
   return ugp::rmsprop_conv_packed(w, square_avgs, dw_packed, wf, wd, cout, cin, n_tensors, lr, alpha,
                                   eps, weight_decay, grad_scale, S(stream));
+}
+int ugp_global_avg_pool(const void* x, int B, int HW, int C, float* out, void* stream) {
+  return ugp::global_avg_pool(x, B, HW, C, out, S(stream));
+}
+int ugp_global_avg_pool_bwd(const float* dy, int B, int HW, int C, void* dx, void* stream) {
+  return ugp::global_avg_pool_bwd(dy, B, HW, C, dx, S(stream));
 }
 }  // extern "C"

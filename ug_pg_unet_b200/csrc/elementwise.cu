@@ -378,4 +378,70 @@ int upsample2x_bwd(const void* dout, int B, int h, int w, int C, void* dx,
 
 
 
+// ----------------------------------------------------------------------------
+// Global average pool over H*W of an NHWC bf16 feature map -> fp32 [B, C], and its adjoint
+// (nn.AdaptiveAvgPool2d(1) + Flatten in front of the Herlev classifier head,
+// Herlev/train_herlev.py:66-68).  Deterministic: fixed-order tree, no atomics.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+global_avg_pool_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float* __restrict__ out) {
+  // block = (image b, 64-channel slab); thread = (pixel lane 0..31, 8-channel group 0..7)
+  __shared__ float red[32][65];
+  const int slabs = C >> 6;
+  const int b = blockIdx.x / slabs;
+  const int c0 = (blockIdx.x - b * slabs) * 64;
+  const int cgi = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const __nv_bfloat16* base = x + static_cast<long long>(b) * HW * C + c0 + cgi * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int p = pl; p < HW; p += 32) {
+    const Vec8 v = load8(base + static_cast<long long>(p) * C);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v.v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[pl][cgi * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+    out[static_cast<long long>(b) * C + c0 + threadIdx.x] = s / static_cast<float>(HW);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+global_avg_pool_bwd_kernel(const float* __restrict__ dy, int HW, int C, __nv_bfloat16* __restrict__ dx) {
+  const int cg = C >> 3;
+  const int b = blockIdx.y;
+  const float inv = 1.f / static_cast<float>(HW);
+  const int items = HW * cg;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
+    const int c0 = (i % cg) * 8;
+    Vec8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = __ldg(dy + static_cast<long long>(b) * C + c0 + j) * inv;
+    store8(dx + (static_cast<long long>(b) * HW) * C + static_cast<long long>(i) * 8, o);
+  }
+}
+
+int global_avg_pool(const void* x, int B, int HW, int C, float* out, cudaStream_t stream) {
+  UGP_REQUIRE(x && out && B > 0 && HW > 0, "global_avg_pool: bad arguments");
+  UGP_REQUIRE(C % 64 == 0, "global_avg_pool: C %d must be a multiple of 64", C);
+  global_avg_pool_kernel<<<B * (C / 64), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), HW, C, out);
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
+}
+
+int global_avg_pool_bwd(const float* dy, int B, int HW, int C, void* dx, cudaStream_t stream) {
+  UGP_REQUIRE(dy && dx && B > 0 && B <= 65535 && HW > 0, "global_avg_pool_bwd: bad arguments");
+  UGP_REQUIRE(C % 8 == 0, "global_avg_pool_bwd: C %d must be a multiple of 8", C);
+  int gx = (HW * (C / 8) + 255) / 256;
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, B);
+  global_avg_pool_bwd_kernel<<<grid, 256, 0, stream>>>(dy, HW, C, static_cast<__nv_bfloat16*>(dx));
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
+}
+
 }  // namespace ugp

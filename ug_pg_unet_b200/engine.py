@@ -336,6 +336,19 @@ class HeadCombineFn(torch.autograd.Function):
         return tuple(ops.head_combine_bwd(dlogits, s) for s in ctx.sizes)
 
 
+class GlobalAvgPoolFn(torch.autograd.Function):
+    """AdaptiveAvgPool2d(1) + Flatten on an NHWC bf16 feature map -> fp32 [B, C]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.hw = (x.shape[1], x.shape[2])
+        return ops.global_avg_pool(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.global_avg_pool_bwd(dy.contiguous().float(), *ctx.hw)
+
+
 # ----------------------------------------------------------------------------- losses
 class BCEUncertaintyLossFn(torch.autograd.Function):
     """mean(BCEWithLogits(pos_weight)(z, t) * (1 + alpha*A)) with dlogits produced in the same pass;

@@ -1,0 +1,343 @@
+"""Herlev classification variant on the sm_100a kernels — interface mirror of the reference's
+`Herlev/train_herlev.py`: `HerlevClassificationModel` (:29-120) and `HerlevTrainer` (:123-463).
+
+The encoder of the stage's PGUNet (`inc`, downs up to `down3`) runs on the tcgen05 implicit-GEMM
+convolutions exactly as in the segmentation path (NHWC bf16, fused BN/ReLU/pool); the
+`AdaptiveAvgPool2d(1)` in front of the MLP head is a hand-written reduction kernel; the softmax
+entropy of the previous stage (`u = H(softmax)/ln K`, :253-257) and the uncertainty-weighted
+cross entropy with its gradient and the accuracy count (:266-281, :318-320) are one kernel each.
+The 3-layer MLP head (512 -> 512 -> 256 -> K on a [B, 512] vector, < 0.002 % of the step's FLOPs)
+stays stock `nn.Linear` / `nn.Dropout`, so `state_dict` keys (`unet.*`, `classifier.{3,6,9}.*`)
+and checkpoints are the reference's.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from datetime import datetime
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import engine, ops
+from .parallel import GradBucketReducer, broadcast_module_state
+from .unet import STAGE_MODELS, _PGUNetBase
+from .unet_parts import _require_cuda
+
+_RES = {1: 32, 2: 64, 3: 128, 4: 256}
+
+
+def _encode_resized(unet: _PGUNetBase, x: torch.Tensor, resolution: int, depth: int) -> torch.Tensor:
+    """Inference-only encoder forward of `F.interpolate(x, resolution, bilinear, align_corners=True)`
+    with the resize folded into the first-layer packer; returns the deepest NHWC bf16 feature map."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    col = ops.im2col_first(x.contiguous(), resolution, resolution)
+    dc = unet.inc.conv
+    downs = [getattr(unet, n).mpconv[1] for n in unet._downs][:depth]
+    a, _, _ = engine.cbr_forward([col], 1, dc.conv_op[0], dc.conv_op[1], dc._packs[0], False, False)
+    a, p, _ = engine.cbr_forward([a], 9, dc.conv_op[3], dc.conv_op[4], dc._packs[1], bool(downs), False)
+    for i, d in enumerate(downs):
+        a, _, _ = engine.cbr_forward([p], 9, d.conv_op[0], d.conv_op[1], d._packs[0], False, False)
+        a, p, _ = engine.cbr_forward([a], 9, d.conv_op[3], d.conv_op[4], d._packs[1], i + 1 < len(downs), False)
+    return a
+
+
+class HerlevClassificationModel(nn.Module):
+    """U-Net encoder as feature extractor + MLP head — reference Herlev/train_herlev.py:29-120."""
+
+    def __init__(self, stage: int, num_classes: int, pretrained_unet_path: Optional[str] = None):
+        super().__init__()
+        if stage not in STAGE_MODELS:
+            raise ValueError("Stage must be 1, 2, 3, or 4")
+        self.stage = stage
+        self.num_classes = num_classes
+        self.unet = STAGE_MODELS[stage](in_channels=3, num_classes=1)
+        if pretrained_unet_path and os.path.exists(pretrained_unet_path):
+            print(f"Loading pretrained U-Net weights from: {pretrained_unet_path}")
+            state_dict = torch.load(pretrained_unet_path, map_location="cpu")
+            if "model_state_dict" in state_dict:
+                state_dict = state_dict["model_state_dict"]
+            self.unet.load_state_dict(state_dict)
+        # the reference probes this with a forward pass (:58-63); the encoder always ends at 512 channels
+        feature_dim = 512
+        self.classifier = nn.Sequential(
+            nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Dropout(0.5),
+            nn.Linear(feature_dim, 512), nn.ReLU(), nn.Dropout(0.3),
+            nn.Linear(512, 256), nn.ReLU(), nn.Dropout(0.2),
+            nn.Linear(256, num_classes),
+        )
+        if pretrained_unet_path:
+            self._freeze_encoder()
+
+    @property
+    def _depth(self) -> int:
+        return self.stage - 1            # inc only | +down3 | +down2,down3 | +down1,down2,down3  (:83-102)
+
+    def encoder_parameters(self):
+        """Parameters that `_extract_features` touches (what receives gradients)."""
+        mods = [self.unet.inc] + [getattr(self.unet, n) for n in self.unet._downs][: self._depth]
+        for m in mods:
+            yield from m.parameters()
+
+    def _features_nhwc(self, x: torch.Tensor) -> torch.Tensor:
+        _require_cuda(x, "HerlevClassificationModel")
+        return self.unet.encode(x, self._depth)[-1]
+
+    def _extract_features(self, x):
+        """Reference :83-102 — fp32 NCHW feature map of the last encoder block."""
+        a = self._features_nhwc(x)
+        return engine.nhwc_as_nchw(a).float().contiguous()
+
+    def _freeze_encoder(self):
+        for p in self.unet.parameters():
+            p.requires_grad = False
+
+    def unfreeze_encoder(self):
+        for p in self.unet.parameters():
+            p.requires_grad = True
+
+    def _head(self, pooled: torch.Tensor) -> torch.Tensor:
+        for m in list(self.classifier)[2:]:       # [0] pool and [1] flatten ran in the kernel
+            pooled = m(pooled)
+        return pooled
+
+    def forward(self, x):
+        pooled = engine.GlobalAvgPoolFn.apply(self._features_nhwc(x))
+        return self._head(pooled)
+
+    @torch.no_grad()
+    def forward_resized(self, x, resolution: int):
+        """`self(F.interpolate(x, resolution, bilinear, align_corners=True))` in eval mode, resize
+        folded into the first-layer packer (reference :243-248)."""
+        if x.shape[-1] == resolution and x.shape[-2] == resolution:
+            return self(x)
+        a = _encode_resized(self.unet, x, resolution, self._depth)
+        return self._head(ops.global_avg_pool(a))
+
+
+class HerlevTrainer:
+    """Progressive trainer for Herlev cervical cell classification — reference :123-463.
+
+    Same constructor (`config` dict), attributes (`models`, `optimizers`, `schedulers`, `criterion`,
+    `uncertainty_alpha`, `history`, `stage_configs`) and methods.  With `torch.distributed`
+    initialised the step is batch-sharded: gradients of the encoder + classifier are averaged with
+    the bucketed NCCL all-reduce of `parallel.GradBucketReducer`."""
+
+    def __init__(self, config):
+        self.config = config
+        self.device = config["device"]
+        self.stage_configs = {
+            1: {"resolution": 32, "epochs": config["epochs_per_stage"], "lr": 3e-4},
+            2: {"resolution": 64, "epochs": config["epochs_per_stage"], "lr": 1e-4},
+            3: {"resolution": 128, "epochs": config["epochs_per_stage"], "lr": 1e-4},
+            # the reference trains stage 4 at 224 (:137); 224 -> 112 -> 56 -> 28 pixel maps do not tile into
+            # the 128-pixel TMA boxes of the conv kernels, so this port uses the U-Net's native 256
+            # (BASELINE.json configs[3]) unless the config overrides it with a supported size
+            4: {"resolution": config.get("stage4_resolution", 256), "epochs": config["epochs_per_stage"], "lr": 1e-4},
+        }
+        self.current_stage = 1
+        self.models, self.optimizers, self.schedulers = {}, {}, {}
+        for stage in range(1, 5):
+            self.models[stage] = HerlevClassificationModel(
+                stage=stage, num_classes=config["num_classes"],
+                pretrained_unet_path=config.get("pretrained_unet_paths", {}).get(stage)).to(self.device)
+        self.distributed = dist.is_initialized() and dist.get_world_size() > 1
+        self.world_size = dist.get_world_size() if self.distributed else 1
+        if self.distributed:
+            for m in self.models.values():
+                broadcast_module_state(m)
+        self._reducers = {}
+        self.setup_loss_function()
+        from .unet import UncertaintyGuidedLoss
+        self.uncertainty_loss = UncertaintyGuidedLoss(self.device)
+        self.uncertainty_alpha = config.get("uncertainty_alpha", 1.0)
+        self.history = {"train_loss": [], "val_loss": [], "train_acc": [], "val_acc": [],
+                        "uncertainty_weights_mean": [], "uncertainty_weights_std": [], "base_loss": [],
+                        "stage_transitions": []}
+
+    def setup_loss_function(self):
+        if self.config.get("class_weights") is not None:
+            cw = torch.FloatTensor(self.config["class_weights"]).to(self.device)
+            self.criterion = nn.CrossEntropyLoss(weight=cw)
+        else:
+            self.criterion = nn.CrossEntropyLoss()
+
+    def setup_optimizer_scheduler(self, stage):
+        model = self.models[stage]
+        lr = self.stage_configs[stage]["lr"]
+        self.optimizers[stage] = torch.optim.Adam(model.parameters(), lr=lr,
+                                                  weight_decay=self.config.get("weight_decay", 1e-4))
+        self.schedulers[stage] = torch.optim.lr_scheduler.ReduceLROnPlateau(
+            self.optimizers[stage], mode="min", factor=0.5, patience=5)
+        if self.distributed:
+            old = self._reducers.pop(stage, None)
+            if old is not None:
+                old.remove()
+            used = [p for p in list(model.encoder_parameters()) + list(model.classifier.parameters())
+                    if p.requires_grad]
+            self._reducers[stage] = GradBucketReducer(used, bucket_mb=self.config.get("bucket_mb", 16.0))
+
+    def transfer_weights(self, prev_stage, current_stage):
+        """reference :200-217 — copies classifier tensors whose shapes match."""
+        print(f"Transferring weights from stage {prev_stage} to {current_stage}")
+        prev_c, cur_c = self.models[prev_stage].classifier, self.models[current_stage].classifier
+        with torch.no_grad():
+            for (pn, pp), (cn, cp) in zip(prev_c.named_parameters(), cur_c.named_parameters()):
+                if pp.shape == cp.shape:
+                    cp.copy_(pp)
+                    print(f"  Transferred {cn}")
+
+    # ------------------------------------------------------------------ the step
+    def _uncertainty(self, data, stage):
+        """Per-sample uncertainty from the previous stage (reference :232-263), detached [B]."""
+        prev = self.models[stage - 1]
+        prev.eval()
+        prev_res = self.stage_configs[stage - 1]["resolution"]
+        with torch.no_grad():
+            out_prev = prev.forward_resized(data, prev_res).float().contiguous()
+            K = self.config["num_classes"]
+            if K > 2:
+                return ops.softmax_entropy(out_prev)
+            # binary head: the reference's sigmoid margin on the [B, 2] logits (:258-261), stock ops
+            return 1.0 - 2.0 * torch.abs(torch.sigmoid(out_prev) - 0.5)
+
+    def _forward_loss(self, data, target, stage):
+        """-> (final_loss, base_loss tensor, logits, uncertainty weights or None, fused out or None)."""
+        model = self.models[stage]
+        logits = model(data)
+        u = self._uncertainty(data, stage) if stage > 1 else None
+        fused = self.criterion.weight is None and logits.is_cuda and (u is None or u.dim() == 1) \
+            and getattr(self.criterion, "label_smoothing", 0.0) == 0.0
+        if fused:
+            final, out = engine.CEWeightedLossFn.apply(logits.float(), target, u, float(self.uncertainty_alpha))
+            base = (out[1] / logits.shape[0]).float()
+            w = None if u is None else 1.0 + self.uncertainty_alpha * u
+            return final, base, logits, w, out
+        # class-weighted / binary configurations: the reference's own arithmetic (:265-281)
+        base = self.criterion(logits, target)
+        if u is not None:
+            w = 1.0 + self.uncertainty_alpha * u.squeeze()
+            if w.dim() == 0:
+                w = w.unsqueeze(0)
+            final = torch.mean(F.cross_entropy(logits, target, reduction="none") * w.detach())
+        else:
+            final, w = base, None
+        return final, base, logits, w, None
+
+    def uncertainty_guided_forward_pass(self, data, target, stage):
+        """reference :219-296 — returns (final_loss, metrics dict)."""
+        final, base, logits, w, _ = self._forward_loss(data, target, stage)
+        metrics = {
+            "final_loss": final.item(), "base_loss": base.item(), "output": logits,
+            "uncertainty_weight_mean": torch.mean(w).item() if w is not None else 0.0,
+            "uncertainty_weight_std": torch.std(w).item() if w is not None and w.numel() > 1 else 0.0,
+        }
+        return final, metrics
+
+    def train_step(self, data, target, stage):
+        """One optimisation step; returns device tensors (final, base, #correct, w mean, w std) — no host
+        synchronisation."""
+        opt = self.optimizers[stage]
+        opt.zero_grad(set_to_none=True)
+        final, base, logits, w, out = self._forward_loss(data, target, stage)
+        final.backward()
+        red = self._reducers.get(stage)
+        if red is not None:
+            red.wait()
+        opt.step()
+        with torch.no_grad():
+            correct = out[2] if out is not None else (logits.argmax(dim=1) == target).sum()
+            zero = torch.zeros((), device=logits.device)
+            wm = torch.mean(w) if w is not None else zero
+            ws = torch.std(w) if w is not None and w.numel() > 1 else zero
+        return torch.stack([final.detach().double(), base.detach().double(), correct.double(), wm.double(),
+                            ws.double()])
+
+    def _epoch(self, dataloader, stage, train: bool):
+        acc = None
+        total = 0
+        log_every = self.config.get("log_interval", 10)
+        for batch_idx, (data, target) in enumerate(dataloader):
+            data = data.to(self.device, non_blocking=True)
+            target = target.to(self.device, non_blocking=True)
+            if train:
+                m = self.train_step(data, target, stage)
+            else:
+                final, base, logits, w, out = self._forward_loss(data, target, stage)
+                correct = out[2] if out is not None else (logits.argmax(dim=1) == target).sum()
+                zero = torch.zeros((), device=logits.device)
+                m = torch.stack([final.double(), base.double(), correct.double(),
+                                 (torch.mean(w) if w is not None else zero).double(),
+                                 (torch.std(w) if w is not None and w.numel() > 1 else zero).double()])
+            acc = m if acc is None else acc + m
+            total += target.size(0)
+            if train and log_every and batch_idx % log_every == 0:
+                f, b, c, um, us = m.tolist()
+                info = f", Unc_mean: {um:.4f}, Unc_std: {us:.4f}" if stage > 1 else ""
+                print(f"Stage {stage}, Batch {batch_idx}/{len(dataloader)} Loss: {f:.6f} Base_Loss: {b:.6f} "
+                      f"Acc: {100.0 * acc[2].item() / total:.2f}%{info}")
+        n = max(len(dataloader), 1)
+        f, b, c, um, us = (acc if acc is not None else torch.zeros(5)).tolist()
+        return f / n, b / n, 100.0 * c / max(total, 1), um / n, us / n
+
+    def train_epoch(self, dataloader, stage):
+        """reference :298-357 — (avg_loss, avg_base_loss, accuracy %, unc mean, unc std)."""
+        self.models[stage].train()
+        if stage > 1:
+            self.models[stage - 1].eval()
+        return self._epoch(dataloader, stage, True)
+
+    def validate_epoch(self, dataloader, stage):
+        """reference :359-400."""
+        self.models[stage].eval()
+        if stage > 1:
+            self.models[stage - 1].eval()
+        with torch.no_grad():
+            return self._epoch(dataloader, stage, False)
+
+    def train_progressive(self, train_loaders, val_loaders, save_dir):
+        """reference :402-497 (checkpoint dict layout and history file preserved)."""
+        os.makedirs(save_dir, exist_ok=True)
+        rank0 = (not self.distributed) or dist.get_rank() == 0
+        for stage in self.config["stages"]:
+            print(f"\n{'=' * 60}\nTraining Stage {stage} - Resolution: {self.stage_configs[stage]['resolution']}\n{'=' * 60}")
+            self.current_stage = stage
+            self.setup_optimizer_scheduler(stage)
+            if stage > 1 and (stage - 1) in self.models:
+                self.transfer_weights(stage - 1, stage)
+            best_val_loss, best_val_acc, stale = float("inf"), 0, 0
+            for epoch in range(self.stage_configs[stage]["epochs"]):
+                print(f"\nStage {stage}, Epoch {epoch + 1}/{self.stage_configs[stage]['epochs']}")
+                tl, tb, ta, tum, tus = self.train_epoch(train_loaders[stage], stage)
+                vl, vb, va, vum, vus = self.validate_epoch(val_loaders[stage], stage)
+                self.schedulers[stage].step(vl)
+                for k, v in (("train_loss", tl), ("val_loss", vl), ("train_acc", ta), ("val_acc", va),
+                             ("uncertainty_weights_mean", vum), ("uncertainty_weights_std", vus), ("base_loss", vb)):
+                    self.history[k].append(v)
+                print(f"Train Loss: {tl:.4f}, Base Loss: {tb:.4f}, Train Acc: {ta:.2f}%")
+                print(f"Val Loss: {vl:.4f}, Base Loss: {vb:.4f}, Val Acc: {va:.2f}%")
+                if va > best_val_acc:
+                    best_val_loss, best_val_acc, stale = vl, va, 0
+                    if rank0:
+                        torch.save({"model_state_dict": self.models[stage].state_dict(),
+                                    "optimizer_state_dict": self.optimizers[stage].state_dict(),
+                                    "stage": stage, "epoch": epoch + 1, "train_loss": tl, "val_loss": vl,
+                                    "train_acc": ta, "val_acc": va, "config": self.config},
+                                   os.path.join(save_dir, f"herlev_stage{stage}_best.pth"))
+                        print(f"New best model saved! Val Acc: {va:.2f}%")
+                else:
+                    stale += 1
+                if stale >= self.config.get("early_stopping_patience", 15):
+                    print(f"Early stopping after {stale} epochs without improvement")
+                    break
+            self.history["stage_transitions"].append({"stage": stage, "completed_at": datetime.now().isoformat(),
+                                                      "best_val_acc": best_val_acc, "best_val_loss": best_val_loss})
+            print(f"Stage {stage} completed. Best Val Acc: {best_val_acc:.2f}%")
+        if rank0:
+            with open(os.path.join(save_dir, "training_history.json"), "w") as f:
+                json.dump(self.history, f, indent=2)

@@ -267,6 +267,23 @@ def upsample2x_bwd(dout):
     return dx
 
 
+def global_avg_pool(x):
+    """NHWC bf16 [B,H,W,C] -> fp32 [B,C] (AdaptiveAvgPool2d(1) + Flatten)."""
+    _req(x, bf16, "x")
+    B, H, W, Cn = x.shape
+    out = torch.empty((B, Cn), dtype=torch.float32, device=x.device)
+    check(lib().ugp_global_avg_pool(_ptr(x), B, H * W, Cn, _ptr(out), _stream()), "ugp_global_avg_pool")
+    return out
+
+
+def global_avg_pool_bwd(dy, H: int, W: int):
+    _req(dy, torch.float32, "dy")
+    B, Cn = dy.shape
+    dx = torch.empty((B, H, W, Cn), dtype=bf16, device=dy.device)
+    check(lib().ugp_global_avg_pool_bwd(_ptr(dy), B, H * W, Cn, _ptr(dx), _stream()), "ugp_global_avg_pool_bwd")
+    return dx
+
+
 # ----------------------------------------------------------------------------- head / loss
 def outconv_fwd(x, w, bias):
     """x NHWC bf16 [B,h,w,C], w fp32 [nc,C(,1,1)] -> fp32 NCHW [B,nc,h,w]."""
