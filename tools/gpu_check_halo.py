@@ -60,10 +60,10 @@ def main():
             bias = torch.randn(cout, device="cuda", generator=g)
             wf, _ = ops.pack_weights(w)
             _lib.set_option("conv_halo", 0)
-            st0 = torch.zeros(2, cout, device="cuda")
+            st0 = ops.new_stats(cout, "cuda")
             base = ops.conv_gemm(x0, x1, wf, 9, cout, bias=bias, stats=st0, split_n=split)
             _lib.set_option("conv_halo", mode)
-            st1 = torch.zeros(2, cout, device="cuda")
+            st1 = ops.new_stats(cout, "cuda")
             try:
                 out = ops.conv_gemm(x0, x1, wf, 9, cout, bias=bias, stats=st1, split_n=split)
                 torch.cuda.synchronize()
@@ -80,7 +80,7 @@ def main():
             ref = F.conv2d(xin, w.bfloat16().float(), bias, padding=1)
             e_ref = rel(nchw(out_c), ref)
             e_base = rel(out_c, base_c)
-            e_st = rel(st1, st0)
+            e_st = rel(st1.sum(0), st0.sum(0))
             good = e_ref < 6e-3 and e_st < 1e-4
             all_ok &= good
             print(f"[{'PASS' if good else 'FAIL'}] mode {mode} B{B} {H}x{W} {c0}+{c1}->{cout} split={split}: "
@@ -97,7 +97,7 @@ def main():
         w = torch.randn(cout, c0 + c1, 3, 3, device="cuda", generator=g) / 30
         wf, _ = ops.pack_weights(w)
         out = torch.empty(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
-        st = torch.zeros(2, cout, device="cuda")
+        st = ops.new_stats(cout, "cuda")
         flops = 2.0 * B * H * W * cout * 9 * (c0 + c1)
         res = []
         for mode in (0, good_mode) if good_mode else (0,):

@@ -60,15 +60,16 @@ def group_conv_fwd():
         w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3.0 * cin ** 0.5)
         bias = torch.randn(cout, device="cuda", generator=g)
         wf, wd = ops.pack_weights(w)
-        stats = torch.zeros(2, cout, device="cuda")
+        stats = ops.new_stats(cout, "cuda")
         out = ops.conv_gemm(x0, x1, wf, 9, cout, bias=bias, stats=stats)
         torch.cuda.synchronize()
         xin = to_nchw(x0) if x1 is None else torch.cat([to_nchw(x0), to_nchw(x1)], 1)
         ref = F.conv2d(xin, w.bfloat16().float(), bias, padding=1)
         e, m = rel_err(to_nchw(out), ref)
         o64 = out.double().reshape(-1, cout)
-        se, _ = rel_err(stats[0], o64.sum(0))
-        s2e, _ = rel_err(stats[1], (o64 * o64).sum(0))
+        tot = stats.sum(0)                      # [P][2][C] per-CTA partials -> [2][C]
+        se, _ = rel_err(tot[0], o64.sum(0))
+        s2e, _ = rel_err(tot[1], (o64 * o64).sum(0))
         ok &= report(f"conv_fwd B{B} {H}x{W} {c0}+{c1}->{cout}", e < 6e-3 and se < 1e-4 and s2e < 1e-4,
                      f"rel={e:.2e} max={m:.2e} stats_rel={se:.1e}/{s2e:.1e}")
     # eval-mode epilogue: affine + relu
@@ -200,7 +201,7 @@ def group_elementwise():
     # BN finalize
     n = B * H * W
     zz = z.double().reshape(-1, Cn)
-    stats = torch.stack([zz.sum(0), (zz * zz).sum(0)]).float().contiguous()
+    stats = torch.stack([zz.sum(0), (zz * zz).sum(0)]).float().unsqueeze(0).contiguous()   # one partial slot
     gamma = torch.rand(Cn, device="cuda", generator=g) + 0.5
     beta = torch.randn(Cn, device="cuda", generator=g)
     rm = torch.zeros(Cn, device="cuda")

@@ -28,7 +28,7 @@ def main():
     _lib.set_option("conv_halo", halo)
     if kind == "fwd":
         out = torch.empty(B, H, W, cout, device="cuda", dtype=torch.bfloat16)
-        st = torch.zeros(2, cout, device="cuda")
+        st = ops.new_stats(cout, "cuda")
         bias = torch.zeros(cout, device="cuda")
         for _ in range(iters):
             ops.conv_gemm(x0, x1, wf, 9, cout, bias=bias, stats=st, out0=out)

@@ -53,7 +53,7 @@ def main():
         x1 = torch.randn(B, R, R, c1, device=dev).bfloat16() if c1 else None
         w = torch.randn(cout, cin, 3, 3, device=dev) / (3.0 * cin ** 0.5)
         wf, wd = ops.pack_weights(w)
-        stats = torch.zeros(2, cout, device=dev)
+        stats = ops.new_stats(cout, "cuda")
         dz = torch.randn(B, R, R, cout, device=dev).bfloat16()
         dwp = torch.zeros(9 * cin * cout, device=dev)
         out = torch.empty(B, R, R, cout, dtype=torch.bfloat16, device=dev)

@@ -11,7 +11,7 @@ for (B,H,W,c0,c1,cout) in [(16,256,256,64,0,64),(16,256,256,64,64,64),(16,128,12
     w = torch.randn(cout, c0+c1, 3,3, device="cuda", generator=g)/30
     wf,_ = ops.pack_weights(w)
     out = torch.empty(B,H,W,cout, device="cuda", dtype=torch.bfloat16)
-    st = torch.zeros(2,cout, device="cuda"); bias = torch.zeros(cout, device="cuda")
+    st = ops.new_stats(cout, "cuda"); bias = torch.zeros(cout, device="cuda")
     flops = 2.0*B*H*W*cout*9*(c0+c1)
     _lib.set_option("conv_halo", 1)
     for dbg, name in ((0, "full"), (1, "no MMA"), (2, "no epilogue"), (3, "loads only")):

@@ -21,7 +21,7 @@ SIGNATURES = {
     "ugp_pack_weights": [_p, _i, _i, _p, _p, _p],
     "ugp_unpack_wgrad": [_p, _i, _i, _p, _i, _p],
     "ugp_im2col_first": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
-    "ugp_bn_finalize": [_p, _i, _ll, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    "ugp_bn_finalize": [_p, _i, _i, _ll, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "ugp_bn_eval_coeffs": [_i, _p, _p, _p, _p, _f, _p, _p, _p],
     "ugp_bn_relu_apply": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p],
     "ugp_bn_relu_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
@@ -39,6 +39,7 @@ SIGNATURES = {
     "ugp_ce_weighted_loss": [_p, _p, _p, _f, _i, _i, _f, _p, _p, _p],
     "ugp_global_avg_pool": [_p, _i, _i, _i, _p, _p],
     "ugp_global_avg_pool_bwd": [_p, _i, _i, _i, _p, _p],
+    "ugp_bench_mma": [_i, _i, _i, _i, _i, _i, _p, _p],
     "ugp_rmsprop_step": [_p, _p, _p, _ll, _f, _f, _f, _f, _f, _p],
     "ugp_rmsprop_multi": [_p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _p],
     "ugp_rmsprop_conv_packed": [_p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _p],

@@ -14,7 +14,7 @@ int conv_gemm_bf16(const void*, int, const void*, int, int, int, int, int, const
 int conv_wgrad_bf16(const void*, int, const void*, int, const void*, int, int, int, int, int,
                     float*, cudaStream_t);
 int im2col_first(const float*, int, int, int, int, int, int, void*, cudaStream_t);
-int bn_finalize(float*, int, long long, const float*, const float*, float, float, float*,
+int bn_finalize(float*, int, int, long long, const float*, const float*, float, float, float*,
                 float*, long long*, float*, float*, float*, float*, cudaStream_t);
 int bn_eval_coeffs(int, const float*, const float*, const float*, const float*, float, float*,
                    float*, cudaStream_t);
@@ -47,6 +47,7 @@ int rmsprop_multi(float* const*, const float* const*, float* const*, const long 
                   float, float, float, float, cudaStream_t);
 int global_avg_pool(const void*, int, int, int, float*, cudaStream_t);
 int global_avg_pool_bwd(const float*, int, int, int, void*, cudaStream_t);
+int bench_mma(int, int, int, int, int, int, long long*, cudaStream_t);
 int rmsprop_conv_packed(float* const*, float* const*, float* const*, void* const*, void* const*,
                         const int*, const int*, int, float, float, float, float, float, cudaStream_t);
 }  // namespace ugp
@@ -83,11 +84,11 @@ int ugp_im2col_first(const float* x, int B, int Cin, int Hin, int Win, int H, in
                      void* stream) {
   return ugp::im2col_first(x, B, Cin, Hin, Win, H, W, out, S(stream));
 }
-int ugp_bn_finalize(float* stats, int C, long long count, const float* gamma, const float* beta,
+int ugp_bn_finalize(float* stats, int parts, int C, long long count, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var,
                     long long* nbt, float* scale, float* shift, float* save_mean,
                     float* save_rstd, void* stream) {
-  return ugp::bn_finalize(stats, C, count, gamma, beta, eps, momentum, running_mean, running_var,
+  return ugp::bn_finalize(stats, parts, C, count, gamma, beta, eps, momentum, running_mean, running_var,
                           nbt, scale, shift, save_mean, save_rstd, S(stream));
 }
 int ugp_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* rm,
@@ -179,5 +180,9 @@ int ugp_global_avg_pool(const void* x, int B, int HW, int C, float* out, void* s
 }
 int ugp_global_avg_pool_bwd(const float* dy, int B, int HW, int C, void* dx, void* stream) {
   return ugp::global_avg_pool_bwd(dy, B, HW, C, dx, S(stream));
+}
+int ugp_bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int ctas, long long* out_cycles,
+                  void* stream) {
+  return ugp::bench_mma(n, pair, iters, nacc, a_tiles, ctas, out_cycles, S(stream));
 }
 }  // extern "C"

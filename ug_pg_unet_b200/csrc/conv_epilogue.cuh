@@ -31,12 +31,15 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, float v) {
   asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+constexpr int kStatsScratchBytes = 4 * 32 * 16;
+
 struct EpilogueCtx {
   uint32_t bias_addr;    // smem byte addresses of the per-channel arrays
   uint32_t scale_addr;
   uint32_t shift_addr;
-  uint32_t stats_addr;   // [2][stats_stride] floats
+  uint32_t stats_addr;   // [2][stats_stride] floats: this CTA's running per-channel sum / sum of squares
   uint32_t stats_stride; // in floats
+  uint32_t scratch_addr; // 2 KB: the four row-quarter partials of one chunk (kStatsScratchBytes)
   bool has_bias, has_affine, relu, do_stats;
 };
 
@@ -101,11 +104,29 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint3
       s0a += a0; s1a += a1; q0a = fmaf(a0, a0, q0a); q1a = fmaf(a1, a1, q1a);
       s0b += b0; s1b += b1; q0b = fmaf(b0, b0, q0b); q1b = fmaf(b1, b1, q1b);
     }
-    const int c = n_base + 2 * wcol;
-    red_shared_add(e.stats_addr + c * 4, s0a + s0b);
-    red_shared_add(e.stats_addr + (c + 1) * 4, s1a + s1b);
-    red_shared_add(e.stats_addr + (e.stats_stride + c) * 4, q0a + q0b);
-    red_shared_add(e.stats_addr + (e.stats_stride + c + 1) * 4, q1a + q1b);
+    // Deterministic reduction (no atomics): the four row quarters meet in scratch and are summed in
+    // a fixed order by the first warp, which owns channel pair (c, c+1) of the CTA's running sums.
+    // Run-to-run identical statistics keep the whole bf16 forward bit-reproducible.
+    st_shared_v4(e.scratch_addr + ((et >> 5) * 32 + wcol) * 16, __float_as_uint(s0a + s0b),
+                 __float_as_uint(s1a + s1b), __float_as_uint(q0a + q0b), __float_as_uint(q1a + q1b));
+    named_bar_sync(3, 128);
+    if (et < 32) {
+      const float4 p0 = ld_shared_f4(e.scratch_addr + (0 * 32 + wcol) * 16);
+      const float4 p1 = ld_shared_f4(e.scratch_addr + (1 * 32 + wcol) * 16);
+      const float4 p2 = ld_shared_f4(e.scratch_addr + (2 * 32 + wcol) * 16);
+      const float4 p3 = ld_shared_f4(e.scratch_addr + (3 * 32 + wcol) * 16);
+      const int c = n_base + 2 * wcol;
+      const uint32_t sa = e.stats_addr + c * 4, qa = e.stats_addr + (e.stats_stride + c) * 4;
+      float2 s, q;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(s.x), "=f"(s.y) : "r"(sa) : "memory");
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(q.x), "=f"(q.y) : "r"(qa) : "memory");
+      s.x += ((p0.x + p1.x) + p2.x) + p3.x;
+      s.y += ((p0.y + p1.y) + p2.y) + p3.y;
+      q.x += ((p0.z + p1.z) + p2.z) + p3.z;
+      q.y += ((p0.w + p1.w) + p2.w) + p3.w;
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa), "f"(s.x), "f"(s.y) : "memory");
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(qa), "f"(q.x), "f"(q.y) : "memory");
+    }
   }
 }
 

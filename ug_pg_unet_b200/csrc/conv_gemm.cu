@@ -41,7 +41,7 @@ struct ConvCfg {
   static constexpr int kTmemCols = 2 * kN;  // 128 / 256 / 512: powers of two
   // dynamic smem: stages + staging buffers + stats/bias/scale/shift + barriers
   static constexpr int kSmemBytes = kStages * kG * kBlockBytes + kStagingBufs * kOutChunkBytes +
-                                    5 * kMaxCoutT * 4 + 256 + 1024;
+                                    5 * kMaxCoutT * 4 + kStatsScratchBytes + 256 + 1024;
 };
 
 template <int kN>
@@ -67,7 +67,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   float* sBias = sStats + 2 * kMaxC;
   float* sScale = sBias + kMaxC;
   float* sShift = sScale + kMaxC;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + kMaxC);
+  uint8_t* sScratch = reinterpret_cast<uint8_t*>(sShift + kMaxC);   // kStatsScratchBytes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sScratch + kStatsScratchBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -108,11 +109,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  // lane-0 broadcast: marks the value warp-uniform so the MMA operands stay in uniform registers
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // whole-warp loop, elected lane issues (keeps tensor-map / barrier operands in uniform registers)
+    const bool leader = elect_one() != 0;
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int chunks = p.chunks0 + p.chunks1;
@@ -127,7 +131,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         for (int kb0 = 0; kb0 < k_blocks; kb0 += kG) {
           const int g = (k_blocks - kb0 < kG) ? (k_blocks - kb0) : kG;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], g * Cfg::kBlockBytes);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], g * Cfg::kBlockBytes);
           for (int i = 0; i < g; ++i) {
             const int kb = kb0 + i;
             const int tap = kb / chunks;
@@ -135,13 +139,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
             const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
             uint8_t* a_dst = sA + (stage * kG + i) * kATileBytes;
-            if (c < p.chunks0)
-              tma_load_4d(&tmA0, &full_bar[stage], a_dst, c * kBlockK, x0 + dx, y0 + dy, b);
-            else
-              tma_load_4d(&tmA1, &full_bar[stage], a_dst, (c - p.chunks0) * kBlockK, x0 + dx,
-                          y0 + dy, b);
-            tma_load_2d(&tmW, &full_bar[stage], sB + (stage * kG + i) * Cfg::kBTileBytes,
-                        c * kBlockK, tap * p.cout + n_tile * kN);
+            if (leader) {
+              if (c < p.chunks0)
+                tma_load_4d(&tmA0, &full_bar[stage], a_dst, c * kBlockK, x0 + dx, y0 + dy, b);
+              else
+                tma_load_4d(&tmA1, &full_bar[stage], a_dst, (c - p.chunks0) * kBlockK, x0 + dx,
+                            y0 + dy, b);
+              tma_load_2d(&tmW, &full_bar[stage], sB + (stage * kG + i) * Cfg::kBTileBytes,
+                          c * kBlockK, tap * p.cout + n_tile * kN);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -149,6 +155,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
+    // whole-warp issue loop (uniform-datapath operands), one elected lane executes tcgen05 (conv_halo.cu)
+    const bool leader = elect_one() != 0;
     constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
@@ -163,7 +171,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         const int g = (k_blocks - kb0 < kG) ? (k_blocks - kb0) : kG;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
-        if (lane == 0) {
+        {
           for (int i = 0; i < g; ++i) {
             const uint64_t a_desc =
                 umma_desc_sw128(smem_u32(sA + (stage * kG + i) * kATileBytes), 16, 1024);
@@ -172,12 +180,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               // +32 B per K=16 step inside the 128 B swizzle row
-              umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                        (kb0 + i > 0 || k > 0) ? 1u : 0u);
+              const uint32_t acc = (kb0 + i > 0 || k > 0) ? 1u : 0u;
+              if (leader) umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
             }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb0 + g >= k_blocks) umma_commit(&tfull_bar[as]);
+          if (leader) {
+            umma_commit(&empty_bar[stage]);
+            if (kb0 + g >= k_blocks) umma_commit(&tfull_bar[as]);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -194,6 +204,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     ectx.scale_addr = smem_u32(sScale);
     ectx.shift_addr = smem_u32(sShift);
     ectx.stats_addr = smem_u32(sStats);
+    ectx.scratch_addr = smem_u32(sScratch);
     ectx.stats_stride = kMaxC;
     ectx.has_bias = p.bias != nullptr;
     ectx.has_affine = p.scale != nullptr;
@@ -234,8 +245,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     if (do_stats) {
       named_bar_sync(1, 128);
       for (int i = et; i < p.cout; i += 128) {
-        atomicAdd(p.stats + i, sStats[i]);
-        atomicAdd(p.stats + p.cout + i, sStats[kMaxC + i]);
+        // this CTA's slot of the [SMs][2][C] partial-statistics buffer (bn_finalize sums the slots in order)
+        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 0) * p.cout + i] = sStats[i];
+        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 1) * p.cout + i] = sStats[kMaxC + i];
       }
     }
   }
@@ -316,7 +328,7 @@ int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
               "conv_gemm: unsupported spatial size %dx%d (need W in {16,32,64,128} or a "
               "multiple of 128, and H a multiple of 128/min(W,128))", H, W);
   int kn = 256;
-  while (kn > 64 && (cout % kn != 0 || split_n % kn != 0 || (cout - split_n) % kn != 0)) kn >>= 1;
+  while (kn > 64 && cout % kn != 0) kn >>= 1;   // the epilogue routes each 64-column chunk to dst0 / dst1
 
   UGP_REQUIRE(kn == 256 || cout <= 512, "conv_gemm: cout %d with a %d-wide tile unsupported", cout, kn);
 

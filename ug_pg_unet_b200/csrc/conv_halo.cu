@@ -43,26 +43,33 @@ constexpr int kHaloBytes = (kHaloRows + 2) * kHaloW * 128;  // 66,560 B = 65 * 1
 constexpr int kHaloStages = 2;
 constexpr int kHaloMaxCout = 256;
 
-template <int kN>
+template <int kN, bool kPair = false>
 struct HaloCfg {
   // One mbarrier wait of the single MMA-issuing thread costs ~100+ cycles, so a B slot must carry
   // enough tensor work to hide it: a slot holds kTapsPerSlot weight tiles (one kernel row of taps
   // for N = 64: 3 taps x 2 rows x 4 = 24 MMAs of 32 cycles per wait; N = 128: 8 MMAs of 64 cycles).
   static constexpr int kTapsPerSlot = (kN == 64) ? 3 : 1;
-  static constexpr int kBStages = (kN == 64) ? 2 : 3;
-  static constexpr int kTapBytes = kN * 128;
+  // a pair's weight slots are half the size and their refill crosses SMs (longer round trip): twice the depth
+  static constexpr int kBStages = ((kN == 64) ? 2 : 3) * (kPair ? 2 : 1);
+  static constexpr int kRowsB = kPair ? kN / 2 : kN;      // weight rows (output channels) this CTA stages
+  static constexpr int kTapBytes = kRowsB * 128;
   static constexpr int kBBytes = kTapsPerSlot * kTapBytes;
-  static constexpr int kTmemCols = 2 * kHaloRows * kN;     // 256 / 512
+  static constexpr int kTmemCols = 2 * kHaloRows * kN;     // 256 / 512 (per CTA, also in a pair)
   static constexpr int kSmemBytes = kHaloStages * kHaloBytes + kBStages * kBBytes + 2 * 16384 +
-                                    5 * kHaloMaxCout * 4 + 256 + 1024;
+                                    5 * kHaloMaxCout * 4 + kStatsScratchBytes + 256 + 1024;
 };
 
-template <int kN>
-__global__ void __launch_bounds__(192, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
-                 const __grid_constant__ CUtensorMap tmO1, const ConvHaloParams p) {
-  using Cfg = HaloCfg<kN>;
+// kPair: the kernel is launched as clusters of 2 CTAs (cta_group::2).  CTA `rank` of pair `q` owns
+// m tile 2q + rank (its own halo, accumulators and output rows) and stages rows
+// [rank * kN/2, (rank + 1) * kN/2) of every weight tile; the leader (rank 0) issues one M = 256 MMA
+// per (tap, k, row) that reads A and the two B halves from both CTAs' shared memory.  Per-CTA operand
+// fetch per MMA drops from 4 KB + kN*32 B to 4 KB + kN*16 B.  Barrier protocol as in
+// conv_pair.cu: hfull / bfull / tempty live in the leader, hempty / bempty / tfull in both CTAs.
+template <int kN, bool kPair>
+__device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CUtensorMap& tmA1,
+                                               const CUtensorMap& tmW, const CUtensorMap& tmO0,
+                                               const CUtensorMap& tmO1, const ConvHaloParams& p) {
+  using Cfg = HaloCfg<kN, kPair>;
   constexpr int kBStages = Cfg::kBStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -75,7 +82,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   float* sBias = sStats + 2 * kHaloMaxCout;
   float* sScale = sBias + kHaloMaxCout;
   float* sShift = sScale + kHaloMaxCout;
-  uint64_t* hfull = reinterpret_cast<uint64_t*>(sShift + kHaloMaxCout);
+  uint8_t* sScratch = reinterpret_cast<uint8_t*>(sShift + kHaloMaxCout);   // kStatsScratchBytes
+  uint64_t* hfull = reinterpret_cast<uint64_t*>(sScratch + kStatsScratchBytes);
   uint64_t* hempty = hfull + kHaloStages;
   uint64_t* bfull = hempty + kHaloStages;
   uint64_t* bempty = bfull + kBStages;
@@ -85,7 +93,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  // work items: (m tile, n tile) for single CTAs, (pair of m tiles, n tile) for pairs
+  const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_tiles = (kPair ? p.m_tiles >> 1 : p.m_tiles) * p.n_tiles;
   const int chunks = p.chunks0 + p.chunks1;
 
   if (warp_idx == 0 && lane == 0) {
@@ -96,10 +108,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmO1);
     for (int i = 0; i < kHaloStages; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
     for (int i = 0; i < kBStages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kPair ? 8 : 128); }
     fence_mbar_init();
   }
-  if (warp_idx == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp_idx == 1) {
+    if (kPair) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   if (warp_idx >= 2) {
     const int et = threadIdx.x - 64;
     for (int i = et; i < p.cout; i += 128) {
@@ -112,17 +127,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (kPair) cluster_sync_all();       // the peer's barriers exist, both TMEM halves are allocated
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  // lane-0 broadcast: marks the value warp-uniform so the MMA operands stay in uniform registers
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    const bool leader = elect_one() != 0;     // whole-warp loop, elected lane issues (uniform operands)
+    {
       int hs = 0, bs = 0;
       uint32_t hph = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
-        const int n_tile = tile - m_tile * p.n_tiles;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int m_tile = kPair ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
+        const int n_tile = tile % p.n_tiles;
         const int tx = m_tile % p.tiles_x;
         const int t2 = m_tile / p.tiles_x;
         const int ty = t2 % p.tiles_y;
@@ -130,32 +148,55 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int x0 = tx * 128, y0 = ty * kHaloRows;
         for (int c = 0; c < chunks; ++c) {
           mbar_wait(&hempty[hs], hph ^ 1);
-          mbar_arrive_expect_tx(&hfull[hs], kHaloBytes);
-          if (c < p.chunks0)
-            tma_load_4d(&tmA0, &hfull[hs], sHalo + hs * kHaloBytes, c * 64, x0 - 1, y0 - 1, b);
-          else
-            tma_load_4d(&tmA1, &hfull[hs], sHalo + hs * kHaloBytes, (c - p.chunks0) * 64, x0 - 1,
-                        y0 - 1, b);
+          const CUtensorMap* tmA = (c < p.chunks0) ? &tmA0 : &tmA1;
+          const int cc0 = ((c < p.chunks0) ? c : c - p.chunks0) * 64;
+          if (kPair) {
+            // the leader arms its barrier with the bytes of both CTAs; both CTAs' loads complete on it
+            const uint32_t hbar = mapa_u32(smem_u32(&hfull[hs]), 0);
+            if (leader) {
+              if (rank == 0) mbar_arrive_expect_tx(&hfull[hs], 2 * kHaloBytes);
+              tma_load_4d_pair(tmA, hbar, sHalo + hs * kHaloBytes, cc0, x0 - 1, y0 - 1, b);
+            }
+          } else if (leader) {
+            mbar_arrive_expect_tx(&hfull[hs], kHaloBytes);
+            tma_load_4d(tmA, &hfull[hs], sHalo + hs * kHaloBytes, cc0, x0 - 1, y0 - 1, b);
+          }
           if (++hs == kHaloStages) { hs = 0; hph ^= 1; }
           for (int tap = 0; tap < 9; tap += Cfg::kTapsPerSlot) {
             mbar_wait(&bempty[bs], bph ^ 1);
-            mbar_arrive_expect_tx(&bfull[bs], Cfg::kBBytes);
+            if (kPair) {
+              const uint32_t bar = mapa_u32(smem_u32(&bfull[bs]), 0);
+              if (leader) {
+                if (rank == 0) mbar_arrive_expect_tx(&bfull[bs], 2 * Cfg::kBBytes);
 #pragma unroll
-            for (int t = 0; t < Cfg::kTapsPerSlot; ++t)
-              tma_load_2d(&tmW, &bfull[bs], sB + bs * Cfg::kBBytes + t * Cfg::kTapBytes, c * 64,
-                          (tap + t) * p.cout + n_tile * kN);
+                for (int t = 0; t < Cfg::kTapsPerSlot; ++t)
+                  tma_load_2d_pair(&tmW, bar, sB + bs * Cfg::kBBytes + t * Cfg::kTapBytes, c * 64,
+                                   (tap + t) * p.cout + n_tile * kN + static_cast<int>(rank) * Cfg::kRowsB);
+              }
+            } else if (leader) {
+              mbar_arrive_expect_tx(&bfull[bs], Cfg::kBBytes);
+#pragma unroll
+              for (int t = 0; t < Cfg::kTapsPerSlot; ++t)
+                tma_load_2d(&tmW, &bfull[bs], sB + bs * Cfg::kBBytes + t * Cfg::kTapBytes, c * 64,
+                            (tap + t) * p.cout + n_tile * kN);
+            }
             if (++bs == kBStages) { bs = 0; bph ^= 1; }
           }
         }
       }
     }
   } else if (warp_idx == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(128, kN, 0, 0);
+    // ===================== MMA issuer (the leader CTA of a pair) =====================
+    // The whole warp runs the issue loop so that descriptors, TMEM addresses and barrier addresses are
+    // computed on the uniform datapath; one elected lane executes the tcgen05 instructions.  (Issuing
+    // from inside `if (lane == 0)` made ptxas wrap every MMA in an ELECT / R2UR waterfall: 87 cycles
+    // per instruction instead of max(N/2, 32 + N/4), tools/t_mma.py.)
+    const bool leader = elect_one() != 0;
+    constexpr uint32_t idesc = umma_idesc_bf16(kPair ? 256 : 128, kN, 0, 0);
     int hs = 0, bs = 0;
     uint32_t hph = 0, bph = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; rank == 0 && tile < num_tiles; tile += num_workers, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty[as], aphase ^ 1);
@@ -170,7 +211,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int tap = 0; tap < 9; tap += Cfg::kTapsPerSlot) {
           mbar_wait(&bfull[bs], bph);
           tc_fence_after_sync();
-          if (lane == 0) {
+          {
             const uint32_t slot_addr = smem_u32(sB + bs * Cfg::kBBytes);
 #pragma unroll
             for (int t = 0; t < Cfg::kTapsPerSlot; ++t) {
@@ -182,16 +223,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
                 for (int r = 0; r < kHaloRows; ++r) {
                   const uint64_t a_desc = desc0 + ((halo_addr + ((r + dy) * kHaloW + dx) * 128) >> 4);
-                  if (!(p.debug & 1))
-                    umma_bf16(d_tmem + r * kN, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                              (c > 0 || tap + t > 0 || k > 0) ? 1u : 0u);
+                  const uint32_t acc = (c > 0 || tap + t > 0 || k > 0) ? 1u : 0u;
+                  if (leader && !(p.debug & 1)) {
+                    if (kPair) umma_bf16_pair(d_tmem + r * kN, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+                    else umma_bf16(d_tmem + r * kN, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+                  }
                 }
               }
             }
-            umma_commit(&bempty[bs]);
-            if (tap + Cfg::kTapsPerSlot >= 9) {
-              umma_commit(&hempty[hs]);
-              if (c == chunks - 1) umma_commit(&tfull[as]);
+            const bool last_tap = tap + Cfg::kTapsPerSlot >= 9;
+            if (leader) {
+              if (kPair) {
+                umma_commit_pair(&bempty[bs], 3);
+                if (last_tap) {
+                  umma_commit_pair(&hempty[hs], 3);
+                  if (c == chunks - 1) umma_commit_pair(&tfull[as], 3);
+                }
+              } else {
+                umma_commit(&bempty[bs]);
+                if (last_tap) {
+                  umma_commit(&hempty[hs]);
+                  if (c == chunks - 1) umma_commit(&tfull[as]);
+                }
+              }
             }
           }
           __syncwarp();
@@ -211,16 +265,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     ectx.scale_addr = smem_u32(sScale);
     ectx.shift_addr = smem_u32(sShift);
     ectx.stats_addr = smem_u32(sStats);
+    ectx.scratch_addr = smem_u32(sScratch);
     ectx.stats_stride = kHaloMaxCout;
     ectx.has_bias = p.bias != nullptr;
     ectx.has_affine = p.scale != nullptr;
     ectx.relu = p.relu != 0;
     ectx.do_stats = do_stats;
+    const uint32_t tempty_leader[2] = {kPair ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u,
+                                       kPair ? mapa_u32(smem_u32(&tempty[1]), 0) : 0u};
+    auto release_accumulator = [&](int as) {
+      tc_fence_before_sync();
+      if (kPair) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader[as]);
+      } else {
+        mbar_arrive(&tempty[as]);
+      }
+    };
     uint32_t chunk_counter = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / p.n_tiles;
-      const int n_tile = tile - m_tile * p.n_tiles;
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+      const int m_tile = kPair ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
+      const int n_tile = tile % p.n_tiles;
       const int tx = m_tile % p.tiles_x;
       const int t2 = m_tile / p.tiles_x;
       const int ty = t2 % p.tiles_y;
@@ -230,8 +296,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_wait(&tfull[as], aphase);
       tc_fence_after_sync();
       if (p.debug & 2) {
-        tc_fence_before_sync();
-        mbar_arrive(&tempty[as]);
+        release_accumulator(as);
         continue;
       }
 #pragma unroll 1
@@ -245,10 +310,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           tmem_ld_32x32(taddr, v);
           tmem_ld_32x32(taddr + 32, v + 32);
           tmem_ld_wait();
-          if (r == kHaloRows - 1 && cc == kN / 64 - 1) {
-            tc_fence_before_sync();
-            mbar_arrive(&tempty[as]);
-          }
+          if (r == kHaloRows - 1 && cc == kN / 64 - 1) release_accumulator(as);
           const int n_base = n_tile * kN + cc * 64;
           const uint32_t buf_addr = smem_u32(sOut) + (chunk_counter & 1) * 16384;
           if (n_base < p.split_n)
@@ -262,18 +324,58 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (do_stats) {
       named_bar_sync(1, 128);
       for (int i = et; i < p.cout; i += 128) {
-        atomicAdd(p.stats + i, sStats[i]);
-        atomicAdd(p.stats + p.cout + i, sStats[kHaloMaxCout + i]);
+        // this CTA's slot of the [SMs][2][C] partial-statistics buffer (bn_finalize sums the slots in order)
+        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 0) * p.cout + i] = sStats[i];
+        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 1) * p.cout + i] = sStats[kHaloMaxCout + i];
       }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
+  if (kPair) cluster_sync_all();       // the peer may still read this CTA's smem / signal its barriers
   if (warp_idx == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (kPair) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+template <int kN>
+__global__ void __launch_bounds__(192, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
+                 const __grid_constant__ CUtensorMap tmO1, const ConvHaloParams p) {
+  conv_halo_body<kN, false>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+}
+
+template <int kN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                      const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
+                      const __grid_constant__ CUtensorMap tmO1, const ConvHaloParams p) {
+  conv_halo_body<kN, true>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+}
+
+extern int g_conv_pair_mode;   // conv_pair.cu
+
+template <int kN>
+static int launch_halo_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW,
+                            const CUtensorMap& tmO0, const CUtensorMap& tmO1, const ConvHaloParams& p,
+                            cudaStream_t stream) {
+  using Cfg = HaloCfg<kN, true>;
+  static bool configured = false;
+  if (!configured) {
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_pair_kernel<kN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = (p.m_tiles / 2) * p.n_tiles;
+  const int max_pairs = device_sm_count() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  conv_halo_pair_kernel<kN><<<2 * pairs, 192, Cfg::kSmemBytes, stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
 }
 
 template <int kN>
@@ -298,7 +400,7 @@ static int launch_halo(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const C
 bool conv_halo_eligible(int H, int W, int cout, int split_n, int taps) {
   if (taps != 9 || W % 128 != 0 || H % kHaloRows != 0 || cout > kHaloMaxCout) return false;
   int kn = 128;
-  while (kn > 64 && (cout % kn != 0 || split_n % kn != 0 || (cout - split_n) % kn != 0)) kn >>= 1;
+  while (kn > 64 && cout % kn != 0) kn >>= 1;   // the epilogue routes each 64-column chunk to dst0 / dst1
   return cout % kn == 0;
 }
 
@@ -308,7 +410,7 @@ int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, in
                    cudaStream_t stream) {
   if (dst1 == nullptr) split_n = cout;
   int kn = 128;
-  while (kn > 64 && (cout % kn != 0 || split_n % kn != 0 || (cout - split_n) % kn != 0)) kn >>= 1;
+  while (kn > 64 && cout % kn != 0) kn >>= 1;   // the epilogue routes each 64-column chunk to dst0 / dst1
   ConvHaloParams p;
   p.chunks0 = c0 / 64;
   p.chunks1 = c1 / 64;
@@ -331,13 +433,20 @@ int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, in
   } else {
     tmA1 = tmA0;
   }
-  if ((rc = make_tmap_2d_bf16(&tmW, wpack, 9LL * cout, c0 + c1, 64, kn))) return rc;
+  // pairs pay a cross-SM handshake per tile: worth it from two 64-channel chunks per tile on (measured)
+  const bool pair = (g_conv_pair_mode & 2) != 0 && p.m_tiles % 2 == 0 &&
+                    (p.chunks0 + p.chunks1 >= 2 || (g_conv_pair_mode & 4) != 0);
+  if ((rc = make_tmap_2d_bf16(&tmW, wpack, 9LL * cout, c0 + c1, 64, pair ? kn / 2 : kn))) return rc;
   const long long M = static_cast<long long>(B) * H * W;
   if ((rc = make_tmap_2d_bf16(&tmO0, dst0, M, split_n, 64, 128))) return rc;
   if (split_n < cout) {
     if ((rc = make_tmap_2d_bf16(&tmO1, dst1, M, cout - split_n, 64, 128))) return rc;
   } else {
     tmO1 = tmO0;
+  }
+  if (pair) {
+    if (kn == 128) return launch_halo_pair<128>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
+    return launch_halo_pair<64>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
   }
   if (kn == 128) return launch_halo<128>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
   return launch_halo<64>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);

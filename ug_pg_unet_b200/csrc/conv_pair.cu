@@ -29,81 +29,7 @@ constexpr int kPairStageBytes = kATileBytes + kPairBHalfBytes;       // 32 KB pe
 constexpr int kPairStagingBufs = 2;
 constexpr int kPairTmemCols = 2 * kPairN;                            // 512: two accumulator stages
 constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kPairStagingBufs * kOutChunkBytes +
-                               5 * kMaxCout * 4 + 256 + 1024;
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
-}
-// TMA loads of a CTA pair: data lands in THIS CTA's smem, the bytes complete on the mbarrier at
-// `bar_cluster_addr` (the leader's), which may belong to the peer CTA.
-__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, uint32_t bar_cluster_addr,
-                                                 void* smem, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      :
-      : "r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0),
-        "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t bar_cluster_addr,
-                                                 void* smem, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      :
-      : "r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0),
-        "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                   smem_u32(dst_smem)),
-               "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                               uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n"
-      :
-      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Arrives (once every previously issued MMA of the pair retired) on the mbarrier at this smem
-// offset in every CTA of `cta_mask`.
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
-      "[%0], %1;" ::"r"(smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
+                               5 * kMaxCout * 4 + kStatsScratchBytes + 256 + 1024;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -121,7 +47,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   float* sBias = sStats + 2 * kMaxC;
   float* sScale = sBias + kMaxC;
   float* sShift = sScale + kMaxC;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sShift + kMaxC);
+  uint8_t* sScratch = reinterpret_cast<uint8_t*>(sShift + kMaxC);   // kStatsScratchBytes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sScratch + kStatsScratchBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -167,11 +94,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   cluster_sync_all();                  // the peer's barriers exist and both TMEM halves are allocated
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (uniform registers)
 
   if (warp_idx == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    const bool leader = elect_one() != 0;     // whole-warp loop, elected lane issues (uniform operands)
+    {
       int stage = 0;
       uint32_t phase = 0;
       const int chunks = p.chunks0 + p.chunks1;
@@ -186,19 +114,21 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int x0 = tx * p.BW, y0 = ty * p.BH;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+          if (leader && rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
           const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
           const int tap = kb / chunks;
           const int c = kb - tap * chunks;
           const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
           const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
           uint8_t* a_dst = sA + stage * kATileBytes;
-          if (c < p.chunks0)
-            tma_load_4d_pair(&tmA0, bar, a_dst, c * kBlockK, x0 + dx, y0 + dy, b);
-          else
-            tma_load_4d_pair(&tmA1, bar, a_dst, (c - p.chunks0) * kBlockK, x0 + dx, y0 + dy, b);
-          tma_load_2d_pair(&tmW, bar, sB + stage * kPairBHalfBytes, c * kBlockK,
-                           tap * p.cout + n_tile * kPairN + static_cast<int>(rank) * (kPairN / 2));
+          if (leader) {
+            if (c < p.chunks0)
+              tma_load_4d_pair(&tmA0, bar, a_dst, c * kBlockK, x0 + dx, y0 + dy, b);
+            else
+              tma_load_4d_pair(&tmA1, bar, a_dst, (c - p.chunks0) * kBlockK, x0 + dx, y0 + dy, b);
+            tma_load_2d_pair(&tmW, bar, sB + stage * kPairBHalfBytes, c * kBlockK,
+                             tap * p.cout + n_tile * kPairN + static_cast<int>(rank) * (kPairN / 2));
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -206,6 +136,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
+      // whole-warp issue loop (uniform-datapath operands), one elected lane executes tcgen05 (conv_halo.cu)
+      const bool leader = elect_one() != 0;
       constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, kPairN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -219,14 +151,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          if (lane == 0) {
+          {
             const uint64_t a_desc = umma_desc_sw128(smem_u32(sA + stage * kATileBytes), 16, 1024);
             const uint64_t b_desc = umma_desc_sw128(smem_u32(sB + stage * kPairBHalfBytes), 16, 1024);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit_pair(&empty_bar[stage], 3);
-            if (kb == k_blocks - 1) umma_commit_pair(&tfull_bar[as], 3);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+              if (leader) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+            }
+            if (leader) {
+              umma_commit_pair(&empty_bar[stage], 3);
+              if (kb == k_blocks - 1) umma_commit_pair(&tfull_bar[as], 3);
+            }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -244,6 +180,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     ectx.scale_addr = smem_u32(sScale);
     ectx.shift_addr = smem_u32(sShift);
     ectx.stats_addr = smem_u32(sStats);
+    ectx.scratch_addr = smem_u32(sScratch);
     ectx.stats_stride = kMaxC;
     ectx.has_bias = p.bias != nullptr;
     ectx.has_affine = p.scale != nullptr;
@@ -288,8 +225,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (do_stats) {
       named_bar_sync(1, 128);
       for (int i = et; i < p.cout; i += 128) {
-        atomicAdd(p.stats + i, sStats[i]);
-        atomicAdd(p.stats + p.cout + i, sStats[kMaxC + i]);
+        // this CTA's slot of the [SMs][2][C] partial-statistics buffer (bn_finalize sums the slots in order)
+        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 0) * p.cout + i] = sStats[i];
+        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 1) * p.cout + i] = sStats[kMaxC + i];
       }
     }
   }
@@ -304,11 +242,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 }
 
-int g_conv_pair_mode = 1;   // 0 = never use CTA pairs
+int g_conv_pair_mode = 3;   // bit 0: CTA pairs for the 256-wide generic tiles; bit 1: for the halo kernels
 
 bool conv_pair_eligible(int m_tiles, int cout, int split_n) {
-  return g_conv_pair_mode != 0 && m_tiles % 2 == 0 && cout % kPairN == 0 && split_n % kPairN == 0 &&
-         (cout - split_n) % kPairN == 0 && cout <= kMaxCout;
+  return (g_conv_pair_mode & 1) != 0 && m_tiles % 2 == 0 && cout % kPairN == 0 && split_n % 64 == 0 &&
+         cout <= kMaxCout;
 }
 
 int launch_conv_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW,

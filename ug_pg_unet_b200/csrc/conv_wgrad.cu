@@ -24,6 +24,7 @@
 namespace ugp {
 
 extern int g_conv_debug;
+extern int g_wgrad_waves;   // CTA waves the split-K grid is sized for (default 1)
 
 struct WgradParams {
   int taps;
@@ -105,12 +106,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (uniform registers)
 
   const int chunks = p.chunks0 + p.chunks1;
 
   if (warp_idx == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one() != 0;     // whole-warp loop, elected lane issues (uniform operands)
+    {
       const int hw = p.H * p.W;
       const uint32_t stage_bytes = nt * 2 * kWgBoxBytes + Cfg::kBBytes;
       int stage = 0;
@@ -122,7 +124,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
         const int y0 = rem / p.W;
         const int x0 = rem - y0 * p.W;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
         uint8_t* a_dst = sA + stage * Cfg::kABytes;
         for (int i = 0; i < 2 * nt; ++i) {
           // the boxes of this CTA; an odd box count repeats the last box
@@ -132,20 +134,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
           const int ch = id - tap * chunks;
           const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
           const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-          if (ch < p.chunks0)
-            tma_load_4d(&tmX0, &full_bar[stage], a_dst + i * kWgBoxBytes, ch * 64, x0 + dx, y0 + dy, b);
-          else
-            tma_load_4d(&tmX1, &full_bar[stage], a_dst + i * kWgBoxBytes, (ch - p.chunks0) * 64,
-                        x0 + dx, y0 + dy, b);
+          if (leader) {
+            if (ch < p.chunks0)
+              tma_load_4d(&tmX0, &full_bar[stage], a_dst + i * kWgBoxBytes, ch * 64, x0 + dx, y0 + dy, b);
+            else
+              tma_load_4d(&tmX1, &full_bar[stage], a_dst + i * kWgBoxBytes, (ch - p.chunks0) * 64,
+                          x0 + dx, y0 + dy, b);
+          }
         }
         uint8_t* b_dst = sB + stage * Cfg::kBBytes;
-        for (int j = 0; j < kN / 64; ++j)
-          tma_load_4d(&tmDZ, &full_bar[stage], b_dst + j * kWgBoxBytes,
-                      n_tile * kN + j * 64, x0, y0, b);
+        if (leader) {
+          for (int j = 0; j < kN / 64; ++j)
+            tma_load_4d(&tmDZ, &full_bar[stage], b_dst + j * kWgBoxBytes,
+                        n_tile * kN + j * 64, x0, y0, b);
+        }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp_idx == 1) {
+    // whole-warp issue loop (uniform-datapath operands), one elected lane executes tcgen05 (conv_halo.cu)
+    const bool leader = elect_one() != 0;
     constexpr uint32_t idesc = umma_idesc_bf16(128, kN, 1, 1);
     // MN-major SWIZZLE_128B descriptor template: LBO = one box (next 64 channels), SBO = 1024 B
     const uint64_t desc0 = umma_desc_sw128(0, kWgBoxBytes, 1024);
@@ -154,7 +162,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
     for (int i = 0; i < n_k; ++i) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after_sync();
-      if (lane == 0) {
+      {
         const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
         const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
         for (int t = 0; t < nt; ++t) {
@@ -163,12 +171,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
             // 16 pixels (K) per MMA = 16 rows of 128 B
             const uint64_t a_desc = desc0 + ((a_addr + t * 2 * kWgBoxBytes + k * 2048) >> 4);
             const uint64_t b_desc = desc0 + ((b_addr + k * 2048) >> 4);
-            if (!(p.debug & 1))
-              umma_bf16(tmem_base + t * kN, a_desc, b_desc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+            if (leader && !(p.debug & 1)) umma_bf16(tmem_base + t * kN, a_desc, b_desc, idesc, acc);
           }
         }
-        umma_commit(&empty_bar[stage]);
-        if (i == n_k - 1) umma_commit(done_bar);
+        if (leader) {
+          umma_commit(&empty_bar[stage]);
+          if (i == n_k - 1) umma_commit(done_bar);
+        }
       }
       __syncwarp();
       if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -219,7 +229,10 @@ static int launch_wgrad(const CUtensorMap& tmX0, const CUtensorMap& tmX1,
   }
   p.m_groups = (p.m_tiles + Cfg::kT - 1) / Cfg::kT;
   const int items = p.m_groups * p.n_tiles;
-  int splits = (2 * device_sm_count() + items - 1) / items;
+  // split K (pixels) so that the grid is ONE full wave of CTAs (one CTA per SM: 512 TMEM columns):
+  // more splits only add fp32 reduction traffic and a ragged last wave
+  const int sms = device_sm_count();
+  int splits = g_wgrad_waves * sms / items;
   if (splits < 1) splits = 1;
   // keep at least 8 K chunks (512 pixels) per split
   int max_splits = p.kchunks_total / 8;

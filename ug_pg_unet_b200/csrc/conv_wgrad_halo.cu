@@ -18,6 +18,7 @@
 namespace ugp {
 
 extern int g_conv_debug;
+extern int g_wgrad_waves;
 
 struct WgradHaloParams {
   int chunks0, chunks1;
@@ -85,10 +86,11 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_co
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (uniform registers)
 
   if (warp_idx == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one() != 0;     // whole-warp loop, elected lane issues (uniform operands)
+    {
       const int hw = p.H * p.W;
       int stage = 0;
       uint32_t phase = 0;
@@ -99,17 +101,21 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_co
         const int y0 = rem / p.W;
         const int x0 = rem - y0 * p.W;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], kWhHaloBytes + kWhDzBytes);
-        if (chunk < p.chunks0)
-          tma_load_4d(&tmX0, &full_bar[stage], sX + stage * kWhHaloStride, chunk * 64, x0 - 1, y0 - 1, b);
-        else
-          tma_load_4d(&tmX1, &full_bar[stage], sX + stage * kWhHaloStride, (chunk - p.chunks0) * 64,
-                      x0 - 1, y0 - 1, b);
-        tma_load_4d(&tmDZ, &full_bar[stage], sD + stage * kWhDzBytes, n_tile * 64, x0, y0, b);
+        if (leader) {
+          mbar_arrive_expect_tx(&full_bar[stage], kWhHaloBytes + kWhDzBytes);
+          if (chunk < p.chunks0)
+            tma_load_4d(&tmX0, &full_bar[stage], sX + stage * kWhHaloStride, chunk * 64, x0 - 1, y0 - 1, b);
+          else
+            tma_load_4d(&tmX1, &full_bar[stage], sX + stage * kWhHaloStride, (chunk - p.chunks0) * 64,
+                        x0 - 1, y0 - 1, b);
+          tma_load_4d(&tmDZ, &full_bar[stage], sD + stage * kWhDzBytes, n_tile * 64, x0, y0, b);
+        }
         if (++stage == kWhStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp_idx == 1) {
+    // whole-warp issue loop (uniform-datapath operands), one elected lane executes tcgen05 (conv_halo.cu)
+    const bool leader = elect_one() != 0;
     constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
     // tap pairs per accumulator and the byte distance between the pair (descriptor LBO)
     const int first_tap[5] = {0, 2, 4, 6, 7};
@@ -125,7 +131,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_co
     for (int i = 0; i < n_k; ++i) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after_sync();
-      if (lane == 0) {
+      {
         const uint32_t x_addr = smem_u32(sX + stage * kWhHaloStride);
         const uint32_t d_addr = smem_u32(sD + stage * kWhDzBytes);
 #pragma unroll
@@ -134,12 +140,14 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_co
           for (int k = 0; k < 4; ++k) {
             const uint64_t a_desc = a_tmpl[t] + ((x_addr + k * 2048) >> 4);
             const uint64_t b_desc = b_tmpl + ((d_addr + k * 2048) >> 4);
-            if (!(p.debug & 1))
-              umma_bf16(tmem_base + t * 64, a_desc, b_desc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+            if (leader && !(p.debug & 1)) umma_bf16(tmem_base + t * 64, a_desc, b_desc, idesc, acc);
           }
         }
-        umma_commit(&empty_bar[stage]);
-        if (i == n_k - 1) umma_commit(done_bar);
+        if (leader) {
+          umma_commit(&empty_bar[stage]);
+          if (i == n_k - 1) umma_commit(done_bar);
+        }
       }
       __syncwarp();
       if (++stage == kWhStages) { stage = 0; phase ^= 1; }
@@ -201,7 +209,7 @@ int conv_wgrad_halo_bf16(const void* src0, int c0, const void* src1, int c1, con
   p.dw = dw_packed;
   p.debug = g_conv_debug;
   const int items = (p.chunks0 + p.chunks1) * p.n_tiles;
-  int splits = (2 * device_sm_count() + items - 1) / items;
+  int splits = g_wgrad_waves * device_sm_count() / items;
   int max_splits = p.kchunks_total / 8;
   if (max_splits < 1) max_splits = 1;
   if (splits > max_splits) splits = max_splits;

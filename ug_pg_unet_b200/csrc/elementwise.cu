@@ -12,23 +12,42 @@ namespace ugp {
 
 // ----------------------------------------------------------------------------
 // BatchNorm statistics -> per-channel scale/shift (+ running stats update).
-// stats = [sum[C], sumsq[C]] of the stored conv outputs; zeroed after use.
+// stats = [parts][2][C]: per-CTA partial {sum, sum of squares} of the stored conv outputs, summed here
+// in slot order (deterministic) and zeroed after use.
 // ----------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(float* __restrict__ stats, int C, float count,
-                                   const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float eps,
-                                   float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var,
-                                   long long* __restrict__ num_batches_tracked,
-                                   float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ save_mean,
-                                   float* __restrict__ save_rstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  if (c >= C) return;
-  const float s = stats[c], s2 = stats[C + c];
-  stats[c] = 0.f;
-  stats[C + c] = 0.f;
+// Block = 32 channels x 8 slot groups: group g sums slots g, g+8, ... (independent loads in flight),
+// the eight group sums are then added in a fixed order -> deterministic, ~20 dependent steps.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(float* __restrict__ stats, int parts, int C, float count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                   long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
+                   float* __restrict__ shift, float* __restrict__ save_mean,
+                   float* __restrict__ save_rstd) {
+  __shared__ float red[2][8][33];
+  const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  float s = 0.f, s2 = 0.f;
+  if (c < C) {
+    for (int q = g; q < parts; q += 8) {
+      const float* sl = stats + static_cast<size_t>(q) * 2 * C;
+      s += __ldcg(sl + c);
+      s2 += __ldcg(sl + C + c);
+    }
+    for (int q = g; q < parts; q += 8) {
+      float* sl = stats + static_cast<size_t>(q) * 2 * C;
+      sl[c] = 0.f;
+      sl[C + c] = 0.f;
+    }
+  }
+  red[0][g][cx] = s;
+  red[1][g][cx] = s2;
+  __syncthreads();
+  if (g != 0 || c >= C) return;
+  s = 0.f; s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s += red[0][i][cx]; s2 += red[1][i][cx]; }
   const float mean = s / count;
   float var = s2 / count - mean * mean;
   var = fmaxf(var, 0.f);
@@ -283,14 +302,15 @@ upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int B, int h, int 
 // ----------------------------------------------------------------------------
 
 
-int bn_finalize(float* stats, int C, long long count, const float* gamma,
+int bn_finalize(float* stats, int parts, int C, long long count, const float* gamma,
                 const float* beta, float eps, float momentum, float* running_mean,
                 float* running_var, long long* nbt, float* scale, float* shift,
                 float* save_mean, float* save_rstd, cudaStream_t stream) {
   UGP_REQUIRE(stats && gamma && beta && scale && shift && save_mean && save_rstd,
               "bn_finalize: null pointer");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(
-      stats, C, static_cast<float>(count), gamma, beta, eps, momentum, running_mean,
+  UGP_REQUIRE(parts >= 1, "bn_finalize: parts must be >= 1");
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(
+      stats, parts, C, static_cast<float>(count), gamma, beta, eps, momentum, running_mean,
       running_var, nbt, scale, shift, save_mean, save_rstd);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;

@@ -37,15 +37,15 @@ class PackedWeights:
         self.key = None
         self.wf = None
         self.wd = None
-        self._stats = None   # persistent fp32 [2, C] BN statistics accumulator (bn_finalize re-zeroes it)
+        self._stats = None   # persistent fp32 [SMs, 2, C] per-CTA partial BN statistics (bn_finalize re-zeroes it)
         self._dwp = None     # persistent packed fp32 weight-gradient accumulator (its consumer re-zeroes it)
         self.defer = False
         self.grad_pending = False      # a backward accumulated into _dwp since the last optimiser step
         self.on_grad_ready = None      # data-parallel reducer callback, called after the wgrad launch
 
     def stats_buffer(self, cout: int, device) -> torch.Tensor:
-        if self._stats is None or self._stats.device != device or self._stats.shape[1] != cout:
-            self._stats = torch.zeros((2, cout), dtype=torch.float32, device=device)
+        if self._stats is None or self._stats.device != device or self._stats.shape[2] != cout:
+            self._stats = ops.new_stats(cout, device)
         return self._stats
 
     def dwp_buffer(self, numel: int, device) -> torch.Tensor:

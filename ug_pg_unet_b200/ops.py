@@ -121,6 +121,8 @@ def conv_gemm(src0: torch.Tensor, src1: Optional[torch.Tensor], wpack: torch.Ten
     _req(out0, bf16, "out0")
     if out1 is not None:
         _req(out1, bf16, "out1")
+    if stats is not None and tuple(stats.shape) != (stat_parts(), 2, cout):
+        raise RuntimeError(f"conv_gemm: stats must be a zeroed [{stat_parts()}, 2, {cout}] buffer (ops.new_stats)")
     with _timed("conv_gemm", 2.0 * B * H * W * cout * taps * (c0 + c1)):
         rc = lib().ugp_conv_gemm_bf16(_ptr(src0), c0, _ptr(src1), c1, B, H, W, taps, _ptr(wpack), cout,
                                       _ptr(out0), _ptr(out1), split_n,
@@ -193,10 +195,27 @@ def im2col_first(x: torch.Tensor, H: Optional[int] = None, W: Optional[int] = No
 
 
 # ----------------------------------------------------------------------------- BN / pool / upsample
+_STAT_PARTS = None
+
+
+def stat_parts() -> int:
+    """Slots of a partial-statistics buffer = SM count (one per CTA of a convolution launch)."""
+    global _STAT_PARTS
+    if _STAT_PARTS is None:
+        _STAT_PARTS = int(lib().ugp_device_sm_count())
+    return _STAT_PARTS
+
+
+def new_stats(cout: int, device) -> torch.Tensor:
+    """Zeroed [P][2][cout] buffer for conv_gemm(..., stats=); `stats.sum(0)` gives [sum, sum of squares]."""
+    return torch.zeros((stat_parts(), 2, cout), dtype=torch.float32, device=device)
+
+
 def bn_finalize(stats, count: int, gamma, beta, eps: float, momentum: float, running_mean,
                 running_var, num_batches_tracked, scale, shift, save_mean, save_rstd):
     Cn = gamma.numel()
-    check(lib().ugp_bn_finalize(_ptr(_req(stats, torch.float32, "stats")), Cn, count, _ptr(gamma),
+    assert stats.dim() == 3 and stats.shape[1] == 2 and stats.shape[2] == Cn, stats.shape
+    check(lib().ugp_bn_finalize(_ptr(_req(stats, torch.float32, "stats")), stats.shape[0], Cn, count, _ptr(gamma),
                                 _ptr(beta), eps, momentum, _ptr(running_mean), _ptr(running_var),
                                 _ptr(num_batches_tracked), _ptr(scale), _ptr(shift), _ptr(save_mean),
                                 _ptr(save_rstd), _stream()), "ugp_bn_finalize")
