@@ -132,6 +132,28 @@ def enable_deferred_wgrad(model: nn.Module, enable: bool = True):
     return elig, arena
 
 
+class WgradOverlap:
+    """Optional second stream for the weight-gradient convolutions (set by the trainer around
+    `backward()`): wgrad(l) only feeds the optimiser, so it can run beside the dgrad(l) -> BN-backward(l-1)
+    chain on the main stream (tensor-bound next to HBM-bound work).  Tensors the side stream reads are
+    kept alive in `keep` until the trainer has joined the streams."""
+    stream: Optional[torch.cuda.Stream] = None
+    keep: list = []
+
+    @classmethod
+    def begin(cls, stream):
+        cls.stream, cls.keep = stream, []
+
+    @classmethod
+    def end(cls):
+        """Joins the side stream into the current one and releases the kept tensors."""
+        st = cls.stream
+        cls.stream = None
+        if st is not None:
+            torch.cuda.current_stream().wait_stream(st)
+        cls.keep = []
+
+
 class CBRSaved:
     __slots__ = ("srcs", "z", "coef", "taps", "pooled")
 
@@ -193,14 +215,25 @@ def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch
                          small[:2], small[2])
     kdim = sum(s.shape[3] for s in saved.srcs)
     dwp = packs.dwp_buffer(saved.taps * kdim * cout, dev)
-    ops.conv_wgrad(src0, src1, dz, saved.taps, dwp)
-    if packs.defer:
-        dW = None                      # stays packed in the arena; FusedRMSprop consumes it
-        packs.grad_pending = True
-        if packs.on_grad_ready is not None:
-            packs.on_grad_ready(packs)
+    side = WgradOverlap.stream if packs.defer else None
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream())
+        WgradOverlap.keep.append((src0, src1, dz))
+        with torch.cuda.stream(side):
+            ops.conv_wgrad(src0, src1, dz, saved.taps, dwp)
+            dW = None
+            packs.grad_pending = True
+            if packs.on_grad_ready is not None:
+                packs.on_grad_ready(packs)         # the reducer forks from the stream the wgrad runs on
     else:
-        dW = ops.unpack_wgrad(dwp, cout, cin)
+        ops.conv_wgrad(src0, src1, dz, saved.taps, dwp)
+        if packs.defer:
+            dW = None                      # stays packed in the arena; FusedRMSprop consumes it
+            packs.grad_pending = True
+            if packs.on_grad_ready is not None:
+                packs.on_grad_ready(packs)
+        else:
+            dW = ops.unpack_wgrad(dwp, cout, cin)
     d_srcs = None
     if need_dgrad:
         _, wd = packs.get()

@@ -30,7 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 import torch.optim as optim
 
-from .engine import PackedWeights, conv_packs, enable_deferred_wgrad
+from .engine import PackedWeights, WgradOverlap, conv_packs, enable_deferred_wgrad
 from .optim import FusedRMSprop
 from .parallel import GradBucketReducer, broadcast_module_state
 from .unet import PGUNet1, PGUNet2, PGUNet3, PGUNet4, UncertaintyGuidedLoss, transfer_state
@@ -48,6 +48,10 @@ class UncertaintyGuidedProgressiveTrainer:
         self.bucket_mb = bucket_mb
         self.use_cuda_graph = use_cuda_graph and os.environ.get("UGP_NO_CUDA_GRAPH", "0") != "1"
         self.defer_conv_grads = os.environ.get("UGP_NO_DEFERRED_WGRAD", "0") != "1"
+        # two side streams inside the step: the previous stage's uncertainty forward beside the current
+        # model's forward, and the weight-gradient convolutions beside the dgrad / BN-backward chain
+        self.overlap_streams = os.environ.get("UGP_NO_STREAM_OVERLAP", "0") != "1"
+        self._side_streams = None
         self._graph = None
         self._grad_arena = None
 
@@ -151,12 +155,24 @@ class UncertaintyGuidedProgressiveTrainer:
     def _forward_loss(self, data, target, stage):
         """Forward + fused loss.  Returns (final_loss tensor, logits, metrics device tensor or None,
         base_loss float or None)."""
-        output_current = self.current_model(data)
         uncertainty_map = None
-        if stage > 1:
-            uncertainty_map = self.uncertainty_loss.generate_uncertainty_map(
-                data, self.models[stage - 1], self.stage_configs[stage - 1]["resolution"],
-                self.stage_configs[stage]["resolution"])
+        side = self._streams(data)[0] if (stage > 1 and self.overlap_streams and data.is_cuda) else None
+        if side is not None:
+            # independent of the current model until the loss: runs beside its forward
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                uncertainty_map = self.uncertainty_loss.generate_uncertainty_map(
+                    data, self.models[stage - 1], self.stage_configs[stage - 1]["resolution"],
+                    self.stage_configs[stage]["resolution"])
+            output_current = self.current_model(data)
+            main.wait_stream(side)
+        else:
+            output_current = self.current_model(data)
+            if stage > 1:
+                uncertainty_map = self.uncertainty_loss.generate_uncertainty_map(
+                    data, self.models[stage - 1], self.stage_configs[stage - 1]["resolution"],
+                    self.stage_configs[stage]["resolution"])
         self.uncertainty_loss.last_metrics = None
         ul = self.uncertainty_loss
         if ul.fused_criterion(self.base_criterion, output_current, uncertainty_map):
@@ -207,10 +223,23 @@ class UncertaintyGuidedProgressiveTrainer:
             target = F.interpolate(target, size=(resolution, resolution), mode="nearest")
         return data, target
 
+    def _streams(self, like):
+        if self._side_streams is None:
+            dev = like.device
+            self._side_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        return self._side_streams
+
     def _eager_step(self, data, target, stage):
         self.optimizer.zero_grad(set_to_none=True)
         final_loss, output_current, unc, _ = self._forward_loss(data, target, stage)
-        final_loss.backward()
+        if self.overlap_streams and data.is_cuda and self._grad_arena is not None:
+            WgradOverlap.begin(self._streams(data)[1])
+            try:
+                final_loss.backward()
+            finally:
+                WgradOverlap.end()
+        else:
+            final_loss.backward()
         if self._reducer is not None:
             self._reducer.wait()
         self.optimizer.step()
