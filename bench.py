@@ -237,10 +237,14 @@ def run_ours(args):
     if rank != 0:
         trainer._eager_step(x, y, STAGE)
     if rank == 0:
+        # same kernels as the captured graph, launched one by one on ONE stream (the step's two side
+        # streams are switched off here so that each launch's CUDA events time that kernel alone)
+        trainer.overlap_streams = False
         ops.start_profile()
-        trainer._eager_step(x, y, STAGE)      # same kernels as the captured graph, launched one by one
+        trainer._eager_step(x, y, STAGE)
         torch.cuda.synchronize()
         prof = ops.stop_profile()
+        trainer.overlap_streams = True
     launches = ops.launch_count() * args.steps
     if rank == 0:
         conv = [(f, t_ms) for (name, f, t_ms) in prof if name == "conv_gemm"]
