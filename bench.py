@@ -140,8 +140,11 @@ def run_reference(args):
         "impl": "reference", "metric": "stage-4 256x256 train images/sec", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: PGUNet4(3,1) stage-4 256x256 trainer step, CPU sample batch {batch}",
-                   "stage": 4, "resolution": 256, "batch": batch},
+        "config": {"workload": "configs[1]: PGUNet4(3,1) stage-4 256x256 MoNuSeg-shaped trainer step "
+                               "(train fwd + PGUNet3 uncertainty fwd + fused loss + bwd + RMSprop)",
+                   "stage": 4, "resolution": 256, "batch_per_gpu": args.batch_per_gpu,
+                   "global_batch": args.batch_per_gpu * args.gpus, "parallelism": "cpu",
+                   "cpu_sample_batch": batch, "gflop_per_image": GF_PER_IMG_MODEL + GF_PER_IMG_UNC},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} step(s) of the stage-4 trainer step at batch {batch} "
                                    "(oracle/ug_oracle.py, fp32, torch CPU)"},
