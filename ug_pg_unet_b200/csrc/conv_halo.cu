@@ -29,6 +29,9 @@ struct ConvHaloParams {
   int split_n;
   int relu;
   int debug;                 // what-if timing only: 1 = skip MMA issue, 2 = skip epilogue body
+  int resident;              // 1: all weights of the layer stay in shared memory for the whole kernel
+  int b_region_bytes;        // shared memory reserved for weights (slots, or the resident set)
+  int staging_bufs;          // epilogue staging buffers (2, or 1 when the resident weights need the room)
   const float* bias;
   const float* scale;
   const float* shift;
@@ -36,6 +39,7 @@ struct ConvHaloParams {
 };
 
 extern int g_conv_debug;
+extern int g_conv_halo_resident;
 
 constexpr int kHaloRows = 2;                               // image rows per CTA tile
 constexpr int kHaloW = 130;                                // 128 pixels + 1 halo pixel each side
@@ -55,8 +59,18 @@ struct HaloCfg {
   static constexpr int kTapBytes = kRowsB * 128;
   static constexpr int kBBytes = kTapsPerSlot * kTapBytes;
   static constexpr int kTmemCols = 2 * kHaloRows * kN;     // 256 / 512 (per CTA, also in a pair)
-  static constexpr int kSmemBytes = kHaloStages * kHaloBytes + kBStages * kBBytes + 2 * 16384 +
-                                    5 * kHaloMaxCout * 4 + kStatsScratchBytes + 256 + 1024;
+  static constexpr int kFixedBytes = kHaloStages * kHaloBytes + 5 * kHaloMaxCout * 4 + kStatsScratchBytes + 256 + 1024;
+  static constexpr int kSmemBytes = kFixedBytes + kBStages * kBBytes + 2 * 16384;    // streaming weights
+  static constexpr int kSmemLimit = 232448;                                            // 227 KB per CTA
+  // plans the weight region: resident when the layer has one N tile and everything fits
+  static void plan(ConvHaloParams* p, int chunks) {
+    const int wbytes = chunks * 9 * kTapBytes;
+    p->resident = 0; p->b_region_bytes = kBStages * kBBytes; p->staging_bufs = 2;
+    if (p->n_tiles != 1) return;
+    if (kFixedBytes + wbytes + 2 * 16384 <= kSmemLimit) { p->resident = 1; p->b_region_bytes = wbytes; }
+    else if (kFixedBytes + wbytes + 16384 <= kSmemLimit) { p->resident = 1; p->b_region_bytes = wbytes; p->staging_bufs = 1; }
+  }
+  static int smem_bytes(const ConvHaloParams& p) { return kFixedBytes + p.b_region_bytes + p.staging_bufs * 16384; }
 };
 
 // kPair: the kernel is launched as clusters of 2 CTAs (cta_group::2).  CTA `rank` of pair `q` owns
@@ -77,8 +91,8 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sHalo = smem;
   uint8_t* sB = sHalo + kHaloStages * kHaloBytes;
-  uint8_t* sOut = sB + kBStages * Cfg::kBBytes;
-  float* sStats = reinterpret_cast<float*>(sOut + 2 * 16384);     // [2][kHaloMaxCout]
+  uint8_t* sOut = sB + p.b_region_bytes;
+  float* sStats = reinterpret_cast<float*>(sOut + p.staging_bufs * 16384);     // [2][kHaloMaxCout]
   float* sBias = sStats + 2 * kHaloMaxCout;
   float* sScale = sBias + kHaloMaxCout;
   float* sShift = sScale + kHaloMaxCout;
@@ -89,11 +103,16 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
   uint64_t* bempty = bfull + kBStages;
   uint64_t* tfull = bempty + kBStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* wfull = tempty + 2;          // resident weights landed (leader's barrier in a pair)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  // Resident mode (one N tile, small Cin): the layer's weights are loaded once per CTA and stay in
+  // shared memory; per tile only the halo is fetched.  On the 64 -> 64 layers the weights (74 KB) are
+  // otherwise re-fetched for every 256-pixel tile and are half of the kernel's L2 traffic.
+  const bool resident = p.resident != 0;
   // work items: (m tile, n tile) for single CTAs, (pair of m tiles, n tile) for pairs
   const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int num_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -109,6 +128,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     for (int i = 0; i < kHaloStages; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
     for (int i = 0; i < kBStages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kPair ? 8 : 128); }
+    mbar_init(wfull, 1);
     fence_mbar_init();
   }
   if (warp_idx == 1) {
@@ -138,6 +158,19 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     {
       int hs = 0, bs = 0;
       uint32_t hph = 0, bph = 0;
+      if (resident && worker < num_tiles) {
+        const uint32_t wbytes = static_cast<uint32_t>(chunks) * 9 * Cfg::kTapBytes;
+        const uint32_t wbar = kPair ? mapa_u32(smem_u32(wfull), 0) : 0u;
+        if (leader) {
+          if (!kPair || rank == 0) mbar_arrive_expect_tx(wfull, (kPair ? 2 : 1) * wbytes);
+          for (int c = 0; c < chunks; ++c)
+            for (int tap = 0; tap < 9; ++tap) {
+              uint8_t* dst = sB + (c * 9 + tap) * Cfg::kTapBytes;
+              if (kPair) tma_load_2d_pair(&tmW, wbar, dst, c * 64, tap * p.cout + static_cast<int>(rank) * Cfg::kRowsB);
+              else tma_load_2d(&tmW, wfull, dst, c * 64, tap * p.cout);
+            }
+        }
+      }
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int m_tile = kPair ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
         const int n_tile = tile % p.n_tiles;
@@ -162,7 +195,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
             tma_load_4d(tmA, &hfull[hs], sHalo + hs * kHaloBytes, cc0, x0 - 1, y0 - 1, b);
           }
           if (++hs == kHaloStages) { hs = 0; hph ^= 1; }
-          for (int tap = 0; tap < 9; tap += Cfg::kTapsPerSlot) {
+          for (int tap = 0; !resident && tap < 9; tap += Cfg::kTapsPerSlot) {
             mbar_wait(&bempty[bs], bph ^ 1);
             if (kPair) {
               const uint32_t bar = mapa_u32(smem_u32(&bfull[bs]), 0);
@@ -196,6 +229,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     int hs = 0, bs = 0;
     uint32_t hph = 0, bph = 0;
     int it = 0;
+    if (resident && rank == 0 && worker < num_tiles) mbar_wait(wfull, 0);
     for (int tile = worker; rank == 0 && tile < num_tiles; tile += num_workers, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -209,10 +243,11 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
         // changes the start-address field (absolute-address swizzle, base_offset stays 0)
         const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);
         for (int tap = 0; tap < 9; tap += Cfg::kTapsPerSlot) {
-          mbar_wait(&bfull[bs], bph);
+          if (!resident) mbar_wait(&bfull[bs], bph);
           tc_fence_after_sync();
           {
-            const uint32_t slot_addr = smem_u32(sB + bs * Cfg::kBBytes);
+            const uint32_t slot_addr = resident ? smem_u32(sB + (c * 9 + tap) * Cfg::kTapBytes)
+                                                : smem_u32(sB + bs * Cfg::kBBytes);
 #pragma unroll
             for (int t = 0; t < Cfg::kTapsPerSlot; ++t) {
               const int dy = (tap + t) / 3, dx = (tap + t) % 3;   // halo-relative (+1 folded in)
@@ -234,13 +269,13 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
             const bool last_tap = tap + Cfg::kTapsPerSlot >= 9;
             if (leader) {
               if (kPair) {
-                umma_commit_pair(&bempty[bs], 3);
+                if (!resident) umma_commit_pair(&bempty[bs], 3);
                 if (last_tap) {
                   umma_commit_pair(&hempty[hs], 3);
                   if (c == chunks - 1) umma_commit_pair(&tfull[as], 3);
                 }
               } else {
-                umma_commit(&bempty[bs]);
+                if (!resident) umma_commit(&bempty[bs]);
                 if (last_tap) {
                   umma_commit(&hempty[hs]);
                   if (c == chunks - 1) umma_commit(&tfull[as]);
@@ -249,7 +284,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
             }
           }
           __syncwarp();
-          if (++bs == kBStages) { bs = 0; bph ^= 1; }
+          if (!resident && ++bs == kBStages) { bs = 0; bph ^= 1; }
         }
         if (++hs == kHaloStages) { hs = 0; hph ^= 1; }
       }
@@ -312,11 +347,13 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
           tmem_ld_wait();
           if (r == kHaloRows - 1 && cc == kN / 64 - 1) release_accumulator(as);
           const int n_base = n_tile * kN + cc * 64;
-          const uint32_t buf_addr = smem_u32(sOut) + (chunk_counter & 1) * 16384;
-          if (n_base < p.split_n)
-            epilogue_chunk<2>(ectx, v, n_base, buf_addr, row, et, &tmO0, n_base, out_row0);
+          const CUtensorMap* tmo = (n_base < p.split_n) ? &tmO0 : &tmO1;
+          const int ocol = (n_base < p.split_n) ? n_base : n_base - p.split_n;
+          if (p.staging_bufs == 2)
+            epilogue_chunk<2>(ectx, v, n_base, smem_u32(sOut) + (chunk_counter & 1) * 16384, row, et, tmo, ocol,
+                              out_row0);
           else
-            epilogue_chunk<2>(ectx, v, n_base, buf_addr, row, et, &tmO1, n_base - p.split_n, out_row0);
+            epilogue_chunk<1>(ectx, v, n_base, smem_u32(sOut), row, et, tmo, ocol, out_row0);
         }
       }
     }
@@ -358,40 +395,45 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 }
 
 extern int g_conv_pair_mode;   // conv_pair.cu
+int g_conv_halo_resident = 1;  // 0 = always stream the weights through the slot ring
 
 template <int kN>
 static int launch_halo_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW,
-                            const CUtensorMap& tmO0, const CUtensorMap& tmO1, const ConvHaloParams& p,
+                            const CUtensorMap& tmO0, const CUtensorMap& tmO1, ConvHaloParams p,
                             cudaStream_t stream) {
   using Cfg = HaloCfg<kN, true>;
   static bool configured = false;
   if (!configured) {
     UGP_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_pair_kernel<kN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::kSmemBytes));
+                                        Cfg::kSmemLimit));
     configured = true;
   }
+  Cfg::plan(&p, p.chunks0 + p.chunks1);
+  if (g_conv_halo_resident == 0) { p.resident = 0; p.b_region_bytes = Cfg::kBStages * Cfg::kBBytes; p.staging_bufs = 2; }
   const int tiles = (p.m_tiles / 2) * p.n_tiles;
   const int max_pairs = device_sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  conv_halo_pair_kernel<kN><<<2 * pairs, 192, Cfg::kSmemBytes, stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+  conv_halo_pair_kernel<kN><<<2 * pairs, 192, Cfg::smem_bytes(p), stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
 
 template <int kN>
 static int launch_halo(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW,
-                       const CUtensorMap& tmO0, const CUtensorMap& tmO1, const ConvHaloParams& p,
+                       const CUtensorMap& tmO0, const CUtensorMap& tmO1, ConvHaloParams p,
                        cudaStream_t stream) {
   using Cfg = HaloCfg<kN>;
   static bool configured = false;
   if (!configured) {
     UGP_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<kN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::kSmemBytes));
+                                        Cfg::kSmemLimit));
     configured = true;
   }
+  Cfg::plan(&p, p.chunks0 + p.chunks1);
+  if (g_conv_halo_resident == 0) { p.resident = 0; p.b_region_bytes = Cfg::kBStages * Cfg::kBBytes; p.staging_bufs = 2; }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  conv_halo_kernel<kN><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+  conv_halo_kernel<kN><<<grid, 192, Cfg::smem_bytes(p), stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }

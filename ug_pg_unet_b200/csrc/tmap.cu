@@ -88,6 +88,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, long long rows,
 int g_conv_halo_mode = 1;
 int g_wgrad_halo_mode = 1;
 extern int g_conv_pair_mode;   // conv_pair.cu
+extern int g_conv_halo_resident;   // conv_halo.cu
 int g_wgrad_waves = 1;
 int g_conv_debug = 0;   // what-if timing switches (results are wrong): 1 = skip MMA issue, 2 = skip epilogue body
 
@@ -98,6 +99,10 @@ int set_option(const char* name, int value) {
   }
   if (strcmp(name, "wgrad_halo") == 0) {
     g_wgrad_halo_mode = value;
+    return UGP_OK;
+  }
+  if (strcmp(name, "halo_resident") == 0) {
+    g_conv_halo_resident = value;
     return UGP_OK;
   }
   if (strcmp(name, "conv_pair") == 0) {
