@@ -11,6 +11,7 @@ the SAME oracle with tensors rounded to bf16 where the kernels store bf16
 (`ug_oracle.bf16_storage`).  The CUDA path must be within 1.5x of that floor (+2e-2 slack on
 gradients), i.e. as close to the reference as bf16 storage allows; losses within 1e-3 relative.
 """
+import math
 import os
 import sys
 
@@ -485,3 +486,98 @@ def test_global_avg_pool_kernels(dev):
     dx = ops.global_avg_pool_bwd(dy, 16, 16)
     want = (dy / 256.0).bfloat16()[:, None, None, :].expand(3, 16, 16, 128)
     assert torch.equal(dx, want)
+
+
+# --------------------------------------------------------------------------- BASELINE.json configs as test cases
+def test_config2_full_progressive_pipeline(dev, tmp_path):
+    """configs[2]: stages 1 -> 4 (32 -> 64 -> 128 -> 256) with weight transfer between stages, cross-stage
+    uncertainty weighting, validation and checkpoints — `train_progressive` end to end (1 epoch of 2
+    batches per stage, batch 2)."""
+    import contextlib
+    import io
+    import ug_pg_unet_b200 as U
+
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(2, 3, 256, 256, generator=g), torch.randint(0, 2, (2, 1, 256, 256), generator=g).float())
+               for _ in range(2)]
+
+    class Loader(list):
+        pass
+
+    torch.manual_seed(0)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        tr = U.UncertaintyGuidedProgressiveTrainer(3, 1, device=dev, log_interval=1)
+        for s in tr.stage_configs.values():
+            s["epochs_per_stage"] = 1
+        before = {s: {k: v.clone() for k, v in tr.models[s].state_dict().items()} for s in (1, 2, 3, 4)}
+        tr.train_progressive(Loader(batches), Loader(batches[:1]), max_stages=4, save_dir=str(tmp_path))
+    log = buf.getvalue()
+    assert "Transferring weights from stage 3 to stage 4" in log and "Unc_mean" in log
+    assert len(tr.history["train_loss"]) == 4 and all(math.isfinite(v) for v in tr.history["train_loss"])
+    assert tr.history["stage_transitions"] == [0, 1, 2, 3]
+    assert tr.history["uncertainty_weights_mean"][0] == 0.0 and tr.history["uncertainty_weights_mean"][3] > 0.0
+    for s in (1, 2, 3, 4):       # every stage trained: weights moved, BN counters advanced by its 2 steps
+        sd = tr.models[s].state_dict()
+        assert not torch.equal(sd["up1.conv.conv_op.0.weight"], before[s]["up1.conv.conv_op.0.weight"])
+        # the scalar BN step counter transfers with the weights (same key, same shape), so it accumulates
+        assert int(sd["inc.conv.conv_op.1.num_batches_tracked"]) == 2 * s
+    # checkpoints: reference layout, loadable into a fresh model
+    ck = torch.load(tmp_path / "ug_pgunet_stage4_best.pth", map_location="cpu", weights_only=False)
+    assert {"stage", "epoch", "model_state_dict", "optimizer_state_dict", "val_dice", "history"} <= set(ck)
+    m = U.PGUNet4(3, 1)
+    m.load_state_dict(ck["model_state_dict"], strict=True)
+    assert len(ck["optimizer_state_dict"]["state"]) == len(list(m.parameters()))
+
+
+def test_config3_herlev_stage4_256_seven_classes(dev):
+    """configs[3]: Herlev-shaped 7-class classification, stage 4 at 256x256 with the stage-3 model supplying
+    the entropy weights; two optimiser steps, then validation."""
+    import contextlib
+    import io
+    import ug_pg_unet_b200.herlev as H
+
+    cfg = {"device": dev, "epochs_per_stage": 1, "num_classes": 7, "uncertainty_alpha": 1.0, "log_interval": 0}
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = H.HerlevTrainer(cfg)
+        tr.setup_optimizer_scheduler(4)
+        tr.transfer_weights(3, 4)
+    assert tr.stage_configs[4]["resolution"] == 256
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(4, 3, 256, 256, generator=g)
+    y = torch.randint(0, 7, (4,), generator=g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        loss, base, acc, um, us = tr.train_epoch([(x, y), (x, y)], 4)
+        vl, vb, va, vum, vus = tr.validate_epoch([(x, y)], 4)
+    assert all(math.isfinite(v) for v in (loss, base, vl, vb)) and 0.0 <= acc <= 100.0
+    assert 1.0 <= um <= 2.0 and 1.0 <= vum <= 2.0          # weights 1 + alpha*u with u in [0, 1]
+    m = tr.models[4]
+    assert m.unet.down3.mpconv[1].conv_op[0].weight.grad is not None
+    assert m.unet.down4.mpconv[1].conv_op[0].weight.grad is None and m.unet.up1.conv.conv_op[0].weight.grad is None
+    assert int(m.unet.inc.conv.conv_op[1].num_batches_tracked) == 2
+
+
+def test_config5_batch64_step(dev):
+    """configs[4] per-GPU shape: batch 64 at stage 4, 256x256 — eager warm-ups, graph capture, replays."""
+    import contextlib
+    import io
+    import ug_pg_unet_b200 as U
+
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = U.UncertaintyGuidedProgressiveTrainer(3, 1, device=dev, log_interval=0)
+    tr.current_stage, tr.current_model = 4, tr.models[4]
+    tr.setup_optimizer(4)
+    tr.current_model.train()
+    tr.models[3].eval()
+    g = torch.Generator().manual_seed(64)
+    x = torch.randn(64, 3, 256, 256, generator=g).to(dev)
+    y = (torch.rand(64, 1, 256, 256, generator=g) < 0.2).float().to(dev)      # sparse positives, SURVEY §8d
+    ms = [tr.train_step(x, y, 4)[0] for _ in range(6)]
+    torch.cuda.synchronize()
+    f = [tr._metrics_from_device(m, y.numel(), 64, True) for m in ms]
+    assert all(math.isfinite(v[0]) and math.isfinite(v[1]) for v in f)
+    assert f[-1][0] < f[0][0]                      # the repeated batch is being fitted
+    assert 0.0 < f[-1][4] < 1.0                    # uncertainty mean
+    assert torch.cuda.max_memory_allocated() < 40e9
