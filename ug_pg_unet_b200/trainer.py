@@ -52,6 +52,7 @@ class UncertaintyGuidedProgressiveTrainer:
         # model's forward, and the weight-gradient convolutions beside the dgrad / BN-backward chain
         self.overlap_streams = os.environ.get("UGP_NO_STREAM_OVERLAP", "0") != "1"
         self._side_streams = None
+        self._copy_stream = None
         self._graph = None
         self._grad_arena = None
 
@@ -286,6 +287,44 @@ class UncertaintyGuidedProgressiveTrainer:
         m, logits, unc = g["out"]
         return m.clone(), logits, unc
 
+    def _prefetch(self, dataloader):
+        """Yields device batches with the host -> device copy of batch i+1 issued on a copy stream while
+        step i runs (reference :204-205 copies synchronously inside the step)."""
+        dev = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device
+        if dev.type != "cuda" or not self.overlap_streams:
+            for data, target in dataloader:
+                yield data.to(self.device, non_blocking=True), target.to(self.device, non_blocking=True)
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy = self._copy_stream
+
+        def stage_in(batch):
+            data, target = batch
+            with torch.cuda.stream(copy):
+                d = data.to(dev, non_blocking=True)
+                t = target.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return d, t, ev
+
+        it = iter(dataloader)
+        try:
+            nxt = stage_in(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            d, t, ev = nxt
+            try:
+                nxt = stage_in(next(it))          # overlaps the step that consumes (d, t)
+            except StopIteration:
+                nxt = None
+            main = torch.cuda.current_stream(dev)
+            main.wait_event(ev)
+            d.record_stream(main)
+            t.record_stream(main)
+            yield d, t
+
     def _epoch(self, dataloader, stage, train: bool):
         resolution = self.stage_configs[stage]["resolution"]
         totals = [0.0] * 6
@@ -302,9 +341,7 @@ class UncertaintyGuidedProgressiveTrainer:
             pending.clear()
             return last
 
-        for batch_idx, (data, target) in enumerate(dataloader):
-            data = data.to(self.device, non_blocking=True)
-            target = target.to(self.device, non_blocking=True)
+        for batch_idx, (data, target) in enumerate(self._prefetch(dataloader)):
             data, target = self._resize(data, target, resolution)
             if train:
                 m, out, unc = self.train_step(data, target, stage)
