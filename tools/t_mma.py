@@ -1,4 +1,4 @@
-"""tcgen05.mma cost model: cycles per MMA vs N, accumulator rotation, CTA pairs (ugp_bench_mma)."""
+"""tcgen05.mma cost model: cycles per MMA vs N, A-window alignment, CTA pairs (ugp_bench_mma)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,15 +7,16 @@ from ug_pg_unet_b200 import _lib
 lib = _lib.lib()
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 iters = 2000
-print("   N pair nacc atiles ctas | cycles per MMA (min / max over CTAs) | math floor")
+print("   N pair nacc shift ctas | cycles per MMA (min / max over CTAs) | math floor")
 for ctas in (1, 148):
     for pair in (0, 1):
         for n in (64, 128, 256):
-            for nacc, at in ((1, 1), (2, 2), (4, 4)):
+            for nacc, shift in ((1, 0), (2, 0), (2, 1), (2, 4), (2, 7)):
                 if nacc * n > 512:
                     continue
                 out.zero_()
-                _lib.check(lib.ugp_bench_mma(n, pair, iters, nacc, at, ctas, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "bench")
+                _lib.check(lib.ugp_bench_mma(n, pair, iters, nacc, nacc, shift, ctas, out.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "bench")
                 torch.cuda.synchronize()
                 v = out[out > 0].double() / (iters * 4)
-                print(f"{n:4d} {pair:4d} {nacc:4d} {at:6d} {ctas:4d} | {v.min().item():8.1f} {v.max().item():8.1f}   | {n / 2:5.0f}", flush=True)
+                print(f"{n:4d} {pair:4d} {nacc:4d} {shift:5d} {ctas:4d} | {v.min().item():8.1f} {v.max().item():8.1f}   | {n / 2:5.0f}", flush=True)

@@ -10,6 +10,7 @@ struct MmaBenchParams {
   int iters;    // MMAs issued = iters * 4 (four K = 16 steps of one 64-wide K block)
   int nacc;     // accumulators cycled through (1, 2 or 4; nacc * n <= 512)
   int a_tiles;  // distinct A tiles cycled through (1..4)
+  int a_shift;  // A window start in 128-byte rows past the 1024-byte swizzle-atom boundary (0..7)
   long long* out;   // [gridDim.x] cycles
 };
 
@@ -17,13 +18,13 @@ template <bool kPair>
 __device__ __forceinline__ void mma_bench_body(const MmaBenchParams& p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;                      // 4 x 16 KB
-  uint8_t* sB = smem + 4 * 16384;          // up to 32 KB
+  uint8_t* sA = smem;                      // 4 x 16 KB (+ 1 KB so a shifted window stays inside)
+  uint8_t* sB = smem + 4 * 16384 + 1024;   // up to 32 KB
   uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 32768);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
-  for (int i = threadIdx.x; i < (4 * 16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < (4 * 16384 + 1024 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   if (warp == 0) { if (kPair) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   fence_proxy_async_smem();
@@ -42,7 +43,7 @@ __device__ __forceinline__ void mma_bench_body(const MmaBenchParams& p) {
     {
       t0 = clock64();
       for (int i = 0; i < p.iters; ++i) {
-        const uint64_t a_desc = umma_desc_sw128(smem_u32(sA + (i & (p.a_tiles - 1)) * 16384), 16, 1024);
+        const uint64_t a_desc = umma_desc_sw128(smem_u32(sA + (i & (p.a_tiles - 1)) * 16384 + p.a_shift * 128), 16, 1024);
         const uint64_t b_desc = umma_desc_sw128(smem_u32(sB), 16, 1024);
         const uint32_t d = tmem_base + (i & (p.nacc - 1)) * p.n;
 #pragma unroll
@@ -73,13 +74,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_bench_pa
   mma_bench_body<true>(p);
 }
 
-int bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int ctas, long long* out_cycles,
+int bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int a_shift, int ctas, long long* out_cycles,
               cudaStream_t stream) {
-  UGP_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 512 && a_tiles >= 1 && a_tiles <= 4 &&
+  UGP_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 512 && a_tiles >= 1 && a_tiles <= 4 && a_shift >= 0 && a_shift < 8 &&
                   iters > 0 && ctas > 0 && out_cycles,
               "bench_mma: bad arguments");
-  constexpr int kSmem = 4 * 16384 + 32768 + 1024 + 256;
-  MmaBenchParams p{n, iters, nacc, a_tiles, out_cycles};
+  constexpr int kSmem = 4 * 16384 + 1024 + 32768 + 1024 + 256;
+  MmaBenchParams p{n, iters, nacc, a_tiles, a_shift, out_cycles};
   if (pair) {
     UGP_CHECK_CUDA(cudaFuncSetAttribute(mma_bench_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     mma_bench_pair_kernel<<<2 * ((ctas + 1) / 2), 128, kSmem, stream>>>(p);

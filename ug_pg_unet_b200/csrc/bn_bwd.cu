@@ -287,8 +287,12 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
   const long long M = static_cast<long long>(B) * H * W;
   a.inv_count = 1.f / static_cast<float>(M);
   const int rows_per_block = kBnThreads / (C / 8);
-  UGP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
-  if (dbias) UGP_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, stream));
+  if (dbias == sums + 2 * C) {          // the engine's [3][C] block: one fill instead of two
+    UGP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 3 * C, stream));
+  } else {
+    UGP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
+    if (dbias) UGP_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, stream));
+  }
   // two resident blocks per SM keep ~64 KB of loads in flight per SM; more blocks only add
   // same-address atomic traffic in the final per-channel reduction
   const long long cap = static_cast<long long>(device_sm_count()) * 2;

@@ -47,7 +47,7 @@ int rmsprop_multi(float* const*, const float* const*, float* const*, const long 
                   float, float, float, float, cudaStream_t);
 int global_avg_pool(const void*, int, int, int, float*, cudaStream_t);
 int global_avg_pool_bwd(const float*, int, int, int, void*, cudaStream_t);
-int bench_mma(int, int, int, int, int, int, long long*, cudaStream_t);
+int bench_mma(int, int, int, int, int, int, int, long long*, cudaStream_t);
 int rmsprop_conv_packed(float* const*, float* const*, float* const*, void* const*, void* const*,
                         const int*, const int*, int, float, float, float, float, float, cudaStream_t);
 }  // namespace ugp
@@ -181,8 +181,8 @@ int ugp_global_avg_pool(const void* x, int B, int HW, int C, float* out, void* s
 int ugp_global_avg_pool_bwd(const float* dy, int B, int HW, int C, void* dx, void* stream) {
   return ugp::global_avg_pool_bwd(dy, B, HW, C, dx, S(stream));
 }
-int ugp_bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int ctas, long long* out_cycles,
+int ugp_bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int a_shift, int ctas, long long* out_cycles,
                   void* stream) {
-  return ugp::bench_mma(n, pair, iters, nacc, a_tiles, ctas, out_cycles, S(stream));
+  return ugp::bench_mma(n, pair, iters, nacc, a_tiles, a_shift, ctas, out_cycles, S(stream));
 }
 }  // extern "C"

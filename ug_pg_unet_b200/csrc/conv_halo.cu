@@ -32,6 +32,7 @@ struct ConvHaloParams {
   int resident;              // 1: all weights of the layer stay in shared memory for the whole kernel
   int b_region_bytes;        // shared memory reserved for weights (slots, or the resident set)
   int staging_bufs;          // epilogue staging buffers (2, or 1 when the resident weights need the room)
+  int prefetch;              // L2-prefetch the halo of the tile `prefetch` tiles ahead (0 = off)
   const float* bias;
   const float* scale;
   const float* shift;
@@ -40,6 +41,7 @@ struct ConvHaloParams {
 
 extern int g_conv_debug;
 extern int g_conv_halo_resident;
+extern int g_conv_halo_prefetch;
 
 constexpr int kHaloRows = 2;                               // image rows per CTA tile
 constexpr int kHaloW = 130;                                // 128 pixels + 1 halo pixel each side
@@ -188,11 +190,30 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
             const uint32_t hbar = mapa_u32(smem_u32(&hfull[hs]), 0);
             if (leader) {
               if (rank == 0) mbar_arrive_expect_tx(&hfull[hs], 2 * kHaloBytes);
-              tma_load_4d_pair(tmA, hbar, sHalo + hs * kHaloBytes, cc0, x0 - 1, y0 - 1, b);
+              // one box per halo row: several smaller TMA requests in flight instead of one 66 KB box
+#pragma unroll
+              for (int j = 0; j < kHaloRows + 2; ++j)
+                tma_load_4d_pair(tmA, hbar, sHalo + hs * kHaloBytes + j * (kHaloW * 128), cc0, x0 - 1,
+                                 y0 - 1 + j, b);
             }
           } else if (leader) {
             mbar_arrive_expect_tx(&hfull[hs], kHaloBytes);
-            tma_load_4d(tmA, &hfull[hs], sHalo + hs * kHaloBytes, cc0, x0 - 1, y0 - 1, b);
+#pragma unroll
+            for (int j = 0; j < kHaloRows + 2; ++j)
+              tma_load_4d(tmA, &hfull[hs], sHalo + hs * kHaloBytes + j * (kHaloW * 128), cc0, x0 - 1,
+                          y0 - 1 + j, b);
+          }
+          // the halo of the tile this CTA loads two tiles from now: DRAM -> L2 ahead of time, so that its
+          // TMA load finds it in L2 (a DRAM round trip is longer than one short tile of MMAs)
+          if (leader && p.prefetch) {
+            const int ptile = tile + p.prefetch * num_workers;
+            if (ptile < num_tiles) {
+              const int pm = kPair ? 2 * (ptile / p.n_tiles) + static_cast<int>(rank) : ptile / p.n_tiles;
+              const int ptx = pm % p.tiles_x, pt2 = pm / p.tiles_x;
+              const int px0 = ptx * 128, py0 = (pt2 % p.tiles_y) * kHaloRows, pb = pt2 / p.tiles_y;
+#pragma unroll
+              for (int j = 0; j < kHaloRows + 2; ++j) tma_prefetch_4d(tmA, cc0, px0 - 1, py0 - 1 + j, pb);
+            }
           }
           if (++hs == kHaloStages) { hs = 0; hph ^= 1; }
           for (int tap = 0; !resident && tap < 9; tap += Cfg::kTapsPerSlot) {
@@ -248,20 +269,29 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
           {
             const uint32_t slot_addr = resident ? smem_u32(sB + (c * 9 + tap) * Cfg::kTapBytes)
                                                 : smem_u32(sB + bs * Cfg::kBBytes);
+            // Bases broadcast from lane 0 so that ptxas keeps them (and everything derived from them by
+            // compile-time offsets) in uniform registers: descriptor of the slot's first weight tile, of
+            // the halo pixel (row dy0, column 0) and the accumulator address.
+            const int dy0 = tap / 3, dx0 = tap % 3;     // kTapsPerSlot = 3: dx0 = 0; = 1: t = 0
+            const uint64_t b_base = __shfl_sync(0xffffffffu, desc0 + (slot_addr >> 4), 0);
+            const uint64_t a_base =
+                __shfl_sync(0xffffffffu, desc0 + ((halo_addr + (dy0 * kHaloW + dx0) * 128) >> 4), 0);
+            const uint32_t d_base = __shfl_sync(0xffffffffu, d_tmem, 0);
+            const uint32_t acc0 = __shfl_sync(0xffffffffu, (c > 0 || tap > 0) ? 1u : 0u, 0);
+            if (leader && !(p.debug & 1)) {
 #pragma unroll
-            for (int t = 0; t < Cfg::kTapsPerSlot; ++t) {
-              const int dy = (tap + t) / 3, dx = (tap + t) % 3;   // halo-relative (+1 folded in)
-              const uint64_t b_desc = desc0 + ((slot_addr + t * Cfg::kTapBytes) >> 4);
-              // alternate the two accumulators MMA by MMA (independent TMEM targets back to back)
+              for (int t = 0; t < Cfg::kTapsPerSlot; ++t) {
+                // alternate the two accumulators MMA by MMA (independent TMEM targets back to back)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int r = 0; r < kHaloRows; ++r) {
-                  const uint64_t a_desc = desc0 + ((halo_addr + ((r + dy) * kHaloW + dx) * 128) >> 4);
-                  const uint32_t acc = (c > 0 || tap + t > 0 || k > 0) ? 1u : 0u;
-                  if (leader && !(p.debug & 1)) {
-                    if (kPair) umma_bf16_pair(d_tmem + r * kN, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
-                    else umma_bf16(d_tmem + r * kN, a_desc + 2 * k, b_desc + 2 * k, idesc, acc);
+                  for (int r = 0; r < kHaloRows; ++r) {
+                    // halo-relative window (+1 folded in): +8 descriptor units per pixel, +2 per K step
+                    const uint64_t a_desc = a_base + ((r * kHaloW + t) * 8 + 2 * k);
+                    const uint64_t b_desc = b_base + (t * (Cfg::kTapBytes >> 4) + 2 * k);
+                    const uint32_t acc = (t > 0 || k > 0) ? 1u : acc0;
+                    if (kPair) umma_bf16_pair(d_base + r * kN, a_desc, b_desc, idesc, acc);
+                    else umma_bf16(d_base + r * kN, a_desc, b_desc, idesc, acc);
                   }
                 }
               }
@@ -396,6 +426,7 @@ conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 
 extern int g_conv_pair_mode;   // conv_pair.cu
 int g_conv_halo_resident = 1;  // 0 = always stream the weights through the slot ring
+int g_conv_halo_prefetch = 0;  // tiles of L2 prefetch distance for the halo loads (measured: no gain, off)
 
 template <int kN>
 static int launch_halo_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmW,
@@ -465,13 +496,14 @@ int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, in
   p.split_n = split_n;
   p.relu = relu;
   p.debug = g_conv_debug;
+  p.prefetch = g_conv_halo_prefetch;
   p.bias = bias; p.scale = scale; p.shift = shift; p.stats = stats;
 
   CUtensorMap tmA0, tmA1, tmW, tmO0, tmO1;
   int rc;
-  if ((rc = make_tmap_nhwc_bf16(&tmA0, src0, B, H, W, c0, 64, kHaloW, kHaloRows + 2))) return rc;
+  if ((rc = make_tmap_nhwc_bf16(&tmA0, src0, B, H, W, c0, 64, kHaloW, 1))) return rc;
   if (c1 > 0) {
-    if ((rc = make_tmap_nhwc_bf16(&tmA1, src1, B, H, W, c1, 64, kHaloW, kHaloRows + 2))) return rc;
+    if ((rc = make_tmap_nhwc_bf16(&tmA1, src1, B, H, W, c1, 64, kHaloW, 1))) return rc;
   } else {
     tmA1 = tmA0;
   }

@@ -89,6 +89,7 @@ int g_conv_halo_mode = 1;
 int g_wgrad_halo_mode = 1;
 extern int g_conv_pair_mode;   // conv_pair.cu
 extern int g_conv_halo_resident;   // conv_halo.cu
+extern int g_conv_halo_prefetch;
 int g_wgrad_waves = 1;
 int g_conv_debug = 0;   // what-if timing switches (results are wrong): 1 = skip MMA issue, 2 = skip epilogue body
 
@@ -99,6 +100,10 @@ int set_option(const char* name, int value) {
   }
   if (strcmp(name, "wgrad_halo") == 0) {
     g_wgrad_halo_mode = value;
+    return UGP_OK;
+  }
+  if (strcmp(name, "halo_prefetch") == 0) {
+    g_conv_halo_prefetch = value;
     return UGP_OK;
   }
   if (strcmp(name, "halo_resident") == 0) {

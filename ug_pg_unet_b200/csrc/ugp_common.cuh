@@ -155,6 +155,14 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
         "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// L2 prefetch of a 4-D box (no shared memory, no barrier): pulls a tile that will be loaded a few
+// steps later from DRAM into L2 ahead of time.
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
                                             void* smem, int c0, int c1) {
   asm volatile(

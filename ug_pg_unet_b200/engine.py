@@ -39,6 +39,8 @@ class PackedWeights:
         self.wd = None
         self._stats = None   # persistent fp32 [SMs, 2, C] per-CTA partial BN statistics (bn_finalize re-zeroes it)
         self._dwp = None     # persistent packed fp32 weight-gradient accumulator (its consumer re-zeroes it)
+        self._eval_coef = None   # cached eval-mode BN scale / shift of the BatchNorm behind this conv
+        self._eval_key = None
         self.defer = False
         self.grad_pending = False      # a backward accumulated into _dwp since the last optimiser step
         self.on_grad_ready = None      # data-parallel reducer callback, called after the wgrad launch
@@ -52,6 +54,17 @@ class PackedWeights:
         if self._dwp is None or self._dwp.device != device or self._dwp.numel() != numel:
             self._dwp = torch.zeros((numel,), dtype=torch.float32, device=device)
         return self._dwp
+
+    def eval_coef(self, bn: nn.BatchNorm2d, device) -> torch.Tensor:
+        ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        key = tuple((t.data_ptr(), t._version) for t in ts) + (float(bn.eps), PackedWeights.epoch)
+        if self._eval_coef is None or self._eval_key != key or self._eval_coef.device != device:
+            coef = torch.empty((2, bn.num_features), dtype=torch.float32, device=device) \
+                if self._eval_coef is None or self._eval_coef.device != device else self._eval_coef
+            ops.bn_eval_coeffs(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                               float(bn.eps), coef[0], coef[1])
+            self._eval_coef, self._eval_key = coef, key
+        return self._eval_coef
 
     def assign_dwp(self, buf: Optional[torch.Tensor]) -> None:
         """Use `buf` (a zeroed slice of a flat gradient arena) as the packed-gradient accumulator."""
@@ -183,6 +196,7 @@ def cbr_forward(srcs: Sequence[torch.Tensor], taps: int, conv: nn.Conv2d, bn: nn
         track = bn.track_running_stats and bn.running_mean is not None
         if track and bn.momentum is None:   # cumulative moving average
             momentum = 1.0 / float(int(bn.num_batches_tracked) + 1)
+        packs._eval_key = None      # bn_finalize updates the running statistics behind autograd's back
         ops.bn_finalize(stats, B * H * W, bn.weight.detach(), bn.bias.detach(), float(bn.eps), momentum,
                         bn.running_mean if track else None, bn.running_var if track else None,
                         bn.num_batches_tracked if track else None, coef[0], coef[1], coef[2], coef[3])
@@ -192,10 +206,9 @@ def cbr_forward(srcs: Sequence[torch.Tensor], taps: int, conv: nn.Conv2d, bn: nn
             a, p = ops.bn_relu_apply(z, coef[0], coef[1]), None
         saved = CBRSaved(list(srcs), z, coef, taps, emit_pool) if save else None
         return a, p, saved
-    # eval: BatchNorm folds into the conv epilogue (running statistics)
-    coef = torch.empty((2, cout), dtype=torch.float32, device=dev)
-    ops.bn_eval_coeffs(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, float(bn.eps),
-                       coef[0], coef[1])
+    # eval: BatchNorm folds into the conv epilogue (running statistics); the folded scale / shift are
+    # cached until any of the four BN tensors changes (a frozen previous-stage model never recomputes)
+    coef = packs.eval_coef(bn, dev)
     a = ops.conv_gemm(src0, src1, wf, taps, cout, bias=bias, scale=coef[0], shift=coef[1], relu=True)
     p = ops.maxpool2x2(a) if emit_pool else None
     return a, p, None   # nothing saved: backward through eval-mode BatchNorm is not supported

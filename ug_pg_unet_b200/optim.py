@@ -45,6 +45,7 @@ class FusedRMSprop(torch.optim.RMSprop):
             return
         fresh = {id(pk) for pk in rewritten}
         for pk in self._packs.values():
+            pk._eval_key = None          # BN affine parameters / running statistics moved as well
             if id(pk) in fresh:
                 pk.grad_pending = False
                 pk.mark_fresh()
