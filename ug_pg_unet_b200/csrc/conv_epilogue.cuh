@@ -71,7 +71,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint3
     packed[j / 2] = pack_bf16x2(f0, f1);
     packed[j / 2 + 1] = pack_bf16x2(f2, f3);
   }
-  // the TMA store that last read this staging buffer must be done
+  // the TMA store that last read this staging buffer must be done (folding this wait into the
+  // previous chunk's statistics barrier was measured slower: it puts the store's read latency on
+  // every thread's path instead of hiding it behind the next chunk's TMEM load and conversion)
   if (et == 0) tma_store_wait_read<kStagingBufs - 1>();
   named_bar_sync(1, 128);
   const uint32_t rowp = buf_addr + row * 128;

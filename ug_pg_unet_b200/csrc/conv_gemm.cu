@@ -91,7 +91,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], 4);      // one elected lane per epilogue warp arrives
     }
     fence_mbar_init();
   }
@@ -229,7 +229,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         tmem_ld_wait();
         if (cc == kN / 64 - 1) {
           tc_fence_before_sync();
-          mbar_arrive(&tempty_bar[as]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
         const int n_base = n_tile * kN + cc * 64;
         const uint32_t buf_addr = smem_u32(sOut) + (chunk_counter % Cfg::kStagingBufs) * kOutChunkBytes;

@@ -129,7 +129,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     tma_prefetch_desc(&tmO1);
     for (int i = 0; i < kHaloStages; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
     for (int i = 0; i < kBStages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kPair ? 8 : 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kPair ? 8 : 4); }   // one elected lane per epilogue warp (and CTA)
     mbar_init(wfull, 1);
     fence_mbar_init();
   }
@@ -340,11 +340,10 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
                                        kPair ? mapa_u32(smem_u32(&tempty[1]), 0) : 0u};
     auto release_accumulator = [&](int as) {
       tc_fence_before_sync();
-      if (kPair) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty_leader[as]);
-      } else {
-        mbar_arrive(&tempty[as]);
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(tempty_leader[as]);
+        else mbar_arrive(&tempty[as]);
       }
     };
     uint32_t chunk_counter = 0;

@@ -295,9 +295,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive on the leader's barrier.  Default semantics (release at CTA scope), as CUTLASS's
+// umma_arrive_2x1SM_sm0: the TMEM reads it publishes are ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync; `.release.cluster` would add MEMBAR.ALL.GPU + ERRBAR per arrive
+// (14 % of all warp samples in the first ncu capture of the pair halo kernel).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in THIS CTA's smem, the bytes complete on the mbarrier at
 // `bar_cluster_addr` (the leader's), which may belong to the peer CTA.
