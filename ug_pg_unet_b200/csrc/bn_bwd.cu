@@ -15,6 +15,8 @@
 
 namespace ugp {
 
+int g_bn_pool_vec4 = 0;   // pooled backward: 1 = 4-channel threads at 3 blocks/SM (measured: same speed; the kernel is issue-bound)
+
 struct BnBwdArgs {
   const __nv_bfloat16* z;
   const __nv_bfloat16* dA;   // nullable (full-resolution gradient)
@@ -269,6 +271,138 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_pool_kernel(const B
   }
 }
 
+// ---------------------------------------------------------------------------
+// pooled variant, 4 channels per thread (8-byte loads): half the register footprint of the 8-channel
+// version, so 3 blocks (24 warps) per SM hide the DRAM latency of its load -> compute -> store trips.
+// ---------------------------------------------------------------------------
+constexpr int kPoolBlocksPerSM = 3;
+
+template <bool kApply>
+__global__ void __launch_bounds__(kBnThreads, kPoolBlocksPerSM) bn_relu_bwd_pool4_kernel(const BnBwdArgs a) {
+  const int cg = a.C >> 2;
+  const int Ho = a.H >> 1, Wo = a.W >> 1;
+  const long long windows = static_cast<long long>(a.B) * Ho * Wo;
+  const int my_cg = threadIdx.x % cg;
+  const int c0 = my_cg * 4;
+  const int rows_per_block = kBnThreads / cg;
+  const int my_row = threadIdx.x / cg;
+
+  float sc[4], sh[4], k0[4], kz[4], kc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = __ldg(a.scale + c0 + j);
+    sh[j] = __ldg(a.shift + c0 + j);
+    const float mu = __ldg(a.mean + c0 + j);
+    if (kApply) {
+      const float rs = __ldg(a.rstd + c0 + j);
+      const float gr = __ldg(a.gamma + c0 + j) * rs;
+      const float mg = __ldg(a.sums + a.C + c0 + j) * a.inv_count;
+      const float mgx = __ldg(a.sums + c0 + j) * a.inv_count;
+      k0[j] = gr;
+      kz[j] = -gr * rs * mgx;
+      kc[j] = -gr * mg - mu * kz[j];
+    } else {
+      kz[j] = mu;
+      k0[j] = 0.f;
+      kc[j] = 0.f;
+    }
+  }
+  float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (long long win = static_cast<long long>(blockIdx.x) * rows_per_block + my_row;
+       win < windows; win += static_cast<long long>(gridDim.x) * rows_per_block) {
+    const int xo = static_cast<int>(win % Wo);
+    const long long t2 = win / Wo;
+    const int yo = static_cast<int>(t2 % Ho);
+    const int b = static_cast<int>(t2 / Ho);
+    uint32_t zr[4][2], gr[4][2], pr[2];
+    long long pix[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pix[i] = (static_cast<long long>(b) * a.H + (2 * yo + (i >> 1))) * a.W + 2 * xo + (i & 1);
+      const uint2 zq = *reinterpret_cast<const uint2*>(a.z + pix[i] * a.C + c0);
+      zr[i][0] = zq.x; zr[i][1] = zq.y;
+      if (a.dA) {
+        const uint2 gq = *reinterpret_cast<const uint2*>(a.dA + pix[i] * a.C + c0);
+        gr[i][0] = gq.x; gr[i][1] = gq.y;
+      } else {
+        gr[i][0] = gr[i][1] = 0u;
+      }
+    }
+    {
+      const uint2 pq = *reinterpret_cast<const uint2*>(a.dP + win * a.C + c0);
+      pr[0] = pq.x; pr[1] = pq.y;
+    }
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      float dlo[4], dhi[4];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int j = 2 * w + hh;
+        float zf[4];
+        int arg = 0;
+        float best = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          zf[i] = hh ? bf16_hi(zr[i][w]) : bf16_lo(zr[i][w]);
+          const float av = round_bf16(bn_relu_val(zf[i], sc[j], sh[j]));
+          if (i == 0 || av > best) { best = av; arg = i; }     // first max wins (MaxPool2d)
+        }
+        const float gpv = hh ? bf16_hi(pr[w]) : bf16_lo(pr[w]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float g = hh ? bf16_hi(gr[i][w]) : bf16_lo(gr[i][w]);
+          if (arg == i) g += gpv;
+          g = (fmaf(zf[i], sc[j], sh[j]) > 0.f) ? g : 0.f;
+          if (!kApply) {
+            acc0[j] = fmaf(g, zf[i] - kz[j], acc0[j]);
+            acc1[j] += g;
+          } else {
+            const float d = fmaf(k0[j], g, fmaf(kz[j], zf[i], kc[j]));
+            if (hh) dhi[i] = d; else dlo[i] = d;
+            acc0[j] += d;
+          }
+        }
+      }
+      if (kApply) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gr[i][w] = pack_bf16x2(dlo[i], dhi[i]);
+      }
+    }
+    if (kApply) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint2*>(a.dz + pix[i] * a.C + c0) = make_uint2(gr[i][0], gr[i][1]);
+    }
+  }
+  // block reduction over the windows that share a channel group, one atomic per channel per block
+  __shared__ float red[2][kBnThreads][5];
+  if (!kApply) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc0[j] *= __ldg(a.rstd + c0 + j);
+  } else if (!a.dbias) {
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[0][threadIdx.x][j] = acc0[j]; red[1][threadIdx.x][j] = acc1[j]; }
+  __syncthreads();
+  if (my_row == 0) {
+    for (int r = 1; r < rows_per_block; ++r) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc0[j] += red[0][r * cg + my_cg][j]; acc1[j] += red[1][r * cg + my_cg][j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!kApply) {
+        atomicAdd(a.sums + c0 + j, acc0[j]);
+        atomicAdd(a.sums + a.C + c0 + j, acc1[j]);
+      } else {
+        atomicAdd(a.dbias + c0 + j, acc0[j]);
+      }
+    }
+  }
+}
+
 int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scale,
                 const float* shift, const float* mean, const float* rstd,
                 const float* gamma, int B, int H, int W, int C, float* sums,
@@ -298,12 +432,23 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
   const long long cap = static_cast<long long>(device_sm_count()) * 2;
   if (dP) {
     UGP_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_bwd: pooled gradient needs even H, W");
-    long long blocks = (M / 4 + rows_per_block * 4 - 1) / (rows_per_block * 4);
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    bn_relu_bwd_pool_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
-    UGP_CHECK_CUDA(cudaGetLastError());
-    bn_relu_bwd_pool_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+    if (g_bn_pool_vec4 != 0 && kBnThreads % (C / 4) == 0) {
+      const int rows4 = kBnThreads / (C / 4);
+      long long blocks = (M / 4 + rows4 * 4 - 1) / (rows4 * 4);
+      const long long cap4 = static_cast<long long>(device_sm_count()) * kPoolBlocksPerSM;
+      if (blocks > cap4) blocks = cap4;
+      if (blocks < 1) blocks = 1;
+      bn_relu_bwd_pool4_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      UGP_CHECK_CUDA(cudaGetLastError());
+      bn_relu_bwd_pool4_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+    } else {
+      long long blocks = (M / 4 + rows_per_block * 4 - 1) / (rows_per_block * 4);
+      if (blocks > cap) blocks = cap;
+      if (blocks < 1) blocks = 1;
+      bn_relu_bwd_pool_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      UGP_CHECK_CUDA(cudaGetLastError());
+      bn_relu_bwd_pool_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+    }
   } else {
     // at least two trips of kBnUnroll pixels per thread: small tensors get few blocks, which
     // keeps the per-channel atomic tail short (16 pixels per thread at least)

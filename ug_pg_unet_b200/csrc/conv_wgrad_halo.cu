@@ -5,14 +5,14 @@
 //   dWp[tap][ci][co] += sum_p X[p + shift(tap), ci] * dZ[p, co]
 //
 // A CTA owns one 64-channel input chunk, one 64-wide Cout tile and a range of
-// 64-pixel K chunks (one image row segment each).  Per K chunk ONE TMA box
-// brings the 3 x 66-pixel halo of the segment (25 KB) plus the dZ box (8 KB);
+// 128-pixel K chunks (a 64-pixel segment of TWO image rows each).  Per K chunk ONE TMA box
+// brings the 4 x 66-pixel halo of the segment (33 KB) plus the 2 x 64-pixel dZ box (16 KB);
 // all nine taps are MN-major A operands read out of that halo: a tap is a
 // start-address offset (+128 B per pixel, +66*128 B per row) and the two taps
 // that share a 128-row accumulator are one "leading byte offset" apart, so no
 // data is duplicated in shared memory.  Five accumulators (tap pairs 0/1, 2/3,
-// 4/5, 6/7, 7/8) x 64 columns live in TMEM.  L2 bytes per K chunk: 33 KB instead
-// of 88 KB.
+// 4/5, 6/7, 7/8) x 64 columns live in TMEM.  L2 bytes per 128 pixels: 49 KB instead
+// of 176 KB with per-tap loads (66 KB with one-row chunks).
 #include "ugp_common.cuh"
 
 namespace ugp {
@@ -26,17 +26,18 @@ struct WgradHaloParams {
   int n_tiles;
   int cout;
   int cin_total;
-  int kchunks_total;      // B*H*W / 64
+  int kchunks_total;      // B*H*W / 128
   int kchunks_per_split;
   float* dw;              // [9][cin_total][cout] fp32, accumulated
   int debug;
 };
 
 constexpr int kWhW = 66;                                   // 64 pixels + 1 halo pixel each side
-constexpr int kWhHaloBytes = 3 * kWhW * 128;               // 25,344 B
-constexpr int kWhHaloStride = 26 * 1024;                   // 1024-aligned slot
-constexpr int kWhDzBytes = 64 * 128;                       // 8 KB
-constexpr int kWhStages = 5;
+constexpr int kWhRows = 2;                                 // image rows per K chunk
+constexpr int kWhHaloBytes = (kWhRows + 2) * kWhW * 128;   // 33,792 B
+constexpr int kWhHaloStride = 34 * 1024;                   // 1024-aligned slot
+constexpr int kWhDzBytes = kWhRows * 64 * 128;             // 16 KB
+constexpr int kWhStages = 4;
 constexpr int kWhSmemBytes = kWhStages * (kWhHaloStride + kWhDzBytes) + 256 + 1024;
 
 __device__ __forceinline__ void red_add_v4_h(float* addr, float a, float b, float c, float d) {
@@ -91,15 +92,16 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_co
   if (warp_idx == 0) {
     const bool leader = elect_one() != 0;     // whole-warp loop, elected lane issues (uniform operands)
     {
-      const int hw = p.H * p.W;
+      const int xsegs = p.W / 64, ypairs = p.H / kWhRows;
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = kc_begin; kc < kc_end; ++kc) {
-        const int p0 = kc * 64;
-        const int b = p0 / hw;
-        const int rem = p0 - b * hw;
-        const int y0 = rem / p.W;
-        const int x0 = rem - y0 * p.W;
+        // K chunk -> (image, row pair, 64-pixel segment)
+        const int xs = kc % xsegs;
+        const int t2 = kc / xsegs;
+        const int b = t2 / ypairs;
+        const int y0 = (t2 - b * ypairs) * kWhRows;
+        const int x0 = xs * 64;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) {
           mbar_arrive_expect_tx(&full_bar[stage], kWhHaloBytes + kWhDzBytes);
@@ -137,11 +139,15 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_co
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t a_desc = a_tmpl[t] + ((x_addr + k * 2048) >> 4);
-            const uint64_t b_desc = b_tmpl + ((d_addr + k * 2048) >> 4);
-            const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-            if (leader && !(p.debug & 1)) umma_bf16(tmem_base + t * 64, a_desc, b_desc, idesc, acc);
+          for (int r = 0; r < kWhRows; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // 16 pixels (K) per MMA: halo row r (+66 pixels), 16-pixel group k; dZ row r (+8 KB)
+              const uint64_t a_desc = a_tmpl[t] + ((x_addr + r * (kWhW * 128) + k * 2048) >> 4);
+              const uint64_t b_desc = b_tmpl + ((d_addr + r * 8192 + k * 2048) >> 4);
+              const uint32_t acc = (i > 0 || r > 0 || k > 0) ? 1u : 0u;
+              if (leader && !(p.debug & 1)) umma_bf16(tmem_base + t * 64, a_desc, b_desc, idesc, acc);
+            }
           }
         }
         if (leader) {
@@ -187,7 +193,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_co
 }
 
 bool conv_wgrad_halo_eligible(int H, int W, int cout, int taps) {
-  return taps == 9 && W % 64 == 0 && cout % 64 == 0 && cout <= 128 && H >= 1;
+  return taps == 9 && W % 64 == 0 && H % kWhRows == 0 && cout % 64 == 0 && cout <= 128;
 }
 
 int conv_wgrad_halo_bf16(const void* src0, int c0, const void* src1, int c1, const void* dz, int cout,
@@ -205,12 +211,12 @@ int conv_wgrad_halo_bf16(const void* src0, int c0, const void* src1, int c1, con
   p.n_tiles = cout / 64;
   p.cout = cout;
   p.cin_total = c0 + c1;
-  p.kchunks_total = static_cast<int>((static_cast<long long>(B) * H * W) / 64);
+  p.kchunks_total = static_cast<int>((static_cast<long long>(B) * H * W) / (64 * kWhRows));
   p.dw = dw_packed;
   p.debug = g_conv_debug;
   const int items = (p.chunks0 + p.chunks1) * p.n_tiles;
   int splits = g_wgrad_waves * device_sm_count() / items;
-  int max_splits = p.kchunks_total / 8;
+  int max_splits = p.kchunks_total / 4;
   if (max_splits < 1) max_splits = 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -219,13 +225,13 @@ int conv_wgrad_halo_bf16(const void* src0, int c0, const void* src1, int c1, con
 
   CUtensorMap tmX0, tmX1, tmDZ;
   int rc;
-  if ((rc = make_tmap_nhwc_bf16(&tmX0, src0, B, H, W, c0, 64, kWhW, 3))) return rc;
+  if ((rc = make_tmap_nhwc_bf16(&tmX0, src0, B, H, W, c0, 64, kWhW, kWhRows + 2))) return rc;
   if (c1 > 0) {
-    if ((rc = make_tmap_nhwc_bf16(&tmX1, src1, B, H, W, c1, 64, kWhW, 3))) return rc;
+    if ((rc = make_tmap_nhwc_bf16(&tmX1, src1, B, H, W, c1, 64, kWhW, kWhRows + 2))) return rc;
   } else {
     tmX1 = tmX0;
   }
-  if ((rc = make_tmap_nhwc_bf16(&tmDZ, dz, B, H, W, cout, 64, 64, 1))) return rc;
+  if ((rc = make_tmap_nhwc_bf16(&tmDZ, dz, B, H, W, cout, 64, 64, kWhRows))) return rc;
   dim3 grid(items, splits);
   conv_wgrad_halo_kernel<<<grid, 192, kWhSmemBytes, stream>>>(tmX0, tmX1, tmDZ, p);
   UGP_CHECK_CUDA(cudaGetLastError());

@@ -90,6 +90,7 @@ int g_wgrad_halo_mode = 1;
 extern int g_conv_pair_mode;   // conv_pair.cu
 extern int g_conv_halo_resident;   // conv_halo.cu
 extern int g_conv_halo_prefetch;
+extern int g_bn_pool_vec4;         // bn_bwd.cu
 int g_wgrad_waves = 1;
 int g_conv_debug = 0;   // what-if timing switches (results are wrong): 1 = skip MMA issue, 2 = skip epilogue body
 
@@ -100,6 +101,10 @@ int set_option(const char* name, int value) {
   }
   if (strcmp(name, "wgrad_halo") == 0) {
     g_wgrad_halo_mode = value;
+    return UGP_OK;
+  }
+  if (strcmp(name, "bn_pool_vec4") == 0) {
+    g_bn_pool_vec4 = value;
     return UGP_OK;
   }
   if (strcmp(name, "halo_prefetch") == 0) {
