@@ -11,7 +11,7 @@ print("   N pair nacc shift ctas | cycles per MMA (min / max over CTAs) | math f
 for ctas in (1, 148):
     for pair in (0, 1):
         for n in (64, 128, 256):
-            for nacc, shift in ((1, 0), (2, 0), (2, 1), (2, 4), (2, 7)):
+            for nacc, shift in ((1, 0), (2, 0), (2, 1), (2, 7), (2, 8), (2, 9)):
                 if nacc * n > 512:
                     continue
                 out.zero_()

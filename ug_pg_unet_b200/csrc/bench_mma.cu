@@ -10,6 +10,7 @@ struct MmaBenchParams {
   int iters;    // MMAs issued = iters * 4 (four K = 16 steps of one 64-wide K block)
   int nacc;     // accumulators cycled through (1, 2 or 4; nacc * n <= 512)
   int a_tiles;  // distinct A tiles cycled through (1..4)
+  int gap;      // issue gap (in ~100-cycle units) inserted every 24 MMAs
   int a_shift;  // A window start in 128-byte rows past the 1024-byte swizzle-atom boundary (0..7)
   long long* out;   // [gridDim.x] cycles
 };
@@ -37,20 +38,28 @@ __device__ __forceinline__ void mma_bench_body(const MmaBenchParams& p) {
   if (warp == 0 && rank == 0) {
     const uint32_t idesc = umma_idesc_bf16(kPair ? 256 : 128, p.n, 0, 0);
     long long t0 = 0, t1 = 0;
+    uint32_t gapv = threadIdx.x;
     // the whole warp runs the issue loop (uniform control flow -> descriptors live in uniform
     // registers); one elected lane executes the tcgen05 instructions
     const bool leader = elect_one() != 0;
     {
       t0 = clock64();
       for (int i = 0; i < p.iters; ++i) {
-        const uint64_t a_desc = umma_desc_sw128(smem_u32(sA + (i & (p.a_tiles - 1)) * 16384 + p.a_shift * 128), 16, 1024);
+        // nacc >= 8 encodes an issue gap: every 6 iterations (24 MMAs) the warp burns ~(nacc / 8) * 100
+        // cycles of dependent shuffles before it issues again (is the gap hidden by queued MMAs?)
+        if (p.gap > 0 && i % 6 == 0) {
+          for (int gI = 0; gI < p.gap * 4; ++gI) gapv = __shfl_sync(0xffffffffu, gapv * 3 + 1, (gapv >> 3) & 31);
+        }
+        const uint64_t a_desc = umma_desc_sw128(smem_u32(sA + (i & (p.a_tiles - 1)) * 16384 + (p.a_shift & 7) * 128), 16, 1024);
         const uint64_t b_desc = umma_desc_sw128(smem_u32(sB), 16, 1024);
         const uint32_t d = tmem_base + (i & (p.nacc - 1)) * p.n;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+          // a_shift >= 8: switch the accumulator on EVERY MMA (k parity) instead of every 4 MMAs
+          const uint32_t dk = (p.a_shift >= 8) ? tmem_base + (k & 1) * p.n : d;
           if (leader) {
-            if (kPair) umma_bf16_pair(d, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
-            else umma_bf16(d, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
+            if (kPair) umma_bf16_pair(dk, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
+            else umma_bf16(dk, a_desc + 2 * k, b_desc + 2 * k, idesc, 1u);
           }
         }
       }
@@ -60,7 +69,7 @@ __device__ __forceinline__ void mma_bench_body(const MmaBenchParams& p) {
     mbar_wait(bar, 0);
     if (lane == 0) {
       t1 = clock64();
-      p.out[blockIdx.x] = t1 - t0;
+      p.out[blockIdx.x] = t1 - t0 + (gapv == 0x7fffffffu ? 1 : 0);
     }
   }
   tc_fence_before_sync();
@@ -76,11 +85,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_bench_pa
 
 int bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int a_shift, int ctas, long long* out_cycles,
               cudaStream_t stream) {
-  UGP_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 512 && a_tiles >= 1 && a_tiles <= 4 && a_shift >= 0 && a_shift < 8 &&
+  UGP_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && nacc >= 1 && nacc * n <= 512 && a_tiles >= 1 && a_tiles <= 4 && a_shift >= 0 && a_shift < 4096 &&
                   iters > 0 && ctas > 0 && out_cycles,
               "bench_mma: bad arguments");
   constexpr int kSmem = 4 * 16384 + 1024 + 32768 + 1024 + 256;
-  MmaBenchParams p{n, iters, nacc, a_tiles, a_shift, out_cycles};
+  MmaBenchParams p{n, iters, nacc, a_tiles, a_shift >> 4, a_shift & 15, out_cycles};
   if (pair) {
     UGP_CHECK_CUDA(cudaFuncSetAttribute(mma_bench_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     mma_bench_pair_kernel<<<2 * ((ctas + 1) / 2), 128, kSmem, stream>>>(p);

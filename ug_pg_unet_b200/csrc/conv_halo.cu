@@ -13,8 +13,8 @@
 //   * the weight tile of a (chunk, tap) is shared by both accumulators.
 // L2 -> SM bytes per MAC drop ~3x versus the per-tap TMA loads of conv_gemm.cu.
 //
-// Warp roles as in conv_gemm.cu: warp 0 TMA producer, warp 1 MMA issuer / TMEM
-// owner, warps 2..5 epilogue.
+// Warp roles (224 threads): warp 0 TMA producer, warps 1 and 6 MMA issuers (one accumulator row
+// each; warp 1 owns TMEM), warps 2..5 epilogue.
 #include "ugp_common.cuh"
 #include "conv_epilogue.cuh"
 
@@ -60,7 +60,10 @@ struct HaloCfg {
   static constexpr int kRowsB = kPair ? kN / 2 : kN;      // weight rows (output channels) this CTA stages
   static constexpr int kTapBytes = kRowsB * 128;
   static constexpr int kBBytes = kTapsPerSlot * kTapBytes;
-  static constexpr int kTmemCols = 2 * kHaloRows * kN;     // 256 / 512 (per CTA, also in a pair)
+  // accumulator stages: all 512 TMEM columns (4 stages at N = 64, 2 at N = 128) so that the MMA warp can run
+  // several short tiles ahead of the epilogue
+  static constexpr int kAccStages = 512 / (kHaloRows * kN);
+  static constexpr int kTmemCols = kAccStages * kHaloRows * kN;     // 512 (per CTA, also in a pair)
   static constexpr int kFixedBytes = kHaloStages * kHaloBytes + 5 * kHaloMaxCout * 4 + kStatsScratchBytes + 256 + 1024;
   static constexpr int kSmemBytes = kFixedBytes + kBStages * kBBytes + 2 * 16384;    // streaming weights
   static constexpr int kSmemLimit = 232448;                                            // 227 KB per CTA
@@ -104,8 +107,8 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
   uint64_t* bfull = hempty + kHaloStages;
   uint64_t* bempty = bfull + kBStages;
   uint64_t* tfull = bempty + kBStages;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* wfull = tempty + 2;          // resident weights landed (leader's barrier in a pair)
+  uint64_t* tempty = tfull + Cfg::kAccStages;
+  uint64_t* wfull = tempty + Cfg::kAccStages;          // resident weights landed (leader's barrier in a pair)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp_idx = threadIdx.x >> 5;
@@ -127,9 +130,10 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmO0);
     tma_prefetch_desc(&tmO1);
-    for (int i = 0; i < kHaloStages; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
-    for (int i = 0; i < kBStages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kPair ? 8 : 4); }   // one elected lane per epilogue warp (and CTA)
+    // consumer-side barriers take one tcgen05.commit from EACH of the two MMA-issuing warps
+    for (int i = 0; i < kHaloStages; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], kHaloRows); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], kHaloRows); }
+    for (int i = 0; i < Cfg::kAccStages; ++i) { mbar_init(&tfull[i], kHaloRows); mbar_init(&tempty[i], kPair ? 8 : 4); }   // one elected lane per epilogue warp (and CTA)
     mbar_init(wfull, 1);
     fence_mbar_init();
   }
@@ -137,7 +141,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     if (kPair) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
     else tmem_alloc(tmem_slot, Cfg::kTmemCols);
   }
-  if (warp_idx >= 2) {
+  if (warp_idx >= 2 && warp_idx < 6) {
     const int et = threadIdx.x - 64;
     for (int i = et; i < p.cout; i += 128) {
       sStats[i] = 0.f;
@@ -197,11 +201,15 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
                                  y0 - 1 + j, b);
             }
           } else if (leader) {
-            mbar_arrive_expect_tx(&hfull[hs], kHaloBytes);
+            if (p.debug & 4) {            // what-if: no activation loads (stale smem), barrier only
+              mbar_arrive(&hfull[hs]);
+            } else {
+              mbar_arrive_expect_tx(&hfull[hs], kHaloBytes);
 #pragma unroll
-            for (int j = 0; j < kHaloRows + 2; ++j)
-              tma_load_4d(tmA, &hfull[hs], sHalo + hs * kHaloBytes + j * (kHaloW * 128), cc0, x0 - 1,
-                          y0 - 1 + j, b);
+              for (int j = 0; j < kHaloRows + 2; ++j)
+                tma_load_4d(tmA, &hfull[hs], sHalo + hs * kHaloBytes + j * (kHaloW * 128), cc0, x0 - 1,
+                            y0 - 1 + j, b);
+            }
           }
           // the halo of the tile this CTA loads two tiles from now: DRAM -> L2 ahead of time, so that its
           // TMA load finds it in L2 (a DRAM round trip is longer than one short tile of MMAs)
@@ -239,8 +247,21 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
         }
       }
     }
-  } else if (warp_idx == 1) {
-    // ===================== MMA issuer (the leader CTA of a pair) =====================
+  } else if (warp_idx == 1 || warp_idx == 6) {
+    // ===================== MMA issuers (the leader CTA of a pair) =====================
+    // TWO issuing warps, one per accumulator row: the tensor pipe queues only ~2 MMAs, so with N = 64
+    // (48 cycles per MMA) every barrier wait / descriptor setup of a single issuer is dead time
+    // (tools/t_mma_gap.py: a gap between groups of 24 MMAs adds 1:1 to the group time).  The rows use
+    // different accumulators, so the two streams need no ordering; each warp commits for itself.
+    const int my_r = (warp_idx == 1) ? 0 : 1;
+    // descriptor template: start address 0, SBO 1024, SWIZZLE_128B; a shifted A window only changes the
+    // start-address field (absolute-address swizzle, base_offset stays 0).  All bases are computed ONCE,
+    // broadcast from lane 0 (-> uniform registers) and combined with uniform integer offsets in the
+    // loops: no shuffle / R2UR sits between the MMAs of a tile.
+    const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);
+    const uint64_t a_stage0 = __shfl_sync(0xffffffffu, desc0 + ((smem_u32(sHalo) + my_r * (kHaloW * 128)) >> 4), 0);
+    const uint64_t b_region0 = __shfl_sync(0xffffffffu, desc0 + (smem_u32(sB) >> 4), 0);
+    const uint32_t d_row0 = __shfl_sync(0xffffffffu, tmem_base + my_r * kN, 0);
     // The whole warp runs the issue loop so that descriptors, TMEM addresses and barrier addresses are
     // computed on the uniform datapath; one elected lane executes the tcgen05 instructions.  (Issuing
     // from inside `if (lane == 0)` made ptxas wrap every MMA in an ELECT / R2UR waterfall: 87 cycles
@@ -252,47 +273,34 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     int it = 0;
     if (resident && rank == 0 && worker < num_tiles) mbar_wait(wfull, 0);
     for (int tile = worker; rank == 0 && tile < num_tiles; tile += num_workers, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % Cfg::kAccStages;
+      const uint32_t aphase = (it / Cfg::kAccStages) & 1;
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + as * (kHaloRows * kN);
       for (int c = 0; c < chunks; ++c) {
         mbar_wait(&hfull[hs], hph);
-        const uint32_t halo_addr = smem_u32(sHalo + hs * kHaloBytes);
-        // descriptor template: start address 0, SBO 1024, SWIZZLE_128B; the shifted A window only
-        // changes the start-address field (absolute-address swizzle, base_offset stays 0)
-        const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);
         for (int tap = 0; tap < 9; tap += Cfg::kTapsPerSlot) {
           if (!resident) mbar_wait(&bfull[bs], bph);
           tc_fence_after_sync();
           {
-            const uint32_t slot_addr = resident ? smem_u32(sB + (c * 9 + tap) * Cfg::kTapBytes)
-                                                : smem_u32(sB + bs * Cfg::kBBytes);
-            // Bases broadcast from lane 0 so that ptxas keeps them (and everything derived from them by
-            // compile-time offsets) in uniform registers: descriptor of the slot's first weight tile, of
-            // the halo pixel (row dy0, column 0) and the accumulator address.
             const int dy0 = tap / 3, dx0 = tap % 3;     // kTapsPerSlot = 3: dx0 = 0; = 1: t = 0
-            const uint64_t b_base = __shfl_sync(0xffffffffu, desc0 + (slot_addr >> 4), 0);
+            const uint64_t b_base =
+                b_region0 + static_cast<uint32_t>((resident ? (c * 9 + tap) * Cfg::kTapBytes : bs * Cfg::kBBytes) >> 4);
             const uint64_t a_base =
-                __shfl_sync(0xffffffffu, desc0 + ((halo_addr + (dy0 * kHaloW + dx0) * 128) >> 4), 0);
-            const uint32_t d_base = __shfl_sync(0xffffffffu, d_tmem, 0);
-            const uint32_t acc0 = __shfl_sync(0xffffffffu, (c > 0 || tap > 0) ? 1u : 0u, 0);
+                a_stage0 + static_cast<uint32_t>((hs * kHaloBytes + (dy0 * kHaloW + dx0) * 128) >> 4);
+            const uint32_t d_base = d_row0 + as * (kHaloRows * kN);
+            const uint32_t acc0 = (c > 0 || tap > 0) ? 1u : 0u;
             if (leader && !(p.debug & 1)) {
 #pragma unroll
               for (int t = 0; t < Cfg::kTapsPerSlot; ++t) {
-                // alternate the two accumulators MMA by MMA (independent TMEM targets back to back)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                  for (int r = 0; r < kHaloRows; ++r) {
-                    // halo-relative window (+1 folded in): +8 descriptor units per pixel, +2 per K step
-                    const uint64_t a_desc = a_base + ((r * kHaloW + t) * 8 + 2 * k);
-                    const uint64_t b_desc = b_base + (t * (Cfg::kTapBytes >> 4) + 2 * k);
-                    const uint32_t acc = (t > 0 || k > 0) ? 1u : acc0;
-                    if (kPair) umma_bf16_pair(d_base + r * kN, a_desc, b_desc, idesc, acc);
-                    else umma_bf16(d_base + r * kN, a_desc, b_desc, idesc, acc);
-                  }
+                  // halo-relative window (+1 folded in): +8 descriptor units per pixel, +2 per K step
+                  const uint64_t a_desc = a_base + (t * 8 + 2 * k);
+                  const uint64_t b_desc = b_base + (t * (Cfg::kTapBytes >> 4) + 2 * k);
+                  const uint32_t acc = (t > 0 || k > 0) ? 1u : acc0;
+                  if (kPair) umma_bf16_pair(d_base, a_desc, b_desc, idesc, acc);
+                  else umma_bf16(d_base, a_desc, b_desc, idesc, acc);
                 }
               }
             }
@@ -336,13 +344,12 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     ectx.has_affine = p.scale != nullptr;
     ectx.relu = p.relu != 0;
     ectx.do_stats = do_stats;
-    const uint32_t tempty_leader[2] = {kPair ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u,
-                                       kPair ? mapa_u32(smem_u32(&tempty[1]), 0) : 0u};
+    const uint32_t tempty_leader0 = kPair ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
     auto release_accumulator = [&](int as) {
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
-        if (kPair) mbar_arrive_cluster(tempty_leader[as]);
+        if (kPair) mbar_arrive_cluster(tempty_leader0 + as * 8);
         else mbar_arrive(&tempty[as]);
       }
     };
@@ -355,8 +362,8 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
       const int t2 = m_tile / p.tiles_x;
       const int ty = t2 % p.tiles_y;
       const int b = t2 / p.tiles_y;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % Cfg::kAccStages;
+      const uint32_t aphase = (it / Cfg::kAccStages) & 1;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after_sync();
       if (p.debug & 2) {
@@ -408,7 +415,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
 }
 
 template <int kN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(224, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
                  const __grid_constant__ CUtensorMap tmO1, const ConvHaloParams p) {
@@ -416,7 +423,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 }
 
 template <int kN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
 conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO0,
                       const __grid_constant__ CUtensorMap tmO1, const ConvHaloParams p) {
@@ -443,7 +450,7 @@ static int launch_halo_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, co
   const int tiles = (p.m_tiles / 2) * p.n_tiles;
   const int max_pairs = device_sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  conv_halo_pair_kernel<kN><<<2 * pairs, 192, Cfg::smem_bytes(p), stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+  conv_halo_pair_kernel<kN><<<2 * pairs, 224, Cfg::smem_bytes(p), stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
@@ -463,7 +470,7 @@ static int launch_halo(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const C
   if (g_conv_halo_resident == 0) { p.resident = 0; p.b_region_bytes = Cfg::kBStages * Cfg::kBBytes; p.staging_bufs = 2; }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  conv_halo_kernel<kN><<<grid, 192, Cfg::smem_bytes(p), stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+  conv_halo_kernel<kN><<<grid, 224, Cfg::smem_bytes(p), stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
