@@ -77,6 +77,31 @@ int ugp_pack_weights(const float* w_oihw, int Cout, int Cin, void* wf, void* wd,
 int ugp_unpack_wgrad(float* dw_packed, int Cout, int Cin, float* grad_oihw,
                      int accumulate, void* stream);
 
+/* ---- nn.ConvTranspose2d(Cin, Cout, kernel_size=2, stride=2) ------------------
+ * Reference: UpSample.up (UG_unet_parts.py:57-67), the up path of the legacy UNet (UG_unet.py:430-462).
+ *   out[b, 2y+i, 2x+j, co] = bias[co] + sum_ci x[b, y, x, ci] * W[ci, co, i, j]
+ * Stride == kernel size, so the layer is a 1x1 tcgen05 GEMM [B*H*W, Cin] x [Cin, (i,j,co)] whose
+ * epilogue writes each output-row phase i through a strided TMA view of the NHWC result (the pixel
+ * shuffle is free); the input gradient walks the two phases as the K dimension and the weight gradient
+ * is one GEMM per phase.  x: NHWC bf16 [B,H,W,cin]; out / dout: NHWC bf16 [B,2H,2W,cout];
+ * cin <= 1024, cout <= 512, multiples of 64.
+ * wf: bf16 [(i*2+j)*cout + co][ci];  wd: bf16 [ci][(i*2+j)*cout + co]  (ugp_pack_weights_tconv).
+ * dw_packed: fp32 [i][ci][j*cout + co], accumulated (caller zeroes; ugp_unpack_wgrad_tconv re-zeroes). */
+int ugp_conv_transpose2x2_fwd(const void* x, int B, int H, int W, int cin, const void* wf, int cout,
+                              const float* bias, void* out, void* stream);
+int ugp_conv_transpose2x2_dgrad(const void* dout, int B, int H, int W, int cout, const void* wd,
+                                int cin, void* dx, void* stream);
+int ugp_conv_transpose2x2_wgrad(const void* x, const void* dout, int B, int H, int W, int cin,
+                                int cout, float* dw_packed, void* stream);
+/* fp32 [cin][cout][2][2] (nn.ConvTranspose2d.weight layout) -> the two bf16 operand packs (wd nullable),
+ * and the packed fp32 gradient back to that layout (.grad of the weight). */
+int ugp_pack_weights_tconv(const float* w, int cin, int cout, void* wf, void* wd, void* stream);
+int ugp_unpack_wgrad_tconv(float* dw_packed, int cin, int cout, float* grad, int accumulate,
+                           void* stream);
+/* out[c] += sum_p x[p][c] over an NHWC bf16 tensor [pixels][C] (bias gradient of a layer with no
+ * BatchNorm behind it: ConvTranspose2d.bias); out fp32 [C], caller zeroes.  C % 8 == 0, C <= 2048. */
+int ugp_channel_sum(const void* x, long long pixels, int C, float* out, void* stream);
+
 /* First-layer input packing: fp32 NCHW [B,Cin,Hin,Win] -> bf16 [B,H,W,64]
  * 3x3 neighbourhoods (zero padding), with the bilinear align_corners=True
  * resize of uncertainty_guided_trainer.py:208 / UG_unet.py:36-41 folded in

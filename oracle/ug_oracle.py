@@ -193,6 +193,86 @@ def pgunet_forward(sd: StateDict, x: Tensor, stage: int, training: bool = True, 
     return logits
 
 
+# --------------------------------------------------------------------------- legacy UNet (ConvTranspose2d up path)
+_LEGACY_DOWN = [("down_convolution_1", None, 64), ("down_convolution_2", 64, 128),
+                ("down_convolution_3", 128, 256), ("down_convolution_4", 256, 512)]   # UG_unet.py:435-438
+_LEGACY_UP = [("up_convolution_1", 1024, 512), ("up_convolution_2", 512, 256),
+              ("up_convolution_3", 256, 128), ("up_convolution_4", 128, 64)]           # UG_unet.py:442-445
+
+
+def legacy_unet_shapes(in_channels: int, num_classes: int) -> Dict[str, Tuple[int, ...]]:
+    """Every key/shape of UNet(in_channels, num_classes).state_dict() — UG_unet.py:430-447,
+    UG_unet_parts.py:31-41 (DownSample), :57-67 (UpSample)."""
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def dconv(prefix, cin, cout):
+        for conv_i, bn_i, ci in ((0, 1, cin), (3, 4, cout)):
+            shapes[f"{prefix}.conv_op.{conv_i}.weight"] = (cout, ci, 3, 3)
+            shapes[f"{prefix}.conv_op.{conv_i}.bias"] = (cout,)
+            shapes[f"{prefix}.conv_op.{bn_i}.weight"] = (cout,)
+            shapes[f"{prefix}.conv_op.{bn_i}.bias"] = (cout,)
+            shapes[f"{prefix}.conv_op.{bn_i}.running_mean"] = (cout,)
+            shapes[f"{prefix}.conv_op.{bn_i}.running_var"] = (cout,)
+            shapes[f"{prefix}.conv_op.{bn_i}.num_batches_tracked"] = ()
+
+    for name, cin, cout in _LEGACY_DOWN:
+        dconv(f"{name}.conv", in_channels if cin is None else cin, cout)
+    dconv("bottle_neck", 512, 1024)
+    for name, cin, cout in _LEGACY_UP:
+        shapes[f"{name}.up.weight"] = (cin, cin // 2, 2, 2)      # nn.ConvTranspose2d: [Cin, Cout, kH, kW]
+        shapes[f"{name}.up.bias"] = (cin // 2,)
+        dconv(f"{name}.conv", cin, cout)
+    shapes["out.weight"] = (num_classes, 64, 1, 1)
+    shapes["out.bias"] = (num_classes,)
+    return shapes
+
+
+def seeded_legacy_state_dict(in_channels: int, num_classes: int, seed: int = 0) -> StateDict:
+    """Deterministic legacy-UNet weights, a pure function of (key, shape, seed) like seeded_state_dict."""
+    sd: StateDict = {}
+    for key, shape in legacy_unet_shapes(in_channels, num_classes).items():
+        g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) % (2 ** 31))
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.zeros((), dtype=torch.int64)
+        elif key.endswith("running_mean"):
+            sd[key] = torch.randn(shape, generator=g) * 0.1
+        elif key.endswith("running_var"):
+            sd[key] = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif key.endswith(".up.weight"):
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * math.sqrt(3.0 / shape[0]) * 1.4
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * math.sqrt(3.0 / fan_in) * 1.4
+        elif ".conv_op.1." in key or ".conv_op.4." in key:
+            sd[key] = torch.rand(shape, generator=g) * 0.5 + 0.75 if key.endswith("weight") \
+                else torch.randn(shape, generator=g) * 0.1
+        else:
+            sd[key] = torch.randn(shape, generator=g) * 0.05
+    return sd
+
+
+def conv_transpose2x2(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    """nn.ConvTranspose2d(Cin, Cout, kernel_size=2, stride=2) — UG_unet_parts.py:61,65:
+    out[n, co, 2y+i, 2x+j] = b[co] + sum_ci x[n, ci, y, x] * w[ci, co, i, j]."""
+    bq = _BF16_STORAGE
+    return _q(F.conv_transpose2d(_q(x, bq), _q(w, bq), b, stride=2), bq)
+
+
+def legacy_unet_forward(sd: StateDict, x: Tensor, training: bool = True, bn_out: Optional[StateDict] = None) -> Tensor:
+    """UNet.forward — UG_unet.py:449-462."""
+    skips = []
+    cur = x
+    for name, _, _ in _LEGACY_DOWN:                                    # DownSample, UG_unet_parts.py:38-41
+        d = double_conv(cur, sd, f"{name}.conv", training, bn_out)
+        skips.append(d)
+        cur = F.max_pool2d(d, 2)
+    cur = double_conv(cur, sd, "bottle_neck", training, bn_out)
+    for (name, _, _), skip in zip(_LEGACY_UP, reversed(skips)):         # UpSample, UG_unet_parts.py:64-67
+        up = conv_transpose2x2(cur, sd[f"{name}.up.weight"], sd[f"{name}.up.bias"])
+        cur = double_conv(torch.cat([up, skip], dim=1), sd, f"{name}.conv", training, bn_out)
+    return F.conv2d(cur, sd["out.weight"], sd["out.bias"])
+
+
 # --------------------------------------------------------------------------- uncertainty + loss
 def uncertainty_map(x: Tensor, sd_prev: StateDict, prev_stage: int, cur_res: int) -> Tensor:
     """A = 1 - 2|up(sigmoid(M_prev(down(x)))) - 0.5|, previous model in eval mode — UG_unet.py:19-59."""

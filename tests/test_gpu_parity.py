@@ -581,3 +581,139 @@ def test_config5_batch64_step(dev):
     assert f[-1][0] < f[0][0]                      # the repeated batch is being fitted
     assert 0.0 < f[-1][4] < 1.0                    # uncertainty mean
     assert torch.cuda.max_memory_allocated() < 40e9
+
+
+# --------------------------------------------------------------------------- ConvTranspose2d / legacy UNet
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 64), (1, 32, 32, 256, 128), (1, 16, 16, 1024, 512),
+                                   (1, 128, 128, 128, 64), (3, 64, 64, 512, 256)])
+def test_conv_transpose2x2_kernels_against_torch(dev, shape):
+    """ugp_conv_transpose2x2_{fwd,dgrad,wgrad}, the tconv (un)pack kernels and ugp_channel_sum vs
+    F.conv_transpose2d + autograd on identical bf16-rounded inputs (bf16 output rounding: rel <= 6e-3;
+    the fp32 weight / bias gradients: 2e-3)."""
+    import torch.nn.functional as F
+    from ug_pg_unet_b200 import ops
+
+    B, H, W, cin, cout = shape
+    g = torch.Generator(device="cuda").manual_seed(cin + H)
+    x = torch.randn(B, H, W, cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(cin, cout, 2, 2, device="cuda", generator=g) / math.sqrt(cin)).bfloat16().float()
+    b = torch.randn(cout, device="cuda", generator=g)
+    dout = torch.randn(B, 2 * H, 2 * W, cout, device="cuda", generator=g).bfloat16()
+    wf, wd = ops.pack_weights_tconv(w)
+    # packs are exact re-layouts of the bf16-representable weights
+    assert torch.equal(wf.float().view(2, 2, cout, cin), w.permute(2, 3, 1, 0))
+    assert torch.equal(wd.float().view(cin, 2, 2, cout), w.permute(0, 2, 3, 1))
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.conv_transpose2d(xr, wr, br, stride=2)
+    ref.backward(dout.float().permute(0, 3, 1, 2))
+    out = ops.conv_transpose2x2_fwd(x, wf, cout, bias=b)
+    assert out.shape == (B, 2 * H, 2 * W, cout)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 6e-3
+    dx = ops.conv_transpose2x2_dgrad(dout, wd, cin)
+    assert rel(dx.permute(0, 3, 1, 2), xr.grad) < 6e-3
+    dwp = torch.zeros(4 * cin * cout, device="cuda")
+    ops.conv_transpose2x2_wgrad(x, dout, dwp)
+    dw = ops.unpack_wgrad_tconv(dwp, cin, cout)
+    assert rel(dw, wr.grad) < 2e-3
+    assert float(dwp.abs().max()) == 0.0                      # consumed and re-zeroed
+    ops.conv_transpose2x2_wgrad(x, dout, dwp)
+    dw2 = ops.unpack_wgrad_tconv(dwp, cin, cout, grad=dw.clone(), accumulate=True)
+    assert rel(dw2, 2 * wr.grad) < 2e-3
+    db = ops.channel_sum(dout)
+    assert rel(db, br.grad) < 2e-3
+
+
+def test_upsample_block_against_reference_golden(dev, golden_dir):
+    """UpSample (ConvTranspose2d -> cat([up, skip]) -> DoubleConv) called with fp32 NCHW tensors like the
+    reference's legacy UNet calls it, against the fixture produced by the unmodified UG_unet_parts.UpSample."""
+    import ug_oracle as O
+    import ug_pg_unet_b200 as U
+
+    p = torch.load(os.path.join(golden_dir, "legacy_unet.pt"))["prim"]
+    sd_up = {k[len("up_convolution_4."):]: v for k, v in O.seeded_legacy_state_dict(3, 1, seed=5).items()
+             if k.startswith("up_convolution_4.")}
+    blk = U.UpSample(128, 64).to(dev)
+    blk.load_state_dict(sd_up, strict=True)
+    blk.train()
+    x1 = p["x1"].to(dev).requires_grad_(True)
+    x2 = p["x2"].to(dev).requires_grad_(True)
+    y = blk(x1, x2)
+    assert y.dtype == torch.float32 and tuple(y.shape) == tuple(p["out"].shape)
+    (y * p["gy"].to(dev)).sum().backward()
+    # bf16-storage floor of the oracle for the same block
+    with O.bf16_storage(True):
+        e1 = p["x1"].clone().requires_grad_(True)
+        e2 = p["x2"].clone().requires_grad_(True)
+        ew = {k: v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v
+              for k, v in sd_up.items()}
+        t = O.conv_transpose2x2(e1, ew["up.weight"], ew["up.bias"])
+        ey = O.double_conv(torch.cat([t, e2], 1), ew, "conv", True)
+        (ey * p["gy"]).sum().backward()
+    assert rel(y, p["out"]) <= 1.5 * rel(ey, p["out"]) + 2e-3
+    assert rel(x1.grad, p["dx1"]) <= 1.5 * rel(e1.grad, p["dx1"]) + 2e-2
+    assert rel(x2.grad, p["dx2"]) <= 1.5 * rel(e2.grad, p["dx2"]) + 2e-2
+    for k, prm in blk.named_parameters():
+        if k.endswith(("conv_op.0.bias", "conv_op.3.bias")):
+            continue                                            # analytically zero in front of train-mode BN
+        assert rel(prm.grad, p["grads"][k]) <= 1.5 * rel(ew[k].grad, p["grads"][k]) + 2e-2, k
+
+
+def test_legacy_unet_against_reference_golden(dev, golden_dir):
+    """The legacy UNet (UG_unet.py:430-462: DownSample x4, 512->1024 bottleneck, ConvTranspose2d up path)
+    against the fixture produced by the unmodified reference, same seeded weights and input."""
+    import torch.nn.functional as F
+    import ug_oracle as O
+    import ug_pg_unet_b200 as U
+
+    fx = torch.load(os.path.join(golden_dir, "legacy_unet.pt"))
+    sd = O.seeded_legacy_state_dict(3, 1, seed=6)
+    net = U.UNet(3, 1).to(dev)
+    net.load_state_dict(sd, strict=True)
+    assert list(net.state_dict().keys()) == list(O.legacy_unet_shapes(3, 1).keys()) or \
+        set(net.state_dict().keys()) == set(O.legacy_unet_shapes(3, 1).keys())
+    net.train()
+    x, y = fx["x"].to(dev), fx["y"].float().to(dev)
+    logits = net(x)
+    loss = F.binary_cross_entropy_with_logits(logits, y)
+    loss.backward()
+    torch.cuda.synchronize()
+    esd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+           for k, v in sd.items()}
+    with O.bf16_storage(True):
+        elog = O.legacy_unet_forward(esd, fx["x"], True)
+        eloss = F.binary_cross_entropy_with_logits(elog, fx["y"].float())
+        eloss.backward()
+    floor = rel(elog, fx["logits"])
+    assert rel(logits, fx["logits"]) <= 1.5 * floor + 2e-3, (rel(logits, fx["logits"]), floor)
+    assert abs(loss.item() - fx["loss"]) <= max(1e-3 * fx["loss"], 2.5 * abs(eloss.item() - fx["loss"])) + 2e-4
+    zr = fx["logits"]
+    safe = zr.abs() > 0.05 * zr.abs().max()
+    assert torch.equal((logits.cpu() > 0)[safe], (zr > 0)[safe])
+
+    def sample_rel(t, s):
+        f = t.detach().flatten().cpu().double()
+        if "full" in s:
+            r = s["full"].double()
+            return ((f - r).norm() / (r.norm() + 1e-30)).item()
+        r = s["vals"].double()
+        return ((f[s["idx"]] - r).norm() / (r.norm() + 1e-30)).item()
+
+    for k, prm in net.named_parameters():
+        if k.endswith(("conv_op.0.bias", "conv_op.3.bias")):
+            continue
+        fl = sample_rel(esd[k].grad, fx["grads"][k])
+        got = sample_rel(prm.grad, fx["grads"][k])
+        assert got <= 1.5 * fl + 2e-2, (k, got, fl)
+    net.eval()
+    with torch.no_grad():
+        ev = net(x)
+    # eval-mode logits use the running statistics updated by ONE train step from the seeded buffers
+    esd2 = {k: v.detach() for k, v in sd.items()}
+    bn = {}
+    O.legacy_unet_forward(esd2, fx["x"], True, bn)
+    esd2.update(bn)
+    with O.bf16_storage(True):
+        eev = O.legacy_unet_forward(esd2, fx["x"], False)
+    assert rel(ev, fx["eval_logits"]) <= 1.5 * rel(eev, fx["eval_logits"]) + 5e-3

@@ -123,3 +123,58 @@ def test_herlev_step_matches_reference(golden_dir, name):
             torch.testing.assert_close(out["bn"][k], v, rtol=1e-5, atol=1e-6)
         else:                                      # untouched blocks keep their buffers
             torch.testing.assert_close(sd[k], v, rtol=0, atol=0)
+
+
+def test_legacy_unet_matches_reference(golden_dir):
+    """oracle.conv_transpose2x2 / legacy_unet_forward vs the unmodified UpSample and UNet
+    (UG_unet_parts.py:57-67, UG_unet.py:430-462)."""
+    import torch.nn.functional as F
+
+    fx = torch.load(os.path.join(golden_dir, "legacy_unet.pt"))
+    shapes = O.legacy_unet_shapes(3, 1)
+    assert len(shapes) == 136
+    params = sum(int(torch.tensor(s).prod()) if len(s) else 1 for k, s in shapes.items()
+                 if not k.endswith(("running_mean", "running_var", "num_batches_tracked")))
+    assert params == 31043521
+    # the UpSample block alone: ConvTranspose2d(k2,s2) -> cat([up, skip]) -> DoubleConv
+    p = fx["prim"]
+    sd_up = {k[len("up_convolution_4."):]: v for k, v in O.seeded_legacy_state_dict(3, 1, seed=5).items()
+             if k.startswith("up_convolution_4.")}
+    x1 = p["x1"].clone().requires_grad_(True)
+    x2 = p["x2"].clone().requires_grad_(True)
+    w = sd_up["up.weight"].clone().requires_grad_(True)
+    b = sd_up["up.bias"].clone().requires_grad_(True)
+    t = O.conv_transpose2x2(x1, w, b)
+    torch.testing.assert_close(t, p["tconv_out"], rtol=1e-5, atol=1e-6)
+    # closed form of the stride == kernel case: each output pixel has one contributing input pixel
+    manual = torch.einsum("nchw,cdij->ndhiwj", p["x1"], sd_up["up.weight"]).reshape(1, 64, 32, 32) \
+        + sd_up["up.bias"].view(1, -1, 1, 1)
+    torch.testing.assert_close(manual, p["tconv_out"], rtol=1e-4, atol=1e-5)
+    y = O.double_conv(torch.cat([t, x2], 1), sd_up, "conv", True)
+    torch.testing.assert_close(y, p["out"], rtol=1e-4, atol=1e-4)
+    (y * p["gy"]).sum().backward()
+    torch.testing.assert_close(x1.grad, p["dx1"], rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(x2.grad, p["dx2"], rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(w.grad, p["grads"]["up.weight"], rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(b.grad, p["grads"]["up.bias"], rtol=2e-3, atol=2e-3)
+    if os.environ.get("UGP_FAST_TESTS"):
+        return
+    # the whole legacy UNet, train-mode forward + backward of mean BCE
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+          for k, v in O.seeded_legacy_state_dict(3, 1, seed=6).items()}
+    bn = {}
+    logits = O.legacy_unet_forward(sd, fx["x"], True, bn)
+    torch.testing.assert_close(logits, fx["logits"], rtol=1e-4, atol=1e-4)
+    loss = F.binary_cross_entropy_with_logits(logits, fx["y"].float())
+    assert abs(loss.item() - fx["loss"]) < 1e-5
+    loss.backward()
+    gmax = max(v.grad.abs().max().item() for v in sd.values() if v.requires_grad)
+    for k, s in fx["grads"].items():
+        _check_sample(sd[k].grad, s, rtol=2e-3, atol=2e-5 * gmax)
+    for k, s in fx["bn"].items():
+        _check_sample(bn[k], s, rtol=1e-5, atol=1e-6)
+    with torch.no_grad():
+        sd_eval = {k: v.detach() for k, v in sd.items()}
+        sd_eval.update(bn)
+        torch.testing.assert_close(O.legacy_unet_forward(sd_eval, fx["x"], False), fx["eval_logits"], rtol=1e-4,
+                                   atol=1e-4)

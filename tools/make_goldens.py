@@ -158,8 +158,56 @@ def herlev_case(stage: int, B: int, K: int, seed: int):
     }
 
 
+def legacy_case():
+    """ConvTranspose2d(k=2, s=2) primitive + one forward/backward of the reference's legacy `UNet`
+    (UG_unet.py:430-462) at 1 x 3 x 256 x 256 (the smallest size whose 16x16 bottleneck the GEMM tiles
+    cover), mean-BCE loss.  Weights: oracle.seeded_legacy_state_dict loaded with strict=True."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        import UG_unet_parts as REFP
+    g = torch.Generator().manual_seed(31)
+    # primitive: the UpSample block alone
+    up = REFP.UpSample(128, 64)
+    sd_up = {k[len("up_convolution_4."):]: v for k, v in O.seeded_legacy_state_dict(3, 1, seed=5).items()
+             if k.startswith("up_convolution_4.")}
+    up.load_state_dict(sd_up, strict=True)
+    up.train()
+    x1 = torch.randn(1, 128, 16, 16, generator=g, requires_grad=True)
+    x2 = torch.randn(1, 64, 32, 32, generator=g, requires_grad=True)
+    t_up = up.up(x1)
+    y_up = up(x1, x2)
+    gy = torch.randn(y_up.shape, generator=g)
+    (y_up * gy).sum().backward()
+    prim = {"x1": x1.detach().clone(), "x2": x2.detach().clone(), "gy": gy, "tconv_out": t_up.detach().clone(),
+            "out": y_up.detach().clone(), "dx1": x1.grad.clone(), "dx2": x2.grad.clone(),
+            "grads": {k: p.grad.clone() for k, p in up.named_parameters()}}
+    # full legacy UNet
+    net = REF.UNet(3, 1)
+    net.load_state_dict(O.seeded_legacy_state_dict(3, 1, seed=6), strict=True)
+    net.train()
+    x = torch.randn(1, 3, 256, 256, generator=g)
+    y = torch.randint(0, 2, (1, 1, 256, 256), generator=g).float()
+    logits = net(x)
+    loss = F.binary_cross_entropy_with_logits(logits, y)
+    loss.backward()
+    fx = {"prim": prim, "x": x, "y": y.to(torch.uint8), "logits": logits.detach().clone(), "loss": loss.item(),
+          "grads": {k: sample(p.grad) for k, p in net.named_parameters()},
+          "bn": {k: sample(v.float()) for k, v in net.state_dict().items()
+                 if k.endswith(("running_mean", "running_var"))}}
+    net.eval()
+    with torch.no_grad():
+        fx["eval_logits"] = net(x).clone()
+    return fx
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--legacy-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:
+        fx = legacy_case()
+        path = os.path.join(OUT, "legacy_unet.pt")
+        torch.save(fx, path)
+        print(f"legacy_unet: loss={fx['loss']:.6f} -> {os.path.getsize(path) / 1024:.0f} KiB")
+        if "--legacy-only" in sys.argv:
+            return
     for name, (stage, B, K, seed) in {"herlev_stage1_k7": (1, 4, 7, 21), "herlev_stage2_k7": (2, 4, 7, 22)}.items():
         fx = herlev_case(stage, B, K, seed)
         path = os.path.join(OUT, name + ".pt")

@@ -18,6 +18,12 @@ _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     "ugp_conv_gemm_bf16": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _i, _p, _p],
     "ugp_conv_wgrad_bf16": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _p],
+    "ugp_conv_transpose2x2_fwd": [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p],
+    "ugp_conv_transpose2x2_dgrad": [_p, _i, _i, _i, _i, _p, _i, _p, _p],
+    "ugp_conv_transpose2x2_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "ugp_pack_weights_tconv": [_p, _i, _i, _p, _p, _p],
+    "ugp_unpack_wgrad_tconv": [_p, _i, _i, _p, _i, _p],
+    "ugp_channel_sum": [_p, _ll, _i, _p, _p],
     "ugp_pack_weights": [_p, _i, _i, _p, _p, _p],
     "ugp_unpack_wgrad": [_p, _i, _i, _p, _i, _p],
     "ugp_im2col_first": [_p, _i, _i, _i, _i, _i, _i, _p, _p],

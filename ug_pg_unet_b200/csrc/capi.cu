@@ -48,6 +48,12 @@ int rmsprop_multi(float* const*, const float* const*, float* const*, const long 
 int global_avg_pool(const void*, int, int, int, float*, cudaStream_t);
 int global_avg_pool_bwd(const float*, int, int, int, void*, cudaStream_t);
 int bench_mma(int, int, int, int, int, int, int, long long*, cudaStream_t);
+int conv_transpose2x2_fwd(const void*, int, int, int, int, const void*, int, const float*, void*, cudaStream_t);
+int conv_transpose2x2_dgrad(const void*, int, int, int, int, const void*, int, void*, cudaStream_t);
+int conv_transpose2x2_wgrad(const void*, const void*, int, int, int, int, int, float*, cudaStream_t);
+int pack_weights_tconv(const float*, int, int, void*, void*, cudaStream_t);
+int unpack_wgrad_tconv(float*, int, int, float*, int, cudaStream_t);
+int channel_sum(const void*, long long, int, float*, cudaStream_t);
 int rmsprop_conv_packed(float* const*, float* const*, float* const*, void* const*, void* const*,
                         const int*, const int*, int, float, float, float, float, float, cudaStream_t);
 }  // namespace ugp
@@ -184,5 +190,26 @@ int ugp_global_avg_pool_bwd(const float* dy, int B, int HW, int C, void* dx, voi
 int ugp_bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int a_shift, int ctas, long long* out_cycles,
                   void* stream) {
   return ugp::bench_mma(n, pair, iters, nacc, a_tiles, a_shift, ctas, out_cycles, S(stream));
+}
+int ugp_conv_transpose2x2_fwd(const void* x, int B, int H, int W, int cin, const void* wf, int cout,
+                              const float* bias, void* out, void* stream) {
+  return ugp::conv_transpose2x2_fwd(x, B, H, W, cin, wf, cout, bias, out, S(stream));
+}
+int ugp_conv_transpose2x2_dgrad(const void* dout, int B, int H, int W, int cout, const void* wd, int cin,
+                                void* dx, void* stream) {
+  return ugp::conv_transpose2x2_dgrad(dout, B, H, W, cout, wd, cin, dx, S(stream));
+}
+int ugp_conv_transpose2x2_wgrad(const void* x, const void* dout, int B, int H, int W, int cin, int cout,
+                                float* dw_packed, void* stream) {
+  return ugp::conv_transpose2x2_wgrad(x, dout, B, H, W, cin, cout, dw_packed, S(stream));
+}
+int ugp_pack_weights_tconv(const float* w, int cin, int cout, void* wf, void* wd, void* stream) {
+  return ugp::pack_weights_tconv(w, cin, cout, wf, wd, S(stream));
+}
+int ugp_unpack_wgrad_tconv(float* dw_packed, int cin, int cout, float* grad, int accumulate, void* stream) {
+  return ugp::unpack_wgrad_tconv(dw_packed, cin, cout, grad, accumulate, S(stream));
+}
+int ugp_channel_sum(const void* x, long long pixels, int C, float* out, void* stream) {
+  return ugp::channel_sum(x, pixels, C, out, S(stream));
 }
 }  // extern "C"

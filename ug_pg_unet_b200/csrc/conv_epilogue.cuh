@@ -48,7 +48,8 @@ struct EpilogueCtx {
 template <int kStagingBufs>
 __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint32_t* v, int n_base,
                                                uint32_t buf_addr, int row, int et,
-                                               const CUtensorMap* tm_out, int out_col, int out_row) {
+                                               const CUtensorMap* tm_out, int out_col, int out_row,
+                                               int out_y = -1, int out_b = 0) {
   uint32_t packed[32];
 #pragma unroll
   for (int j = 0; j < 64; j += 4) {
@@ -84,10 +85,19 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint3
   fence_proxy_async_smem();
   named_bar_sync(2, 128);
   if (et == 0) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                     reinterpret_cast<uint64_t>(tm_out)),
-                 "r"(buf_addr), "r"(out_col), "r"(out_row)
-                 : "memory");
+    if (out_y < 0) {
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                       reinterpret_cast<uint64_t>(tm_out)),
+                   "r"(buf_addr), "r"(out_col), "r"(out_row)
+                   : "memory");
+    } else {
+      // strided 4-D destination (C, x, y, b): the tile's BW x BH pixel box of a ConvTranspose2d phase view
+      asm volatile(
+          "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+              reinterpret_cast<uint64_t>(tm_out)),
+          "r"(buf_addr), "r"(out_col), "r"(out_row), "r"(out_y), "r"(out_b)
+          : "memory");
+    }
     tma_store_commit();
   }
   if (e.do_stats) {

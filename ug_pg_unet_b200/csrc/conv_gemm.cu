@@ -101,7 +101,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     for (int i = et; i < p.cout; i += 128) {
       sStats[i] = 0.f;
       sStats[kMaxC + i] = 0.f;
-      sBias[i] = p.bias ? p.bias[i] : 0.f;
+      sBias[i] = p.bias ? p.bias[i % p.bias_period] : 0.f;
       sScale[i] = p.scale ? p.scale[i] : 1.f;
       sShift[i] = p.shift ? p.shift[i] : 0.f;
     }
@@ -217,6 +217,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int n_tile = tile - m_tile * p.n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      // 2-D destination: (channel, first pixel of the tile); strided 4-D view: (channel, x0, y0, b)
+      int o_row = m_tile * kBlockM, o_y = -1, o_b = 0;
+      if (p.out4d) {
+        const int t2 = m_tile / p.tiles_x;
+        o_row = (m_tile - t2 * p.tiles_x) * p.BW;
+        o_b = t2 / p.tiles_y;
+        o_y = (t2 - o_b * p.tiles_y) * p.BH;
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after_sync();
 #pragma unroll 1
@@ -236,10 +244,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         const uint32_t buf_addr = smem_u32(sOut) + (chunk_counter % Cfg::kStagingBufs) * kOutChunkBytes;
         if (n_base < p.split_n)
           epilogue_chunk<Cfg::kStagingBufs>(ectx, v, n_base, buf_addr, row, et, &tmO0, n_base,
-                                            m_tile * kBlockM);
+                                            o_row, o_y, o_b);
         else
           epilogue_chunk<Cfg::kStagingBufs>(ectx, v, n_base, buf_addr, row, et, &tmO1,
-                                            n_base - p.split_n, m_tile * kBlockM);
+                                            n_base - p.split_n, o_row, o_y, o_b);
       }
     }
     if (et == 0) tma_store_wait_all();
@@ -307,11 +315,14 @@ int launch_conv_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUt
                      const CUtensorMap& tmO0, const CUtensorMap& tmO1, const ConvGemmParams& p,
                      cudaStream_t stream);
 
-int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
-                   int H, int W, int taps, const void* wpack, int cout,
-                   void* dst0, void* dst1, int split_n, const float* bias,
-                   const float* scale, const float* shift, int relu,
-                   float* stats, cudaStream_t stream) {
+// src_view / dst_view (nullable): the sources / destinations are strided NHWC views instead of dense
+// tensors (ConvTranspose2d phases, conv_transpose.cu); bias_period > 0: bias[n % bias_period].
+int conv_gemm_bf16_ex(const void* src0, int c0, const void* src1, int c1, int B,
+                      int H, int W, int taps, const void* wpack, int cout,
+                      void* dst0, void* dst1, int split_n, const float* bias,
+                      const float* scale, const float* shift, int relu,
+                      float* stats, const ConvView* src_view, const ConvView* dst_view,
+                      int bias_period, cudaStream_t stream) {
   UGP_REQUIRE(src0 && wpack && dst0, "conv_gemm: null pointer");
   UGP_REQUIRE(taps == 9 || taps == 1, "conv_gemm: taps must be 9 or 1 (got %d)", taps);
   UGP_REQUIRE(c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
@@ -321,7 +332,8 @@ int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
   if (dst1 == nullptr) split_n = cout;
   UGP_REQUIRE(split_n > 0 && split_n <= cout && split_n % 64 == 0,
               "conv_gemm: bad split_n %d", split_n);
-  if (g_conv_halo_mode != 0 && conv_halo_eligible(H, W, cout, split_n, taps))
+  const bool viewed = src_view != nullptr || dst_view != nullptr;
+  if (!viewed && g_conv_halo_mode != 0 && conv_halo_eligible(H, W, cout, split_n, taps))
     return conv_halo_bf16(src0, c0, src1, c1, B, H, W, wpack, cout, dst0, dst1, split_n, bias, scale,
                           shift, relu, stats, stream);
   int BW, BH;
@@ -345,32 +357,51 @@ int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
   p.cout = cout;
   p.split_n = split_n;
   p.relu = relu;
+  p.bias_period = bias_period > 0 ? bias_period : cout;
+  p.out4d = dst_view != nullptr;
   p.bias = bias; p.scale = scale; p.shift = shift; p.stats = stats;
 
   CUtensorMap tmA0, tmA1, tmW, tmO0, tmO1;
   int rc;
-  if ((rc = make_tmap_nhwc_bf16(&tmA0, src0, B, H, W, c0, 64, BW, BH))) return rc;
-  if (c1 > 0) {
-    if ((rc = make_tmap_nhwc_bf16(&tmA1, src1, B, H, W, c1, 64, BW, BH))) return rc;
+  if (src_view) {
+    if ((rc = make_tmap_nhwc_view_bf16(&tmA0, src0, B, H, W, c0, src_view->pix, src_view->row,
+                                       src_view->img, 64, BW, BH))) return rc;
+    if (c1 > 0 && (rc = make_tmap_nhwc_view_bf16(&tmA1, src1, B, H, W, c1, src_view->pix, src_view->row,
+                                                 src_view->img, 64, BW, BH))) return rc;
   } else {
-    tmA1 = tmA0;
+    if ((rc = make_tmap_nhwc_bf16(&tmA0, src0, B, H, W, c0, 64, BW, BH))) return rc;
+    if (c1 > 0 && (rc = make_tmap_nhwc_bf16(&tmA1, src1, B, H, W, c1, 64, BW, BH))) return rc;
   }
+  if (c1 == 0) tmA1 = tmA0;
   // CTA pairs (cta_group::2) for the 256-wide tiles: each CTA stages half of the weight tile
-  const bool pair = kn == 256 && conv_pair_eligible(p.m_tiles, cout, split_n);
+  const bool pair = !viewed && kn == 256 && conv_pair_eligible(p.m_tiles, cout, split_n);
   if ((rc = make_tmap_2d_bf16(&tmW, wpack, (long long)taps * cout, c0 + c1, 64, pair ? 128 : kn))) return rc;
   const long long M = (long long)B * H * W;
-  if ((rc = make_tmap_2d_bf16(&tmO0, dst0, M, split_n, 64, kBlockM))) return rc;
-  if (split_n < cout) {
-    if ((rc = make_tmap_2d_bf16(&tmO1, dst1, M, cout - split_n, 64, kBlockM))) return rc;
+  if (dst_view) {
+    if ((rc = make_tmap_nhwc_view_bf16(&tmO0, dst0, B, H, W, split_n, dst_view->pix, dst_view->row,
+                                       dst_view->img, 64, BW, BH))) return rc;
+    if (split_n < cout && (rc = make_tmap_nhwc_view_bf16(&tmO1, dst1, B, H, W, cout - split_n, dst_view->pix,
+                                                         dst_view->row, dst_view->img, 64, BW, BH))) return rc;
   } else {
-    tmO1 = tmO0;
+    if ((rc = make_tmap_2d_bf16(&tmO0, dst0, M, split_n, 64, kBlockM))) return rc;
+    if (split_n < cout && (rc = make_tmap_2d_bf16(&tmO1, dst1, M, cout - split_n, 64, kBlockM))) return rc;
   }
+  if (split_n >= cout) tmO1 = tmO0;
   if (pair) return launch_conv_pair(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
   switch (kn) {
     case 256: return launch_conv<256>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
     case 128: return launch_conv<128>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
     default:  return launch_conv<64>(tmA0, tmA1, tmW, tmO0, tmO1, p, stream);
   }
+}
+
+int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
+                   int H, int W, int taps, const void* wpack, int cout,
+                   void* dst0, void* dst1, int split_n, const float* bias,
+                   const float* scale, const float* shift, int relu,
+                   float* stats, cudaStream_t stream) {
+  return conv_gemm_bf16_ex(src0, c0, src1, c1, B, H, W, taps, wpack, cout, dst0, dst1, split_n, bias,
+                           scale, shift, relu, stats, nullptr, nullptr, 0, stream);
 }
 
 }  // namespace ugp

@@ -15,6 +15,8 @@ struct ConvGemmParams {
   int cout;
   int split_n;
   int relu;
+  int bias_period;   // bias[n % bias_period] (= cout for a plain convolution)
+  int out4d;         // destinations are strided 4-D views (C, x, y, b): ConvTranspose2d phases
   const float* bias;
   const float* scale;
   const float* shift;

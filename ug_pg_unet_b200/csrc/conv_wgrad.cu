@@ -252,15 +252,16 @@ int conv_wgrad_halo_bf16(const void* src0, int c0, const void* src1, int c1, con
                          int B, int H, int W, float* dw_packed, cudaStream_t stream);
 extern int g_wgrad_halo_mode;
 
-int conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
-                    const void* dz, int cout, int B, int H, int W, int taps,
-                    float* dw_packed, cudaStream_t stream) {
+// dz_view (nullable): dz is a strided NHWC view (a ConvTranspose2d output-row phase, conv_transpose.cu).
+int conv_wgrad_bf16_ex(const void* src0, int c0, const void* src1, int c1,
+                       const void* dz, int cout, int B, int H, int W, int taps,
+                       float* dw_packed, const ConvView* dz_view, cudaStream_t stream) {
   UGP_REQUIRE(src0 && dz && dw_packed, "conv_wgrad: null pointer");
   UGP_REQUIRE(taps == 9 || taps == 1, "conv_wgrad: taps must be 9 or 1");
   UGP_REQUIRE(c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
               "conv_wgrad: source channels must be multiples of 64");
-  UGP_REQUIRE(cout % 64 == 0 && cout <= 512, "conv_wgrad: cout %d unsupported", cout);
-  if (g_wgrad_halo_mode != 0 && conv_wgrad_halo_eligible(H, W, cout, taps))
+  UGP_REQUIRE(cout % 64 == 0 && cout <= 1024, "conv_wgrad: cout %d unsupported", cout);
+  if (!dz_view && g_wgrad_halo_mode != 0 && conv_wgrad_halo_eligible(H, W, cout, taps))
     return conv_wgrad_halo_bf16(src0, c0, src1, c1, dz, cout, B, H, W, dw_packed, stream);
   int BWp = W < 64 ? W : 64;
   int BHp = 64 / BWp;
@@ -292,12 +293,23 @@ int conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
   } else {
     tmX1 = tmX0;
   }
-  if ((rc = make_tmap_nhwc_bf16(&tmDZ, dz, B, H, W, cout, 64, BWp, BHp))) return rc;
+  if (dz_view) {
+    if ((rc = make_tmap_nhwc_view_bf16(&tmDZ, dz, B, H, W, cout, dz_view->pix, dz_view->row, dz_view->img,
+                                       64, BWp, BHp))) return rc;
+  } else {
+    if ((rc = make_tmap_nhwc_bf16(&tmDZ, dz, B, H, W, cout, 64, BWp, BHp))) return rc;
+  }
   switch (kn) {
     case 256: return launch_wgrad<256>(tmX0, tmX1, tmDZ, p, stream);
     case 128: return launch_wgrad<128>(tmX0, tmX1, tmDZ, p, stream);
     default:  return launch_wgrad<64>(tmX0, tmX1, tmDZ, p, stream);
   }
+}
+
+int conv_wgrad_bf16(const void* src0, int c0, const void* src1, int c1,
+                    const void* dz, int cout, int B, int H, int W, int taps,
+                    float* dw_packed, cudaStream_t stream) {
+  return conv_wgrad_bf16_ex(src0, c0, src1, c1, dz, cout, B, H, W, taps, dw_packed, nullptr, stream);
 }
 
 }  // namespace ugp

@@ -76,6 +76,19 @@ int make_tmap_nhwc_bf16(CUtensorMap* out, const void* ptr, int B, int H, int W,
   return encode(out, ptr, 4, dims, strides, box);
 }
 
+// Strided NHWC view (C, W, H, B) with explicit pixel / row / image strides in ELEMENTS: one output-row
+// phase of a ConvTranspose2d(k=2, s=2) result, where a "pixel" is the (j, co) pair of 2*Cout channels
+// and consecutive rows of the view are two image rows apart.  Strides must be multiples of 8 elements.
+int make_tmap_nhwc_view_bf16(CUtensorMap* out, const void* ptr, int B, int H, int W, int C,
+                             long long pix_stride, long long row_stride, long long img_stride,
+                             int boxC, int boxW, int boxH) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)pix_stride * 2, (cuuint64_t)row_stride * 2,
+                           (cuuint64_t)img_stride * 2};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+  return encode(out, ptr, 4, dims, strides, box);
+}
+
 // Row-major bf16 matrix [rows][cols]; cols innermost.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, long long rows,
                       int cols, int boxCols, int boxRows) {

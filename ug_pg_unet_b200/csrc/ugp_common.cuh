@@ -48,6 +48,13 @@ int make_tmap_nhwc_bf16(CUtensorMap* out, const void* ptr, int B, int H, int W,
                         int C, int boxC, int boxW, int boxH);
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, long long rows,
                       int cols, int boxCols, int boxRows);
+int make_tmap_nhwc_view_bf16(CUtensorMap* out, const void* ptr, int B, int H, int W, int C,
+                             long long pix_stride, long long row_stride, long long img_stride,
+                             int boxC, int boxW, int boxH);
+// Element strides of a strided NHWC activation view (see make_tmap_nhwc_view_bf16).
+struct ConvView {
+  long long pix, row, img;
+};
 int device_sm_count();
 
 #ifdef __CUDACC__

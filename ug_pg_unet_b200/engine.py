@@ -282,6 +282,7 @@ class DoubleConvFn(torch.autograd.Function):
           'first'  x fp32 NCHW image, first conv runs through im2col (9*Cin <= 64)
           'pool'   MaxPool2d(2) then DoubleConv  (Down, UG_unet_parts.py:44-54)
           'up'     bilinear x2 of x, concat [skip, up], DoubleConv (Up, UG_unet_parts.py:70-81)
+          'cat'    concat [x, skip] walked as two sources (UpSample, UG_unet_parts.py:64-67)
     emit_pool: also return MaxPool2d(2) of the output (fused into the BN/ReLU pass).
     """
 
@@ -297,6 +298,8 @@ class DoubleConvFn(torch.autograd.Function):
             srcs, taps = [ops.maxpool2x2(x)], 9
         elif kind == "up":
             srcs, taps = [skip, ops.upsample2x(x)], 9
+        elif kind == "cat":
+            srcs, taps = [x, skip], 9
         else:
             srcs, taps = [x], 9
         a1, _, s1 = cbr_forward(srcs, taps, conv1, bn1, mod._packs[0], False, need_grad)
@@ -328,6 +331,8 @@ class DoubleConvFn(torch.autograd.Function):
             elif ctx.kind == "up":
                 dskip = d0[0]
                 dx = ops.upsample2x_bwd(d0[1])
+            elif ctx.kind == "cat":
+                dx, dskip = d0[0], d0[1]
             else:
                 dx = d0[0]
         ctx.s1 = ctx.s2 = ctx.pre = None
@@ -342,6 +347,66 @@ def double_conv_params(mod) -> Tuple[torch.Tensor, ...]:
 
 def run_double_conv(mod, kind: str, x, skip=None, emit_pool: bool = False):
     return DoubleConvFn.apply(mod, kind, emit_pool, x, skip, *double_conv_params(mod))
+
+
+# ----------------------------------------------------------------------------- ConvTranspose2d(k=2, s=2)
+class TConvPackedWeights:
+    """bf16 GEMM operands of one nn.ConvTranspose2d(k=2, s=2) weight (refreshed like PackedWeights) and
+    its persistent packed fp32 weight-gradient accumulator."""
+
+    def __init__(self, conv: nn.ConvTranspose2d):
+        self.conv = conv
+        self.key = None
+        self.wf = None
+        self.wd = None
+        self._dwp = None
+
+    def get(self):
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version, w.device, PackedWeights.epoch)
+        if key != self.key:
+            same = self.wf is not None and self.wf.device == w.device and self.wf.numel() == w.numel()
+            self.wf, self.wd = ops.pack_weights_tconv(w.detach(), wf=self.wf if same else None,
+                                                      wd=self.wd if same else None)
+            self.key = key
+        return self.wf, self.wd
+
+    def dwp_buffer(self, device) -> torch.Tensor:
+        n = self.conv.weight.numel()
+        if self._dwp is None or self._dwp.device != device or self._dwp.numel() != n:
+            self._dwp = torch.zeros((n,), dtype=torch.float32, device=device)
+        return self._dwp
+
+
+class ConvTranspose2x2Fn(torch.autograd.Function):
+    """nn.ConvTranspose2d(Cin, Cout, 2, 2) on an NHWC bf16 activation (UpSample.up,
+    UG_unet_parts.py:61,65): forward, input gradient and weight gradient are tcgen05 GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, packs: TConvPackedWeights):
+        wf, _ = packs.get()
+        out = ops.conv_transpose2x2_fwd(x, wf, weight.shape[1], bias=None if bias is None else bias.detach())
+        ctx.packs, ctx.has_bias = packs, bias is not None
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        packs = ctx.packs
+        dout = dout.contiguous()
+        cin, cout = packs.conv.weight.shape[0], packs.conv.weight.shape[1]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            _, wd = packs.get()
+            dx = ops.conv_transpose2x2_dgrad(dout, wd, cin)
+        if ctx.needs_input_grad[1]:
+            dwp = packs.dwp_buffer(x.device)
+            ops.conv_transpose2x2_wgrad(x, dout, dwp)
+            dw = ops.unpack_wgrad_tconv(dwp, cin, cout)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.channel_sum(dout)
+        return dx, dw, db, None
 
 
 # ----------------------------------------------------------------------------- OutConv / head

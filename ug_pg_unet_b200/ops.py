@@ -183,6 +183,86 @@ def unpack_wgrad(dw_packed, cout: int, cin: int, grad=None, accumulate: bool = F
     return grad
 
 
+# ----------------------------------------------------------------------------- ConvTranspose2d(k=2, s=2)
+def pack_weights_tconv(w: torch.Tensor, wf=None, wd=None):
+    """fp32 [Cin, Cout, 2, 2] (nn.ConvTranspose2d.weight) -> (wf [4*Cout, Cin], wd [Cin, 4*Cout]) bf16."""
+    _req(w, torch.float32, "weight")
+    cin, cout = w.shape[0], w.shape[1]
+    assert tuple(w.shape[2:]) == (2, 2)
+    if wf is None:
+        wf = torch.empty((4 * cout, cin), dtype=bf16, device=w.device)
+    if wd is None:
+        wd = torch.empty((cin, 4 * cout), dtype=bf16, device=w.device)
+    check(lib().ugp_pack_weights_tconv(_ptr(w), cin, cout, _ptr(wf), _ptr(wd), _stream()), "ugp_pack_weights_tconv")
+    return wf, wd
+
+
+def conv_transpose2x2_fwd(x, wf, cout: int, bias=None, out=None):
+    """x NHWC bf16 [B,H,W,Cin] -> NHWC bf16 [B,2H,2W,Cout]; see ugp_conv_transpose2x2_fwd."""
+    _req(x, bf16, "x")
+    _req(wf, bf16, "wf")
+    B, H, W, cin = x.shape
+    assert wf.numel() == 4 * cout * cin
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, cout), dtype=bf16, device=x.device)
+    _req(out, bf16, "out")
+    with _timed("conv_transpose_fwd", 2.0 * B * H * W * cin * 4 * cout):
+        rc = lib().ugp_conv_transpose2x2_fwd(_ptr(x), B, H, W, cin, _ptr(wf), cout,
+                                             _ptr(_opt(bias, torch.float32, "bias")), _ptr(out), _stream())
+    check(rc, "ugp_conv_transpose2x2_fwd")
+    if 4 * cout > 1024:
+        _count()
+    return out
+
+
+def conv_transpose2x2_dgrad(dout, wd, cin: int):
+    _req(dout, bf16, "dout")
+    _req(wd, bf16, "wd")
+    B, H2, W2, cout = dout.shape
+    assert wd.numel() == 4 * cout * cin
+    dx = torch.empty((B, H2 // 2, W2 // 2, cin), dtype=bf16, device=dout.device)
+    with _timed("conv_transpose_dgrad", 2.0 * B * (H2 // 2) * (W2 // 2) * cin * 4 * cout):
+        rc = lib().ugp_conv_transpose2x2_dgrad(_ptr(dout), B, H2 // 2, W2 // 2, cout, _ptr(wd), cin, _ptr(dx), _stream())
+    check(rc, "ugp_conv_transpose2x2_dgrad")
+    return dx
+
+
+def conv_transpose2x2_wgrad(x, dout, dw_packed):
+    """dw_packed[i][ci][j*Cout+co] += sum_p x[p, ci] * dout[phase (i,j) of p, co]."""
+    _req(x, bf16, "x")
+    _req(dout, bf16, "dout")
+    _req(dw_packed, torch.float32, "dw_packed")
+    B, H, W, cin = x.shape
+    cout = dout.shape[3]
+    assert tuple(dout.shape) == (B, 2 * H, 2 * W, cout) and dw_packed.numel() == 4 * cin * cout
+    with _timed("conv_transpose_wgrad", 2.0 * B * H * W * cin * 4 * cout):
+        rc = lib().ugp_conv_transpose2x2_wgrad(_ptr(x), _ptr(dout), B, H, W, cin, cout, _ptr(dw_packed), _stream())
+    check(rc, "ugp_conv_transpose2x2_wgrad")
+    _count()
+    return dw_packed
+
+
+def unpack_wgrad_tconv(dw_packed, cin: int, cout: int, grad=None, accumulate: bool = False):
+    _req(dw_packed, torch.float32, "dw_packed")
+    if grad is None:
+        grad = torch.empty((cin, cout, 2, 2), dtype=torch.float32, device=dw_packed.device)
+        accumulate = False
+    check(lib().ugp_unpack_wgrad_tconv(_ptr(dw_packed), cin, cout, _ptr(_req(grad, torch.float32, "grad")),
+                                       int(accumulate), _stream()), "ugp_unpack_wgrad_tconv")
+    return grad
+
+
+def channel_sum(x, out=None):
+    """Per-channel sum over all pixels of an NHWC bf16 tensor -> fp32 [C] (added to `out` when given)."""
+    _req(x, bf16, "x")
+    Cn = x.shape[-1]
+    if out is None:
+        out = torch.zeros((Cn,), dtype=torch.float32, device=x.device)
+    check(lib().ugp_channel_sum(_ptr(x), x.numel() // Cn, Cn, _ptr(_req(out, torch.float32, "out")), _stream()),
+          "ugp_channel_sum")
+    return out
+
+
 def im2col_first(x: torch.Tensor, H: Optional[int] = None, W: Optional[int] = None):
     """fp32 NCHW image -> bf16 [B,H,W,64] 3x3 neighbourhoods (optional bilinear resize)."""
     _req(x, torch.float32, "x")

@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import engine, ops
-from .unet_parts import DoubleConv, Down, InConv, OutConv, Up, _require_cuda
+from .unet_parts import DoubleConv, Down, DownSample, InConv, OutConv, Up, UpSample, _require_cuda
 
 
 class _PGUNetBase(nn.Module):
@@ -324,3 +324,39 @@ def _forward_from_col(model: _PGUNetBase, col: torch.Tensor) -> torch.Tensor:
     maps = [ops.outconv_fwd(d, h.conv.weight.detach().reshape(h.conv.out_channels, -1).contiguous(),
                             h.conv.bias.detach()) for h, d in zip(heads, dec)]
     return ops.head_combine_fwd(maps)
+
+
+class UNet(nn.Module):
+    """The reference's legacy U-Net (UG_unet.py:430-462): DownSample x4, a 512->1024 bottleneck, four
+    UpSample blocks (ConvTranspose2d(k=2, s=2) + concat + DoubleConv) and a 1x1 head; same attribute
+    names and `state_dict` keys.  fp32 NCHW image in, raw fp32 NCHW logits out; H and W must be
+    multiples of 256 (the 16x-downsampled bottleneck runs 16-pixel-wide GEMM tiles)."""
+
+    def __init__(self, in_channels, num_classes):
+        super().__init__()
+        self.down_convolution_1 = DownSample(in_channels, 64)
+        self.down_convolution_2 = DownSample(64, 128)
+        self.down_convolution_3 = DownSample(128, 256)
+        self.down_convolution_4 = DownSample(256, 512)
+        self.bottle_neck = DoubleConv(512, 1024)
+        self.up_convolution_1 = UpSample(1024, 512)
+        self.up_convolution_2 = UpSample(512, 256)
+        self.up_convolution_3 = UpSample(256, 128)
+        self.up_convolution_4 = UpSample(128, 64)
+        self.out = nn.Conv2d(in_channels=64, out_channels=num_classes, kernel_size=1)
+        if not 1 <= num_classes <= 8:
+            raise ValueError(f"UNet: num_classes={num_classes} unsupported (1..8)")
+
+    def forward(self, x):
+        _require_cuda(x, "UNet")
+        x = x.float().contiguous()
+        d1, p1 = self.down_convolution_1._run(x)
+        d2, p2 = self.down_convolution_2._run(p1)
+        d3, p3 = self.down_convolution_3._run(p2)
+        d4, p4 = self.down_convolution_4._run(p3)
+        b = self.bottle_neck._run("plain", p4)
+        u1 = self.up_convolution_1._run(b, d4)
+        u2 = self.up_convolution_2._run(u1, d3)
+        u3 = self.up_convolution_3._run(u2, d2)
+        u4 = self.up_convolution_4._run(u3, d1)
+        return engine.OutConvFn.apply(u4, self.out.weight, self.out.bias)

@@ -1,8 +1,8 @@
 """Drop-in U-Net building blocks backed by the sm_100a kernels.
 
 Same constructors, attribute names and `state_dict` keys as the reference's
-`UG_unet_parts.py` (DoubleConv :5-19, InConv :21-28, Down :44-54, Up :70-81,
-OutConv :84-91): the stock `nn.Conv2d` / `nn.BatchNorm2d` objects are kept as
+`UG_unet_parts.py` (DoubleConv :5-19, InConv :21-28, DownSample :31-41, Down :44-54,
+UpSample :57-67, Up :70-81, OutConv :84-91): the stock `nn.Conv2d` / `nn.BatchNorm2d` objects are kept as
 parameter containers (initialisation, `.to()`, `load_state_dict`, checkpoints
 all behave as in the reference), while `forward` runs the tcgen05 implicit-GEMM
 convolution and the fused BN/ReLU/pool/upsample kernels.
@@ -59,8 +59,8 @@ class DoubleConv(nn.Module):
         if first and 9 * in_channels > 64:
             raise ValueError(f"DoubleConv: in_channels={in_channels} unsupported "
                              "(must be a multiple of 64, or <= 7 for the image layer)")
-        if out_channels % 64 != 0 or out_channels > 512:
-            raise ValueError(f"DoubleConv: out_channels={out_channels} unsupported (multiple of 64, <= 512)")
+        if out_channels % 64 != 0 or out_channels > 1024:
+            raise ValueError(f"DoubleConv: out_channels={out_channels} unsupported (multiple of 64, <= 1024)")
         self._first = first
         # private bf16 operand caches (not parameters, not in state_dict)
         self._packs = (PackedWeights(self.conv_op[0], need_dgrad=not first),
@@ -92,6 +92,30 @@ class InConv(nn.Module):
         return self.conv(x)
 
 
+class DownSample(nn.Module):
+    """DoubleConv then MaxPool2d(2); returns (features, pooled) — reference UG_unet_parts.py:31-41
+    (legacy UNet encoder block).  The pool is fused into the second BN/ReLU pass."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = DoubleConv(in_channels, out_channels)
+        self.pool = nn.MaxPool2d(kernel_size=2, stride=2)
+
+    def _run(self, x):
+        """fp32 NCHW image (first block) or NHWC bf16 -> (features, pooled), both NHWC bf16."""
+        return self.conv._run("first" if self.conv._first else "plain", x, emit_pool=True)
+
+    def forward(self, x):
+        _require_cuda(x, "DownSample")
+        if self.conv._first:
+            x = x.float().contiguous()
+            a, p = self._run(x)
+            return _out(a, False, x), _out(p, False, x)
+        xin, fast = _in(x)
+        a, p = self._run(xin)
+        return _out(a, fast, x), _out(p, fast, x)
+
+
 class Down(nn.Module):
     """MaxPool2d(2) then DoubleConv — reference UG_unet_parts.py:44-54."""
 
@@ -103,6 +127,34 @@ class Down(nn.Module):
         _require_cuda(x, "Down")
         xin, fast = _in(x)
         return _out(self.mpconv[1]._run("pool", xin), fast, x)
+
+
+class UpSample(nn.Module):
+    """ConvTranspose2d(in, in//2, 2, 2) of x1, cat([x1, x2]), DoubleConv — reference
+    UG_unet_parts.py:57-67 (legacy UNet decoder block).  The transposed convolution is a tcgen05 GEMM
+    whose epilogue writes the pixel-shuffled result; the concat is walked as two sources."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+        self.conv = DoubleConv(in_channels, out_channels)
+        if in_channels % 128 != 0 or in_channels > 1024:
+            raise ValueError(f"UpSample: in_channels={in_channels} unsupported (multiple of 128, <= 1024)")
+        self._tpack = engine.TConvPackedWeights(self.up)
+
+    def _run(self, low, skip):
+        """NHWC bf16 (low-res, skip) -> NHWC bf16."""
+        up = engine.ConvTranspose2x2Fn.apply(low, self.up.weight, self.up.bias, self._tpack)
+        return self.conv._run("cat", up, skip)
+
+    def forward(self, x1, x2):
+        _require_cuda(x1, "UpSample")
+        low, fast1 = _in(x1)
+        skip, fast2 = _in(x2)
+        if low.shape[3] // 2 + skip.shape[3] != self.conv.conv_op[0].in_channels:
+            raise RuntimeError(f"UpSample: expected {self.conv.conv_op[0].in_channels} concatenated channels, got "
+                               f"{low.shape[3] // 2} + {skip.shape[3]}")
+        return _out(self._run(low, skip), fast1 and fast2, x1)
 
 
 class Up(nn.Module):
