@@ -109,6 +109,13 @@ int ugp_channel_sum(const void* x, long long pixels, int C, float* out, void* st
 int ugp_im2col_first(const float* x, int B, int Cin, int Hin, int Win, int H,
                      int W, void* out, void* stream);
 
+/* The same packer fed with the loaders' native bytes: uint8 HWC images [B,Hin,Win,Cin] (np.array of a
+ * PIL image; MoNuSegImprove/test_monuseg.py:178-181, monuseg_dataset.py:137-187) with ToTensor's /255
+ * and an optional Normalize(mean, std) (Herlev/herlev_dataset.py:200-228) folded in:
+ *   value = (byte / 255 - mean[c]) / std[c].   mean / std: HOST arrays of Cin floats, nullable (0 / 1). */
+int ugp_im2col_first_u8(const unsigned char* x, int B, int Cin, int Hin, int Win, int H, int W,
+                        const float* mean, const float* stddev, void* out, void* stream);
+
 /* ---- BatchNorm2d / ReLU / MaxPool2d / bilinear x2 ------------------------ */
 /* Train-mode statistics -> scale/shift, running-stat update (eps, momentum as
  * nn.BatchNorm2d: biased var to normalise, unbiased into running_var,
@@ -180,6 +187,10 @@ int ugp_bce_uncertainty_loss(const float* z, const float* t, const float* A,
                              float alpha, float pos_weight, int B,
                              long long per_image, float grad_scale, float* dlogits,
                              double* out, void* stream);
+/* The same with the mask stored as uint8 0/1 bytes (the loaders' format before `.float()`). */
+int ugp_bce_uncertainty_loss_u8(const float* z, const unsigned char* t, const float* A, float alpha,
+                                float pos_weight, int B, long long per_image, float grad_scale,
+                                float* dlogits, double* out, void* stream);
 /* mean(CE_i * (1 + alpha*u_i)) pieces (Herlev/train_herlev.py:274-281):
  * out: double[3] = {sum CE*w, sum CE, #correct}. */
 int ugp_ce_weighted_loss(const float* logits, const long long* labels,
@@ -192,6 +203,19 @@ int ugp_ce_weighted_loss(const float* logits, const long long* labels,
  * dx[b][p][c] = dy[b][c] / HW (bf16).  C multiple of 64 (fwd) / 8 (bwd). */
 int ugp_global_avg_pool(const void* x, int B, int HW, int C, float* out, void* stream);
 int ugp_global_avg_pool_bwd(const float* dy, int B, int HW, int C, void* dx, void* stream);
+
+/* ---- evaluation reductions ---------------------------------------------------------
+ * Segmentation evaluator (MoNuSegImprove/test_monuseg.py:186-201, 244-258, 264-297): pred = z > 0
+ * (sigmoid(z) > 0.5); out: double[B][4] = {TP, sum pred, sum gt, sum sigmoid(z)} per image - IoU, Dice,
+ * accuracy, precision, recall, specificity and the mean-probability "confidence" follow from these and the
+ * pixel count.  gt: fp32 or (gt_is_u8) uint8 0/1, nullable; mask (nullable): uint8 0/1 prediction. */
+int ugp_seg_confusion(const float* z, const void* gt, int gt_is_u8, int B, long long per_image,
+                      unsigned char* mask, double* out, void* stream);
+/* Classification evaluator (Herlev/test_herlev.py:128-133, 196-204, 232): probs = softmax(logits)
+ * [B][K], preds = argmax int64 [B], confusion[label][pred] += 1 (int64 [K][K], caller zeroes);
+ * probs / preds / labels+confusion nullable. */
+int ugp_cls_eval(const float* logits, const long long* labels, int B, int K, float* probs,
+                 long long* preds, long long* confusion, void* stream);
 
 /* ---- optimiser ----------------------------------------------------------- */
 /* torch.optim.RMSprop step (uncertainty_guided_trainer.py:84-88; alpha,

@@ -314,6 +314,37 @@ def accuracy(pred: Tensor, target: Tensor) -> float:
     return 1.0 - pred.ne(target).sum().item() / pred.numel()
 
 
+def seg_metrics(pred: Tensor, gt: Tensor) -> Dict[str, float]:
+    """IoU / Dice / accuracy / precision / recall / specificity of one 0/1 prediction against one 0/1
+    mask with eps = 1e-8 — MoNuSegEvaluator.calculate_metrics, MoNuSegImprove/test_monuseg.py:264-297."""
+    p, g = pred.double().flatten(), gt.double().flatten()
+    tp = float((p * g).sum())
+    fp = float(p.sum()) - tp
+    fn = float(g.sum()) - tp
+    tn = p.numel() - tp - fp - fn
+    eps = 1e-8
+    return {"iou": (tp + eps) / (tp + fp + fn + eps), "dice": (2 * tp + eps) / (2 * tp + fp + fn + eps),
+            "accuracy": (tp + tn + eps) / (tp + tn + fp + fn + eps), "precision": (tp + eps) / (tp + fp + eps),
+            "recall": (tp + eps) / (tp + fn + eps), "specificity": (tn + eps) / (tn + fp + eps)}
+
+
+def evaluate_segmentation(sd: StateDict, stage: int, images_u8: Tensor, gts: Tensor):
+    """MoNuSegEvaluator.evaluate_dataset / predict_image on tensors — test_monuseg.py:176-201, 236-258:
+    x = bytes/255 (HWC -> CHW), eval-mode logits, mask = sigmoid > 0.5, confidence = mean sigmoid,
+    per-image metrics, then np.mean / np.std (population) over images.
+    Returns (masks [B,1,H,W] float, confidences [B], per-image metric dicts, avg, std, logits)."""
+    x = images_u8.permute(0, 3, 1, 2).float() / 255.0
+    with torch.no_grad():
+        logits = pgunet_forward(sd, x, stage, training=False)
+    probs = torch.sigmoid(logits)
+    masks = (probs > 0.5).float()
+    conf = probs.flatten(1).mean(1)
+    per = [seg_metrics(masks[i], gts[i]) for i in range(x.shape[0])]
+    avg = {k: sum(m[k] for m in per) / len(per) for k in per[0]}
+    std = {k: math.sqrt(sum((m[k] - avg[k]) ** 2 for m in per) / len(per)) for k in per[0]}
+    return masks, conf, per, avg, std, logits
+
+
 def softmax_entropy_uncertainty(logits: Tensor) -> Tensor:
     """u = H(softmax(z)) / ln K per sample — Herlev/train_herlev.py:253-257."""
     p = F.softmax(logits, dim=1)

@@ -717,3 +717,167 @@ def test_legacy_unet_against_reference_golden(dev, golden_dir):
     with O.bf16_storage(True):
         eev = O.legacy_unet_forward(esd2, fx["x"], False)
     assert rel(ev, fx["eval_logits"]) <= 1.5 * rel(eev, fx["eval_logits"]) + 5e-3
+
+
+# --------------------------------------------------------------------------- uint8 input path / evaluators
+def test_byte_input_packer_matches_float_packer(dev):
+    """ugp_im2col_first_u8 (uint8 HWC bytes, /255 + Normalize + resize folded in) against the fp32 NCHW
+    packer fed with the tensor the reference's loaders would build (ToTensor, Normalize)."""
+    from ug_pg_unet_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    img = torch.randint(0, 256, (3, 96, 80, 3), device="cuda", generator=g, dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    for m, s in ((None, None), (mean, std)):
+        x = img.permute(0, 3, 1, 2).float() / 255.0
+        if m is not None:
+            x = (x - torch.tensor(m, device="cuda").view(1, 3, 1, 1)) / torch.tensor(s, device="cuda").view(1, 3, 1, 1)
+        for (H, W) in ((96, 80), (64, 64)):
+            a = ops.im2col_first_u8(img, H, W, m, s).float()
+            b = ops.im2col_first(x.contiguous(), H, W).float()
+            # same arithmetic up to one fp32 rounding before the bf16 store: at most 1 bf16 ulp, rarely
+            assert (a - b).abs().max().item() <= 2.0 ** -7 * b.abs().max().item()
+            assert (a != b).float().mean().item() < 0.02
+            assert torch.equal(a[..., 27:], torch.zeros_like(a[..., 27:]))
+
+
+def test_byte_targets_and_byte_images_train_like_float_tensors(dev):
+    """The fused loss with uint8 masks is bit-identical to the float-mask kernel, and a model fed uint8
+    HWC bytes produces the logits / gradients of the same model fed the loader's float tensor."""
+    import ug_oracle as O
+    import ug_pg_unet_b200 as U
+    from ug_pg_unet_b200 import ops
+
+    g = torch.Generator().manual_seed(9)
+    z = (torch.randn(2, 1, 64, 64, generator=g) * 2).to(dev)
+    t8 = torch.randint(0, 2, (2, 1, 64, 64), generator=g, dtype=torch.uint8).to(dev)
+    A = torch.rand(2, 1, 64, 64, generator=g).to(dev)
+    o1, d1 = ops.bce_uncertainty_loss(z, t8.float(), A, 1.0, 5.0, True, 1.0 / z.numel())
+    o2, d2 = ops.bce_uncertainty_loss(z, t8, A, 1.0, 5.0, True, 1.0 / z.numel())
+    assert torch.equal(d1, d2) and torch.allclose(o1, o2, rtol=1e-12, atol=0)
+
+    img = torch.randint(0, 256, (2, 64, 64, 3), generator=g, dtype=torch.uint8).to(dev)
+    model = U.PGUNet2(3, 1).to(dev)
+    model.load_state_dict(O.seeded_state_dict(2, 3, 1, seed=8))
+    model.train()
+    outs = []
+    for x in (img, (img.permute(0, 3, 1, 2).float() / 255.0).contiguous()):
+        model.zero_grad(set_to_none=True)
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.reset_running_stats()
+        logits = model(x)
+        ugl = U.UncertaintyGuidedLoss(dev)
+        crit = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([5.0], device=dev), reduction="none")
+        loss, _ = ugl.apply_uncertainty_weighted_loss(crit, logits, t8 if x.dtype == torch.uint8 else t8.float(), None, 1.0)
+        loss.backward()
+        outs.append((logits.detach().clone(), loss.item(), model.up2.conv.conv_op[3].weight.grad.clone()))
+    assert rel(outs[0][0], outs[1][0]) < 2e-2 and abs(outs[0][1] - outs[1][1]) < 2e-3 * abs(outs[1][1])
+    assert rel(outs[0][2], outs[1][2]) < 1e-1
+    # resize folded into the packer: 64 x 64 bytes -> the 32 x 32 stage-1 model
+    prev = U.PGUNet1(3, 1).to(dev)
+    prev.load_state_dict(O.seeded_state_dict(1, 3, 1, seed=1))
+    A8 = U.UncertaintyGuidedLoss(dev).generate_uncertainty_map(img, prev, 32, 64)
+    Af = U.UncertaintyGuidedLoss(dev).generate_uncertainty_map((img.permute(0, 3, 1, 2).float() / 255.0).contiguous(),
+                                                               prev, 32, 64)
+    assert (A8 - Af).abs().max().item() < 5e-2 and rel(A8, Af) < 2e-2
+
+
+def test_trainer_step_accepts_loader_bytes(dev):
+    """UncertaintyGuidedProgressiveTrainer.train_step with uint8 HWC images + uint8 masks (eager and
+    CUDA-graph replays) tracks the same trainer fed float tensors."""
+    import ug_oracle as O
+    import ug_pg_unet_b200 as U
+
+    g = torch.Generator().manual_seed(12)
+    img = torch.randint(0, 256, (2, 64, 64, 3), generator=g, dtype=torch.uint8).to(dev)
+    y8 = torch.randint(0, 2, (2, 1, 64, 64), generator=g, dtype=torch.uint8).to(dev)
+    losses = []
+    for as_bytes in (True, False):
+        tr = U.UncertaintyGuidedProgressiveTrainer(3, 1, device=dev, uncertainty_alpha=1.0)
+        tr.models[1].load_state_dict(O.seeded_state_dict(1, 3, 1, seed=1))
+        tr.models[2].load_state_dict(O.seeded_state_dict(2, 3, 1, seed=2))
+        tr.current_stage, tr.current_model = 2, tr.models[2]
+        tr.setup_optimizer(2)
+        tr.current_model.train()
+        tr.models[1].eval()
+        x = img if as_bytes else (img.permute(0, 3, 1, 2).float() / 255.0).contiguous()
+        y = y8 if as_bytes else y8.float()
+        ls = []
+        for _ in range(6):                       # 3 eager warm-ups, capture, 2 replays
+            m, out, unc = tr.train_step(x, y, 2)
+            ls.append(tr._metrics_from_device(m, out.numel(), out.shape[0], unc is not None)[0])
+        losses.append(ls)
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 2e-2 * abs(b) + 1e-3, (losses)
+    assert losses[0][-1] < losses[0][0]          # it trains
+
+
+def test_segmentation_evaluator_against_reference_golden(dev, golden_dir):
+    """MoNuSegEvaluator mirror (uint8 bytes and float tensors) vs the fixture produced by the unmodified
+    MoNuSegImprove/test_monuseg.py arithmetic: masks bit-exact away from the decision boundary, metrics
+    within the effect of the flipped pixels."""
+    import ug_oracle as O
+    import ug_pg_unet_b200 as U
+
+    fx = torch.load(os.path.join(golden_dir, "evaluator.pt"))
+    model = U.PGUNet2(3, 1).to(dev)
+    model.load_state_dict(O.seeded_state_dict(2, 3, 1, seed=8))
+    ev = U.MoNuSegEvaluator(model, device=dev)
+    zr = fx["logits"]
+    safe = zr.abs() > 0.05 * zr.abs().max()
+    for images in (fx["images"], (fx["images"].permute(0, 3, 1, 2).float() / 255.0).contiguous()):
+        mask, conf = ev.predict_batch(images)
+        assert mask.dtype == torch.uint8 and tuple(mask.shape) == tuple(fx["masks"].shape)
+        assert torch.equal(mask.cpu()[safe], fx["masks"][safe])
+        flips = (mask.cpu() != fx["masks"]).float().flatten(1).mean(1)
+        for i in range(4):
+            assert abs(conf[i].item() - fx["confidence"][i]) < 2e-2
+        avg, std = ev.evaluate_batches([(images[:2], fx["gts"][:2]), (images[2:], fx["gts"][2:].float())])
+        for k in fx["avg"]:
+            assert abs(avg[k] - fx["avg"][k]) <= 4 * flips.max().item() + 1e-3, (k, avg[k], fx["avg"][k])
+            assert abs(std[k] - fx["std"][k]) <= 4 * flips.max().item() + 1e-3
+    # the counting kernel itself is exact: feed it the reference's logits
+    from ug_pg_unet_b200 import ops
+    counts, m2 = ops.seg_confusion(zr.to(dev).contiguous(), fx["gts"].to(dev).view(4, -1), want_mask=True)
+    assert torch.equal(m2.cpu(), fx["masks"])
+    got = U.metrics_from_counts(counts[:, 0], counts[:, 1], counts[:, 2], 64.0 * 64.0)
+    for i, m in enumerate(fx["per_image"]):
+        for k, v in m.items():
+            assert abs(got[k][i].item() - v) < 1e-6
+    up, _ = ev.predict_batch(fx["images"], out_size=(100, 90))
+    assert tuple(up.shape[-2:]) == (100, 90)
+
+
+def test_classification_evaluator_kernels(dev):
+    """ugp_cls_eval vs torch softmax / argmax / a host confusion matrix; HerlevEvaluator on uint8 bytes
+    equals the same model on the ImageNet-normalised float tensor."""
+    import ug_pg_unet_b200 as U
+    from ug_pg_unet_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    z = (torch.randn(37, 7, generator=g) * 3).to(dev)
+    y = torch.randint(0, 7, (37,), generator=g).to(dev)
+    probs, preds, cm = ops.cls_eval(z, y)
+    assert torch.equal(preds, z.argmax(1))
+    assert torch.allclose(probs, torch.softmax(z, 1), rtol=1e-5, atol=1e-7)
+    ref = torch.zeros(7, 7, dtype=torch.int64)
+    for a, b in zip(y.tolist(), z.argmax(1).tolist()):
+        ref[a, b] += 1
+    assert torch.equal(cm.cpu(), ref)
+    _, _, cm = ops.cls_eval(z, y, cm)
+    assert torch.equal(cm.cpu(), 2 * ref)
+
+    torch.manual_seed(0)
+    model = U.HerlevClassificationModel(stage=2, num_classes=7).to(dev)
+    ev = U.HerlevEvaluator(model, device=dev)
+    img = torch.randint(0, 256, (5, 64, 64, 3), generator=g, dtype=torch.uint8)
+    x = img.permute(0, 3, 1, 2).float() / 255.0
+    x = (x - torch.tensor(U.evaluate.IMAGENET_MEAN).view(1, 3, 1, 1)) / torch.tensor(U.evaluate.IMAGENET_STD).view(1, 3, 1, 1)
+    p8, pr8, c8 = ev.predict_batch(img)
+    pf, prf, cf = ev.predict_batch(x.contiguous())
+    assert rel(pr8, prf) < 2e-2 and pr8.shape == (5, 7) and torch.allclose(pr8.sum(1), torch.ones(5, device=dev), atol=1e-5)
+    labels = torch.randint(0, 7, (5,), generator=g)
+    res = ev.evaluate_batches([(img[:3], labels[:3]), (img[3:], labels[3:])])
+    assert res["total_samples"] == 5 and int(res["confusion_matrix"].sum()) == 5
+    assert abs(res["accuracy"] - (p8.cpu() == labels).float().mean().item()) < 1e-9

@@ -180,3 +180,21 @@ def test_herlev_model_surface_matches_reference_tables():
     m = H.HerlevClassificationModel(1, 7)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 3, 32, 32))
+
+
+def test_metrics_from_counts_matches_the_oracle():
+    """evaluate.metrics_from_counts (host arithmetic on the kernel's confusion counts) vs
+    oracle.seg_metrics (MoNuSegImprove/test_monuseg.py:264-297), including empty masks."""
+    import torch
+    import ug_oracle as O
+    from ug_pg_unet_b200.evaluate import metrics_from_counts
+
+    g = torch.Generator().manual_seed(0)
+    cases = [((torch.rand(16, 16, generator=g) > 0.5).float(), (torch.rand(16, 16, generator=g) > 0.7).float()),
+             (torch.zeros(8, 8), torch.zeros(8, 8)), (torch.ones(8, 8), torch.zeros(8, 8)),
+             (torch.zeros(8, 8), torch.ones(8, 8))]
+    for p, t in cases:
+        want = O.seg_metrics(p, t)
+        got = metrics_from_counts(float((p * t).sum()), float(p.sum()), float(t.sum()), float(p.numel()))
+        for k, v in want.items():
+            assert abs(got[k] - v) < 1e-12, k

@@ -178,3 +178,19 @@ def test_legacy_unet_matches_reference(golden_dir):
         sd_eval.update(bn)
         torch.testing.assert_close(O.legacy_unet_forward(sd_eval, fx["x"], False), fx["eval_logits"], rtol=1e-4,
                                    atol=1e-4)
+
+
+def test_evaluator_matches_reference(golden_dir):
+    """oracle.seg_metrics / evaluate_segmentation vs the unmodified MoNuSegEvaluator arithmetic
+    (MoNuSegImprove/test_monuseg.py:176-201, 236-258, 264-297)."""
+    fx = torch.load(os.path.join(golden_dir, "evaluator.pt"))
+    sd = O.seeded_state_dict(2, 3, 1, seed=8)
+    masks, conf, per, avg, std, logits = O.evaluate_segmentation(sd, 2, fx["images"], fx["gts"].float())
+    torch.testing.assert_close(logits, fx["logits"], rtol=1e-4, atol=1e-4)
+    assert torch.equal(masks.to(torch.uint8), fx["masks"])
+    for i, m in enumerate(fx["per_image"]):
+        for k, v in m.items():
+            assert abs(per[i][k] - v) < 1e-6, (i, k)        # the reference accumulates in float32
+        assert abs(float(conf[i]) - fx["confidence"][i]) < 1e-6
+    for k in fx["avg"]:
+        assert abs(avg[k] - fx["avg"][k]) < 1e-6 and abs(std[k] - fx["std"][k]) < 1e-6

@@ -199,8 +199,48 @@ def legacy_case():
     return fx
 
 
+def evaluator_case():
+    """The reference's MoNuSegEvaluator (MoNuSegImprove/test_monuseg.py) driven on tensors: the
+    predict_image / evaluate_dataset arithmetic (:176-201, :236-258) and calculate_metrics (:264-297)
+    with a seeded stage-2 model on four 64 x 64 uint8 images."""
+    import numpy as np
+    sys.path.insert(0, "/root/reference/MoNuSegImprove")
+    with contextlib.redirect_stdout(io.StringIO()):
+        import test_monuseg as REFE
+    g = torch.Generator().manual_seed(41)
+    imgs = torch.randint(0, 256, (4, 64, 64, 3), generator=g, dtype=torch.uint8)
+    gts = (torch.rand(4, 64, 64, generator=g) > 0.6).float()
+    ev = REFE.MoNuSegEvaluator.__new__(REFE.MoNuSegEvaluator)
+    ev.device = "cpu"
+    ev.model = REF.PGUNet2(3, 1)
+    ev.model.load_state_dict(O.seeded_state_dict(2, 3, 1, seed=8), strict=True)
+    ev.model.eval()
+    masks, confs, per, logits = [], [], [], []
+    for i in range(imgs.shape[0]):
+        image_tensor = torch.from_numpy(np.array(imgs[i].numpy())).permute(2, 0, 1).float() / 255.0   # :180
+        image_tensor = image_tensor.unsqueeze(0)
+        with torch.no_grad():
+            output = ev.model(image_tensor)
+            probs = torch.sigmoid(output)
+            pred_mask = (probs > 0.5).float()
+        masks.append(pred_mask[0].to(torch.uint8))
+        confs.append(probs.mean().item())
+        logits.append(output[0])
+        m = ev.calculate_metrics(pred_mask.squeeze().numpy(), gts[i].numpy())
+        per.append({k: float(v) for k, v in m.items()})
+    avg = {k: float(np.mean([m[k] for m in per])) for k in per[0]}
+    std = {k: float(np.std([m[k] for m in per])) for k in per[0]}
+    return {"images": imgs, "gts": gts.to(torch.uint8), "masks": torch.stack(masks), "confidence": confs,
+            "per_image": per, "avg": avg, "std": std, "logits": torch.stack(logits)}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--evaluator-only" in sys.argv or len(sys.argv) == 1:
+        torch.save(evaluator_case(), os.path.join(OUT, "evaluator.pt"))
+        print("evaluator.pt written")
+        if "--evaluator-only" in sys.argv:
+            return
     if "--legacy-only" in sys.argv or "--all" in sys.argv or len(sys.argv) == 1:
         fx = legacy_case()
         path = os.path.join(OUT, "legacy_unet.pt")

@@ -7,6 +7,7 @@ uncertainty_guided_trainer.py):
     PGUNet1..4, ProgressiveUNet, UncertaintyGuidedLoss, UNet (legacy, ConvTranspose2d up path)
     UncertaintyGuidedProgressiveTrainer
     HerlevClassificationModel, HerlevTrainer          (Herlev/train_herlev.py)
+    MoNuSegEvaluator, HerlevEvaluator                 (MoNuSegImprove/test_monuseg.py, Herlev/test_herlev.py)
 
 Everything executes through libugp_b200.so (C ABI in include/ugp_b200.h);
 there is no CPU or library fallback.
@@ -16,10 +17,11 @@ from .unet import (PGUNet1, PGUNet2, PGUNet3, PGUNet4, ProgressiveUNet, STAGE_MO
                    UncertaintyGuidedLoss, transfer_state)
 from .trainer import UncertaintyGuidedProgressiveTrainer
 from .herlev import HerlevClassificationModel, HerlevTrainer
+from .evaluate import HerlevEvaluator, MoNuSegEvaluator, metrics_from_counts
 
 __all__ = [
     "DoubleConv", "InConv", "Down", "Up", "OutConv", "DownSample", "UpSample", "UNet",
     "PGUNet1", "PGUNet2", "PGUNet3", "PGUNet4", "ProgressiveUNet", "STAGE_MODELS",
     "UncertaintyGuidedLoss", "transfer_state", "UncertaintyGuidedProgressiveTrainer",
-    "HerlevClassificationModel", "HerlevTrainer",
+    "HerlevClassificationModel", "HerlevTrainer", "MoNuSegEvaluator", "HerlevEvaluator", "metrics_from_counts",
 ]

@@ -24,6 +24,10 @@ SIGNATURES = {
     "ugp_pack_weights_tconv": [_p, _i, _i, _p, _p, _p],
     "ugp_unpack_wgrad_tconv": [_p, _i, _i, _p, _i, _p],
     "ugp_channel_sum": [_p, _ll, _i, _p, _p],
+    "ugp_im2col_first_u8": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "ugp_bce_uncertainty_loss_u8": [_p, _p, _p, _f, _f, _i, _ll, _f, _p, _p, _p],
+    "ugp_seg_confusion": [_p, _p, _i, _i, _ll, _p, _p, _p],
+    "ugp_cls_eval": [_p, _p, _i, _i, _p, _p, _p, _p],
     "ugp_pack_weights": [_p, _i, _i, _p, _p, _p],
     "ugp_unpack_wgrad": [_p, _i, _i, _p, _i, _p],
     "ugp_im2col_first": [_p, _i, _i, _i, _i, _i, _i, _p, _p],

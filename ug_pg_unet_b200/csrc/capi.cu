@@ -54,6 +54,12 @@ int conv_transpose2x2_wgrad(const void*, const void*, int, int, int, int, int, f
 int pack_weights_tconv(const float*, int, int, void*, void*, cudaStream_t);
 int unpack_wgrad_tconv(float*, int, int, float*, int, cudaStream_t);
 int channel_sum(const void*, long long, int, float*, cudaStream_t);
+int im2col_first_u8(const unsigned char*, int, int, int, int, int, int, const float*, const float*, void*,
+                    cudaStream_t);
+int bce_uncertainty_loss_u8(const float*, const unsigned char*, const float*, float, float, int, long long,
+                            float, float*, double*, cudaStream_t);
+int seg_confusion(const float*, const void*, int, int, long long, unsigned char*, double*, cudaStream_t);
+int cls_eval(const float*, const long long*, int, int, float*, long long*, long long*, cudaStream_t);
 int rmsprop_conv_packed(float* const*, float* const*, float* const*, void* const*, void* const*,
                         const int*, const int*, int, float, float, float, float, float, cudaStream_t);
 }  // namespace ugp
@@ -211,5 +217,23 @@ int ugp_unpack_wgrad_tconv(float* dw_packed, int cin, int cout, float* grad, int
 }
 int ugp_channel_sum(const void* x, long long pixels, int C, float* out, void* stream) {
   return ugp::channel_sum(x, pixels, C, out, S(stream));
+}
+int ugp_im2col_first_u8(const unsigned char* x, int B, int Cin, int Hin, int Win, int H, int W,
+                        const float* mean, const float* stddev, void* out, void* stream) {
+  return ugp::im2col_first_u8(x, B, Cin, Hin, Win, H, W, mean, stddev, out, S(stream));
+}
+int ugp_bce_uncertainty_loss_u8(const float* z, const unsigned char* t, const float* A, float alpha,
+                                float pos_weight, int B, long long per_image, float grad_scale,
+                                float* dlogits, double* out, void* stream) {
+  return ugp::bce_uncertainty_loss_u8(z, t, A, alpha, pos_weight, B, per_image, grad_scale, dlogits, out,
+                                      S(stream));
+}
+int ugp_seg_confusion(const float* z, const void* gt, int gt_is_u8, int B, long long per_image,
+                      unsigned char* mask, double* out, void* stream) {
+  return ugp::seg_confusion(z, gt, gt_is_u8, B, per_image, mask, out, S(stream));
+}
+int ugp_cls_eval(const float* logits, const long long* labels, int B, int K, float* probs, long long* preds,
+                 long long* confusion, void* stream) {
+  return ugp::cls_eval(logits, labels, B, K, probs, preds, confusion, S(stream));
 }
 }  // extern "C"

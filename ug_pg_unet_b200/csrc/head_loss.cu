@@ -286,21 +286,22 @@ __global__ void softmax_entropy_kernel(const float* __restrict__ logits, int B, 
 //   out[4] = #(pred != target)          out[5 + 3*b + {0,1,2}] = per-image
 //   sum(pred*t), sum(pred), sum(t)      (pred = z > 0  <=>  sigmoid(z) > 0.5)
 // ----------------------------------------------------------------------------
+template <typename T>   // target storage: float (the reference's mask tensors) or uint8 (loader bytes)
 __global__ void __launch_bounds__(256)
-bce_uncertainty_loss_kernel(const float* __restrict__ z, const float* __restrict__ t,
+bce_uncertainty_loss_kernel(const float* __restrict__ z, const T* __restrict__ t,
                             const float* __restrict__ A, float alpha, float pos_weight,
                             int B, long long per_image, float grad_scale,
                             float* __restrict__ dlogits, double* __restrict__ out) {
   // gridDim.y = B; blocks of one image stride over its pixels
   const int b = blockIdx.y;
   const float* zb = z + b * per_image;
-  const float* tb = t + b * per_image;
+  const T* tb = t + b * per_image;
   const float* Ab = A ? A + b * per_image : nullptr;
   float* db = dlogits ? dlogits + b * per_image : nullptr;
   float s_lw = 0.f, s_l = 0.f, s_a = 0.f, s_a2 = 0.f, s_ne = 0.f, s_pt = 0.f, s_p = 0.f, s_t = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
        i < per_image; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float zz = zb[i], y = tb[i];
+    const float zz = zb[i], y = static_cast<float>(tb[i]);
     const float a = Ab ? Ab[i] : 0.f;
     const float wgt = Ab ? 1.f + alpha * a : 1.f;
     // softplus(-z) = log1p(exp(-|z|)) + max(-z, 0)
@@ -472,9 +473,10 @@ int softmax_entropy(const float* logits, int B, int K, float* u, cudaStream_t st
   return UGP_OK;
 }
 
-int bce_uncertainty_loss(const float* z, const float* t, const float* A, float alpha,
-                         float pos_weight, int B, long long per_image, float grad_scale,
-                         float* dlogits, double* out, cudaStream_t stream) {
+template <typename T>
+static int bce_uncertainty_loss_t(const float* z, const T* t, const float* A, float alpha,
+                                  float pos_weight, int B, long long per_image, float grad_scale,
+                                  float* dlogits, double* out, cudaStream_t stream) {
   UGP_REQUIRE(z && t && out, "bce_uncertainty_loss: null pointer");
   UGP_REQUIRE(B >= 1 && B <= 65535, "bce_uncertainty_loss: bad batch %d", B);
   UGP_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (5 + 3 * B), stream));
@@ -483,10 +485,24 @@ int bce_uncertainty_loss(const float* z, const float* t, const float* A, float a
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   dim3 grid(static_cast<unsigned>(bx), B);
-  bce_uncertainty_loss_kernel<<<grid, 256, 0, stream>>>(z, t, A, alpha, pos_weight, B, per_image,
-                                                       grad_scale, dlogits, out);
+  bce_uncertainty_loss_kernel<T><<<grid, 256, 0, stream>>>(z, t, A, alpha, pos_weight, B, per_image,
+                                                          grad_scale, dlogits, out);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
+}
+
+int bce_uncertainty_loss(const float* z, const float* t, const float* A, float alpha,
+                         float pos_weight, int B, long long per_image, float grad_scale,
+                         float* dlogits, double* out, cudaStream_t stream) {
+  return bce_uncertainty_loss_t<float>(z, t, A, alpha, pos_weight, B, per_image, grad_scale, dlogits, out,
+                                       stream);
+}
+
+int bce_uncertainty_loss_u8(const float* z, const unsigned char* t, const float* A, float alpha,
+                            float pos_weight, int B, long long per_image, float grad_scale,
+                            float* dlogits, double* out, cudaStream_t stream) {
+  return bce_uncertainty_loss_t<unsigned char>(z, t, A, alpha, pos_weight, B, per_image, grad_scale, dlogits,
+                                               out, stream);
 }
 
 int ce_weighted_loss(const float* logits, const long long* labels, const float* u, float alpha,

@@ -280,6 +280,7 @@ class DoubleConvFn(torch.autograd.Function):
 
     kind: 'plain'  x NHWC bf16
           'first'  x fp32 NCHW image, first conv runs through im2col (9*Cin <= 64)
+          'col'    x already packed first-layer rows [B,H,W,64] (uint8 loader bytes -> ops.im2col_first_u8)
           'pool'   MaxPool2d(2) then DoubleConv  (Down, UG_unet_parts.py:44-54)
           'up'     bilinear x2 of x, concat [skip, up], DoubleConv (Up, UG_unet_parts.py:70-81)
           'cat'    concat [x, skip] walked as two sources (UpSample, UG_unet_parts.py:64-67)
@@ -293,6 +294,8 @@ class DoubleConvFn(torch.autograd.Function):
         pre = None
         if kind == "first":
             srcs, taps = [ops.im2col_first(x)], 1
+        elif kind == "col":
+            srcs, taps = [x], 1
         elif kind == "pool":
             pre = x
             srcs, taps = [ops.maxpool2x2(x)], 9
@@ -306,7 +309,7 @@ class DoubleConvFn(torch.autograd.Function):
         a2, p2, s2 = cbr_forward([a1], 9, conv2, bn2, mod._packs[1], emit_pool, need_grad)
         ctx.mod, ctx.kind, ctx.emit_pool = mod, kind, emit_pool
         ctx.s1, ctx.s2, ctx.pre = s1, s2, pre
-        ctx.x_needs_grad = kind != "first" and ctx.needs_input_grad[3]
+        ctx.x_needs_grad = kind not in ("first", "col") and ctx.needs_input_grad[3]
         ctx.skip_needs_grad = skip is not None and ctx.needs_input_grad[4]
         if emit_pool:
             return a2, p2
@@ -470,6 +473,8 @@ class BCEUncertaintyLossFn(torch.autograd.Function):
         zc = z.detach().contiguous()
         n = zc.numel()
         want = ctx.needs_input_grad[0]
+        if t.dtype != torch.uint8 and t.dtype != torch.float32:
+            t = t.float()
         out, dlogits = ops.bce_uncertainty_loss(zc, t.contiguous(), None if A is None else A.contiguous(),
                                                 alpha, pos_weight, want, 1.0 / n)
         ctx.dlogits = dlogits

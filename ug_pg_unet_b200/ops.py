@@ -274,6 +274,21 @@ def im2col_first(x: torch.Tensor, H: Optional[int] = None, W: Optional[int] = No
     return out
 
 
+def im2col_first_u8(x: torch.Tensor, H: Optional[int] = None, W: Optional[int] = None, mean=None, std=None):
+    """uint8 HWC image bytes [B,Hin,Win,Cin] -> bf16 [B,H,W,64] first-layer rows with ToTensor's /255, an
+    optional per-channel Normalize(mean, std) (python sequences) and the bilinear resize folded in."""
+    _req(x, torch.uint8, "x")
+    B, Hin, Win, cin = x.shape
+    H = Hin if H is None else H
+    W = Win if W is None else W
+    m = None if mean is None else (C.c_float * cin)(*[float(v) for v in mean])
+    sd = None if std is None else (C.c_float * cin)(*[float(v) for v in std])
+    out = torch.empty((B, H, W, 64), dtype=bf16, device=x.device)
+    check(lib().ugp_im2col_first_u8(_ptr(x), B, cin, Hin, Win, H, W, m, sd, _ptr(out), _stream()),
+          "ugp_im2col_first_u8")
+    return out
+
+
 # ----------------------------------------------------------------------------- BN / pool / upsample
 _STAT_PARTS = None
 
@@ -444,17 +459,52 @@ def softmax_entropy(logits):
 def bce_uncertainty_loss(z, t, A, alpha: float, pos_weight: float, want_grad: bool, grad_scale: float):
     """Returns (out double[5+3B], dlogits or None); see ugp_bce_uncertainty_loss."""
     _req(z, torch.float32, "logits")
-    _req(t, torch.float32, "target")
+    u8 = t.dtype == torch.uint8          # mask bytes straight from the loader
+    _req(t, torch.uint8 if u8 else torch.float32, "target")
     if t.shape != z.shape:
         raise ValueError(f"Target size ({tuple(t.shape)}) must be the same as input size ({tuple(z.shape)})")
     B = z.shape[0]
     per_image = z.numel() // B
     out = torch.empty((5 + 3 * B,), dtype=torch.float64, device=z.device)
     dlogits = torch.empty_like(z) if want_grad else None
-    check(lib().ugp_bce_uncertainty_loss(_ptr(z), _ptr(t), _ptr(_opt(A, torch.float32, "uncertainty")),
-                                         alpha, pos_weight, B, per_image, grad_scale, _ptr(dlogits),
-                                         _ptr(out), _stream()), "ugp_bce_uncertainty_loss")
+    fn = lib().ugp_bce_uncertainty_loss_u8 if u8 else lib().ugp_bce_uncertainty_loss
+    check(fn(_ptr(z), _ptr(t), _ptr(_opt(A, torch.float32, "uncertainty")), alpha, pos_weight, B, per_image,
+             grad_scale, _ptr(dlogits), _ptr(out), _stream()), "ugp_bce_uncertainty_loss")
     return out, dlogits
+
+
+def seg_confusion(z, gt=None, want_mask: bool = False):
+    """Per-image {TP, sum pred, sum gt, sum sigmoid} (float64 [B,4]) of pred = z > 0 against gt (fp32 or
+    uint8 0/1, optional) and, when asked, the uint8 prediction mask; see ugp_seg_confusion."""
+    _req(z, torch.float32, "logits")
+    B = z.shape[0]
+    per_image = z.numel() // B
+    u8 = gt is not None and gt.dtype == torch.uint8
+    if gt is not None:
+        _req(gt, torch.uint8 if u8 else torch.float32, "gt")
+        if gt.numel() != z.numel():
+            raise ValueError(f"ground truth size {tuple(gt.shape)} does not match logits {tuple(z.shape)}")
+    out = torch.empty((B, 4), dtype=torch.float64, device=z.device)
+    mask = torch.empty(z.shape, dtype=torch.uint8, device=z.device) if want_mask else None
+    check(lib().ugp_seg_confusion(_ptr(z), _ptr(gt), int(u8), B, per_image, _ptr(mask), _ptr(out), _stream()),
+          "ugp_seg_confusion")
+    return out, mask
+
+
+def cls_eval(logits, labels=None, confusion=None):
+    """softmax probabilities, argmax predictions and (with labels) the confusion matrix update."""
+    _req(logits, torch.float32, "logits")
+    B, K = logits.shape
+    probs = torch.empty_like(logits)
+    preds = torch.empty((B,), dtype=torch.int64, device=logits.device)
+    if labels is not None:
+        _req(labels, torch.int64, "labels")
+        if confusion is None:
+            confusion = torch.zeros((K, K), dtype=torch.int64, device=logits.device)
+        _req(confusion, torch.int64, "confusion")
+    check(lib().ugp_cls_eval(_ptr(logits), _ptr(labels), B, K, _ptr(probs), _ptr(preds),
+                             _ptr(confusion) if labels is not None else None, _stream()), "ugp_cls_eval")
+    return probs, preds, confusion
 
 
 def ce_weighted_loss(logits, labels, u, alpha: float, want_grad: bool, grad_scale: float):

@@ -157,6 +157,11 @@ class UncertaintyGuidedProgressiveTrainer:
         """Forward + fused loss.  Returns (final_loss tensor, logits, metrics device tensor or None,
         base_loss float or None)."""
         uncertainty_map = None
+        if data.dtype == torch.uint8:     # loader bytes: /255, Normalize and the stage resize run in the packer
+            res = self.stage_configs[stage]["resolution"]
+            run_model = lambda d: self.current_model(d, resolution=res)
+        else:
+            run_model = self.current_model
         side = self._streams(data)[0] if (stage > 1 and self.overlap_streams and data.is_cuda) else None
         if side is not None:
             # independent of the current model until the loss: runs beside its forward
@@ -166,10 +171,10 @@ class UncertaintyGuidedProgressiveTrainer:
                 uncertainty_map = self.uncertainty_loss.generate_uncertainty_map(
                     data, self.models[stage - 1], self.stage_configs[stage - 1]["resolution"],
                     self.stage_configs[stage]["resolution"])
-            output_current = self.current_model(data)
+            output_current = run_model(data)
             main.wait_stream(side)
         else:
-            output_current = self.current_model(data)
+            output_current = run_model(data)
             if stage > 1:
                 uncertainty_map = self.uncertainty_loss.generate_uncertainty_map(
                     data, self.models[stage - 1], self.stage_configs[stage - 1]["resolution"],
@@ -217,7 +222,12 @@ class UncertaintyGuidedProgressiveTrainer:
         return final_loss, metrics
 
     def _resize(self, data, target, resolution):
-        """reference :208-209; identity when the loader already yields the stage resolution."""
+        """reference :208-209; identity when the loader already yields the stage resolution.  uint8 HWC
+        image bytes are left alone: their resize happens inside the first-layer packer."""
+        if data.dtype == torch.uint8:
+            if target.shape[-2:] != (resolution, resolution):
+                target = F.interpolate(target, size=(resolution, resolution), mode="nearest")
+            return data, target
         if data.shape[-2:] != (resolution, resolution):
             data = F.interpolate(data, size=(resolution, resolution), mode="bilinear", align_corners=True)
         if target.shape[-2:] != (resolution, resolution):

@@ -26,23 +26,47 @@ class _PGUNetBase(nn.Module):
     _downs: tuple = ()
     _ups: tuple = ()
     _heads: tuple = ()
+    # Normalisation folded into the first-layer packer for uint8 inputs: (byte/255 - mean) / std per
+    # channel (ToTensor + optional Normalize of the reference's loaders); None = ToTensor only.
+    input_mean = None
+    input_std = None
 
-    def encode(self, x: torch.Tensor, depth: Optional[int] = None):
-        """Runs `inc` and the first `depth` Down blocks (all by default) on an fp32 NCHW image; returns
-        the list of NHWC bf16 feature maps.  The max-pool feeding each Down is fused into the
-        producer's BN/ReLU pass."""
+    def set_input_norm(self, mean=None, std=None):
+        """Per-channel Normalize(mean, std) applied to uint8 image inputs (python sequences or None)."""
+        self.input_mean = None if mean is None else tuple(float(v) for v in mean)
+        self.input_std = None if std is None else tuple(float(v) for v in std)
+        return self
+
+    def pack_bytes(self, x: torch.Tensor, resolution: Optional[int] = None) -> torch.Tensor:
+        """uint8 HWC image bytes [B,H,W,C] -> first-layer rows at `resolution` (bilinear,
+        align_corners=True, like uncertainty_guided_trainer.py:208) with /255 + Normalize folded in."""
+        if x.dim() != 4 or x.shape[-1] != self.inc.conv.conv_op[0].in_channels:
+            raise ValueError(f"{type(self).__name__}: uint8 input must be [B, H, W, "
+                             f"{self.inc.conv.conv_op[0].in_channels}] image bytes, got {tuple(x.shape)}")
+        return ops.im2col_first_u8(x.contiguous(), resolution, resolution, self.input_mean, self.input_std)
+
+    def encode(self, x: torch.Tensor, depth: Optional[int] = None, resolution: Optional[int] = None):
+        """Runs `inc` and the first `depth` Down blocks (all by default) on an fp32 NCHW image - or on
+        uint8 HWC image bytes, see `pack_bytes` - and returns the list of NHWC bf16 feature maps.  The
+        max-pool feeding each Down is fused into the producer's BN/ReLU pass."""
         _require_cuda(x, type(self).__name__)
-        if x.dtype != torch.float32:
-            x = x.float()
         downs = [getattr(self, n) for n in self._downs]
         if depth is not None:
             downs = downs[:depth]
-        x = x.contiguous()
+        if x.dtype == torch.uint8:
+            kind, x = "col", self.pack_bytes(x, resolution)
+        else:
+            kind = "first"
+            if x.dtype != torch.float32:
+                x = x.float()
+            if resolution is not None and tuple(x.shape[-2:]) != (resolution, resolution):
+                kind, x = "col", ops.im2col_first(x.contiguous(), resolution, resolution)
+            x = x.contiguous()
         feats = []
         if downs:
-            a, p = self.inc.conv._run("first", x, emit_pool=True)
+            a, p = self.inc.conv._run(kind, x, emit_pool=True)
         else:
-            a, p = self.inc.conv._run("first", x), None
+            a, p = self.inc.conv._run(kind, x), None
         feats.append(a)
         for i, d in enumerate(downs):
             dc = d.mpconv[1]
@@ -53,8 +77,10 @@ class _PGUNetBase(nn.Module):
             feats.append(a)
         return feats
 
-    def forward(self, x):
-        feats = self.encode(x)
+    def forward(self, x, resolution: Optional[int] = None):
+        """fp32 NCHW image (the reference's call) or uint8 HWC bytes -> raw fp32 NCHW logits.
+        `resolution` (optional) resizes the input inside the first-layer packer."""
+        feats = self.encode(x, resolution=resolution)
         cur = feats[-1]
         dec = []
         n = len(feats) - 1
@@ -252,8 +278,10 @@ class UncertaintyGuidedLoss(nn.Module):
             raise ValueError(f"Target size ({target_current.size()}) must be the same as input size "
                              f"({output_current.size()})")
         pw = 1.0 if loss_fn.pos_weight is None else _pos_weight_value(loss_fn)
+        if target_current.dtype != torch.uint8:      # uint8 masks feed the kernel as bytes
+            target_current = target_current.float()
         final_loss, out = engine.BCEUncertaintyLossFn.apply(
-            output_current, target_current.float(), uncertainty_map, float(alpha), pw)
+            output_current, target_current, uncertainty_map, float(alpha), pw)
         self.last_metrics = out
         return final_loss, out
 
@@ -288,6 +316,8 @@ def _pos_weight_value(loss_fn) -> float:
 def _forward_resized(model: _PGUNetBase, x: torch.Tensor, resolution: int) -> torch.Tensor:
     """model(F.interpolate(x, resolution, bilinear, align_corners=True)) with the resize folded into the
     first-layer packer (UG_unet.py:36-43)."""
+    if x.dtype == torch.uint8:
+        return _forward_from_col(model, model.pack_bytes(x, resolution))
     if x.shape[-1] == resolution and x.shape[-2] == resolution:
         return model(x)
     if x.dtype != torch.float32:
