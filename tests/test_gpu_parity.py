@@ -808,8 +808,11 @@ def test_trainer_step_accepts_loader_bytes(dev):
             m, out, unc = tr.train_step(x, y, 2)
             ls.append(tr._metrics_from_device(m, out.numel(), out.shape[0], unc is not None)[0])
         losses.append(ls)
+    # same trajectory: identical first step, then within the drift RMSprop's sign-like first updates
+    # give two bf16 runs (tools/check_noise.py)
+    assert abs(losses[0][0] - losses[1][0]) <= 1e-3 * abs(losses[1][0])
     for a, b in zip(*losses):
-        assert abs(a - b) <= 2e-2 * abs(b) + 1e-3, (losses)
+        assert abs(a - b) <= 5e-2 * abs(b) + 1e-3, (losses)
     assert losses[0][-1] < losses[0][0]          # it trains
 
 

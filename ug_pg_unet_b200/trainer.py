@@ -254,7 +254,9 @@ class UncertaintyGuidedProgressiveTrainer:
         if self._reducer is not None:
             self._reducer.wait()
         self.optimizer.step()
-        return self.uncertainty_loss.last_metrics, output_current, unc
+        # detached: a caller holding the logits must not keep this step's autograd graph (and its
+        # AccumulateGrad nodes, created on the warm-up stream) alive into the CUDA-graph capture
+        return self.uncertainty_loss.last_metrics, output_current.detach(), unc
 
     def train_step(self, data, target, stage):
         """One optimisation step on already-resident device tensors; no host synchronisation.
