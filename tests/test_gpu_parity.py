@@ -537,7 +537,8 @@ def test_config3_herlev_stage4_256_seven_classes(dev):
     import io
     import ug_pg_unet_b200.herlev as H
 
-    cfg = {"device": dev, "epochs_per_stage": 1, "num_classes": 7, "uncertainty_alpha": 1.0, "log_interval": 0}
+    cfg = {"device": dev, "epochs_per_stage": 1, "num_classes": 7, "uncertainty_alpha": 1.0, "log_interval": 0,
+           "stage4_resolution": 256}
     torch.manual_seed(1)
     with contextlib.redirect_stdout(io.StringIO()):
         tr = H.HerlevTrainer(cfg)
@@ -884,3 +885,112 @@ def test_classification_evaluator_kernels(dev):
     res = ev.evaluate_batches([(img[:3], labels[:3]), (img[3:], labels[3:])])
     assert res["total_samples"] == 5 and int(res["confusion_matrix"].sum()) == 5
     assert abs(res["accuracy"] - (p8.cpu() == labels).float().mean().item()) < 1e-9
+
+
+# --------------------------------------------------------------------------- general image sizes
+@pytest.mark.parametrize("shape", [(2, 56, 56, 64, 0, 128), (1, 28, 28, 128, 64, 256), (1, 112, 112, 64, 0, 64),
+                                   (2, 24, 40, 64, 0, 64), (1, 224, 224, 64, 0, 64), (1, 14, 14, 256, 0, 512),
+                                   (3, 12, 20, 128, 128, 128), (1, 48, 48, 64, 0, 256)])
+def test_convolutions_at_general_sizes_against_torch(dev, shape):
+    """Forward (+ BN statistics), input gradient and weight gradient of the 3x3 convolution at sizes that
+    do not tile into 128-pixel runs (the reference's Herlev stage 4 runs 224 -> 112 -> 56 -> 28; H != W):
+    boxes with BW*BH <= 128 pixels, masked accumulator rows, 4-D stores."""
+    import torch.nn.functional as F
+    from ug_pg_unet_b200 import ops
+
+    B, H, W, c0, c1, cout = shape
+    cin = c0 + c1
+    g = torch.Generator(device="cuda").manual_seed(H * W + cout)
+    x0 = torch.randn(B, H, W, c0, device="cuda", generator=g).bfloat16()
+    x1 = torch.randn(B, H, W, c1, device="cuda", generator=g).bfloat16() if c1 else None
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3.0 * math.sqrt(cin))).bfloat16().float()
+    bias = torch.randn(cout, device="cuda", generator=g)
+    dz = torch.randn(B, H, W, cout, device="cuda", generator=g).bfloat16()
+    wf, wd = ops.pack_weights(w)
+    xin = x0.float().permute(0, 3, 1, 2) if x1 is None else torch.cat([x0, x1], 3).float().permute(0, 3, 1, 2)
+    xin = xin.contiguous().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    ref = F.conv2d(xin, wr, bias, padding=1)
+    ref.backward(dz.float().permute(0, 3, 1, 2))
+    stats = ops.new_stats(cout, "cuda")
+    out = ops.conv_gemm(x0, x1, wf, 9, cout, bias=bias, stats=stats)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 6e-3
+    o = out.float().reshape(-1, cout)
+    s = stats.sum(0)
+    assert rel(s[0], o.sum(0)) < 1e-4 and rel(s[1], (o * o).sum(0)) < 1e-4      # masked rows contribute nothing
+    if c1:
+        d0, d1 = ops.conv_gemm(dz, None, wd, 9, cin, split_n=c0)
+        dx = torch.cat([d0, d1], 3)
+    else:
+        dx = ops.conv_gemm(dz, None, wd, 9, cin)
+    assert rel(dx.permute(0, 3, 1, 2), xin.grad) < 6e-3
+    dwp = torch.zeros(9 * cin * cout, device="cuda")
+    ops.conv_wgrad(x0, x1, dz, 9, dwp)
+    assert rel(ops.unpack_wgrad(dwp, cout, cin), wr.grad) < 2e-3
+    # eval-mode epilogue (affine + ReLU) on the same tiles
+    sc = torch.rand(cout, device="cuda", generator=g) + 0.5
+    sh = torch.randn(cout, device="cuda", generator=g) * 0.2
+    oe = ops.conv_gemm(x0, x1, wf, 9, cout, bias=bias, scale=sc, shift=sh, relu=True)
+    assert rel(oe.permute(0, 3, 1, 2), F.relu(ref.detach() * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))) < 6e-3
+
+
+@pytest.mark.parametrize("size", [(224, 224), (96, 160)])
+def test_pgunet_at_general_sizes_against_oracle(dev, size):
+    """A whole PGUNet4 training step at 224 x 224 (14 x 14 bottleneck) and at H != W against the oracle."""
+    import ug_oracle as O
+    import ug_pg_unet_b200 as U
+
+    H, W = size
+    g = torch.Generator().manual_seed(H)
+    x = torch.randn(1, 3, H, W, generator=g)
+    y = torch.randint(0, 2, (1, 1, H, W), generator=g).float()
+    sd = O.seeded_state_dict(4, 3, 1, seed=4)
+    model = U.PGUNet4(3, 1).to(dev)
+    model.load_state_dict(sd)
+    model.train()
+    logits = model(x.to(dev))
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y.to(dev))
+    loss.backward()
+
+    def oracle(bf):
+        esd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+               for k, v in sd.items()}
+        with O.bf16_storage(bf):
+            z = O.pgunet_forward(esd, x, 4, training=True)
+            l = torch.nn.functional.binary_cross_entropy_with_logits(z, y)
+            l.backward()
+        return z.detach(), l.item(), esd
+
+    zr, lr_, rsd = oracle(False)
+    ze, le, esd = oracle(True)
+    assert tuple(logits.shape) == (1, 1, H, W)
+    assert rel(logits, zr) <= 1.5 * rel(ze, zr) + 2e-3, (rel(logits, zr), rel(ze, zr))
+    assert abs(loss.item() - lr_) <= max(1e-3 * lr_, 2.5 * abs(le - lr_)) + 2e-4
+    for k, prm in model.named_parameters():
+        if k.endswith(("conv_op.0.bias", "conv_op.3.bias")):
+            continue
+        fl = rel(esd[k].grad, rsd[k].grad)
+        assert rel(prm.grad, rsd[k].grad) <= 1.5 * fl + 2e-2, (k, rel(prm.grad, rsd[k].grad), fl)
+
+
+def test_herlev_stage4_at_the_reference_resolution_224(dev):
+    """Herlev/train_herlev.py:138 trains stage 4 at 224 x 224 (encoder maps 224 / 112 / 56 / 28)."""
+    import contextlib
+    import io
+    import ug_pg_unet_b200.herlev as Hm
+
+    cfg = {"device": dev, "epochs_per_stage": 1, "num_classes": 7, "uncertainty_alpha": 1.0, "log_interval": 0}
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = Hm.HerlevTrainer(cfg)
+        tr.setup_optimizer_scheduler(4)
+        tr.transfer_weights(3, 4)
+    assert tr.stage_configs[4]["resolution"] == 224
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(4, 3, 224, 224, generator=g)
+    y = torch.randint(0, 7, (4,), generator=g)
+    with contextlib.redirect_stdout(io.StringIO()):
+        loss, base, acc, um, us = tr.train_epoch([(x, y), (x, y)], 4)
+        vl, vb, va, vum, vus = tr.validate_epoch([(x, y)], 4)
+    assert all(math.isfinite(v) for v in (loss, base, vl, vb)) and 0.0 <= acc <= 100.0
+    assert tr.models[4].unet.down3.mpconv[1].conv_op[0].weight.grad is not None

@@ -41,6 +41,7 @@ struct EpilogueCtx {
   uint32_t stats_stride; // in floats
   uint32_t scratch_addr; // 2 KB: the four row-quarter partials of one chunk (kStatsScratchBytes)
   bool has_bias, has_affine, relu, do_stats;
+  int valid_rows = 128;  // tile rows >= valid_rows hold no pixel (BW*BH < 128 boxes): stored / counted as zero
 };
 
 // v: 64 fp32 accumulator values of this thread's row (columns n_base .. n_base+63).
@@ -51,6 +52,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint3
                                                const CUtensorMap* tm_out, int out_col, int out_row,
                                                int out_y = -1, int out_b = 0) {
   uint32_t packed[32];
+  const bool live_row = row < e.valid_rows;
 #pragma unroll
   for (int j = 0; j < 64; j += 4) {
     float f0 = __uint_as_float(v[j + 0]), f1 = __uint_as_float(v[j + 1]);
@@ -69,8 +71,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint3
       f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f);
       f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f);
     }
-    packed[j / 2] = pack_bf16x2(f0, f1);
-    packed[j / 2 + 1] = pack_bf16x2(f2, f3);
+    packed[j / 2] = live_row ? pack_bf16x2(f0, f1) : 0u;
+    packed[j / 2 + 1] = live_row ? pack_bf16x2(f2, f3) : 0u;
   }
   // the TMA store that last read this staging buffer must be done (folding this wait into the
   // previous chunk's statistics barrier was measured slower: it puts the store's read latency on

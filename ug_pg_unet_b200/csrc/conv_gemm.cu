@@ -131,7 +131,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         for (int kb0 = 0; kb0 < k_blocks; kb0 += kG) {
           const int g = (k_blocks - kb0 < kG) ? (k_blocks - kb0) : kG;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], g * Cfg::kBlockBytes);
+          // an A box carries valid_rows (= BW*BH <= 128) rows of 128 B
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], g * (p.valid_rows * 128 + Cfg::kBTileBytes));
           for (int i = 0; i < g; ++i) {
             const int kb = kb0 + i;
             const int tap = kb / chunks;
@@ -210,6 +211,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     ectx.has_affine = p.scale != nullptr;
     ectx.relu = p.relu != 0;
     ectx.do_stats = do_stats;
+    ectx.valid_rows = p.valid_rows;
     uint32_t chunk_counter = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -290,7 +292,8 @@ static int launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1,
   return UGP_OK;
 }
 
-// Picks the 128-pixel box (BW x BH) for an H x W image.
+// Picks the 128-pixel box (BW x BH) for an H x W image whose tiles are runs of consecutive NHWC pixels
+// (full rows, or pieces of one row): the destination is then a plain 2-D [pixels, C] map.
 static bool pick_box(int H, int W, int pixels, int* BW, int* BH) {
   int bw = W < pixels ? W : pixels;
   if (W % bw != 0) return false;
@@ -299,6 +302,22 @@ static bool pick_box(int H, int W, int pixels, int* BW, int* BH) {
   *BW = bw;
   *BH = bh;
   return true;
+}
+
+// Any other image size (224 -> 112 -> 56 -> 28 ..., H != W): the box with the most pixels <= `pixels`
+// whose sides divide W and H, so tiles never overhang the image.  BW*BH may be < `pixels`: the unused
+// accumulator rows are masked in the epilogue; the tile is stored through a 4-D (C, x, y, b) map.
+bool pick_box_general(int H, int W, int pixels, int* BW, int* BH) {
+  int best = 0;
+  for (int bw = 1; bw <= W && bw <= pixels; ++bw) {
+    if (W % bw != 0) continue;
+    for (int bh = pixels / bw; bh >= 1; --bh) {
+      if (H % bh != 0 || bh > 256) continue;
+      if (bw * bh > best || (bw * bh == best && bw > *BW)) { best = bw * bh; *BW = bw; *BH = bh; }
+      break;
+    }
+  }
+  return best > 0;
 }
 
 // conv_halo.cu
@@ -336,10 +355,13 @@ int conv_gemm_bf16_ex(const void* src0, int c0, const void* src1, int c1, int B,
   if (!viewed && g_conv_halo_mode != 0 && conv_halo_eligible(H, W, cout, split_n, taps))
     return conv_halo_bf16(src0, c0, src1, c1, B, H, W, wpack, cout, dst0, dst1, split_n, bias, scale,
                           shift, relu, stats, stream);
-  int BW, BH;
-  UGP_REQUIRE(pick_box(H, W, kBlockM, &BW, &BH),
-              "conv_gemm: unsupported spatial size %dx%d (need W in {16,32,64,128} or a "
-              "multiple of 128, and H a multiple of 128/min(W,128))", H, W);
+  int BW = 0, BH = 0;
+  const bool general = !pick_box(H, W, kBlockM, &BW, &BH);
+  if (general) {
+    UGP_REQUIRE(H > 0 && W > 0 && pick_box_general(H, W, kBlockM, &BW, &BH),
+                "conv_gemm: unsupported spatial size %dx%d", H, W);
+    UGP_REQUIRE(dst_view == nullptr && src_view == nullptr, "conv_gemm: strided views need power-of-two tiles");
+  }
   int kn = 256;
   while (kn > 64 && cout % kn != 0) kn >>= 1;   // the epilogue routes each 64-column chunk to dst0 / dst1
 
@@ -358,7 +380,8 @@ int conv_gemm_bf16_ex(const void* src0, int c0, const void* src1, int c1, int B,
   p.split_n = split_n;
   p.relu = relu;
   p.bias_period = bias_period > 0 ? bias_period : cout;
-  p.out4d = dst_view != nullptr;
+  p.out4d = dst_view != nullptr || general;
+  p.valid_rows = BW * BH;
   p.bias = bias; p.scale = scale; p.shift = shift; p.stats = stats;
 
   CUtensorMap tmA0, tmA1, tmW, tmO0, tmO1;
@@ -374,7 +397,7 @@ int conv_gemm_bf16_ex(const void* src0, int c0, const void* src1, int c1, int B,
   }
   if (c1 == 0) tmA1 = tmA0;
   // CTA pairs (cta_group::2) for the 256-wide tiles: each CTA stages half of the weight tile
-  const bool pair = !viewed && kn == 256 && conv_pair_eligible(p.m_tiles, cout, split_n);
+  const bool pair = !viewed && !general && kn == 256 && conv_pair_eligible(p.m_tiles, cout, split_n);
   if ((rc = make_tmap_2d_bf16(&tmW, wpack, (long long)taps * cout, c0 + c1, 64, pair ? 128 : kn))) return rc;
   const long long M = (long long)B * H * W;
   if (dst_view) {
@@ -382,6 +405,9 @@ int conv_gemm_bf16_ex(const void* src0, int c0, const void* src1, int c1, int B,
                                        dst_view->img, 64, BW, BH))) return rc;
     if (split_n < cout && (rc = make_tmap_nhwc_view_bf16(&tmO1, dst1, B, H, W, cout - split_n, dst_view->pix,
                                                          dst_view->row, dst_view->img, 64, BW, BH))) return rc;
+  } else if (general) {
+    if ((rc = make_tmap_nhwc_bf16(&tmO0, dst0, B, H, W, split_n, 64, BW, BH))) return rc;
+    if (split_n < cout && (rc = make_tmap_nhwc_bf16(&tmO1, dst1, B, H, W, cout - split_n, 64, BW, BH))) return rc;
   } else {
     if ((rc = make_tmap_2d_bf16(&tmO0, dst0, M, split_n, 64, kBlockM))) return rc;
     if (split_n < cout && (rc = make_tmap_2d_bf16(&tmO1, dst1, M, cout - split_n, 64, kBlockM))) return rc;

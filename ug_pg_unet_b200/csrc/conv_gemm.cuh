@@ -16,7 +16,8 @@ struct ConvGemmParams {
   int split_n;
   int relu;
   int bias_period;   // bias[n % bias_period] (= cout for a plain convolution)
-  int out4d;         // destinations are strided 4-D views (C, x, y, b): ConvTranspose2d phases
+  int out4d;         // destinations are 4-D views (C, x, y, b): ConvTranspose2d phases, non-contiguous tiles
+  int valid_rows;    // BW * BH <= 128: accumulator rows that are real pixels (general image sizes)
   const float* bias;
   const float* scale;
   const float* shift;

@@ -23,19 +23,23 @@
 
 namespace ugp {
 
+bool pick_box_general(int H, int W, int pixels, int* BW, int* BH);   // conv_gemm.cu
 extern int g_conv_debug;
 extern int g_wgrad_waves;   // CTA waves the split-K grid is sized for (default 1)
 
 struct WgradParams {
   int taps;
   int chunks0, chunks1;   // 64-channel chunks of source 0 / 1
-  int H, W, BHp, BWp;     // 64-pixel K box
+  int H, W, BHp, BWp;     // K box of BWp x BHp <= 64 pixels
+  int tiles_x, tiles_y;   // boxes per image row / column
+  int box_bytes;          // BWp * BHp * 128: bytes one TMA box delivers (8 KB for a full 64-pixel box)
+  int zero_fill;          // box < 64 pixels: the unused K rows of every stage buffer must be zero
   int boxes;              // taps * (chunks0 + chunks1)
   int m_tiles;            // ceil(boxes / 2)
   int m_groups;           // ceil(m_tiles / kT)
   int n_tiles;
   int cout;
-  int kchunks_total;      // B*H*W / 64
+  int kchunks_total;      // B * tiles_x * tiles_y
   int kchunks_per_split;
   float* dw;              // [boxes*64][cout] fp32, accumulated
   int debug;              // what-if timing only: 1 = skip MMA issue, 2 = skip the reduction stores
@@ -103,6 +107,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc(tmem_slot, 512);
+  if (p.zero_fill) {
+    // partial K boxes (general image sizes): TMA only writes the first BWp*BHp rows of each 64-row
+    // box, the MMAs read all 64 -> the rest must contribute zero
+    uint4* z4 = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < kStages * Cfg::kStageBytes / 16; i += blockDim.x) z4[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -113,16 +124,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
   if (warp_idx == 0) {
     const bool leader = elect_one() != 0;     // whole-warp loop, elected lane issues (uniform operands)
     {
-      const int hw = p.H * p.W;
-      const uint32_t stage_bytes = nt * 2 * kWgBoxBytes + Cfg::kBBytes;
+      const uint32_t stage_bytes = (nt * 2 + kN / 64) * p.box_bytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = kc_begin; kc < kc_end; ++kc) {
-        const int p0 = kc * 64;
-        const int b = p0 / hw;
-        const int rem = p0 - b * hw;
-        const int y0 = rem / p.W;
-        const int x0 = rem - y0 * p.W;
+        const int t2 = kc / p.tiles_x;
+        const int x0 = (kc - t2 * p.tiles_x) * p.BWp;
+        const int b = t2 / p.tiles_y;
+        const int y0 = (t2 - b * p.tiles_y) * p.BHp;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
         uint8_t* a_dst = sA + stage * Cfg::kABytes;
@@ -265,8 +274,12 @@ int conv_wgrad_bf16_ex(const void* src0, int c0, const void* src1, int c1,
     return conv_wgrad_halo_bf16(src0, c0, src1, c1, dz, cout, B, H, W, dw_packed, stream);
   int BWp = W < 64 ? W : 64;
   int BHp = 64 / BWp;
-  UGP_REQUIRE(W % BWp == 0 && BWp * BHp == 64 && H % BHp == 0,
-              "conv_wgrad: unsupported spatial size %dx%d", H, W);
+  if (!(W % BWp == 0 && BWp * BHp == 64 && H % BHp == 0)) {
+    // general image sizes: the largest box <= 64 pixels whose sides divide W and H
+    BWp = BHp = 0;
+    UGP_REQUIRE(H > 0 && W > 0 && pick_box_general(H, W, 64, &BWp, &BHp),
+                "conv_wgrad: unsupported spatial size %dx%d", H, W);
+  }
   int kn = 256;
   while (kn > 64 && cout % kn != 0) kn >>= 1;
 
@@ -280,7 +293,11 @@ int conv_wgrad_bf16_ex(const void* src0, int c0, const void* src1, int c1,
   p.m_groups = 0;
   p.n_tiles = cout / kn;
   p.cout = cout;
-  p.kchunks_total = (int)(((long long)B * H * W) / 64);
+  p.tiles_x = W / BWp;
+  p.tiles_y = H / BHp;
+  p.box_bytes = BWp * BHp * 128;
+  p.zero_fill = BWp * BHp < 64;
+  p.kchunks_total = B * p.tiles_x * p.tiles_y;
   p.kchunks_per_split = 0;
   p.dw = dw_packed;
   p.debug = g_conv_debug;

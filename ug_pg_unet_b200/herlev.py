@@ -138,10 +138,10 @@ class HerlevTrainer:
             1: {"resolution": 32, "epochs": config["epochs_per_stage"], "lr": 3e-4},
             2: {"resolution": 64, "epochs": config["epochs_per_stage"], "lr": 1e-4},
             3: {"resolution": 128, "epochs": config["epochs_per_stage"], "lr": 1e-4},
-            # the reference trains stage 4 at 224 (:137); 224 -> 112 -> 56 -> 28 pixel maps do not tile into
-            # the 128-pixel TMA boxes of the conv kernels, so this port uses the U-Net's native 256
-            # (BASELINE.json configs[3]) unless the config overrides it with a supported size
-            4: {"resolution": config.get("stage4_resolution", 256), "epochs": config["epochs_per_stage"], "lr": 1e-4},
+            # the reference trains stage 4 at 224 (:138): 224 -> 112 -> 56 -> 28 pixel maps run on the
+            # general-size tiles of the conv kernels (boxes of <= 128 pixels whose sides divide the map);
+            # BASELINE.json configs[3] quotes 256 (power-of-two tiles, the fast halo / pair kernels)
+            4: {"resolution": config.get("stage4_resolution", 224), "epochs": config["epochs_per_stage"], "lr": 1e-4},
         }
         self.current_stage = 1
         self.models, self.optimizers, self.schedulers = {}, {}, {}
