@@ -170,6 +170,11 @@ int ugp_head_combine_fwd(const float* const* maps, const int* sizes, int n,
                          int planes, int R, float* logits, void* stream);
 int ugp_head_combine_bwd(const float* dlogits, int planes, int R, int size,
                          float* dl, void* stream);
+/* The same for rectangular images (H != W): map s is heights[s] x widths[s], logits RH x RW. */
+int ugp_head_combine_fwd_hw(const float* const* maps, const int* heights, const int* widths, int n,
+                            int planes, int RH, int RW, float* logits, void* stream);
+int ugp_head_combine_bwd_hw(const float* dlogits, int planes, int RH, int RW, int h, int w,
+                            float* dl, void* stream);
 
 /* ---- uncertainty + loss -------------------------------------------------- */
 /* A = 1 - 2*|up(sigmoid(z_prev)) - 0.5| (UG_unet.py:44-57). */

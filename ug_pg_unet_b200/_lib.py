@@ -43,6 +43,8 @@ SIGNATURES = {
     "ugp_outconv_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p],
     "ugp_head_combine_fwd": [_p, _p, _i, _i, _i, _p, _p],
     "ugp_head_combine_bwd": [_p, _i, _i, _i, _p, _p],
+    "ugp_head_combine_fwd_hw": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "ugp_head_combine_bwd_hw": [_p, _i, _i, _i, _i, _i, _p, _p],
     "ugp_uncertainty_margin": [_p, _i, _i, _i, _i, _i, _p, _p],
     "ugp_softmax_entropy": [_p, _i, _i, _p, _p],
     "ugp_bce_uncertainty_loss": [_p, _p, _p, _f, _f, _i, _ll, _f, _p, _p, _p],

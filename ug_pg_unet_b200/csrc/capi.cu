@@ -35,6 +35,8 @@ int outconv_bwd(const void*, const float*, const float*, int, int, int, int, int
                 float*, cudaStream_t);
 int head_combine_fwd(const float* const*, const int*, int, int, int, float*, cudaStream_t);
 int head_combine_bwd(const float*, int, int, int, float*, cudaStream_t);
+int head_combine_fwd_hw(const float* const*, const int*, const int*, int, int, int, int, float*, cudaStream_t);
+int head_combine_bwd_hw(const float*, int, int, int, int, int, float*, cudaStream_t);
 int uncertainty_margin(const float*, int, int, int, int, int, float*, cudaStream_t);
 int softmax_entropy(const float*, int, int, float*, cudaStream_t);
 int bce_uncertainty_loss(const float*, const float*, const float*, float, float, int, long long,
@@ -235,5 +237,13 @@ int ugp_seg_confusion(const float* z, const void* gt, int gt_is_u8, int B, long 
 int ugp_cls_eval(const float* logits, const long long* labels, int B, int K, float* probs, long long* preds,
                  long long* confusion, void* stream) {
   return ugp::cls_eval(logits, labels, B, K, probs, preds, confusion, S(stream));
+}
+int ugp_head_combine_fwd_hw(const float* const* maps, const int* heights, const int* widths, int n, int planes,
+                            int RH, int RW, float* logits, void* stream) {
+  return ugp::head_combine_fwd_hw(maps, heights, widths, n, planes, RH, RW, logits, S(stream));
+}
+int ugp_head_combine_bwd_hw(const float* dlogits, int planes, int RH, int RW, int h, int w, float* dl,
+                            void* stream) {
+  return ugp::head_combine_bwd_hw(dlogits, planes, RH, RW, h, w, dl, S(stream));
 }
 }  // extern "C"

@@ -151,34 +151,34 @@ outconv_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 struct HeadMaps {
   const float* l[4];
   float* dl[4];
-  int size[4];
+  int h[4], w[4];   // map sizes (rectangular images: H != W)
   int n;
 };
 
-__global__ void head_combine_fwd_kernel(const HeadMaps m, int planes, int R,
+__global__ void head_combine_fwd_kernel(const HeadMaps m, int planes, int RH, int RW,
                                         float* __restrict__ logits) {
-  const long long total = static_cast<long long>(planes) * R * R;
+  const long long total = static_cast<long long>(planes) * RH * RW;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
        idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int X = static_cast<int>(idx % R);
-    const int Y = static_cast<int>((idx / R) % R);
-    const long long plane = idx / (static_cast<long long>(R) * R);
+    const int X = static_cast<int>(idx % RW);
+    const int Y = static_cast<int>((idx / RW) % RH);
+    const long long plane = idx / (static_cast<long long>(RH) * RW);
     // PyTorch evaluates x6_out + x7_out + x8_out + x9_out left to right,
     // coarsest first (UG_unet.py:303).
     float acc = 0.f;
     for (int s = 0; s < m.n; ++s) {
-      const int sz = m.size[s];
-      const float* src = m.l[s] + plane * sz * sz;
+      const int sh = m.h[s], sw = m.w[s];
+      const float* src = m.l[s] + plane * sh * sw;
       float v;
-      if (sz == R) {
-        v = __ldg(src + static_cast<long long>(Y) * R + X);
+      if (sh == RH && sw == RW) {
+        v = __ldg(src + static_cast<long long>(Y) * RW + X);
       } else {
         int y0, y1, x0, x1;
         float ly, lx;
-        bilinear_src_f(Y, sz, R, &y0, &y1, &ly);
-        bilinear_src_f(X, sz, R, &x0, &x1, &lx);
-        v = (1.f - ly) * ((1.f - lx) * __ldg(src + y0 * sz + x0) + lx * __ldg(src + y0 * sz + x1)) +
-            ly * ((1.f - lx) * __ldg(src + y1 * sz + x0) + lx * __ldg(src + y1 * sz + x1));
+        bilinear_src_f(Y, sh, RH, &y0, &y1, &ly);
+        bilinear_src_f(X, sw, RW, &x0, &x1, &lx);
+        v = (1.f - ly) * ((1.f - lx) * __ldg(src + y0 * sw + x0) + lx * __ldg(src + y0 * sw + x1)) +
+            ly * ((1.f - lx) * __ldg(src + y1 * sw + x0) + lx * __ldg(src + y1 * sw + x1));
       }
       acc = (s == 0) ? v : acc + v;
     }
@@ -189,26 +189,27 @@ __global__ void head_combine_fwd_kernel(const HeadMaps m, int planes, int R,
 // Adjoint of one upsampled scale in gather form: dl[y,x] = sum over the
 // high-res pixels whose interpolation stencil touches (y,x).
 __global__ void head_combine_bwd_kernel(const float* __restrict__ dlogits, int planes,
-                                        int R, int sz, float* __restrict__ dl) {
-  const long long total = static_cast<long long>(planes) * sz * sz;
-  const float inv = (sz > 1) ? static_cast<float>(R - 1) / static_cast<float>(sz - 1) : 0.f;
+                                        int RH, int RW, int sh, int sw, float* __restrict__ dl) {
+  const long long total = static_cast<long long>(planes) * sh * sw;
+  const float invy = (sh > 1) ? static_cast<float>(RH - 1) / static_cast<float>(sh - 1) : 0.f;
+  const float invx = (sw > 1) ? static_cast<float>(RW - 1) / static_cast<float>(sw - 1) : 0.f;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
        idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(idx % sz);
-    const int y = static_cast<int>((idx / sz) % sz);
-    const long long plane = idx / (static_cast<long long>(sz) * sz);
-    const float* g = dlogits + plane * R * R;
-    if (sz == R) { dl[idx] = g[static_cast<long long>(y) * R + x]; continue; }
-    int Ylo = static_cast<int>(floorf((y - 1) * inv)) - 1, Yhi = static_cast<int>(ceilf((y + 1) * inv)) + 1;
-    int Xlo = static_cast<int>(floorf((x - 1) * inv)) - 1, Xhi = static_cast<int>(ceilf((x + 1) * inv)) + 1;
+    const int x = static_cast<int>(idx % sw);
+    const int y = static_cast<int>((idx / sw) % sh);
+    const long long plane = idx / (static_cast<long long>(sh) * sw);
+    const float* g = dlogits + plane * RH * RW;
+    if (sh == RH && sw == RW) { dl[idx] = g[static_cast<long long>(y) * RW + x]; continue; }
+    int Ylo = static_cast<int>(floorf((y - 1) * invy)) - 1, Yhi = static_cast<int>(ceilf((y + 1) * invy)) + 1;
+    int Xlo = static_cast<int>(floorf((x - 1) * invx)) - 1, Xhi = static_cast<int>(ceilf((x + 1) * invx)) + 1;
     if (Ylo < 0) Ylo = 0;
     if (Xlo < 0) Xlo = 0;
-    if (Yhi > R - 1) Yhi = R - 1;
-    if (Xhi > R - 1) Xhi = R - 1;
+    if (Yhi > RH - 1) Yhi = RH - 1;
+    if (Xhi > RW - 1) Xhi = RW - 1;
     float acc = 0.f;
     for (int Y = Ylo; Y <= Yhi; ++Y) {
       int i0, i1; float l;
-      bilinear_src_f(Y, sz, R, &i0, &i1, &l);
+      bilinear_src_f(Y, sh, RH, &i0, &i1, &l);
       float wy = 0.f;
       if (i0 == y) wy += 1.f - l;
       if (i1 == y) wy += l;
@@ -216,11 +217,11 @@ __global__ void head_combine_bwd_kernel(const float* __restrict__ dlogits, int p
       float row = 0.f;
       for (int X = Xlo; X <= Xhi; ++X) {
         int j0, j1; float lx;
-        bilinear_src_f(X, sz, R, &j0, &j1, &lx);
+        bilinear_src_f(X, sw, RW, &j0, &j1, &lx);
         float wx = 0.f;
         if (j0 == x) wx += 1.f - lx;
         if (j1 == x) wx += lx;
-        if (wx != 0.f) row = fmaf(wx, __ldg(g + static_cast<long long>(Y) * R + X), row);
+        if (wx != 0.f) row = fmaf(wx, __ldg(g + static_cast<long long>(Y) * RW + X), row);
       }
       acc = fmaf(wy, row, acc);
     }
@@ -432,29 +433,43 @@ int outconv_bwd(const void* x, const float* w, const float* dl, int B, int hw, i
   return UGP_OK;
 }
 
-int head_combine_fwd(const float* const* maps, const int* sizes, int n, int planes, int R,
-                     float* logits, cudaStream_t stream) {
-  UGP_REQUIRE(n >= 1 && n <= 4 && logits, "head_combine_fwd: bad arguments");
+int head_combine_fwd_hw(const float* const* maps, const int* heights, const int* widths, int n, int planes,
+                        int RH, int RW, float* logits, cudaStream_t stream) {
+  UGP_REQUIRE(n >= 1 && n <= 4 && logits && maps && heights && widths, "head_combine_fwd: bad arguments");
   HeadMaps m;
   m.n = n;
   for (int i = 0; i < 4; ++i) {
     m.l[i] = i < n ? maps[i] : nullptr;
     m.dl[i] = nullptr;
-    m.size[i] = i < n ? sizes[i] : 0;
+    m.h[i] = i < n ? heights[i] : 0;
+    m.w[i] = i < n ? widths[i] : 0;
+    UGP_REQUIRE(i >= n || (m.h[i] >= 1 && m.h[i] <= RH && m.w[i] >= 1 && m.w[i] <= RW),
+                "head_combine_fwd: map %d is %dx%d, logits %dx%d", i, m.h[i], m.w[i], RH, RW);
   }
-  const long long total = static_cast<long long>(planes) * R * R;
-  head_combine_fwd_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, stream>>>(m, planes, R, logits);
+  const long long total = static_cast<long long>(planes) * RH * RW;
+  head_combine_fwd_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, stream>>>(m, planes, RH, RW, logits);
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
+}
+
+int head_combine_fwd(const float* const* maps, const int* sizes, int n, int planes, int R,
+                     float* logits, cudaStream_t stream) {
+  return head_combine_fwd_hw(maps, sizes, sizes, n, planes, R, R, logits, stream);
+}
+
+int head_combine_bwd_hw(const float* dlogits, int planes, int RH, int RW, int sh, int sw, float* dl,
+                        cudaStream_t stream) {
+  UGP_REQUIRE(dlogits && dl && sh >= 1 && sh <= RH && sw >= 1 && sw <= RW, "head_combine_bwd: bad arguments");
+  const long long total = static_cast<long long>(planes) * sh * sw;
+  head_combine_bwd_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, stream>>>(dlogits, planes, RH, RW, sh, sw,
+                                                                               dl);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
 
 int head_combine_bwd(const float* dlogits, int planes, int R, int sz, float* dl,
                      cudaStream_t stream) {
-  UGP_REQUIRE(dlogits && dl && sz >= 1 && sz <= R, "head_combine_bwd: bad arguments");
-  const long long total = static_cast<long long>(planes) * sz * sz;
-  head_combine_bwd_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, stream>>>(dlogits, planes, R, sz, dl);
-  UGP_CHECK_CUDA(cudaGetLastError());
-  return UGP_OK;
+  return head_combine_bwd_hw(dlogits, planes, R, R, sz, sz, dl, stream);
 }
 
 int uncertainty_margin(const float* zprev, int planes, int h, int w, int H, int W, float* A,

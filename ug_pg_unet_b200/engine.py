@@ -441,7 +441,7 @@ class HeadCombineFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, *maps):
-        ctx.sizes = [m.shape[-1] for m in maps]
+        ctx.sizes = [(m.shape[-2], m.shape[-1]) for m in maps]
         return ops.head_combine_fwd([m.contiguous() for m in maps])
 
     @staticmethod

@@ -424,19 +424,24 @@ def outconv_bwd(x, w, dl, dx, accumulate: bool, dw, db):
 def head_combine_fwd(maps: Sequence[torch.Tensor]):
     """logits = sum of the maps, each bilinearly upsampled (align_corners) to the last one's size."""
     n = len(maps)
-    B, nc, R, _ = maps[-1].shape
+    B, nc, RH, RW = maps[-1].shape
     logits = torch.empty_like(maps[-1])
     ptrs = (C.c_void_p * n)(*[_req(m, torch.float32, "map").data_ptr() for m in maps])
-    sizes = (C.c_int * n)(*[m.shape[-1] for m in maps])
-    check(lib().ugp_head_combine_fwd(ptrs, sizes, n, B * nc, R, _ptr(logits), _stream()), "ugp_head_combine_fwd")
+    hs = (C.c_int * n)(*[m.shape[-2] for m in maps])
+    ws = (C.c_int * n)(*[m.shape[-1] for m in maps])
+    check(lib().ugp_head_combine_fwd_hw(ptrs, hs, ws, n, B * nc, RH, RW, _ptr(logits), _stream()),
+          "ugp_head_combine_fwd")
     return logits
 
 
-def head_combine_bwd(dlogits, size: int):
+def head_combine_bwd(dlogits, size):
+    """`size`: side of a square map or (h, w)."""
     _req(dlogits, torch.float32, "dlogits")
-    B, nc, R, _ = dlogits.shape
-    dl = torch.empty((B, nc, size, size), dtype=torch.float32, device=dlogits.device)
-    check(lib().ugp_head_combine_bwd(_ptr(dlogits), B * nc, R, size, _ptr(dl), _stream()), "ugp_head_combine_bwd")
+    B, nc, RH, RW = dlogits.shape
+    h, w = (size, size) if isinstance(size, int) else size
+    dl = torch.empty((B, nc, h, w), dtype=torch.float32, device=dlogits.device)
+    check(lib().ugp_head_combine_bwd_hw(_ptr(dlogits), B * nc, RH, RW, h, w, _ptr(dl), _stream()),
+          "ugp_head_combine_bwd")
     return dl
 
 
