@@ -9,8 +9,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libugp_b200.so"
+# UGP_LIB_PATH: load another build of the same library (A/B timing of kernel changes on one box)
+LIB_PATH = Path(os.environ["UGP_LIB_PATH"]).resolve() if os.environ.get("UGP_LIB_PATH") else _PKG / "libugp_b200.so"
 
 _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 

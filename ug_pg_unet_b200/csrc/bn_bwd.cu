@@ -15,6 +15,7 @@
 
 namespace ugp {
 
+int g_bn_skip_reduce = 0;   // what-if timing only (results wrong): skip the reduction pass of the plain variant
 int g_bn_pool_vec4 = 0;   // pooled backward: 1 = 4-channel threads at 3 blocks/SM (measured: same speed; the kernel is issue-bound)
 
 struct BnBwdArgs {
@@ -455,7 +456,7 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
     long long blocks = (M + rows_per_block * 16 - 1) / (rows_per_block * 16);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    bn_relu_bwd_plain_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+    if (!g_bn_skip_reduce) bn_relu_bwd_plain_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
     UGP_CHECK_CUDA(cudaGetLastError());
     bn_relu_bwd_plain_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
   }

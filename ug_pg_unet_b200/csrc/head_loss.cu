@@ -42,33 +42,41 @@ outconv_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     for (int j = 0; j < 8; ++j) wr[k][j] = (k < nc) ? __ldg(w + k * C + sub * 8 + j) : 0.f;
   const long long gthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long pix_per_iter = gthreads / kLanes;
-  const long long iters = (M + pix_per_iter - 1) / pix_per_iter;
+  constexpr int kU = 4;   // independent 16-byte loads in flight per thread
+  const long long iters = (M + pix_per_iter * kU - 1) / (pix_per_iter * kU);
   long long pix = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) / kLanes;
-  for (long long it = 0; it < iters; ++it, pix += pix_per_iter) {
-    const bool live = pix < M;
-    float acc[kNC];
+  for (long long it = 0; it < iters; ++it, pix += pix_per_iter * kU) {
+    uint4 u[kU];
 #pragma unroll
-    for (int k = 0; k < kNC; ++k) acc[k] = 0.f;
-    if (live) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + pix * C + sub * 8);
-      const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                           bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+    for (int q = 0; q < kU; ++q) {
+      const long long pp = pix + q * pix_per_iter;
+      u[q] = (pp < M) ? *reinterpret_cast<const uint4*>(x + pp * C + sub * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int q = 0; q < kU; ++q) {
+      const long long pp = pix + q * pix_per_iter;
+      const bool live = pp < M;      // uniform over the kLanes lanes of a pixel; all lanes join the shuffles
+      float acc[kNC];
+#pragma unroll
+      for (int k = 0; k < kNC; ++k) acc[k] = 0.f;
+      const float xv[8] = {bf16_lo(u[q].x), bf16_hi(u[q].x), bf16_lo(u[q].y), bf16_hi(u[q].y),
+                           bf16_lo(u[q].z), bf16_hi(u[q].z), bf16_lo(u[q].w), bf16_hi(u[q].w)};
 #pragma unroll
       for (int k = 0; k < kNC; ++k)
         if (k < nc) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[k] = fmaf(xv[j], wr[k][j], acc[k]);
         }
-    }
 #pragma unroll
-    for (int k = 0; k < kNC; ++k)
-      if (k < nc) {
+      for (int k = 0; k < kNC; ++k)
+        if (k < nc) {
 #pragma unroll
-        for (int o = kLanes / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+          for (int o = kLanes / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        }
+      if (live && sub == 0) {
+        const long long b = pp / hw, r = pp % hw;
+        for (int k = 0; k < nc; ++k) out[(b * nc + k) * hw + r] = acc[k] + __ldg(bias + k);
       }
-    if (live && sub == 0) {
-      const long long b = pix / hw, r = pix % hw;
-      for (int k = 0; k < nc; ++k) out[(b * nc + k) * hw + r] = acc[k] + __ldg(bias + k);
     }
   }
 }
@@ -457,12 +465,56 @@ int head_combine_fwd(const float* const* maps, const int* sizes, int n, int plan
   return head_combine_fwd_hw(maps, sizes, sizes, n, planes, R, R, logits, stream);
 }
 
+// Warp-per-coarse-pixel form for the large stencils (x4, x8 upsampling: 11^2 .. 19^2 fine pixels per
+// coarse pixel, but only 16 K coarse pixels at batch 16): lanes stride over the window, shuffle reduce.
+__global__ void __launch_bounds__(256)
+head_combine_bwd_warp_kernel(const float* __restrict__ dlogits, int planes, int RH, int RW, int sh, int sw,
+                             float* __restrict__ dl) {
+  const long long total = static_cast<long long>(planes) * sh * sw;
+  const float invy = (sh > 1) ? static_cast<float>(RH - 1) / static_cast<float>(sh - 1) : 0.f;
+  const float invx = (sw > 1) ? static_cast<float>(RW - 1) / static_cast<float>(sw - 1) : 0.f;
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long idx = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; idx < total;
+       idx += warps) {
+    const int x = static_cast<int>(idx % sw);
+    const int y = static_cast<int>((idx / sw) % sh);
+    const long long plane = idx / (static_cast<long long>(sh) * sw);
+    const float* g = dlogits + plane * RH * RW;
+    int Ylo = static_cast<int>(floorf((y - 1) * invy)) - 1, Yhi = static_cast<int>(ceilf((y + 1) * invy)) + 1;
+    int Xlo = static_cast<int>(floorf((x - 1) * invx)) - 1, Xhi = static_cast<int>(ceilf((x + 1) * invx)) + 1;
+    if (Ylo < 0) Ylo = 0;
+    if (Xlo < 0) Xlo = 0;
+    if (Yhi > RH - 1) Yhi = RH - 1;
+    if (Xhi > RW - 1) Xhi = RW - 1;
+    const int wx_n = Xhi - Xlo + 1, n = (Yhi - Ylo + 1) * wx_n;
+    float acc = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const int Y = Ylo + i / wx_n, X = Xlo + i % wx_n;
+      int i0, i1, j0, j1;
+      float l, lx;
+      bilinear_src_f(Y, sh, RH, &i0, &i1, &l);
+      bilinear_src_f(X, sw, RW, &j0, &j1, &lx);
+      const float wy = (i0 == y ? 1.f - l : 0.f) + (i1 == y ? l : 0.f);
+      const float wx = (j0 == x ? 1.f - lx : 0.f) + (j1 == x ? lx : 0.f);
+      if (wy != 0.f && wx != 0.f) acc = fmaf(wy * wx, __ldg(g + static_cast<long long>(Y) * RW + X), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dl[idx] = acc;
+  }
+}
+
 int head_combine_bwd_hw(const float* dlogits, int planes, int RH, int RW, int sh, int sw, float* dl,
                         cudaStream_t stream) {
   UGP_REQUIRE(dlogits && dl && sh >= 1 && sh <= RH && sw >= 1 && sw <= RW, "head_combine_bwd: bad arguments");
   const long long total = static_cast<long long>(planes) * sh * sw;
-  head_combine_bwd_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, stream>>>(dlogits, planes, RH, RW, sh, sw,
-                                                                               dl);
+  if (RH >= 4 * sh || RW >= 4 * sw) {
+    head_combine_bwd_warp_kernel<<<grid_cap((total * 32 + 255) / 256, 16), 256, 0, stream>>>(dlogits, planes, RH,
+                                                                                           RW, sh, sw, dl);
+  } else {
+    head_combine_bwd_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, stream>>>(dlogits, planes, RH, RW, sh,
+                                                                                 sw, dl);
+  }
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }

@@ -18,6 +18,9 @@ import torch.nn as nn
 from . import ops
 
 bf16 = torch.bfloat16
+import os as _os
+# what-if timing switch (results wrong): skip the BatchNorm-backward reduction pass of each DoubleConv's first BN
+_WHATIF_SKIP_BN1_REDUCE = _os.environ.get("UGP_WHATIF_SKIP_BN1_REDUCE", "0") == "1"
 
 
 class PackedWeights:
@@ -326,7 +329,12 @@ class DoubleConvFn(torch.autograd.Function):
         dP = dP.contiguous() if dP is not None else None
         d1, g2 = cbr_backward(ctx.s2, dA, dP, conv2, bn2, mod._packs[1], True)
         need_in = ctx.x_needs_grad or ctx.skip_needs_grad
+        if _WHATIF_SKIP_BN1_REDUCE:
+            from ._lib import set_option
+            set_option("bn_skip_reduce", 1)
         d0, g1 = cbr_backward(ctx.s1, d1[0], None, conv1, bn1, mod._packs[0], need_in)
+        if _WHATIF_SKIP_BN1_REDUCE:
+            set_option("bn_skip_reduce", 0)
         dx = dskip = None
         if need_in:
             if ctx.kind == "pool":
