@@ -89,41 +89,53 @@ __global__ void bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ z,
                                      int W, int C, __nv_bfloat16* __restrict__ a,
                                      __nv_bfloat16* __restrict__ pooled) {
   const int cg = C >> 3;
+  // the grid stride (gridDim.x * 256) is a multiple of cg (256 % cg == 0, checked by the launcher), so
+  // a thread keeps its 8-channel group for the whole loop: scale / shift live in registers
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long first = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int c0 = static_cast<int>(first % cg) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + c0 + j); sh[j] = __ldg(shift + c0 + j); }
   if (!kPool) {
     const long long total = static_cast<long long>(B) * H * W * cg;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-         idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-      const int c0 = static_cast<int>(idx % cg) * 8;
+    for (long long idx = first; idx < total; idx += 2 * stride) {
+      // two independent 16-byte loads in flight per thread
+      const bool two = idx + stride < total;
       Vec8 v = load8(z + idx * 8);
+      Vec8 v2 = two ? load8(z + (idx + stride) * 8) : v;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        v.v[j] = bn_relu_val(v.v[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+      for (int j = 0; j < 8; ++j) {
+        v.v[j] = bn_relu_val(v.v[j], sc[j], sh[j]);
+        v2.v[j] = bn_relu_val(v2.v[j], sc[j], sh[j]);
+      }
       store8(a + idx * 8, v);
+      if (two) store8(a + (idx + stride) * 8, v2);
     }
   } else {
     const int Ho = H >> 1, Wo = W >> 1;
     const long long total = static_cast<long long>(B) * Ho * Wo * cg;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-         idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-      const int c0 = static_cast<int>(idx % cg) * 8;
+    for (long long idx = first; idx < total; idx += stride) {
       const long long op = idx / cg;
       const int xo = static_cast<int>(op % Wo);
       const int yo = static_cast<int>((op / Wo) % Ho);
       const int b = static_cast<int>(op / (static_cast<long long>(Wo) * Ho));
-      float sc[8], sh[8];
+      Vec8 v[4];
+      long long pix[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + c0 + j); sh[j] = __ldg(shift + c0 + j); }
+      for (int i = 0; i < 4; ++i) {
+        pix[i] = (static_cast<long long>(b) * H + (2 * yo + (i >> 1))) * W + 2 * xo + (i & 1);
+        v[i] = load8(z + pix[i] * C + c0);
+      }
       Vec8 best;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const long long pix = (static_cast<long long>(b) * H + (2 * yo + (i >> 1))) * W + 2 * xo + (i & 1);
-        Vec8 v = load8(z + pix * C + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          v.v[j] = round_bf16(bn_relu_val(v.v[j], sc[j], sh[j]));
-          best.v[j] = (i == 0) ? v.v[j] : fmaxf(best.v[j], v.v[j]);
+          v[i].v[j] = round_bf16(bn_relu_val(v[i].v[j], sc[j], sh[j]));
+          best.v[j] = (i == 0) ? v[i].v[j] : fmaxf(best.v[j], v[i].v[j]);
         }
-        store8(a + pix * C + c0, v);
+        store8(a + pix[i] * C + c0, v[i]);
       }
       store8(pooled + op * C + c0, best);
     }
@@ -225,22 +237,41 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int B, int h, int w, int 
   const __nv_bfloat16* r1 = x + (static_cast<long long>(b) * h + y1) * w * C;
   __nv_bfloat16* o = out + static_cast<long long>(row) * W * C;
   const int items = W * cg;
-  for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int X = i / cg;
-    const int c0 = (i - X * cg) * 8;
-    int x0, x1;
-    float lx;
+  for (int i = threadIdx.x; i < items; i += 2 * blockDim.x) {
+    // two output items per trip: eight independent 16-byte loads in flight per thread
+    const int i2 = (i + blockDim.x < items) ? i + blockDim.x : i;
+    const int X = i / cg, X2 = i2 / cg;
+    const int c0 = (i - X * cg) * 8, c2 = (i2 - X2 * cg) * 8;
+    int x0, x1, x02, x12;
+    float lx, lx2;
     bilinear_src(X, w, W, &x0, &x1, &lx);
-    const Vec8 v00 = load8(r0 + x0 * C + c0);
-    const Vec8 v01 = load8(r0 + x1 * C + c0);
-    const Vec8 v10 = load8(r1 + x0 * C + c0);
-    const Vec8 v11 = load8(r1 + x1 * C + c0);
-    Vec8 ov;
+    bilinear_src(X2, w, W, &x02, &x12, &lx2);
+    const uint4 a00 = *reinterpret_cast<const uint4*>(r0 + x0 * C + c0);
+    const uint4 a01 = *reinterpret_cast<const uint4*>(r0 + x1 * C + c0);
+    const uint4 a10 = *reinterpret_cast<const uint4*>(r1 + x0 * C + c0);
+    const uint4 a11 = *reinterpret_cast<const uint4*>(r1 + x1 * C + c0);
+    const uint4 b00 = *reinterpret_cast<const uint4*>(r0 + x02 * C + c2);
+    const uint4 b01 = *reinterpret_cast<const uint4*>(r0 + x12 * C + c2);
+    const uint4 b10 = *reinterpret_cast<const uint4*>(r1 + x02 * C + c2);
+    const uint4 b11 = *reinterpret_cast<const uint4*>(r1 + x12 * C + c2);
+    {
+      const Vec8 v00 = unpack8(a00), v01 = unpack8(a01), v10 = unpack8(a10), v11 = unpack8(a11);
+      Vec8 ov;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      ov.v[j] = (1.f - ly) * ((1.f - lx) * v00.v[j] + lx * v01.v[j]) +
-                ly * ((1.f - lx) * v10.v[j] + lx * v11.v[j]);
-    store8(o + static_cast<long long>(i) * 8, ov);
+      for (int j = 0; j < 8; ++j)
+        ov.v[j] = (1.f - ly) * ((1.f - lx) * v00.v[j] + lx * v01.v[j]) +
+                  ly * ((1.f - lx) * v10.v[j] + lx * v11.v[j]);
+      store8(o + static_cast<long long>(i) * 8, ov);
+    }
+    if (i2 != i) {
+      const Vec8 v00 = unpack8(b00), v01 = unpack8(b01), v10 = unpack8(b10), v11 = unpack8(b11);
+      Vec8 ov;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        ov.v[j] = (1.f - ly) * ((1.f - lx2) * v00.v[j] + lx2 * v01.v[j]) +
+                  ly * ((1.f - lx2) * v10.v[j] + lx2 * v11.v[j]);
+      store8(o + static_cast<long long>(i2) * 8, ov);
+    }
   }
 }
 
@@ -329,7 +360,7 @@ int bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* rm
 int bn_relu_apply(const void* z, const float* scale, const float* shift, int B, int H,
                   int W, int C, void* a, void* pooled, cudaStream_t stream) {
   UGP_REQUIRE(z && scale && shift && a, "bn_relu_apply: null pointer");
-  UGP_REQUIRE(C % 8 == 0, "bn_relu_apply: C must be a multiple of 8");
+  UGP_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "bn_relu_apply: C must be 8 * a power of two <= 2048 (got %d)", C);
   if (pooled) {
     UGP_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_apply: pooling needs even H, W");
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
