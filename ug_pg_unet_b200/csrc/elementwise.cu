@@ -15,27 +15,29 @@ namespace ugp {
 // stats = [parts][2][C]: per-CTA partial {sum, sum of squares} of the stored conv outputs, summed here
 // in slot order (deterministic) and zeroed after use.
 // ----------------------------------------------------------------------------
-// Block = 32 channels x 8 slot groups: group g sums slots g, g+8, ... (independent loads in flight),
-// the eight group sums are then added in a fixed order -> deterministic, ~20 dependent steps.
-__global__ void __launch_bounds__(256)
+// Block = 32 channels x 32 slot groups: group g sums slots g, g+32, ... (all loads of a thread in
+// flight at once), the group sums are then added in a fixed order -> deterministic, ~5 dependent steps.
+constexpr int kFinGroups = 32;
+__global__ void __launch_bounds__(32 * kFinGroups)
 bn_finalize_kernel(float* __restrict__ stats, int parts, int C, float count,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                    long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
                    float* __restrict__ shift, float* __restrict__ save_mean,
                    float* __restrict__ save_rstd) {
-  __shared__ float red[2][8][33];
+  __shared__ float red[2][kFinGroups][33];
   const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
   float s = 0.f, s2 = 0.f;
   if (c < C) {
-    for (int q = g; q < parts; q += 8) {
+#pragma unroll 5
+    for (int q = g; q < parts; q += kFinGroups) {
       const float* sl = stats + static_cast<size_t>(q) * 2 * C;
       s += __ldcg(sl + c);
       s2 += __ldcg(sl + C + c);
     }
-    for (int q = g; q < parts; q += 8) {
+    for (int q = g; q < parts; q += kFinGroups) {
       float* sl = stats + static_cast<size_t>(q) * 2 * C;
       sl[c] = 0.f;
       sl[C + c] = 0.f;
@@ -47,7 +49,7 @@ bn_finalize_kernel(float* __restrict__ stats, int parts, int C, float count,
   if (g != 0 || c >= C) return;
   s = 0.f; s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { s += red[0][i][cx]; s2 += red[1][i][cx]; }
+  for (int i = 0; i < kFinGroups; ++i) { s += red[0][i][cx]; s2 += red[1][i][cx]; }
   const float mean = s / count;
   float var = s2 / count - mean * mean;
   var = fmaxf(var, 0.f);
@@ -340,7 +342,7 @@ int bn_finalize(float* stats, int parts, int C, long long count, const float* ga
   UGP_REQUIRE(stats && gamma && beta && scale && shift && save_mean && save_rstd,
               "bn_finalize: null pointer");
   UGP_REQUIRE(parts >= 1, "bn_finalize: parts must be >= 1");
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(
+  bn_finalize_kernel<<<(C + 31) / 32, 32 * kFinGroups, 0, stream>>>(
       stats, parts, C, static_cast<float>(count), gamma, beta, eps, momentum, running_mean,
       running_var, nbt, scale, shift, save_mean, save_rstd);
   UGP_CHECK_CUDA(cudaGetLastError());

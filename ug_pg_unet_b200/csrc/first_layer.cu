@@ -29,13 +29,17 @@ im2col_first_kernel(const void* __restrict__ xin, int B, int Hin, int Win, int H
                     __nv_bfloat16* __restrict__ out, const ByteNorm norm) {
   const float* x = static_cast<const float*>(xin);
   const uint8_t* xb = static_cast<const uint8_t*>(xin);
+  __shared__ uint4 stage[256 * 8];
   const long long total = static_cast<long long>(B) * H * W;
   const long long plane = static_cast<long long>(Hin) * Win;
-  for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < total;
-       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int xo = static_cast<int>(pix % W);
-    const int yo = static_cast<int>((pix / W) % H);
-    const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  // block-uniform trip count: every thread reaches the barriers, tail pixels are clamped and not stored
+  for (long long pix0 = blockIdx.x * static_cast<long long>(blockDim.x); pix0 < total;
+       pix0 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = pix0 + threadIdx.x;
+    const long long pc = pix < total ? pix : total - 1;
+    const int xo = static_cast<int>(pc % W);
+    const int yo = static_cast<int>((pc / W) % H);
+    const int b = static_cast<int>(pc / (static_cast<long long>(W) * H));
     const float* img = x + static_cast<long long>(b) * kCin * plane;           // fp32 NCHW
     const uint8_t* imgb = xb + static_cast<long long>(b) * kCin * plane;      // uint8 NHWC
     float vals[64];
@@ -84,7 +88,10 @@ im2col_first_kernel(const void* __restrict__ xin, int B, int Hin, int Win, int H
         }
       }
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + pix * 64);
+    // Stage the 256 rows of this block through shared memory (16-byte chunks, XOR-swizzled by the row)
+    // so that the global stores are fully coalesced: lane l writes chunk l of a contiguous 32 KB run
+    // instead of eight 16-byte pieces 128 bytes apart.
+    uint4* srow = stage + threadIdx.x * 8;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       uint4 u;
@@ -92,8 +99,18 @@ im2col_first_kernel(const void* __restrict__ xin, int B, int Hin, int Win, int H
       u.y = pack_bf16x2(vals[g * 8 + 2], vals[g * 8 + 3]);
       u.z = pack_bf16x2(vals[g * 8 + 4], vals[g * 8 + 5]);
       u.w = pack_bf16x2(vals[g * 8 + 6], vals[g * 8 + 7]);
-      dst[g] = u;
+      srow[g ^ (threadIdx.x & 7)] = u;
     }
+    __syncthreads();
+    const long long base_pix = pix - threadIdx.x;            // first pixel of this block's trip
+    uint4* dst = reinterpret_cast<uint4*>(out + base_pix * 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int L = k * 256 + threadIdx.x;                   // linear 16-byte chunk of the 32 KB run
+      const int r = L >> 3;
+      if (base_pix + r < total) dst[L] = stage[r * 8 + ((L & 7) ^ (r & 7))];
+    }
+    __syncthreads();
   }
 }
 

@@ -103,36 +103,53 @@ outconv_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   }
   const long long gthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long pix_per_iter = gthreads / kLanes;
-  for (long long pix = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) / kLanes;
-       pix < M; pix += pix_per_iter) {
-    const long long b = pix / hw, r = pix % hw;
-    const uint4 u = *reinterpret_cast<const uint4*>(x + pix * C + sub * 8);
-    const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                         bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
-    float g[8];
-    if (accumulate) {
-      const uint4 d = *reinterpret_cast<const uint4*>(dx + pix * C + sub * 8);
-      g[0] = bf16_lo(d.x); g[1] = bf16_hi(d.x); g[2] = bf16_lo(d.y); g[3] = bf16_hi(d.y);
-      g[4] = bf16_lo(d.z); g[5] = bf16_hi(d.z); g[6] = bf16_lo(d.w); g[7] = bf16_hi(d.w);
-    } else {
+  constexpr int kU = 2;   // independent pixels in flight per thread
+  for (long long pix0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) / kLanes;
+       pix0 < M; pix0 += pix_per_iter * kU) {
+    uint4 u[kU], dprev[kU];
+    float dlv[kU][kNC];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    for (int q = 0; q < kU; ++q) {
+      const long long pix = pix0 + q * pix_per_iter;
+      if (pix < M) {
+        u[q] = *reinterpret_cast<const uint4*>(x + pix * C + sub * 8);
+        if (accumulate) dprev[q] = *reinterpret_cast<const uint4*>(dx + pix * C + sub * 8);
+        const long long b = pix / hw, r = pix % hw;
+#pragma unroll
+        for (int k = 0; k < kNC; ++k) dlv[q][k] = (k < nc) ? __ldg(dl + (b * nc + k) * hw + r) : 0.f;
+      }
     }
 #pragma unroll
-    for (int k = 0; k < kNC; ++k)
-      if (k < nc) {
-        const float d = __ldg(dl + (b * nc + k) * hw + r);
-        if (sub == 0) dbr[k] += d;
+    for (int q = 0; q < kU; ++q) {
+      const long long pix = pix0 + q * pix_per_iter;
+      if (pix >= M) continue;
+      const float xv[8] = {bf16_lo(u[q].x), bf16_hi(u[q].x), bf16_lo(u[q].y), bf16_hi(u[q].y),
+                           bf16_lo(u[q].z), bf16_hi(u[q].z), bf16_lo(u[q].w), bf16_hi(u[q].w)};
+      float g[8];
+      if (accumulate) {
+        const uint4 d = dprev[q];
+        g[0] = bf16_lo(d.x); g[1] = bf16_hi(d.x); g[2] = bf16_lo(d.y); g[3] = bf16_hi(d.y);
+        g[4] = bf16_lo(d.z); g[5] = bf16_hi(d.z); g[6] = bf16_lo(d.w); g[7] = bf16_hi(d.w);
+      } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          g[j] = fmaf(d, wr[k][j], g[j]);
-          dwr[k][j] = fmaf(d, xv[j], dwr[k][j]);
-        }
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
       }
-    uint4 o;
-    o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
-    o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
-    *reinterpret_cast<uint4*>(dx + pix * C + sub * 8) = o;
+#pragma unroll
+      for (int k = 0; k < kNC; ++k)
+        if (k < nc) {
+          const float d = dlv[q][k];
+          if (sub == 0) dbr[k] += d;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            g[j] = fmaf(d, wr[k][j], g[j]);
+            dwr[k][j] = fmaf(d, xv[j], dwr[k][j]);
+          }
+        }
+      uint4 o;
+      o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
+      o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+      *reinterpret_cast<uint4*>(dx + pix * C + sub * 8) = o;
+    }
   }
   // block reduction of dw / db through shared memory
   __shared__ float red[kNC][C];
