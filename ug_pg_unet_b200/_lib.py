@@ -95,6 +95,10 @@ def lib() -> C.CDLL:
     handle.ugp_set_option.restype = C.c_int
     handle.ugp_set_option.argtypes = [C.c_char_p, C.c_int]
     _lib = handle
+    # UGP_OPTIONS="name=value,name=value": tuning / what-if switches of ugp_set_option applied at load
+    for item in filter(None, os.environ.get("UGP_OPTIONS", "").split(",")):
+        name, _, value = item.partition("=")
+        check(handle.ugp_set_option(name.strip().encode(), int(value)), f"ugp_set_option({name})")
     return handle
 
 

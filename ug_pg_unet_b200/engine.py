@@ -21,6 +21,8 @@ bf16 = torch.bfloat16
 import os as _os
 # what-if timing switch (results wrong): skip the BatchNorm-backward reduction pass of each DoubleConv's first BN
 _WHATIF_SKIP_BN1_REDUCE = _os.environ.get("UGP_WHATIF_SKIP_BN1_REDUCE", "0") == "1"
+# what-if (results wrong): drop the pooled gradient so the pooled BatchNorm backward runs the plain kernels
+_WHATIF_POOL_AS_PLAIN = _os.environ.get("UGP_WHATIF_POOL_AS_PLAIN", "0") == "1"
 
 
 class PackedWeights:
@@ -227,6 +229,8 @@ def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch
     dev = src0.device
     coef = saved.coef
     small = torch.empty((3, cout), dtype=torch.float32, device=dev)   # dgamma, dbeta, dbias (kernel-zeroed)
+    if _WHATIF_POOL_AS_PLAIN and dA is not None:
+        dP = None
     dz = ops.bn_relu_bwd(saved.z, dA, dP, coef[0], coef[1], coef[2], coef[3], bn.weight.detach(),
                          small[:2], small[2])
     kdim = sum(s.shape[3] for s in saved.srcs)

@@ -52,6 +52,7 @@ class UncertaintyGuidedProgressiveTrainer:
         # model's forward, and the weight-gradient convolutions beside the dgrad / BN-backward chain
         self.overlap_streams = os.environ.get("UGP_NO_STREAM_OVERLAP", "0") != "1"
         self._side_streams = None
+        self._capture_stream = None
         self._copy_stream = None
         self._graph = None
         self._grad_arena = None
@@ -284,7 +285,17 @@ class UncertaintyGuidedProgressiveTrainer:
             self.optimizer.zero_grad(set_to_none=True)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # The step is captured on a HIGH-priority stream while its side streams (uncertainty forward,
+            # weight gradients, all-reduce) keep the default priority: a wgrad CTA needs all 512 TMEM
+            # columns, so wgrad and dgrad kernels never share an SM and the block scheduler serialises them
+            # - with priorities the critical-path kernel (main stream) gets the SMs first and the weight
+            # gradient fills in beside the HBM-bound BatchNorm backward that follows.
+            cap = None
+            if os.environ.get("UGP_STREAM_PRIORITY", "1") == "1":
+                if self._capture_stream is None:
+                    self._capture_stream = torch.cuda.Stream(device=data.device, priority=-1)
+                cap = self._capture_stream
+            with torch.cuda.graph(graph, stream=cap):
                 g["out"] = self._eager_step(g["x"], g["y"], stage)
             g["graph"] = graph
             g["counted"] = True            # the capture pass already advanced the optimiser's step counters
