@@ -482,42 +482,50 @@ int head_combine_fwd(const float* const* maps, const int* sizes, int n, int plan
   return head_combine_fwd_hw(maps, sizes, sizes, n, planes, R, R, logits, stream);
 }
 
-// Warp-per-coarse-pixel form for the large stencils (x4, x8 upsampling: 11^2 .. 19^2 fine pixels per
-// coarse pixel, but only 16 K coarse pixels at batch 16): lanes stride over the window, shuffle reduce.
+// Separable row form for the coarse scales: one block per (plane, coarse row y).  Stage 1 folds the
+// <= 2f+4 fine rows that touch y into one fine-resolution row t[X] (coalesced loads, thread = X);
+// stage 2 folds t along X for every coarse x.  Fixed summation order (deterministic); the weights come
+// from the same bilinear_src_f as the forward kernel, so this is its exact adjoint.
+constexpr int kHeadMaxTaps = 64;
 __global__ void __launch_bounds__(256)
-head_combine_bwd_warp_kernel(const float* __restrict__ dlogits, int planes, int RH, int RW, int sh, int sw,
+head_combine_bwd_rows_kernel(const float* __restrict__ dlogits, int RH, int RW, int sh, int sw,
                              float* __restrict__ dl) {
-  const long long total = static_cast<long long>(planes) * sh * sw;
+  extern __shared__ float t[];            // RW floats
+  __shared__ float wys[kHeadMaxTaps];
+  const int plane = blockIdx.x / sh, y = blockIdx.x - plane * sh;
   const float invy = (sh > 1) ? static_cast<float>(RH - 1) / static_cast<float>(sh - 1) : 0.f;
   const float invx = (sw > 1) ? static_cast<float>(RW - 1) / static_cast<float>(sw - 1) : 0.f;
-  const int lane = threadIdx.x & 31;
-  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long idx = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; idx < total;
-       idx += warps) {
-    const int x = static_cast<int>(idx % sw);
-    const int y = static_cast<int>((idx / sw) % sh);
-    const long long plane = idx / (static_cast<long long>(sh) * sw);
-    const float* g = dlogits + plane * RH * RW;
-    int Ylo = static_cast<int>(floorf((y - 1) * invy)) - 1, Yhi = static_cast<int>(ceilf((y + 1) * invy)) + 1;
-    int Xlo = static_cast<int>(floorf((x - 1) * invx)) - 1, Xhi = static_cast<int>(ceilf((x + 1) * invx)) + 1;
-    if (Ylo < 0) Ylo = 0;
-    if (Xlo < 0) Xlo = 0;
-    if (Yhi > RH - 1) Yhi = RH - 1;
-    if (Xhi > RW - 1) Xhi = RW - 1;
-    const int wx_n = Xhi - Xlo + 1, n = (Yhi - Ylo + 1) * wx_n;
+  int Ylo = static_cast<int>(floorf((y - 1) * invy)) - 1, Yhi = static_cast<int>(ceilf((y + 1) * invy)) + 1;
+  if (Ylo < 0) Ylo = 0;
+  if (Yhi > RH - 1) Yhi = RH - 1;
+  const int ny = Yhi - Ylo + 1;           // host guarantees <= kHeadMaxTaps
+  if (threadIdx.x < ny) {
+    int i0, i1;
+    float l;
+    bilinear_src_f(Ylo + threadIdx.x, sh, RH, &i0, &i1, &l);
+    wys[threadIdx.x] = (i0 == y ? 1.f - l : 0.f) + (i1 == y ? l : 0.f);
+  }
+  __syncthreads();
+  const float* g = dlogits + (static_cast<long long>(plane) * RH + Ylo) * RW;
+  for (int X = threadIdx.x; X < RW; X += blockDim.x) {
     float acc = 0.f;
-    for (int i = lane; i < n; i += 32) {
-      const int Y = Ylo + i / wx_n, X = Xlo + i % wx_n;
-      int i0, i1, j0, j1;
-      float l, lx;
-      bilinear_src_f(Y, sh, RH, &i0, &i1, &l);
+    for (int k = 0; k < ny; ++k) acc = fmaf(wys[k], __ldg(g + static_cast<long long>(k) * RW + X), acc);
+    t[X] = acc;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < sw; x += blockDim.x) {
+    int Xlo = static_cast<int>(floorf((x - 1) * invx)) - 1, Xhi = static_cast<int>(ceilf((x + 1) * invx)) + 1;
+    if (Xlo < 0) Xlo = 0;
+    if (Xhi > RW - 1) Xhi = RW - 1;
+    float acc = 0.f;
+    for (int X = Xlo; X <= Xhi; ++X) {
+      int j0, j1;
+      float lx;
       bilinear_src_f(X, sw, RW, &j0, &j1, &lx);
-      const float wy = (i0 == y ? 1.f - l : 0.f) + (i1 == y ? l : 0.f);
       const float wx = (j0 == x ? 1.f - lx : 0.f) + (j1 == x ? lx : 0.f);
-      if (wy != 0.f && wx != 0.f) acc = fmaf(wy * wx, __ldg(g + static_cast<long long>(Y) * RW + X), acc);
+      acc = fmaf(wx, t[X], acc);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) dl[idx] = acc;
+    dl[(static_cast<long long>(plane) * sh + y) * sw + x] = acc;
   }
 }
 
@@ -525,9 +533,10 @@ int head_combine_bwd_hw(const float* dlogits, int planes, int RH, int RW, int sh
                         cudaStream_t stream) {
   UGP_REQUIRE(dlogits && dl && sh >= 1 && sh <= RH && sw >= 1 && sw <= RW, "head_combine_bwd: bad arguments");
   const long long total = static_cast<long long>(planes) * sh * sw;
-  if (RH >= 4 * sh || RW >= 4 * sw) {
-    head_combine_bwd_warp_kernel<<<grid_cap((total * 32 + 255) / 256, 16), 256, 0, stream>>>(dlogits, planes, RH,
-                                                                                           RW, sh, sw, dl);
+  const int taps = (sh > 1) ? 2 * ((RH - 1) / (sh - 1) + 1) + 4 : RH;
+  if ((sh != RH || sw != RW) && taps <= kHeadMaxTaps && RW * 4 <= 48 * 1024 &&
+      static_cast<long long>(planes) * sh < (1LL << 31)) {
+    head_combine_bwd_rows_kernel<<<planes * sh, 256, RW * sizeof(float), stream>>>(dlogits, RH, RW, sh, sw, dl);
   } else {
     head_combine_bwd_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, stream>>>(dlogits, planes, RH, RW, sh,
                                                                                  sw, dl);
