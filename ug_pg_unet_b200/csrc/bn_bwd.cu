@@ -16,6 +16,7 @@
 namespace ugp {
 
 int g_bn_skip_reduce = 0;   // what-if timing only (results wrong): skip the reduction pass of the plain variant
+int g_bn_bwd_blocks_per_sm = 2;   // persistent blocks per SM of the backward kernels (tuning switch)
 int g_bn_pool_vec4 = 0;   // pooled backward: 1 = 4-channel threads at 3 blocks/SM (measured: same speed; the kernel is issue-bound)
 
 struct BnBwdArgs {
@@ -430,7 +431,7 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
   }
   // two resident blocks per SM keep ~64 KB of loads in flight per SM; more blocks only add
   // same-address atomic traffic in the final per-channel reduction
-  const long long cap = static_cast<long long>(device_sm_count()) * 2;
+  const long long cap = static_cast<long long>(device_sm_count()) * g_bn_bwd_blocks_per_sm;
   if (dP) {
     UGP_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_bwd: pooled gradient needs even H, W");
     if (g_bn_pool_vec4 != 0 && kBnThreads % (C / 4) == 0) {
