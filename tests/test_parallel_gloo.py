@@ -57,6 +57,15 @@ def _worker(rank, world, port, overlap, out_dir):
             total.backward()
             for (n, p), q in zip(model.named_parameters(), ref.parameters()):
                 torch.testing.assert_close(p.grad, q.grad, rtol=1e-5, atol=1e-7, msg=lambda m: f"{n}: {m}")
+        # average=False: .grad is a view of the bucket holding the SUM over ranks (the optimiser kernel
+        # applies 1/world_size), and no per-tensor scale runs after the all-reduce
+        reducer.remove()
+        summed = GradBucketReducer(list(model.parameters()), bucket_mb=0.0005, overlap=overlap, average=False)
+        model.zero_grad(set_to_none=True)
+        ((model(xs) - ys) ** 2).mean().backward()
+        summed.wait()
+        for (n, p), q in zip(model.named_parameters(), ref.parameters()):
+            torch.testing.assert_close(p.grad, q.grad * world, rtol=1e-5, atol=1e-7, msg=lambda m: f"{n}: {m}")
         open(os.path.join(out_dir, f"ok{rank}"), "w").close()
     finally:
         dist.destroy_process_group()

@@ -29,6 +29,7 @@ class FusedRMSprop(torch.optim.RMSprop):
         self._targeted = conv_packs is not None
         self._packs = {id(pk.conv.weight): pk for pk in (conv_packs or [])}
         self.deferred_grad_scale = 1.0      # 1/world_size when the packed gradients were sum-all-reduced
+        self.dense_grad_scale = 1.0         # the same for `.grad` tensors a reducer left as sums over ranks
 
     def note_replayed_steps(self, n: int = 1) -> None:
         """A CUDA-graph replay ran `step()`'s kernels without running this Python code."""
@@ -104,7 +105,7 @@ class FusedRMSprop(torch.optim.RMSprop):
                 vs.append(st["square_avg"])
             if ps:
                 ops.rmsprop_multi(ps, gs, vs, float(group["lr"]), float(group["alpha"]), float(group["eps"]),
-                                  float(group["weight_decay"]))
+                                  float(group["weight_decay"]), float(self.dense_grad_scale))
             if dw:
                 ops.rmsprop_conv_packed(dw, dv, dg, dwf, dwd, float(group["lr"]), float(group["alpha"]),
                                         float(group["eps"]), float(group["weight_decay"]),

@@ -54,12 +54,17 @@ class GradBucketReducer:
     """Bucketed, overlapped gradient averaging across ranks."""
 
     def __init__(self, params: Sequence[torch.nn.Parameter], bucket_mb: float = 16.0,
-                 process_group=None, overlap: bool = True, conv_packs=None, arena: Optional[torch.Tensor] = None):
+                 process_group=None, overlap: bool = True, conv_packs=None, arena: Optional[torch.Tensor] = None,
+                 average: bool = True):
         """`conv_packs` / `arena`: the deferred convolutions and their flat packed-gradient arena, in
-        arena order; their weights are skipped in `params` (they get no `.grad`)."""
+        arena order; their weights are skipped in `params` (they get no `.grad`).
+        `average=False`: `.grad` is left pointing at the SUM over ranks inside the flat bucket (no
+        per-tensor scale kernels after the all-reduce); the optimiser applies 1/world_size
+        (`FusedRMSprop.dense_grad_scale`), as it does for the packed arena."""
         self.group = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.overlap = overlap
+        self.average = average
         deferred = {id(pk.conv.weight) for pk in (conv_packs or [])}
         ps = [p for p in params if p.requires_grad and id(p) not in deferred]
         # reverse forward order = the order gradients become ready
@@ -181,7 +186,9 @@ class GradBucketReducer:
                 for p in b.params:
                     n = p.numel()
                     g = b.flat[off:off + n].view_as(p)
-                    if p.grad is None:
+                    if not self.average:
+                        p.grad = g                      # a view of the summed bucket: no kernel
+                    elif p.grad is None:
                         p.grad = g * inv
                     else:
                         torch.mul(g, inv, out=p.grad)

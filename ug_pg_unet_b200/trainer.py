@@ -118,8 +118,11 @@ class UncertaintyGuidedProgressiveTrainer:
         else:
             self.optimizer = optim.RMSprop(self.current_model.parameters(), lr=lr, weight_decay=1e-4)
         if self.distributed:
+            fused = isinstance(self.optimizer, FusedRMSprop) and os.environ.get("UGP_DP_AVERAGE_IN_REDUCER", "0") != "1"
             self._reducer = GradBucketReducer(list(self.current_model.parameters()), bucket_mb=self.bucket_mb,
-                                              conv_packs=packs, arena=arena)
+                                              conv_packs=packs, arena=arena, average=not fused)
+            if fused:       # sums stay in the flat bucket, the optimiser kernel applies 1/world_size
+                self.optimizer.dense_grad_scale = 1.0 / self.world_size
 
     def transfer_weights(self, prev_stage, new_stage):
         """reference :125-141, without the throw-away 49 M-parameter ProgressiveUNet."""
