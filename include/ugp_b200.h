@@ -238,6 +238,15 @@ int ugp_rmsprop_multi(float* const* params, const float* const* grads, float* co
                       const long long* sizes, int n_tensors, float lr, float alpha, float eps,
                       float weight_decay, float grad_scale, void* stream);
 
+/* torch.optim.Adam step (Herlev/train_herlev.py:170-176: betas (.9, .999), eps 1e-8, L2 weight decay, no
+ * amsgrad) for n_tensors tensors in one launch per 64 tensors; `step` = the 1-based step count:
+ *   g = grad*grad_scale + wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g
+ *   p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps) */
+int ugp_adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs,
+                   float* const* exp_avg_sqs, const long long* sizes, int n_tensors, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, long long step,
+                   float grad_scale, void* stream);
+
 /* RMSprop for the 3x3 convolution weights straight from the PACKED gradient that
  * ugp_conv_wgrad_bf16 accumulates (replaces ugp_unpack_wgrad + optimizer.step() of
  * uncertainty_guided_trainer.py:231 + ugp_pack_weights for the next forward).  Per tensor i:

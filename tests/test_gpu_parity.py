@@ -994,3 +994,32 @@ def test_herlev_stage4_at_the_reference_resolution_224(dev):
         vl, vb, va, vum, vus = tr.validate_epoch([(x, y)], 4)
     assert all(math.isfinite(v) for v in (loss, base, vl, vb)) and 0.0 <= acc <= 100.0
     assert tr.models[4].unet.down3.mpconv[1].conv_op[0].weight.grad is not None
+
+
+def test_fused_adam_matches_torch_adam(dev):
+    """FusedAdam (ugp_adam_multi, the Herlev trainer's optimiser) vs torch.optim.Adam: same updates, same
+    state_dict layout, checkpoints interchangeable."""
+    from ug_pg_unet_b200.optim import FusedAdam
+
+    g = torch.Generator().manual_seed(4)
+    shapes = [(512, 256, 3, 3), (64,), (7, 256), (1,), (100003,)]
+    pa = [torch.randn(s, generator=g).to(dev).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = FusedAdam(pa, lr=1e-3, weight_decay=1e-4)
+    ob = torch.optim.Adam(pb, lr=1e-3, weight_decay=1e-4)
+    for step in range(4):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).to(dev)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+        if step == 1:                       # checkpoint round trip through the stock optimiser's format
+            oa.load_state_dict(ob.state_dict())
+    for a, b in zip(pa, pb):
+        assert rel(a, b) < 1e-6
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["param_groups"][0]["lr"] == sb["param_groups"][0]["lr"]
+    for k in sb["state"]:
+        assert set(sa["state"][k]) == set(sb["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
+        assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 4.0
+        assert rel(sa["state"][k]["exp_avg_sq"], sb["state"][k]["exp_avg_sq"]) < 1e-6

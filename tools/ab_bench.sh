@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B of two builds of libugp_b200.so on one box: alternating bench runs
+# A/B of two builds of libugp_b200.so on one box (alternating bench runs): build the old revision, copy its
+# library to ab/libugp_prev.so (git-ignored, travels with gpurun), then `gpurun -- bash tools/ab_bench.sh`.
 for i in 1 2 3; do
   for v in prev new; do
     if [ $v = prev ]; then export UGP_LIB_PATH=ab/libugp_prev.so; else unset UGP_LIB_PATH; fi

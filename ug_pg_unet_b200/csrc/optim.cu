@@ -285,3 +285,77 @@ int rmsprop_conv_packed(float* const* w, float* const* v, float* const* dwp, voi
 }
 
 }  // namespace ugp
+
+// ---------------------------------------------------------------------------
+// Multi-tensor Adam (torch.optim.Adam with L2 weight decay, amsgrad off), the optimiser of the Herlev
+// trainer (Herlev/train_herlev.py:170-176): one launch per <= 64 tensors instead of torch's foreach chain.
+//   g = grad*grad_scale + wd*p;  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g
+//   p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)        bc1 = 1 - b1^t, bc2 = 1 - b2^t
+// ---------------------------------------------------------------------------
+namespace ugp {
+
+constexpr int kAdamMaxTensors = 64;
+
+struct AdamTable {
+  float* p[kAdamMaxTensors];
+  const float* g[kAdamMaxTensors];
+  float* m[kAdamMaxTensors];
+  float* v[kAdamMaxTensors];
+  int n[kAdamMaxTensors];
+};
+
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ AdamTable t, float step_size, float inv_sqrt_bc2, float b1, float b2,
+                  float eps, float wd, float gscale) {
+  const int k = blockIdx.y;
+  float* __restrict__ p = t.p[k];
+  const float* __restrict__ g = t.g[k];
+  float* __restrict__ m = t.m[k];
+  float* __restrict__ v = t.v[k];
+  const int n = t.n[k];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    const float gr = fmaf(wd, pv, g[i] * gscale);
+    const float mn = fmaf(b1, m[i], (1.f - b1) * gr);
+    const float vn = fmaf(b2, v[i], (1.f - b2) * gr * gr);
+    m[i] = mn;
+    v[i] = vn;
+    p[i] = pv - step_size * mn / (sqrtf(vn) * inv_sqrt_bc2 + eps);
+  }
+}
+
+int adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs,
+               float* const* exp_avg_sqs, const long long* sizes, int n_tensors, float lr, float beta1,
+               float beta2, float eps, float weight_decay, long long step, float grad_scale,
+               cudaStream_t stream) {
+  UGP_REQUIRE(params && grads && exp_avgs && exp_avg_sqs && sizes && n_tensors > 0 && step >= 1,
+              "adam_multi: bad arguments");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+  const float step_size = static_cast<float>(lr / bc1);
+  const float inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+  for (int base = 0; base < n_tensors; base += kAdamMaxTensors) {
+    const int cnt = (n_tensors - base < kAdamMaxTensors) ? (n_tensors - base) : kAdamMaxTensors;
+    AdamTable t;
+    long long biggest = 0;
+    for (int i = 0; i < cnt; ++i) {
+      UGP_REQUIRE(sizes[base + i] > 0 && sizes[base + i] < (1LL << 31), "adam_multi: bad size");
+      t.p[i] = params[base + i];
+      t.g[i] = grads[base + i];
+      t.m[i] = exp_avgs[base + i];
+      t.v[i] = exp_avg_sqs[base + i];
+      t.n[i] = static_cast<int>(sizes[base + i]);
+      if (sizes[base + i] > biggest) biggest = sizes[base + i];
+    }
+    int gx = static_cast<int>((biggest + 256 * 8 - 1) / (256 * 8));
+    if (gx > 64) gx = 64;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, cnt);
+    adam_multi_kernel<<<grid, 256, 0, stream>>>(t, step_size, inv_sqrt_bc2, beta1, beta2, eps, weight_decay,
+                                                grad_scale);
+    UGP_CHECK_CUDA(cudaGetLastError());
+  }
+  return UGP_OK;
+}
+
+}  // namespace ugp

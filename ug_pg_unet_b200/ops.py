@@ -546,6 +546,21 @@ def rmsprop_multi(params, grads, square_avgs, lr: float, alpha: float, eps: floa
           "ugp_rmsprop_multi")
 
 
+def adam_multi(params, grads, exp_avgs, exp_avg_sqs, step: int, lr: float, beta1: float, beta2: float, eps: float,
+               weight_decay: float, grad_scale: float = 1.0):
+    """One launch (per 64 tensors) of torch.optim.Adam's update with L2 weight decay; see ugp_adam_multi."""
+    n = len(params)
+    for t in list(params) + list(grads) + list(exp_avgs) + list(exp_avg_sqs):
+        _req(t, torch.float32, "adam tensor")
+    P = (C.c_void_p * n)(*[t.data_ptr() for t in params])
+    G = (C.c_void_p * n)(*[t.data_ptr() for t in grads])
+    M = (C.c_void_p * n)(*[t.data_ptr() for t in exp_avgs])
+    V = (C.c_void_p * n)(*[t.data_ptr() for t in exp_avg_sqs])
+    S = (C.c_longlong * n)(*[t.numel() for t in params])
+    check(lib().ugp_adam_multi(P, G, M, V, S, n, lr, beta1, beta2, eps, weight_decay, int(step), grad_scale,
+                               _stream()), "ugp_adam_multi")
+
+
 def rmsprop_conv_packed(weights, square_avgs, dw_packed, wfs, wds, lr: float, alpha: float, eps: float,
                         weight_decay: float, grad_scale: float = 1.0):
     """RMSprop on 3x3 conv weights straight from the packed gradients; rewrites the bf16 operand

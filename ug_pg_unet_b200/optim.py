@@ -1,4 +1,6 @@
-"""RMSprop with the reference's configuration (uncertainty_guided_trainer.py:84-88) as ONE kernel
+"""Optimisers of the two trainers as single kernel launches.
+
+FusedRMSprop: RMSprop with the reference's configuration (uncertainty_guided_trainer.py:84-88) as ONE kernel
 launch over all parameter tensors.
 
 Subclasses `torch.optim.RMSprop`, so constructor arguments, `param_groups`, `state_dict()` layout
@@ -112,4 +114,54 @@ class FusedRMSprop(torch.optim.RMSprop):
                                         float(self.deferred_grad_scale))
                 rewritten.extend(dpk)
         self._invalidate_packs(rewritten)
+        return loss
+
+
+class FusedAdam(torch.optim.Adam):
+    """`torch.optim.Adam` (L2 weight decay, the Herlev trainer's optimiser, Herlev/train_herlev.py:170-176)
+    with `step()` as one multi-tensor kernel launch.  Same constructor arguments, `param_groups` and
+    `state_dict()` layout (`step`, `exp_avg`, `exp_avg_sq`); amsgrad / maximize / non-CUDA parameters are
+    delegated to the stock implementation.  `grad_scale` multiplies the gradients inside the kernel
+    (1/world_size when a reducer left them as sums over ranks)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, **kw):
+        kw.pop("capturable", None)
+        kw.pop("foreach", None)
+        kw.pop("fused", None)
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, **kw)
+        self.grad_scale = 1.0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        from .engine import PackedWeights
+        for group in self.param_groups:
+            if group["amsgrad"] or group.get("maximize", False):
+                return super().step()
+            by_step = {}
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.grad.is_sparse or p.dtype != torch.float32:
+                    return super().step()
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.zeros((), dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                t = int(st["step"])
+                ps, gs, ms, vs = by_step.setdefault(t, ([], [], [], []))
+                ps.append(p.data)
+                gs.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
+                ms.append(st["exp_avg"])
+                vs.append(st["exp_avg_sq"])
+            b1, b2 = group["betas"]
+            for t, (ps, gs, ms, vs) in by_step.items():
+                ops.adam_multi(ps, gs, ms, vs, t, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                               float(group["weight_decay"]), float(self.grad_scale))
+        PackedWeights.invalidate_all()       # parameters changed behind autograd's version counters
         return loss
