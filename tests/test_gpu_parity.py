@@ -1014,7 +1014,8 @@ def test_fused_adam_matches_torch_adam(dev):
         oa.step()
         ob.step()
         if step == 1:                       # checkpoint round trip through the stock optimiser's format
-            oa.load_state_dict(ob.state_dict())
+            import copy
+            oa.load_state_dict(copy.deepcopy(ob.state_dict()))    # state_dict() hands out the live tensors
     for a, b in zip(pa, pb):
         assert rel(a, b) < 1e-6
     sa, sb = oa.state_dict(), ob.state_dict()
