@@ -243,8 +243,8 @@ int ugp_rmsprop_multi(float* const* params, const float* const* grads, float* co
  *   g = grad*grad_scale + wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g
  *   p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps) */
 int ugp_adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs,
-                   float* const* exp_avg_sqs, const long long* sizes, int n_tensors, float lr,
-                   float beta1, float beta2, float eps, float weight_decay, long long step,
+                   float* const* exp_avg_sqs, const long long* sizes, int n_tensors, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, long long step,
                    float grad_scale, void* stream);
 
 /* RMSprop for the 3x3 convolution weights straight from the PACKED gradient that

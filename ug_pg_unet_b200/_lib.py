@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 # UGP_LIB_PATH: load another build of the same library (A/B timing of kernel changes on one box)
 LIB_PATH = Path(os.environ["UGP_LIB_PATH"]).resolve() if os.environ.get("UGP_LIB_PATH") else _PKG / "libugp_b200.so"
 
-_p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_p, _i, _f, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 
 # name -> argtypes; every function returns int (0 = ok) unless noted
 SIGNATURES = {
@@ -57,7 +57,7 @@ SIGNATURES = {
     "ugp_bench_mma": [_i, _i, _i, _i, _i, _i, _i, _p, _p],
     "ugp_rmsprop_step": [_p, _p, _p, _ll, _f, _f, _f, _f, _f, _p],
     "ugp_rmsprop_multi": [_p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _p],
-    "ugp_adam_multi": [_p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _ll, _f, _p],
+    "ugp_adam_multi": [_p, _p, _p, _p, _p, _i, _d, _d, _d, _d, _d, _ll, _f, _p],
     "ugp_rmsprop_conv_packed": [_p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _p],
 }
 INFO_FUNCS = ("ugp_last_error", "ugp_version", "ugp_device_sm_count", "ugp_set_option")

@@ -56,8 +56,8 @@ int conv_transpose2x2_wgrad(const void*, const void*, int, int, int, int, int, f
 int pack_weights_tconv(const float*, int, int, void*, void*, cudaStream_t);
 int unpack_wgrad_tconv(float*, int, int, float*, int, cudaStream_t);
 int channel_sum(const void*, long long, int, float*, cudaStream_t);
-int adam_multi(float* const*, const float* const*, float* const*, float* const*, const long long*, int, float,
-               float, float, float, float, long long, float, cudaStream_t);
+int adam_multi(float* const*, const float* const*, float* const*, float* const*, const long long*, int, double,
+               double, double, double, double, long long, float, cudaStream_t);
 int im2col_first_u8(const unsigned char*, int, int, int, int, int, int, const float*, const float*, void*,
                     cudaStream_t);
 int bce_uncertainty_loss_u8(const float*, const unsigned char*, const float*, float, float, int, long long,
@@ -249,8 +249,8 @@ int ugp_head_combine_bwd_hw(const float* dlogits, int planes, int RH, int RW, in
   return ugp::head_combine_bwd_hw(dlogits, planes, RH, RW, h, w, dl, S(stream));
 }
 int ugp_adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs,
-                   float* const* exp_avg_sqs, const long long* sizes, int n_tensors, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, long long step, float grad_scale, void* stream) {
+                   float* const* exp_avg_sqs, const long long* sizes, int n_tensors, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, long long step, float grad_scale, void* stream) {
   return ugp::adam_multi(params, grads, exp_avgs, exp_avg_sqs, sizes, n_tensors, lr, beta1, beta2, eps,
                          weight_decay, step, grad_scale, S(stream));
 }

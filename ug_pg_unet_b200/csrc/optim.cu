@@ -306,7 +306,7 @@ struct AdamTable {
 
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const __grid_constant__ AdamTable t, float step_size, float inv_sqrt_bc2, float b1, float b2,
-                  float eps, float wd, float gscale) {
+                  float omb1, float omb2, float eps, float wd, float gscale) {   // omb = 1 - beta (from double)
   const int k = blockIdx.y;
   float* __restrict__ p = t.p[k];
   const float* __restrict__ g = t.g[k];
@@ -316,8 +316,8 @@ adam_multi_kernel(const __grid_constant__ AdamTable t, float step_size, float in
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float pv = p[i];
     const float gr = fmaf(wd, pv, g[i] * gscale);
-    const float mn = fmaf(b1, m[i], (1.f - b1) * gr);
-    const float vn = fmaf(b2, v[i], (1.f - b2) * gr * gr);
+    const float mn = fmaf(b1, m[i], omb1 * gr);
+    const float vn = fmaf(b2, v[i], omb2 * gr * gr);
     m[i] = mn;
     v[i] = vn;
     p[i] = pv - step_size * mn / (sqrtf(vn) * inv_sqrt_bc2 + eps);
@@ -325,13 +325,14 @@ adam_multi_kernel(const __grid_constant__ AdamTable t, float step_size, float in
 }
 
 int adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs,
-               float* const* exp_avg_sqs, const long long* sizes, int n_tensors, float lr, float beta1,
-               float beta2, float eps, float weight_decay, long long step, float grad_scale,
+               float* const* exp_avg_sqs, const long long* sizes, int n_tensors, double lr, double beta1,
+               double beta2, double eps, double weight_decay, long long step, float grad_scale,
                cudaStream_t stream) {
   UGP_REQUIRE(params && grads && exp_avgs && exp_avg_sqs && sizes && n_tensors > 0 && step >= 1,
               "adam_multi: bad arguments");
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+  // hyper-parameters arrive as the optimiser's Python doubles: 1 - beta is formed in double like torch does
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
   const float step_size = static_cast<float>(lr / bc1);
   const float inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
   for (int base = 0; base < n_tensors; base += kAdamMaxTensors) {
@@ -351,8 +352,10 @@ int adam_multi(float* const* params, const float* const* grads, float* const* ex
     if (gx > 64) gx = 64;
     if (gx < 1) gx = 1;
     dim3 grid(gx, cnt);
-    adam_multi_kernel<<<grid, 256, 0, stream>>>(t, step_size, inv_sqrt_bc2, beta1, beta2, eps, weight_decay,
-                                                grad_scale);
+    adam_multi_kernel<<<grid, 256, 0, stream>>>(t, step_size, inv_sqrt_bc2, static_cast<float>(beta1),
+                                                static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
+                                                static_cast<float>(1.0 - beta2), static_cast<float>(eps),
+                                                static_cast<float>(weight_decay), grad_scale);
     UGP_CHECK_CUDA(cudaGetLastError());
   }
   return UGP_OK;
