@@ -575,11 +575,13 @@ def test_config5_batch64_step(dev):
     g = torch.Generator().manual_seed(64)
     x = torch.randn(64, 3, 256, 256, generator=g).to(dev)
     y = (torch.rand(64, 1, 256, 256, generator=g) < 0.2).float().to(dev)      # sparse positives, SURVEY §8d
-    ms = [tr.train_step(x, y, 4)[0] for _ in range(6)]
+    # RMSprop's first (sign-like) updates overshoot: the loss goes 2.68 -> 4.78 -> 3.37 -> ... -> 2.67 (step
+    # 6) -> 2.48 (step 10) in every mode (eager / graph / single stream), so the fit is judged at step 10
+    ms = [tr.train_step(x, y, 4)[0] for _ in range(10)]
     torch.cuda.synchronize()
     f = [tr._metrics_from_device(m, y.numel(), 64, True) for m in ms]
     assert all(math.isfinite(v[0]) and math.isfinite(v[1]) for v in f)
-    assert f[-1][0] < f[0][0]                      # the repeated batch is being fitted
+    assert f[-1][0] < f[0][0] - 0.1                # the repeated batch is being fitted
     assert 0.0 < f[-1][4] < 1.0                    # uncertainty mean
     assert torch.cuda.max_memory_allocated() < 40e9
 
