@@ -1026,3 +1026,23 @@ def test_fused_adam_matches_torch_adam(dev):
         assert set(sa["state"][k]) == set(sb["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
         assert float(sa["state"][k]["step"]) == float(sb["state"][k]["step"]) == 4.0
         assert rel(sa["state"][k]["exp_avg_sq"], sb["state"][k]["exp_avg_sq"]) < 1e-6
+
+
+def test_evaluator_graph_replay_equals_eager(dev):
+    """MoNuSegEvaluator.predict_batch through its CUDA graph (third call on) returns what the eager passes
+    return, and follows new inputs and in-place weight updates."""
+    import ug_oracle as O
+    import ug_pg_unet_b200 as U
+
+    model = U.PGUNet2(3, 1).to(dev)
+    model.load_state_dict(O.seeded_state_dict(2, 3, 1, seed=8))
+    ev_g = U.MoNuSegEvaluator(model, device=dev, use_cuda_graph=True)
+    ev_e = U.MoNuSegEvaluator(model, device=dev, use_cuda_graph=False)
+    g = torch.Generator().manual_seed(2)
+    for i in range(5):
+        img = torch.randint(0, 256, (2, 64, 64, 3), generator=g, dtype=torch.uint8)
+        if i == 4:
+            model.load_state_dict(O.seeded_state_dict(2, 3, 1, seed=9))      # in place: same storages
+        mg, cg = ev_g.predict_batch(img)
+        me, ce = ev_e.predict_batch(img)
+        assert torch.equal(mg, me) and torch.equal(cg, ce), i
