@@ -239,13 +239,17 @@ int ugp_rmsprop_multi(float* const* params, const float* const* grads, float* co
                       float weight_decay, float grad_scale, void* stream);
 
 /* torch.optim.Adam step (Herlev/train_herlev.py:170-176: betas (.9, .999), eps 1e-8, L2 weight decay, no
- * amsgrad) for n_tensors tensors in one launch per 64 tensors; `step` = the 1-based step count:
+ * amsgrad) for n_tensors tensors in one launch per 64 tensors; `step` = the 1-based step count, or, when
+ * step_dev (a DEVICE int64, nullable) is given, read from there at run time so that CUDA-graph replays
+ * advance it with ugp_counter_add:
  *   g = grad*grad_scale + wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g
  *   p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps) */
 int ugp_adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs,
                    float* const* exp_avg_sqs, const long long* sizes, int n_tensors, double lr,
                    double beta1, double beta2, double eps, double weight_decay, long long step,
-                   float grad_scale, void* stream);
+                   const long long* step_dev, float grad_scale, void* stream);
+/* *counter += inc on the device (the optimiser's step count inside a captured graph). */
+int ugp_counter_add(long long* counter, long long inc, void* stream);
 
 /* RMSprop for the 3x3 convolution weights straight from the PACKED gradient that
  * ugp_conv_wgrad_bf16 accumulates (replaces ugp_unpack_wgrad + optimizer.step() of

@@ -1046,3 +1046,37 @@ def test_evaluator_graph_replay_equals_eager(dev):
         mg, cg = ev_g.predict_batch(img)
         me, ce = ev_e.predict_batch(img)
         assert torch.equal(mg, me) and torch.equal(cg, ce), i
+
+
+def test_herlev_graph_step_tracks_eager_step(dev):
+    """HerlevTrainer.train_step: CUDA-graph replays (FusedAdam with its device-side step count inside the
+    graph) follow the eager trajectory, and the optimiser's state_dict reports the true step count."""
+    import contextlib
+    import io
+    import ug_pg_unet_b200.herlev as Hm
+
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(4, 3, 64, 64, generator=g).to(dev)
+    y = torch.randint(0, 7, (4,), generator=g).to(dev)
+    traj = []
+    for use_graph in (False, True):
+        cfg = {"device": dev, "epochs_per_stage": 1, "num_classes": 7, "uncertainty_alpha": 1.0, "log_interval": 0,
+               "use_cuda_graph": use_graph}
+        torch.manual_seed(3)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr = Hm.HerlevTrainer(cfg)
+            tr.setup_optimizer_scheduler(2)
+        model = tr.models[2]
+        model.train()
+        for m in model.classifier:
+            if isinstance(m, torch.nn.Dropout):
+                m.eval()                                  # same trajectory in both modes
+        tr.models[1].eval()
+        ms = torch.stack([tr.train_step(x, y, 2) for _ in range(8)]).cpu()
+        sd = tr.optimizers[2].state_dict()
+        assert {float(s["step"]) for s in sd["state"].values()} == {8.0}
+        traj.append((ms, model.classifier[9].weight.detach().clone()))
+    (me, we), (mg, wg) = traj
+    assert abs(me[0, 0] - mg[0, 0]) <= 1e-3 * abs(me[0, 0])           # identical first step
+    assert rel(mg[:, 0], me[:, 0]) < 5e-2                             # bf16 / atomic-order drift afterwards
+    assert rel(wg, we) < 5e-2 and mg[-1, 0] < mg[0, 0]

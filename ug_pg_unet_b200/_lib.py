@@ -57,7 +57,8 @@ SIGNATURES = {
     "ugp_bench_mma": [_i, _i, _i, _i, _i, _i, _i, _p, _p],
     "ugp_rmsprop_step": [_p, _p, _p, _ll, _f, _f, _f, _f, _f, _p],
     "ugp_rmsprop_multi": [_p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _p],
-    "ugp_adam_multi": [_p, _p, _p, _p, _p, _i, _d, _d, _d, _d, _d, _ll, _f, _p],
+    "ugp_adam_multi": [_p, _p, _p, _p, _p, _i, _d, _d, _d, _d, _d, _ll, _p, _f, _p],
+    "ugp_counter_add": [_p, _ll, _p],
     "ugp_rmsprop_conv_packed": [_p, _p, _p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _p],
 }
 INFO_FUNCS = ("ugp_last_error", "ugp_version", "ugp_device_sm_count", "ugp_set_option")

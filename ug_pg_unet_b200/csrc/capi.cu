@@ -57,7 +57,8 @@ int pack_weights_tconv(const float*, int, int, void*, void*, cudaStream_t);
 int unpack_wgrad_tconv(float*, int, int, float*, int, cudaStream_t);
 int channel_sum(const void*, long long, int, float*, cudaStream_t);
 int adam_multi(float* const*, const float* const*, float* const*, float* const*, const long long*, int, double,
-               double, double, double, double, long long, float, cudaStream_t);
+               double, double, double, double, long long, const long long*, float, cudaStream_t);
+int counter_add(long long*, long long, cudaStream_t);
 int im2col_first_u8(const unsigned char*, int, int, int, int, int, int, const float*, const float*, void*,
                     cudaStream_t);
 int bce_uncertainty_loss_u8(const float*, const unsigned char*, const float*, float, float, int, long long,
@@ -250,8 +251,12 @@ int ugp_head_combine_bwd_hw(const float* dlogits, int planes, int RH, int RW, in
 }
 int ugp_adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs,
                    float* const* exp_avg_sqs, const long long* sizes, int n_tensors, double lr, double beta1,
-                   double beta2, double eps, double weight_decay, long long step, float grad_scale, void* stream) {
+                   double beta2, double eps, double weight_decay, long long step, const long long* step_dev,
+                   float grad_scale, void* stream) {
   return ugp::adam_multi(params, grads, exp_avgs, exp_avg_sqs, sizes, n_tensors, lr, beta1, beta2, eps,
-                         weight_decay, step, grad_scale, S(stream));
+                         weight_decay, step, step_dev, grad_scale, S(stream));
+}
+int ugp_counter_add(long long* counter, long long inc, void* stream) {
+  return ugp::counter_add(counter, inc, S(stream));
 }
 }  // extern "C"

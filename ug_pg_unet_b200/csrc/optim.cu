@@ -304,9 +304,19 @@ struct AdamTable {
   int n[kAdamMaxTensors];
 };
 
+__global__ void counter_add_kernel(long long* counter, long long inc) { *counter += inc; }
+
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const __grid_constant__ AdamTable t, float step_size, float inv_sqrt_bc2, float b1, float b2,
-                  float omb1, float omb2, float eps, float wd, float gscale) {   // omb = 1 - beta (from double)
+                  float omb1, float omb2, float eps, float wd, float gscale,   // omb = 1 - beta (from double)
+                  const long long* __restrict__ step_dev, double lr, double beta1, double beta2) {
+  if (step_dev) {
+    // step count kept on the device (CUDA-graph replays advance it without the host): the bias
+    // corrections are formed here, in double like torch does on the host
+    const double st = static_cast<double>(*step_dev);
+    step_size = static_cast<float>(lr / (1.0 - pow(beta1, st)));
+    inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(1.0 - pow(beta2, st)));
+  }
   const int k = blockIdx.y;
   float* __restrict__ p = t.p[k];
   const float* __restrict__ g = t.g[k];
@@ -326,10 +336,11 @@ adam_multi_kernel(const __grid_constant__ AdamTable t, float step_size, float in
 
 int adam_multi(float* const* params, const float* const* grads, float* const* exp_avgs,
                float* const* exp_avg_sqs, const long long* sizes, int n_tensors, double lr, double beta1,
-               double beta2, double eps, double weight_decay, long long step, float grad_scale,
-               cudaStream_t stream) {
-  UGP_REQUIRE(params && grads && exp_avgs && exp_avg_sqs && sizes && n_tensors > 0 && step >= 1,
+               double beta2, double eps, double weight_decay, long long step, const long long* step_dev,
+               float grad_scale, cudaStream_t stream) {
+  UGP_REQUIRE(params && grads && exp_avgs && exp_avg_sqs && sizes && n_tensors > 0 && (step >= 1 || step_dev),
               "adam_multi: bad arguments");
+  if (step < 1) step = 1;
   // hyper-parameters arrive as the optimiser's Python doubles: 1 - beta is formed in double like torch does
   const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
   const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
@@ -355,9 +366,17 @@ int adam_multi(float* const* params, const float* const* grads, float* const* ex
     adam_multi_kernel<<<grid, 256, 0, stream>>>(t, step_size, inv_sqrt_bc2, static_cast<float>(beta1),
                                                 static_cast<float>(beta2), static_cast<float>(1.0 - beta1),
                                                 static_cast<float>(1.0 - beta2), static_cast<float>(eps),
-                                                static_cast<float>(weight_decay), grad_scale);
+                                                static_cast<float>(weight_decay), grad_scale, step_dev, lr, beta1,
+                                                beta2);
     UGP_CHECK_CUDA(cudaGetLastError());
   }
+  return UGP_OK;
+}
+
+int counter_add(long long* counter, long long inc, cudaStream_t stream) {
+  UGP_REQUIRE(counter, "counter_add: null pointer");
+  counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);
+  UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
 

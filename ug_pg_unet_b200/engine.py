@@ -122,6 +122,20 @@ def conv_packs(model: nn.Module) -> List[PackedWeights]:
     return out
 
 
+def refresh_eval_caches(model: nn.Module) -> None:
+    """Brings the private inference caches of every DoubleConv in `model` up to date IN PLACE (bf16
+    operand packs, folded eval-mode BatchNorm scale / shift): a captured CUDA graph of the inference pass
+    holds their addresses and does not re-run this host logic on replay."""
+    for m in model.modules():
+        pk = getattr(m, "_packs", None)
+        ops_ = getattr(m, "conv_op", None)
+        if pk is None or ops_ is None:
+            continue
+        for pack, bn in zip(pk, (ops_[1], ops_[4])):
+            pack.get()
+            pack.eval_coef(bn, pack.conv.weight.device)
+
+
 def enable_deferred_wgrad(model: nn.Module, enable: bool = True):
     """Switches every eligible 3x3 conv of `model` to deferred (packed) weight gradients and lays
     their accumulators out in ONE flat fp32 arena, in reverse forward order = the order backward

@@ -15,7 +15,7 @@ from typing import Dict, Iterable, Optional, Tuple
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import engine, ops
 from .herlev import HerlevClassificationModel
 from .unet import STAGE_MODELS, _PGUNetBase, _forward_resized
 
@@ -52,8 +52,10 @@ class MoNuSegEvaluator:
         self.model.to(self.device).eval()
         # The inference forward is ~60 short kernels: at batch 1 an eager pass is bound by the host's
         # launch rate, so `predict_batch` replays one CUDA graph per input signature (forward +
-        # thresholding / confidence kernel).  Weights are read at replay time: reloading a state_dict into
-        # the SAME model object needs `reset_graphs()` only if parameter storage was replaced.
+        # thresholding / confidence kernel).  The bf16 operand packs and folded BN coefficients the graph
+        # reads are refreshed in place before every replay, so in-place weight updates (load_state_dict,
+        # optimizer steps) are honoured; `reset_graphs()` is needed only if parameter storage was replaced
+        # (`.to()` to another device, swapping modules).
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
 
@@ -77,6 +79,7 @@ class MoNuSegEvaluator:
                 z = self.logits(g["x"], target_size)
                 g["out"] = (z, ops.seg_confusion(z.contiguous(), None, want_mask=True))
             g["graph"] = graph
+        engine.refresh_eval_caches(self.model)     # weight / BN updates since the capture (in place, no-op if none)
         g["x"].copy_(images, non_blocking=True)
         g["graph"].replay()
         z, (counts, mask) = g["out"]

@@ -156,6 +156,9 @@ class HerlevTrainer:
             for m in self.models.values():
                 broadcast_module_state(m)
         self._reducers = {}
+        self._graph = None
+        self._capture_stream = None
+        self.use_cuda_graph = config.get("use_cuda_graph", True) and os.environ.get("UGP_NO_CUDA_GRAPH", "0") != "1"
         self.setup_loss_function()
         from .unet import UncertaintyGuidedLoss
         self.uncertainty_loss = UncertaintyGuidedLoss(self.device)
@@ -176,6 +179,7 @@ class HerlevTrainer:
         lr = self.stage_configs[stage]["lr"]
         # same hyper-parameters / state_dict layout as the reference's optim.Adam; on CUDA the update of
         # all tensors is one kernel launch (FusedAdam subclasses optim.Adam)
+        self._graph = None
         adam = FusedAdam if torch.device(self.device).type == "cuda" else torch.optim.Adam
         self.optimizers[stage] = adam(model.parameters(), lr=lr, weight_decay=self.config.get("weight_decay", 1e-4))
         self.schedulers[stage] = torch.optim.lr_scheduler.ReduceLROnPlateau(
@@ -186,7 +190,11 @@ class HerlevTrainer:
                 old.remove()
             used = [p for p in list(model.encoder_parameters()) + list(model.classifier.parameters())
                     if p.requires_grad]
-            self._reducers[stage] = GradBucketReducer(used, bucket_mb=self.config.get("bucket_mb", 16.0))
+            fused = isinstance(self.optimizers[stage], FusedAdam)
+            self._reducers[stage] = GradBucketReducer(used, bucket_mb=self.config.get("bucket_mb", 16.0),
+                                                      average=not fused)
+            if fused:       # .grad stays a view of the summed bucket; the optimiser kernel applies 1/world_size
+                self.optimizers[stage].grad_scale = 1.0 / self.world_size
 
     def transfer_weights(self, prev_stage, current_stage):
         """reference :200-217 — copies classifier tensors whose shapes match."""
@@ -246,8 +254,43 @@ class HerlevTrainer:
         return final, metrics
 
     def train_step(self, data, target, stage):
-        """One optimisation step; returns device tensors (final, base, #correct, w mean, w std) — no host
-        synchronisation."""
+        """One optimisation step on device tensors; returns a device tensor (final, base, #correct, w mean,
+        w std) — no host synchronisation.  The step is ~250 short kernels and an eager pass is bound by the
+        host's launch rate, so after three eager warm-ups it is captured once into a CUDA graph per
+        (stage, shapes, learning rate) and replayed (forward, previous-stage uncertainty, fused loss,
+        backward, gradient all-reduce, FusedAdam with its device-side step count)."""
+        opt = self.optimizers[stage]
+        use_graph = (self.use_cuda_graph and data.is_cuda and isinstance(opt, FusedAdam)
+                     and self.criterion.weight is None and self.config["num_classes"] > 2)
+        if not use_graph:
+            return self._eager_step(data, target, stage)
+        key = (stage, tuple(data.shape), data.dtype, tuple(target.shape), id(self.models[stage]), id(opt),
+               tuple(float(gp["lr"]) for gp in opt.param_groups), self.models[stage].training,
+               tuple(bool(m.training) for m in self.models[stage].classifier))
+        g = self._graph
+        if g is None or g["key"] != key:
+            self._graph = g = {"key": key, "warm": 0, "graph": None}
+        if g["graph"] is None:
+            if g["warm"] < 3:
+                g["warm"] += 1
+                return self._eager_step(data, target, stage)
+            g["x"], g["y"] = data.clone(), target.clone()
+            opt.zero_grad(set_to_none=True)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            if self._capture_stream is None:
+                self._capture_stream = torch.cuda.Stream(device=data.device, priority=-1)
+            with torch.cuda.graph(graph, stream=self._capture_stream):
+                g["out"] = self._eager_step(g["x"], g["y"], stage)
+            g["graph"] = graph
+            g["counted"] = True            # the capture pass already advanced the host-side step counts
+        g["x"].copy_(data, non_blocking=True)
+        g["y"].copy_(target, non_blocking=True)
+        g["graph"].replay()
+        opt.note_replayed_steps(0 if g.pop("counted", False) else 1)
+        return g["out"].clone()
+
+    def _eager_step(self, data, target, stage):
         opt = self.optimizers[stage]
         opt.zero_grad(set_to_none=True)
         final, base, logits, w, out = self._forward_loss(data, target, stage)

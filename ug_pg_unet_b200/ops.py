@@ -546,9 +546,15 @@ def rmsprop_multi(params, grads, square_avgs, lr: float, alpha: float, eps: floa
           "ugp_rmsprop_multi")
 
 
+def counter_add(counter: torch.Tensor, inc: int = 1):
+    _req(counter, torch.int64, "counter")
+    check(lib().ugp_counter_add(_ptr(counter), int(inc), _stream()), "ugp_counter_add")
+
+
 def adam_multi(params, grads, exp_avgs, exp_avg_sqs, step: int, lr: float, beta1: float, beta2: float, eps: float,
-               weight_decay: float, grad_scale: float = 1.0):
-    """One launch (per 64 tensors) of torch.optim.Adam's update with L2 weight decay; see ugp_adam_multi."""
+               weight_decay: float, grad_scale: float = 1.0, step_dev: Optional[torch.Tensor] = None):
+    """One launch (per 64 tensors) of torch.optim.Adam's update with L2 weight decay; see ugp_adam_multi.
+    `step_dev`: int64 device scalar holding the step count (graph-safe), overrides `step`."""
     n = len(params)
     for t in list(params) + list(grads) + list(exp_avgs) + list(exp_avg_sqs):
         _req(t, torch.float32, "adam tensor")
@@ -557,8 +563,8 @@ def adam_multi(params, grads, exp_avgs, exp_avg_sqs, step: int, lr: float, beta1
     M = (C.c_void_p * n)(*[t.data_ptr() for t in exp_avgs])
     V = (C.c_void_p * n)(*[t.data_ptr() for t in exp_avg_sqs])
     S = (C.c_longlong * n)(*[t.numel() for t in params])
-    check(lib().ugp_adam_multi(P, G, M, V, S, n, lr, beta1, beta2, eps, weight_decay, int(step), grad_scale,
-                               _stream()), "ugp_adam_multi")
+    check(lib().ugp_adam_multi(P, G, M, V, S, n, lr, beta1, beta2, eps, weight_decay, int(step),
+                               _ptr(_opt(step_dev, torch.int64, "step_dev")), grad_scale, _stream()), "ugp_adam_multi")
 
 
 def rmsprop_conv_packed(weights, square_avgs, dw_packed, wfs, wds, lr: float, alpha: float, eps: float,

@@ -122,7 +122,11 @@ class FusedAdam(torch.optim.Adam):
     with `step()` as one multi-tensor kernel launch.  Same constructor arguments, `param_groups` and
     `state_dict()` layout (`step`, `exp_avg`, `exp_avg_sq`); amsgrad / maximize / non-CUDA parameters are
     delegated to the stock implementation.  `grad_scale` multiplies the gradients inside the kernel
-    (1/world_size when a reducer left them as sums over ranks)."""
+    (1/world_size when a reducer left them as sums over ranks).
+
+    The step count that the bias corrections need also lives in a device int64 (per parameter group,
+    advanced by a one-thread kernel), so a captured CUDA graph containing `step()` stays correct when
+    replayed; `note_replayed_steps` keeps the per-parameter `step` entries of `state_dict()` in sync."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, **kw):
         kw.pop("capturable", None)
@@ -130,6 +134,31 @@ class FusedAdam(torch.optim.Adam):
         kw.pop("fused", None)
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, **kw)
         self.grad_scale = 1.0
+        self._dev_steps = {}           # id(group) -> int64 device scalar
+        self._replayed_steps = 0
+
+    def note_replayed_steps(self, n: int = 1) -> None:
+        """A CUDA-graph replay ran `step()`'s kernels (and advanced the device step count) without
+        running this Python code."""
+        self._replayed_steps += n
+        from .engine import PackedWeights
+        PackedWeights.invalidate_all()
+
+    def _sync_host_steps(self) -> None:
+        if self._replayed_steps:
+            for st in self.state.values():
+                if "step" in st:
+                    st["step"] = st["step"] + self._replayed_steps
+            self._replayed_steps = 0
+
+    def state_dict(self):
+        self._sync_host_steps()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._replayed_steps = 0
+        self._dev_steps = {}           # rebuilt from the loaded per-parameter step counts
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -138,10 +167,14 @@ class FusedAdam(torch.optim.Adam):
             with torch.enable_grad():
                 loss = closure()
         from .engine import PackedWeights
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self._sync_host_steps()
         for group in self.param_groups:
             if group["amsgrad"] or group.get("maximize", False):
                 return super().step()
-            by_step = {}
+            ps, gs, ms, vs = [], [], [], []
+            steps = set()
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -153,15 +186,28 @@ class FusedAdam(torch.optim.Adam):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["step"] += 1
-                t = int(st["step"])
-                ps, gs, ms, vs = by_step.setdefault(t, ([], [], [], []))
+                steps.add(int(st["step"]))
                 ps.append(p.data)
                 gs.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
+            if not ps:
+                continue
+            if len(steps) != 1:        # parameters that joined later: the stock implementation handles them
+                for p in group["params"]:
+                    if p.grad is not None:
+                        self.state[p]["step"] -= 1
+                return super().step()
+            t = steps.pop()
+            dev = self._dev_steps.get(id(group))
+            if dev is None or dev.device != ps[0].device:
+                if capturing:
+                    raise RuntimeError("FusedAdam: run at least one eager step() before capturing a CUDA graph")
+                dev = torch.full((), t - 1, dtype=torch.int64, device=ps[0].device)
+                self._dev_steps[id(group)] = dev
+            ops.counter_add(dev, 1)
             b1, b2 = group["betas"]
-            for t, (ps, gs, ms, vs) in by_step.items():
-                ops.adam_multi(ps, gs, ms, vs, t, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                               float(group["weight_decay"]), float(self.grad_scale))
+            ops.adam_multi(ps, gs, ms, vs, t, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                           float(group["weight_decay"]), float(self.grad_scale), step_dev=dev)
         PackedWeights.invalidate_all()       # parameters changed behind autograd's version counters
         return loss
