@@ -141,8 +141,15 @@ class FusedAdam(torch.optim.Adam):
         """A CUDA-graph replay ran `step()`'s kernels (and advanced the device step count) without
         running this Python code."""
         self._replayed_steps += n
-        from .engine import PackedWeights
-        PackedWeights.invalidate_all()
+        self._bump_versions([p for g in self.param_groups for p in g["params"] if p in self.state])
+
+    @staticmethod
+    def _bump_versions(params) -> None:
+        """The kernel wrote these parameters without autograd noticing: advance their version counters so
+        that exactly the caches keyed on them (bf16 operand packs, folded BN coefficients) refresh - not
+        those of other models, e.g. the frozen previous-stage network."""
+        if params:
+            torch.autograd.graph.increment_version(params)
 
     def _sync_host_steps(self) -> None:
         if self._replayed_steps:
@@ -166,7 +173,7 @@ class FusedAdam(torch.optim.Adam):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        from .engine import PackedWeights
+        updated = []
         capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         if not capturing:
             self._sync_host_steps()
@@ -188,6 +195,7 @@ class FusedAdam(torch.optim.Adam):
                 st["step"] += 1
                 steps.add(int(st["step"]))
                 ps.append(p.data)
+                updated.append(p)
                 gs.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
@@ -209,5 +217,5 @@ class FusedAdam(torch.optim.Adam):
             b1, b2 = group["betas"]
             ops.adam_multi(ps, gs, ms, vs, t, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                            float(group["weight_decay"]), float(self.grad_scale), step_dev=dev)
-        PackedWeights.invalidate_all()       # parameters changed behind autograd's version counters
+        self._bump_versions(updated)
         return loss
