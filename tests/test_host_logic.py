@@ -198,3 +198,28 @@ def test_metrics_from_counts_matches_the_oracle():
         got = metrics_from_counts(float((p * t).sum()), float(p.sum()), float(t.sum()), float(p.numel()))
         for k, v in want.items():
             assert abs(got[k] - v) < 1e-12, k
+
+
+def test_fused_optimizers_delegate_cpu_parameters_to_the_stock_implementation():
+    """FusedAdam / FusedRMSprop subclass the torch optimisers: with parameters the kernels cannot take
+    (CPU tensors here) `step()` is the stock update, and the state_dict layout is the stock one."""
+    import torch
+    from ug_pg_unet_b200.optim import FusedAdam, FusedRMSprop
+
+    g = torch.Generator().manual_seed(0)
+    for fused_cls, stock_cls, kw in ((FusedAdam, torch.optim.Adam, {"lr": 1e-3, "weight_decay": 1e-4}),
+                                     (FusedRMSprop, torch.optim.RMSprop, {"lr": 1e-3, "weight_decay": 1e-4})):
+        pa = [torch.randn(5, 3, generator=g).requires_grad_(True), torch.randn(7, generator=g).requires_grad_(True)]
+        pb = [p.detach().clone().requires_grad_(True) for p in pa]
+        oa, ob = fused_cls(pa, **kw), stock_cls(pb, **kw)
+        for _ in range(3):
+            for a, b in zip(pa, pb):
+                gr = torch.randn(a.shape, generator=g)
+                a.grad, b.grad = gr.clone(), gr.clone()
+            oa.step()
+            ob.step()
+        for a, b in zip(pa, pb):
+            torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+        sa, sb = oa.state_dict(), ob.state_dict()
+        assert set(sa["state"][0]) == set(sb["state"][0])
+        assert float(sa["state"][0]["step"]) == float(sb["state"][0]["step"]) == 3.0

@@ -194,7 +194,7 @@ class HerlevTrainer:
             self._reducers[stage] = GradBucketReducer(used, bucket_mb=self.config.get("bucket_mb", 16.0),
                                                       average=not fused)
             if fused:       # .grad stays a view of the summed bucket; the optimiser kernel applies 1/world_size
-                self.optimizers[stage].grad_scale = 1.0 / self.world_size
+                self.optimizers[stage].dense_grad_scale = 1.0 / self.world_size
 
     def transfer_weights(self, prev_stage, current_stage):
         """reference :200-217 — copies classifier tensors whose shapes match."""

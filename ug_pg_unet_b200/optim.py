@@ -121,7 +121,7 @@ class FusedAdam(torch.optim.Adam):
     """`torch.optim.Adam` (L2 weight decay, the Herlev trainer's optimiser, Herlev/train_herlev.py:170-176)
     with `step()` as one multi-tensor kernel launch.  Same constructor arguments, `param_groups` and
     `state_dict()` layout (`step`, `exp_avg`, `exp_avg_sq`); amsgrad / maximize / non-CUDA parameters are
-    delegated to the stock implementation.  `grad_scale` multiplies the gradients inside the kernel
+    delegated to the stock implementation.  `dense_grad_scale` multiplies the gradients inside the kernel
     (1/world_size when a reducer left them as sums over ranks).
 
     The step count that the bias corrections need also lives in a device int64 (per parameter group,
@@ -133,7 +133,7 @@ class FusedAdam(torch.optim.Adam):
         kw.pop("foreach", None)
         kw.pop("fused", None)
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, **kw)
-        self.grad_scale = 1.0
+        self.dense_grad_scale = 1.0    # (torch.optim.Adam itself uses the attribute name `grad_scale` for AMP)
         self._dev_steps = {}           # id(group) -> int64 device scalar
         self._replayed_steps = 0
 
@@ -177,23 +177,27 @@ class FusedAdam(torch.optim.Adam):
         capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         if not capturing:
             self._sync_host_steps()
+        # eligibility first, nothing mutated yet: anything the kernel cannot take goes to the stock update
         for group in self.param_groups:
-            if group["amsgrad"] or group.get("maximize", False):
+            live = [p for p in group["params"] if p.grad is not None]
+            prospective = {int(self.state[p]["step"]) + 1 if len(self.state[p]) else 1 for p in live}
+            if (group["amsgrad"] or group.get("maximize", False) or len(prospective) > 1
+                    or any(not p.is_cuda or p.grad.is_sparse or p.dtype != torch.float32 for p in live)):
+                self._dev_steps = {}       # rebuilt from the host-side step counts at the next fused step
                 return super().step()
+        for group in self.param_groups:
             ps, gs, ms, vs = [], [], [], []
-            steps = set()
+            t = 0
             for p in group["params"]:
                 if p.grad is None:
                     continue
-                if not p.is_cuda or p.grad.is_sparse or p.dtype != torch.float32:
-                    return super().step()
                 st = self.state[p]
                 if len(st) == 0:
                     st["step"] = torch.zeros((), dtype=torch.float32)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["step"] += 1
-                steps.add(int(st["step"]))
+                t = int(st["step"])
                 ps.append(p.data)
                 updated.append(p)
                 gs.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
@@ -201,12 +205,6 @@ class FusedAdam(torch.optim.Adam):
                 vs.append(st["exp_avg_sq"])
             if not ps:
                 continue
-            if len(steps) != 1:        # parameters that joined later: the stock implementation handles them
-                for p in group["params"]:
-                    if p.grad is not None:
-                        self.state[p]["step"] -= 1
-                return super().step()
-            t = steps.pop()
             dev = self._dev_steps.get(id(group))
             if dev is None or dev.device != ps[0].device:
                 if capturing:
@@ -216,6 +214,6 @@ class FusedAdam(torch.optim.Adam):
             ops.counter_add(dev, 1)
             b1, b2 = group["betas"]
             ops.adam_multi(ps, gs, ms, vs, t, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                           float(group["weight_decay"]), float(self.grad_scale), step_dev=dev)
+                           float(group["weight_decay"]), float(self.dense_grad_scale), step_dev=dev)
         self._bump_versions(updated)
         return loss
