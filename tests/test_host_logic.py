@@ -223,3 +223,38 @@ def test_fused_optimizers_delegate_cpu_parameters_to_the_stock_implementation():
         sa, sb = oa.state_dict(), ob.state_dict()
         assert set(sa["state"][0]) == set(sb["state"][0])
         assert float(sa["state"][0]["step"]) == float(sb["state"][0]["step"]) == 3.0
+
+
+def test_legacy_unet_surface_matches_reference_tables():
+    """UNet / DownSample / UpSample (UG_unet.py:430-462, UG_unet_parts.py:31-41, 57-67): attribute names,
+    the 136 state_dict keys / shapes of the reference (oracle table, itself loaded strict=True into the
+    reference by tools/make_goldens.py) and a strict load of the oracle's seeded weights."""
+    import torch
+    import ug_oracle as O
+    import ug_pg_unet_b200 as U
+
+    net = U.UNet(3, 2)
+    want = O.legacy_unet_shapes(3, 2)
+    got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert got == want and len(got) == 136
+    for name in ("down_convolution_1", "down_convolution_4", "bottle_neck", "up_convolution_1", "up_convolution_4", "out"):
+        assert hasattr(net, name)
+    assert isinstance(net.up_convolution_2.up, torch.nn.ConvTranspose2d) and net.up_convolution_2.up.stride == (2, 2)
+    assert isinstance(net.down_convolution_1.pool, torch.nn.MaxPool2d)
+    net.load_state_dict(O.seeded_legacy_state_dict(3, 2, seed=1), strict=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 3, 256, 256))                      # no CPU fallback
+    with pytest.raises(ValueError):
+        U.UpSample(96, 64)                                    # channel counts the GEMM tiles cannot take
+
+
+def test_byte_inputs_are_validated_on_the_host():
+    import torch
+    import ug_pg_unet_b200 as U
+
+    m = U.PGUNet1(3, 1)
+    assert m.set_input_norm((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)) is m
+    assert m.input_mean == (0.485, 0.456, 0.406) and m.input_std == (0.229, 0.224, 0.225)
+    assert "input_mean" not in m.state_dict()                # not part of the checkpoint format
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 32, 32, 3, dtype=torch.uint8))       # bytes on the CPU: still no fallback
