@@ -8,8 +8,12 @@ routes through it.
 
 Pinning: `tests/golden/*.pt` were produced by importing the UNMODIFIED
 reference (`/root/reference`, PyTorch modules) in the build container with
-`tools/make_goldens.py`; `tests/test_oracle_golden.py` checks every function
-here against those vectors.  The reference itself ships no tests or golden
+`tools/make_goldens.py` — five trainer steps (stages 1-4, BASELINE config 1
+shape included), two Herlev steps, primitive semantics (max-pool indices,
+bilinear resize, BCE pos_weight, uncertainty map, weight transfer), the
+legacy `UNet` / `UpSample` (ConvTranspose2d) forward + backward, and the
+`MoNuSegEvaluator` arithmetic; `tests/test_oracle_golden.py` checks every
+function here against those vectors.  The reference itself ships no tests or golden
 vectors, so these reference-generated fixtures are the pin.
 
 Every function cites the reference lines it restates (paths relative to the
