@@ -17,6 +17,9 @@ import ug_pg_unet_b200.herlev as H
 
 
 def main():
+    if os.environ.get("CHECK_DP_DUMP_AFTER"):      # where is every thread if the run stalls?
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["CHECK_DP_DUMP_AFTER"]), exit=True)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
