@@ -41,7 +41,7 @@ def main():
     B = 16
     x = torch.randn(B, 3, res, res, generator=g).to(dev)
     y = torch.randint(0, 7, (B,), generator=g).to(dev)
-    for _ in range(3):
+    for _ in range(6):                            # 3 eager warm-ups, the graph capture, 2 replays
         tr.train_step(x, y, 4)
     torch.cuda.synchronize()
     dist.barrier()
@@ -64,9 +64,15 @@ def main():
     if rank == 0:
         ok = float(w) == 0.0 and bool(torch.isfinite(out).all())
         print(f"check_dp_herlev {'ok' if ok else 'FAILED'}: world {world}, stage 4 at {res}x{res}, batch {B}/rank, "
-              f"{float(t):.2f} ms/step (eager), {world * B / float(t) * 1e3:.0f} images/s, "
+              f"{float(t):.2f} ms/step ({'graph replay' if tr._graph and tr._graph.get('graph') is not None else 'eager'}), "
+              f"{world * B / float(t) * 1e3:.0f} images/s, "
               f"max weight difference across ranks {float(w):.1e}")
-    dist.destroy_process_group()
+    # NCCL kernels captured into CUDA graphs keep the communicator busy: destroy_process_group() does not
+    # return on this stack (same as bench.py / tools/check_dp.py), so flush and leave
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -260,11 +260,12 @@ class HerlevTrainer:
         (stage, shapes, learning rate) and replayed (forward, previous-stage uncertainty, fused loss,
         backward, gradient all-reduce, FusedAdam with its device-side step count)."""
         opt = self.optimizers[stage]
-        # (single process only for now: the captured data-parallel step did not complete in a 2-GPU run
-        # and is switched off until that is understood — UGP_HERLEV_DP_GRAPH=1 re-enables it)
+        # (data parallel: the all-reduces are captured too; verified on 2 GPUs - rank-identical weights.  A
+        # process that captured NCCL kernels must leave with os._exit() instead of destroy_process_group(),
+        # which does not return on this stack - see bench.py.  UGP_HERLEV_DP_GRAPH=0 keeps DP steps eager.)
         use_graph = (self.use_cuda_graph and data.is_cuda and isinstance(opt, FusedAdam)
                      and self.criterion.weight is None and self.config["num_classes"] > 2
-                     and (not self.distributed or os.environ.get("UGP_HERLEV_DP_GRAPH", "0") == "1"))
+                     and (not self.distributed or os.environ.get("UGP_HERLEV_DP_GRAPH", "1") == "1"))
         if not use_graph:
             return self._eager_step(data, target, stage)
         key = (stage, tuple(data.shape), data.dtype, tuple(target.shape), id(self.models[stage]), id(opt),
