@@ -10,19 +10,23 @@ Activations travel as NHWC bf16 tensors [B, H, W, C].
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
 
 from . import ops
+from ._lib import set_option
 
 bf16 = torch.bfloat16
-import os as _os
-# what-if timing switch (results wrong): skip the BatchNorm-backward reduction pass of each DoubleConv's first BN
-_WHATIF_SKIP_BN1_REDUCE = _os.environ.get("UGP_WHATIF_SKIP_BN1_REDUCE", "0") == "1"
-# what-if (results wrong): drop the pooled gradient so the pooled BatchNorm backward runs the plain kernels
-_WHATIF_POOL_AS_PLAIN = _os.environ.get("UGP_WHATIF_POOL_AS_PLAIN", "0") == "1"
+
+# What-if timing switches: a step is timed with a piece of work REMOVED to bound what
+# fusing it away could gain.  Results are wrong while one is set; both are off unless the variable is set.
+#   UGP_WHATIF_SKIP_BN1_REDUCE: no reduction pass in the BatchNorm backward of each DoubleConv's first BN
+#   UGP_WHATIF_POOL_AS_PLAIN:   pooled gradient dropped, so the pooled BatchNorm backward runs the plain kernels
+_WHATIF_SKIP_BN1_REDUCE = os.environ.get("UGP_WHATIF_SKIP_BN1_REDUCE", "0") == "1"
+_WHATIF_POOL_AS_PLAIN = os.environ.get("UGP_WHATIF_POOL_AS_PLAIN", "0") == "1"
 
 
 class PackedWeights:
@@ -348,7 +352,6 @@ class DoubleConvFn(torch.autograd.Function):
         d1, g2 = cbr_backward(ctx.s2, dA, dP, conv2, bn2, mod._packs[1], True)
         need_in = ctx.x_needs_grad or ctx.skip_needs_grad
         if _WHATIF_SKIP_BN1_REDUCE:
-            from ._lib import set_option
             set_option("bn_skip_reduce", 1)
         d0, g1 = cbr_backward(ctx.s1, d1[0], None, conv1, bn1, mod._packs[0], need_in)
         if _WHATIF_SKIP_BN1_REDUCE:
