@@ -12,7 +12,7 @@ reference (`/root/reference`, PyTorch modules) in the build container with
 shape included), two Herlev steps, primitive semantics (max-pool indices,
 bilinear resize, BCE pos_weight, uncertainty map, weight transfer), the
 legacy `UNet` / `UpSample` (ConvTranspose2d) forward + backward, and the
-`MoNuSegEvaluator` arithmetic; `tests/test_oracle_golden.py` checks every
+`MoNuSegEvaluator` / `HerlevEvaluator` metric arithmetic; `tests/test_oracle_golden.py` checks every
 function here against those vectors.  The reference itself ships no tests or golden
 vectors, so these reference-generated fixtures are the pin.
 
@@ -347,6 +347,29 @@ def evaluate_segmentation(sd: StateDict, stage: int, images_u8: Tensor, gts: Ten
     avg = {k: sum(m[k] for m in per) / len(per) for k in per[0]}
     std = {k: math.sqrt(sum((m[k] - avg[k]) ** 2 for m in per) / len(per)) for k in per[0]}
     return masks, conf, per, avg, std, logits
+
+
+def classification_metrics(y_true: Tensor, y_pred: Tensor, num_classes: int) -> Dict[str, object]:
+    """HerlevEvaluator.calculate_metrics — Herlev/test_herlev.py:217-249: accuracy = mean(y_true == y_pred);
+    sklearn classification_report(zero_division=0): per class precision = tp/(tp+fp), recall = tp/(tp+fn),
+    f1 = 2pr/(p+r) (0 where the denominator is 0), support = #labels, macro / weighted averages;
+    confusion_matrix[label][prediction]; per-class accuracy for the classes present in the labels."""
+    K = num_classes
+    cm = torch.zeros(K, K, dtype=torch.int64)
+    for t, p in zip(y_true.tolist(), y_pred.tolist()):
+        cm[t, p] += 1
+    per = {}
+    for k in range(K):
+        tp = int(cm[k, k]); fp = int(cm[:, k].sum()) - tp; fn = int(cm[k, :].sum()) - tp
+        pr = tp / (tp + fp) if tp + fp else 0.0
+        rc = tp / (tp + fn) if tp + fn else 0.0
+        per[k] = {"precision": pr, "recall": rc, "f1": 2 * pr * rc / (pr + rc) if pr + rc else 0.0, "support": tp + fn}
+    n = max(len(y_true), 1)
+    macro = {m: sum(per[k][m] for k in range(K)) / K for m in ("precision", "recall", "f1")}
+    weighted = {m: sum(per[k][m] * per[k]["support"] for k in range(K)) / n for m in ("precision", "recall", "f1")}
+    return {"accuracy": float((y_true == y_pred).double().mean()), "per_class": per, "confusion_matrix": cm,
+            "macro_avg": macro, "weighted_avg": weighted,
+            "per_class_accuracy": {k: per[k]["recall"] for k in range(K) if per[k]["support"] > 0}}
 
 
 def softmax_entropy_uncertainty(logits: Tensor) -> Tensor:

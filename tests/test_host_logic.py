@@ -258,3 +258,30 @@ def test_byte_inputs_are_validated_on_the_host():
     assert "input_mean" not in m.state_dict()                # not part of the checkpoint format
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 32, 32, 3, dtype=torch.uint8))       # bytes on the CPU: still no fallback
+
+
+def test_classification_metrics_from_confusion_match_the_reference_golden(golden_dir):
+    """evaluate.classification_metrics_from_confusion (host arithmetic on the device-side confusion matrix of
+    ugp_cls_eval) vs the fixture produced by the unmodified HerlevEvaluator.calculate_metrics."""
+    import os
+    import torch
+    from ug_pg_unet_b200.evaluate import classification_metrics_from_confusion
+
+    fx = torch.load(os.path.join(golden_dir, "herlev_evaluator.pt"))
+    K = fx["K"]
+    cm = torch.zeros(K, K, dtype=torch.int64)
+    for t, p in zip(fx["y"].tolist(), fx["p"].tolist()):
+        cm[t, p] += 1                                         # what the kernel accumulates: counts[label][pred]
+    got = classification_metrics_from_confusion(cm)
+    assert torch.equal(got["confusion_matrix"], fx["confusion_matrix"])
+    assert abs(got["accuracy"] - fx["accuracy"]) < 1e-12 and got["total_samples"] == 200
+    for k, rep in fx["per_class"].items():
+        assert abs(got["precision"][k] - rep["precision"]) < 1e-12
+        assert abs(got["recall"][k] - rep["recall"]) < 1e-12
+        assert abs(got["f1"][k] - rep["f1-score"]) < 1e-12
+        assert got["support"][k] == int(rep["support"])
+    for name in ("macro_avg", "weighted_avg"):
+        for m, key in (("precision", "precision"), ("recall", "recall"), ("f1", "f1-score")):
+            assert abs(got[name][m] - fx[name][key]) < 1e-12
+    assert {k: round(v, 12) for k, v in got["per_class_accuracy"].items()} == \
+        {k: round(v, 12) for k, v in fx["per_class_accuracy"].items()}

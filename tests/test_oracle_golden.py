@@ -194,3 +194,24 @@ def test_evaluator_matches_reference(golden_dir):
         assert abs(float(conf[i]) - fx["confidence"][i]) < 1e-6
     for k in fx["avg"]:
         assert abs(avg[k] - fx["avg"][k]) < 1e-6 and abs(std[k] - fx["std"][k]) < 1e-6
+
+
+def test_classification_evaluator_matches_reference(golden_dir):
+    """oracle.classification_metrics vs the unmodified HerlevEvaluator.calculate_metrics (sklearn report and
+    confusion matrix underneath; Herlev/test_herlev.py:217-260), incl. a class absent from the labels and a
+    class that is never predicted (zero_division=0)."""
+    fx = torch.load(os.path.join(golden_dir, "herlev_evaluator.pt"))
+    out = O.classification_metrics(fx["y"], fx["p"], fx["K"])
+    assert abs(out["accuracy"] - fx["accuracy"]) < 1e-12
+    assert torch.equal(out["confusion_matrix"], fx["confusion_matrix"])
+    for k, rep in fx["per_class"].items():
+        assert abs(out["per_class"][k]["precision"] - rep["precision"]) < 1e-12
+        assert abs(out["per_class"][k]["recall"] - rep["recall"]) < 1e-12
+        assert abs(out["per_class"][k]["f1"] - rep["f1-score"]) < 1e-12
+        assert out["per_class"][k]["support"] == int(rep["support"])
+    for name in ("macro_avg", "weighted_avg"):
+        for m, key in (("precision", "precision"), ("recall", "recall"), ("f1", "f1-score")):
+            assert abs(out[name][m] - fx[name][key]) < 1e-12
+    assert out["per_class_accuracy"].keys() == fx["per_class_accuracy"].keys()
+    for k, v in fx["per_class_accuracy"].items():
+        assert abs(out["per_class_accuracy"][k] - v) < 1e-12

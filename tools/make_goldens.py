@@ -234,8 +234,46 @@ def evaluator_case():
             "per_image": per, "avg": avg, "std": std, "logits": torch.stack(logits)}
 
 
+def herlev_evaluator_case():
+    """The reference's HerlevEvaluator.calculate_metrics (Herlev/test_herlev.py:217-260; sklearn
+    classification_report / confusion_matrix underneath) on seeded labels / predictions with one class
+    absent from the labels and one never predicted.  test_herlev.py imports matplotlib / seaborn for its
+    plots at module level; they are not installed here and are stubbed out - no plotting code runs."""
+    import types
+    import numpy as np
+    for m in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.path.insert(0, "/root/reference/Herlev")
+    with contextlib.redirect_stdout(io.StringIO()):
+        import test_herlev as REFHE
+    K = 7
+    ev = REFHE.HerlevEvaluator.__new__(REFHE.HerlevEvaluator)
+    ev.num_classes = K
+    ev.class_names = [f"c{i}" for i in range(K)]
+    rng = np.random.RandomState(3)
+    y = rng.randint(0, K - 1, 200)              # class 6 never occurs
+    p = rng.randint(1, K, 200)                  # class 0 never predicted
+    p[:60] = y[:60]
+    p = np.where(p == 0, 1, p)
+    probs = rng.rand(200, K)
+    probs /= probs.sum(1, keepdims=True)
+    m = ev.calculate_metrics(y, p, probs)
+    rep = m["classification_report"]
+    return {"K": K, "y": torch.from_numpy(y), "p": torch.from_numpy(p), "accuracy": float(m["accuracy"]),
+            "confusion_matrix": torch.tensor(m["confusion_matrix"]),
+            "per_class": {i: {k: float(v) for k, v in rep[f"c{i}"].items()} for i in range(K) if f"c{i}" in rep},
+            "macro_avg": {k: float(v) for k, v in rep["macro avg"].items()},
+            "weighted_avg": {k: float(v) for k, v in rep["weighted avg"].items()},
+            "per_class_accuracy": {int(k[1:]): float(v) for k, v in m["per_class_accuracy"].items()}}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--herlev-evaluator-only" in sys.argv or len(sys.argv) == 1:
+        torch.save(herlev_evaluator_case(), os.path.join(OUT, "herlev_evaluator.pt"))
+        print("herlev_evaluator.pt written")
+        if "--herlev-evaluator-only" in sys.argv:
+            return
     if "--evaluator-only" in sys.argv or len(sys.argv) == 1:
         torch.save(evaluator_case(), os.path.join(OUT, "evaluator.pt"))
         print("evaluator.pt written")

@@ -17,11 +17,12 @@ from .unet import (PGUNet1, PGUNet2, PGUNet3, PGUNet4, ProgressiveUNet, STAGE_MO
                    UncertaintyGuidedLoss, transfer_state)
 from .trainer import UncertaintyGuidedProgressiveTrainer
 from .herlev import HerlevClassificationModel, HerlevTrainer
-from .evaluate import HerlevEvaluator, MoNuSegEvaluator, metrics_from_counts
+from .evaluate import HerlevEvaluator, MoNuSegEvaluator, classification_metrics_from_confusion, metrics_from_counts
 
 __all__ = [
     "DoubleConv", "InConv", "Down", "Up", "OutConv", "DownSample", "UpSample", "UNet",
     "PGUNet1", "PGUNet2", "PGUNet3", "PGUNet4", "ProgressiveUNet", "STAGE_MODELS",
     "UncertaintyGuidedLoss", "transfer_state", "UncertaintyGuidedProgressiveTrainer",
     "HerlevClassificationModel", "HerlevTrainer", "MoNuSegEvaluator", "HerlevEvaluator", "metrics_from_counts",
+    "classification_metrics_from_confusion",
 ]

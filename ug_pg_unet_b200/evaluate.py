@@ -40,6 +40,36 @@ def metrics_from_counts(tp, n_pred, n_gt, n_pixels) -> Dict[str, torch.Tensor]:
     }
 
 
+def classification_metrics_from_confusion(confusion: torch.Tensor) -> Dict[str, object]:
+    """What HerlevEvaluator.calculate_metrics derives from labels and predictions
+    (Herlev/test_herlev.py:217-249: accuracy, sklearn's classification_report with zero_division=0,
+    confusion_matrix, per-class accuracy) computed from the K x K confusion matrix
+    counts[label][prediction] that `ugp_cls_eval` accumulates on the device."""
+    cm = confusion.detach().cpu().double()
+    total = float(cm.sum())
+    tp = cm.diag()
+    support = cm.sum(1)
+    predicted = cm.sum(0)
+    zero = torch.zeros_like(tp)
+    precision = torch.where(predicted > 0, tp / predicted.clamp(min=1), zero)
+    recall = torch.where(support > 0, tp / support.clamp(min=1), zero)
+    f1 = torch.where(precision + recall > 0, 2 * precision * recall / (precision + recall).clamp(min=1e-300), zero)
+    wsum = max(float(support.sum()), 1.0)
+    return {
+        "accuracy": float(tp.sum()) / max(total, 1.0),
+        "confusion_matrix": confusion.detach().cpu(),
+        "precision": precision.tolist(), "recall": recall.tolist(), "f1": f1.tolist(),
+        "support": support.long().tolist(),
+        # classes absent from the labels have no per-class accuracy entry in the reference (:243-247)
+        "per_class_accuracy": {i: float(recall[i]) for i in range(cm.shape[0]) if support[i] > 0},
+        "macro_avg": {"precision": float(precision.mean()), "recall": float(recall.mean()), "f1": float(f1.mean())},
+        "weighted_avg": {"precision": float((precision * support).sum() / wsum),
+                         "recall": float((recall * support).sum() / wsum),
+                         "f1": float((f1 * support).sum() / wsum)},
+        "total_samples": int(total),
+    }
+
+
 class MoNuSegEvaluator:
     """Mirror of MoNuSegImprove/test_monuseg.py:100-297 for tensors.
 
@@ -202,14 +232,4 @@ class HerlevEvaluator:
             total += z.shape[0]
         if confusion is None:
             raise ValueError("evaluate_batches: no batches")
-        cm = confusion.cpu().double()
-        tp = cm.diag()
-        support = cm.sum(1)
-        predicted = cm.sum(0)
-        precision = torch.where(predicted > 0, tp / predicted.clamp(min=1), torch.zeros_like(tp))
-        recall = torch.where(support > 0, tp / support.clamp(min=1), torch.zeros_like(tp))
-        f1 = torch.where(precision + recall > 0, 2 * precision * recall / (precision + recall).clamp(min=1e-30),
-                         torch.zeros_like(tp))
-        return {"accuracy": float(tp.sum() / max(total, 1)), "confusion_matrix": confusion.cpu(),
-                "precision": precision.tolist(), "recall": recall.tolist(), "f1": f1.tolist(),
-                "support": support.long().tolist(), "total_samples": total}
+        return classification_metrics_from_confusion(confusion)
