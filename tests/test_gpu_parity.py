@@ -886,7 +886,7 @@ def test_classification_evaluator_kernels(dev):
     labels = torch.randint(0, 7, (5,), generator=g)
     res = ev.evaluate_batches([(img[:3], labels[:3]), (img[3:], labels[3:])])
     assert res["total_samples"] == 5 and int(res["confusion_matrix"].sum()) == 5
-    assert abs(res["accuracy"] - (p8.cpu() == labels).float().mean().item()) < 1e-9
+    assert abs(res["accuracy"] - (p8.cpu() == labels).double().mean().item()) < 1e-9
 
 
 # --------------------------------------------------------------------------- general image sizes
