@@ -263,13 +263,6 @@ int ugp_rmsprop_conv_packed(float* const* w, float* const* square_avgs, float* c
                             int n_tensors, float lr, float alpha, float eps, float weight_decay,
                             float grad_scale, void* stream);
 
-/* Diagnostics (not on the product path): SM cycles for a chain of iters*4 tcgen05 MMAs of shape
- * 128 x n x 16 (pair != 0: 256 x n x 16 on a CTA pair, cta_group::2) with operands resident in
- * shared memory, on `ctas` CTAs at once; out_cycles[cta] (leaders only for pairs).  a_shift: start of
- * the A window in 128-byte rows past a 1024-byte swizzle-atom boundary (the halo kernels' shifted taps). */
-int ugp_bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int a_shift, int ctas, long long* out_cycles,
-                  void* stream);
-
 #ifdef __cplusplus
 }
 #endif

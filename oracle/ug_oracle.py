@@ -123,6 +123,52 @@ def _q(x: Tensor, bf16_storage: bool) -> Tensor:
     return _RoundBF16.apply(x) if bf16_storage else x
 
 
+def _tf32(x: Tensor) -> Tensor:
+    """Round-to-nearest to TF32's 10-bit mantissa (what a `kind::tf32` tensor-core operand keeps)."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _RoundTF32Fwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _tf32(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundTF32Bwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _tf32(g)
+
+
+# set by `tf32_operands(True)`: fp32 storage everywhere, but every convolution operand (activation,
+# weight, and in backward the output gradient) is rounded to TF32 - the arithmetic of cuDNN's default
+# TF32 convolutions and of a `tcgen05.mma.kind::tf32` path.  Only used to show where north_star's
+# alternative 1e-3 (TF32) bar lands on these networks (DESIGN.md §4); no kernel implements it.
+_TF32_OPERANDS = False
+
+
+class tf32_operands:
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        global _TF32_OPERANDS
+        self.prev, _TF32_OPERANDS = _TF32_OPERANDS, self.on
+
+    def __exit__(self, *a):
+        global _TF32_OPERANDS
+        _TF32_OPERANDS = self.prev
+
+
 # set by `bf16_storage(True)`: every activation / conv weight is rounded to bf16 where the sm_100a
 # path stores it in bf16 (conv inputs, conv outputs, post-ReLU activations, upsampled tensors and
 # their gradients); arithmetic stays fp32.  Used to separate kernel bugs from precision effects.
@@ -152,7 +198,11 @@ def double_conv(x: Tensor, sd: StateDict, prefix: str, training: bool, bn_out: O
     x = _q(x, bq)
     for conv_i, bn_i in ((0, 1), (3, 4)):
         w = sd[f"{prefix}.conv_op.{conv_i}.weight"]
-        x = F.conv2d(x, _q(w, bq), sd[f"{prefix}.conv_op.{conv_i}.bias"], padding=1)
+        if _TF32_OPERANDS:
+            x = _RoundTF32Bwd.apply(F.conv2d(_RoundTF32Fwd.apply(x), _RoundTF32Fwd.apply(w),
+                                             sd[f"{prefix}.conv_op.{conv_i}.bias"], padding=1))
+        else:
+            x = F.conv2d(x, _q(w, bq), sd[f"{prefix}.conv_op.{conv_i}.bias"], padding=1)
         if bq and training:
             x = _q(x, True)        # train: raw conv output stored in bf16; eval: BN+ReLU fused in the epilogue
         rm = sd[f"{prefix}.conv_op.{bn_i}.running_mean"].clone()
@@ -417,7 +467,7 @@ def herlev_forward(sd: StateDict, x: Tensor, stage: int, training: bool = True,
 
 
 def herlev_train_step(sd: StateDict, x: Tensor, y: Tensor, stage: int, sd_prev: Optional[StateDict] = None,
-                      alpha: float = 1.0):
+                      alpha: float = 1.0, prev_resolution: Optional[int] = None):
     """HerlevTrainer.uncertainty_guided_forward_pass + backward for num_classes > 2, no class weights —
     Herlev/train_herlev.py:219-296 (previous stage in eval mode on the bilinearly down-sized input)."""
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
@@ -429,7 +479,7 @@ def herlev_train_step(sd: StateDict, x: Tensor, y: Tensor, stage: int, sd_prev: 
     u = None
     if stage > 1:
         assert sd_prev is not None
-        pr = STAGE_RESOLUTION[stage - 1]
+        pr = STAGE_RESOLUTION[stage - 1] if prev_resolution is None else prev_resolution   # stage_configs, :134-139
         with torch.no_grad():
             xp = F.interpolate(x, size=(pr, pr), mode="bilinear", align_corners=True)
             u = softmax_entropy_uncertainty(herlev_forward(sd_prev, xp, stage - 1, training=False))

@@ -215,3 +215,72 @@ def test_classification_evaluator_matches_reference(golden_dir):
     assert out["per_class_accuracy"].keys() == fx["per_class_accuracy"].keys()
     for k, v in fx["per_class_accuracy"].items():
         assert abs(out["per_class_accuracy"][k] - v) < 1e-12
+
+
+# --------------------------------------------------------------------------- batch-16 fixtures (tools/make_goldens.py --b16)
+def _regen(fx):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import parity_table as P
+    return P.regenerate_inputs(fx)
+
+
+def test_batch16_fixtures_record_the_oracle_pin(golden_dir):
+    """Every batch-16 fixture stores how far the oracle restatement was from the unmodified reference when
+    the fixture was generated (same process): logits identical, gradients at fp32 summation-order noise."""
+    for name in ("trainer_stage3_nc1_b16", "trainer_stage4_nc1_b16", "herlev_stage3_k7_b16",
+                 "herlev_stage4_k7_b16_256", "herlev_stage4_k7_b16_224"):
+        fx = torch.load(os.path.join(golden_dir, name + ".pt"))
+        assert fx["B"] == 16
+        assert fx["oracle_vs_reference"]["logits"] <= 1e-6 and fx["oracle_vs_reference"]["worst_grad"] <= 1e-4, name
+        assert set(fx["emu"]["grads_rel"]) == set(fx["grads"])
+
+
+def test_oracle_reproduces_the_stage3_batch16_fixture(golden_dir):
+    """Re-runs the oracle at batch 16 (stage 3: ~10 s; the stage-4 twin is covered by the recorded pin above
+    and by the batch-1 stage-4 case) on inputs regenerated from the fixture's seed."""
+    fx = torch.load(os.path.join(golden_dir, "trainer_stage3_nc1_b16.pt"))
+    x, y = _regen(fx)
+    sd = O.seeded_state_dict(3, 3, 1, seed=3)
+    out = O.train_step(sd, x, y, 3, O.seeded_state_dict(2, 3, 1, seed=2))
+    torch.testing.assert_close(out["logits"], fx["logits"], rtol=1e-4, atol=1e-4)
+    assert abs(out["final_loss"] - fx["final_loss"]) < 1e-5 and abs(out["base_loss"] - fx["base_loss"]) < 1e-5
+    assert abs(out["dice"] - fx["dice"]) < 1e-6 and abs(out["accuracy"] - fx["accuracy"]) < 1e-9
+    for k, s in fx["grads"].items():
+        if k.endswith(("conv_op.0.bias", "conv_op.3.bias")):
+            continue
+        _check_sample(out["grads"][k], s, rtol=2e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["herlev_stage3_k7_b16", "herlev_stage4_k7_b16_224"])
+def test_oracle_reproduces_the_herlev_batch16_fixtures(golden_dir, name):
+    fx = torch.load(os.path.join(golden_dir, name + ".pt"))
+    x, y = _regen(fx)
+    stage, K = fx["stage"], fx["K"]
+    out = O.herlev_train_step(O.seeded_herlev_state_dict(stage, K, seed=stage), x, y, stage,
+                              O.seeded_herlev_state_dict(stage - 1, K, seed=stage - 1),
+                              prev_resolution=fx["prev_resolution"])
+    torch.testing.assert_close(out["logits"], fx["logits"], rtol=1e-4, atol=1e-5)
+    assert abs(out["final_loss"] - fx["final_loss"]) < 1e-5 and out["correct"] == fx["correct"]
+    for k, s in fx["grads"].items():
+        if k.endswith(("conv_op.0.bias", "conv_op.3.bias")):
+            continue
+        _check_sample(out["grads"][k], s, rtol=2e-3, atol=1e-7)
+
+
+def test_precision_emulations_bracket_the_reference():
+    """bf16-storage and TF32-operand emulations of the oracle: both perturb the fp32 result, TF32 less."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 32, 32, generator=g)
+    y = torch.randint(0, 2, (2, 1, 32, 32), generator=g).float()
+    sd = O.seeded_state_dict(1, 3, 1, seed=1)
+    ref = O.train_step(sd, x, y, 1)
+    with O.bf16_storage(True):
+        b = O.train_step(sd, x, y, 1)
+    with O.tf32_operands(True):
+        t = O.train_step(sd, x, y, 1)
+    rel = lambda a, r: ((a.double() - r.double()).norm() / r.double().norm()).item()
+    eb, et = rel(b["logits"], ref["logits"]), rel(t["logits"], ref["logits"])
+    assert 0 < et < eb < 5e-2 and et < 5e-3
+    v = O._tf32(torch.tensor([1.0 + 2 ** -11, 1.0 + 2 ** -12 + 2 ** -20]))
+    assert v.tolist() == [1.0 + 2 ** -10, 1.0 + 2 ** -10] or v.tolist() == [1.0 + 2 ** -10, 1.0]

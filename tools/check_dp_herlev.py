@@ -64,7 +64,7 @@ def main():
     if rank == 0:
         ok = float(w) == 0.0 and bool(torch.isfinite(out).all())
         print(f"check_dp_herlev {'ok' if ok else 'FAILED'}: world {world}, stage 4 at {res}x{res}, batch {B}/rank, "
-              f"{float(t):.2f} ms/step ({'graph replay' if tr._graph and tr._graph.get('graph') is not None else 'eager'}), "
+              f"{float(t):.2f} ms/step ({'graph replay' if any(g.get('graph') is not None for g in tr._graphs.values()) else 'eager'}), "
               f"{world * B / float(t) * 1e3:.0f} images/s, "
               f"max weight difference across ranks {float(w):.1e}")
     # NCCL kernels captured into CUDA graphs keep the communicator busy: destroy_process_group() does not

@@ -1,7 +1,11 @@
 // Micro-benchmark of the tcgen05.mma issue / operand-fetch cost model: one thread
 // issues a long chain of 128 x N x 16 (or, for a CTA pair, 256 x N x 16) bf16 MMAs whose operands are
 // already resident in shared memory and reports SM cycles per MMA.  Not on the product path.
-#include "ugp_common.cuh"
+// Built as its own library (tools/microbench/libugp_microbench.so) by ug_pg_unet_b200/build.py; the product
+// library and its public header do not contain it.
+#include <stdarg.h>
+
+#include "../../ug_pg_unet_b200/csrc/ugp_common.cuh"
 
 namespace ugp {
 
@@ -102,3 +106,23 @@ int bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int a_shift, in
 }
 
 }  // namespace ugp
+
+namespace ugp {
+// the microbenchmark library carries its own error sink (the product's lives in capi.cu)
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vfprintf(stderr, fmt, ap);
+  fputc('\n', stderr);
+  va_end(ap);
+}
+}  // namespace ugp
+
+/* SM cycles for a chain of iters*4 tcgen05 MMAs of shape 128 x n x 16 (pair != 0: 256 x n x 16 on a CTA
+ * pair, cta_group::2) with operands resident in shared memory, on `ctas` CTAs at once; out_cycles[cta]
+ * (leaders only for pairs).  a_shift: start of the A window in 128-byte rows past a 1024-byte swizzle-atom
+ * boundary (the halo kernels' shifted taps). */
+extern "C" int ugp_bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int a_shift, int ctas,
+                             long long* out_cycles, void* stream) {
+  return ugp::bench_mma(n, pair, iters, nacc, a_tiles, a_shift, ctas, out_cycles, static_cast<cudaStream_t>(stream));
+}

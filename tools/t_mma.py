@@ -4,7 +4,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ug_pg_unet_b200 import _lib
 
-lib = _lib.lib()
+import ctypes
+from ug_pg_unet_b200 import build as _build
+lib = ctypes.CDLL(str(_build.build_microbench()))
+lib.ugp_bench_mma.argtypes = [ctypes.c_int] * 7 + [ctypes.c_void_p, ctypes.c_void_p]
+lib.ugp_bench_mma.restype = ctypes.c_int
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 iters = 2000
 print("   N pair nacc shift ctas | cycles per MMA (min / max over CTAs) | math floor")

@@ -18,7 +18,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libugp_b200.so"
 SOURCES = ["tmap.cu", "conv_gemm.cu", "conv_halo.cu", "conv_pair.cu", "conv_wgrad.cu", "conv_wgrad_halo.cu", "conv_transpose.cu", "elementwise.cu", "bn_bwd.cu", "first_layer.cu",
-           "weights.cu", "head_loss.cu", "eval_metrics.cu", "optim.cu", "bench_mma.cu", "capi.cu"]
+           "weights.cu", "head_loss.cu", "eval_metrics.cu", "optim.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -68,6 +68,24 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+MICROBENCH_SRC = PKG_DIR.parent / "tools" / "microbench" / "bench_mma.cu"
+MICROBENCH_LIB = MICROBENCH_SRC.parent / "libugp_microbench.so"
+
+
+def build_microbench(force: bool = False) -> Path:
+    """tools/microbench/libugp_microbench.so: the tcgen05 issue-cost microbenchmark (tools/t_mma*.py).
+    A diagnostic library of its own - nothing of it is in the product library or its header."""
+    if not force and MICROBENCH_LIB.exists() and MICROBENCH_LIB.stat().st_mtime >= max(
+            MICROBENCH_SRC.stat().st_mtime, (CSRC / "ugp_common.cuh").stat().st_mtime):
+        return MICROBENCH_LIB
+    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", str(MICROBENCH_SRC), "-o", str(MICROBENCH_LIB), "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {MICROBENCH_SRC}:\n{r.stdout}\n{r.stderr}")
+    return MICROBENCH_LIB
+
+
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(p)
+    print(build_microbench(force="--force" in sys.argv))

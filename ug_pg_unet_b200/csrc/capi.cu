@@ -49,7 +49,6 @@ int rmsprop_multi(float* const*, const float* const*, float* const*, const long 
                   float, float, float, float, cudaStream_t);
 int global_avg_pool(const void*, int, int, int, float*, cudaStream_t);
 int global_avg_pool_bwd(const float*, int, int, int, void*, cudaStream_t);
-int bench_mma(int, int, int, int, int, int, int, long long*, cudaStream_t);
 int conv_transpose2x2_fwd(const void*, int, int, int, int, const void*, int, const float*, void*, cudaStream_t);
 int conv_transpose2x2_dgrad(const void*, int, int, int, int, const void*, int, void*, cudaStream_t);
 int conv_transpose2x2_wgrad(const void*, const void*, int, int, int, int, int, float*, cudaStream_t);
@@ -197,10 +196,6 @@ int ugp_global_avg_pool(const void* x, int B, int HW, int C, float* out, void* s
 }
 int ugp_global_avg_pool_bwd(const float* dy, int B, int HW, int C, void* dx, void* stream) {
   return ugp::global_avg_pool_bwd(dy, B, HW, C, dx, S(stream));
-}
-int ugp_bench_mma(int n, int pair, int iters, int nacc, int a_tiles, int a_shift, int ctas, long long* out_cycles,
-                  void* stream) {
-  return ugp::bench_mma(n, pair, iters, nacc, a_tiles, a_shift, ctas, out_cycles, S(stream));
 }
 int ugp_conv_transpose2x2_fwd(const void* x, int B, int H, int W, int cin, const void* wf, int cout,
                               const float* bias, void* out, void* stream) {

@@ -8,7 +8,8 @@ entropy of the previous stage (`u = H(softmax)/ln K`, :253-257) and the uncertai
 cross entropy with its gradient and the accuracy count (:266-281, :318-320) are one kernel each.
 The 3-layer MLP head (512 -> 512 -> 256 -> K on a [B, 512] vector, < 0.002 % of the step's FLOPs)
 stays stock `nn.Linear` / `nn.Dropout`, so `state_dict` keys (`unet.*`, `classifier.{3,6,9}.*`)
-and checkpoints are the reference's.
+and checkpoints are the reference's; in eval mode (the previous stage's uncertainty pass, validation,
+evaluators) GAP + the three Linear layers run as ONE kernel (`ugp_gap_mlp_head`).
 """
 from __future__ import annotations
 
@@ -156,7 +157,9 @@ class HerlevTrainer:
             for m in self.models.values():
                 broadcast_module_state(m)
         self._reducers = {}
-        self._graph = None
+        self._reducer_sig = {}
+        self._graphs = {}                 # captured step graphs keyed by everything a capture bakes in
+        self.max_step_graphs = 4
         self._capture_stream = None
         self.use_cuda_graph = config.get("use_cuda_graph", True) and os.environ.get("UGP_NO_CUDA_GRAPH", "0") != "1"
         self.setup_loss_function()
@@ -179,22 +182,54 @@ class HerlevTrainer:
         lr = self.stage_configs[stage]["lr"]
         # same hyper-parameters / state_dict layout as the reference's optim.Adam; on CUDA the update of
         # all tensors is one kernel launch (FusedAdam subclasses optim.Adam)
-        self._graph = None
+        self._drop_graphs()
         adam = FusedAdam if torch.device(self.device).type == "cuda" else torch.optim.Adam
         self.optimizers[stage] = adam(model.parameters(), lr=lr, weight_decay=self.config.get("weight_decay", 1e-4))
         self.schedulers[stage] = torch.optim.lr_scheduler.ReduceLROnPlateau(
             self.optimizers[stage], mode="min", factor=0.5, patience=5)
-        if self.distributed:
-            old = self._reducers.pop(stage, None)
-            if old is not None:
-                old.remove()
-            used = [p for p in list(model.encoder_parameters()) + list(model.classifier.parameters())
-                    if p.requires_grad]
-            fused = isinstance(self.optimizers[stage], FusedAdam)
-            self._reducers[stage] = GradBucketReducer(used, bucket_mb=self.config.get("bucket_mb", 16.0),
-                                                      average=not fused)
-            if fused:       # .grad stays a view of the summed bucket; the optimiser kernel applies 1/world_size
-                self.optimizers[stage].dense_grad_scale = 1.0 / self.world_size
+        self._build_reducer(stage)
+
+    def _grad_signature(self, stage):
+        model = self.models[stage]
+        return tuple(p.requires_grad for p in list(model.encoder_parameters()) + list(model.classifier.parameters()))
+
+    def _build_reducer(self, stage):
+        """(Re)builds the data-parallel gradient reducer of `stage` over the parameters that receive
+        gradients NOW; called again from the step when `requires_grad` flags changed since (e.g.
+        `unfreeze_encoder()` after `setup_optimizer_scheduler`), so newly trainable tensors are reduced too."""
+        if not self.distributed:
+            return
+        model = self.models[stage]
+        old = self._reducers.pop(stage, None)
+        if old is not None:
+            old.remove()
+        self._drop_graphs()
+        used = [p for p in list(model.encoder_parameters()) + list(model.classifier.parameters())
+                if p.requires_grad]
+        fused = isinstance(self.optimizers[stage], FusedAdam)
+        self._reducers[stage] = GradBucketReducer(used, bucket_mb=self.config.get("bucket_mb", 16.0),
+                                                  average=not fused)
+        self._reducer_sig[stage] = self._grad_signature(stage)
+        if fused:       # .grad stays a view of the summed bucket; the optimiser kernel applies 1/world_size
+            self.optimizers[stage].dense_grad_scale = 1.0 / self.world_size
+
+    def _drop_graphs(self):
+        for g in self._graphs.values():
+            g.pop("out", None)
+            g["graph"] = None
+        self._graphs.clear()
+
+    def close(self, destroy_process_group: bool = False):
+        """Releases the captured step graphs and the reducers, then (optionally) the process group:
+        `dist.destroy_process_group()` does not return while a live CUDA graph holds captured NCCL kernels."""
+        self._drop_graphs()
+        for r in self._reducers.values():
+            r.remove()
+        self._reducers.clear()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        if destroy_process_group and dist.is_initialized():
+            dist.destroy_process_group()
 
     def transfer_weights(self, prev_stage, current_stage):
         """reference :200-217 — copies classifier tensors whose shapes match."""
@@ -260,9 +295,11 @@ class HerlevTrainer:
         (stage, shapes, learning rate) and replayed (forward, previous-stage uncertainty, fused loss,
         backward, gradient all-reduce, FusedAdam with its device-side step count)."""
         opt = self.optimizers[stage]
-        # (data parallel: the all-reduces are captured too; verified on 2 GPUs - rank-identical weights.  A
-        # process that captured NCCL kernels must leave with os._exit() instead of destroy_process_group(),
-        # which does not return on this stack - see bench.py.  UGP_HERLEV_DP_GRAPH=0 keeps DP steps eager.)
+        if self.distributed and self._reducer_sig.get(stage) != self._grad_signature(stage):
+            self._build_reducer(stage)          # requires_grad changed since the reducer was built
+        # (data parallel: the all-reduces are captured too; verified on 2 GPUs - rank-identical weights.
+        # Call close() before dist.destroy_process_group(): a live graph holding captured NCCL kernels keeps
+        # the communicator busy.  UGP_HERLEV_DP_GRAPH=0 keeps DP steps eager.)
         use_graph = (self.use_cuda_graph and data.is_cuda and isinstance(opt, FusedAdam)
                      and self.criterion.weight is None and self.config["num_classes"] > 2
                      and (not self.distributed or os.environ.get("UGP_HERLEV_DP_GRAPH", "1") == "1"))
@@ -270,10 +307,13 @@ class HerlevTrainer:
             return self._eager_step(data, target, stage)
         key = (stage, tuple(data.shape), data.dtype, tuple(target.shape), id(self.models[stage]), id(opt),
                tuple(float(gp["lr"]) for gp in opt.param_groups), self.models[stage].training,
-               tuple(bool(m.training) for m in self.models[stage].classifier))
-        g = self._graph
-        if g is None or g["key"] != key:
-            self._graph = g = {"key": key, "warm": 0, "graph": None}
+               tuple(bool(m.training) for m in self.models[stage].classifier), float(self.uncertainty_alpha),
+               id(self.criterion), self._grad_signature(stage))
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= self.max_step_graphs:
+                return self._eager_step(data, target, stage)       # ragged shapes: keep the captured graphs
+            self._graphs[key] = g = {"key": key, "warm": 0, "graph": None}
         if g["graph"] is None:
             if g["warm"] < 3:
                 g["warm"] += 1
@@ -334,8 +374,20 @@ class HerlevTrainer:
                 info = f", Unc_mean: {um:.4f}, Unc_std: {us:.4f}" if stage > 1 else ""
                 print(f"Stage {stage}, Batch {batch_idx}/{len(dataloader)} Loss: {f:.6f} Base_Loss: {b:.6f} "
                       f"Acc: {100.0 * acc[2].item() / total:.2f}%{info}")
-        n = max(len(dataloader), 1)
-        f, b, c, um, us = (acc if acc is not None else torch.zeros(5)).tolist()
+        n = len(dataloader)
+        sums = (acc if acc is not None else torch.zeros(5, dtype=torch.float64)).double()
+        if self.distributed:
+            # Every rank must see the SAME epoch numbers: they drive ReduceLROnPlateau, the best-model
+            # decision and early stopping (train_progressive), and BatchNorm running statistics are
+            # rank-local, so per-rank validation losses differ.  Rank-local numbers would let ranks pick
+            # different learning rates (silently diverging weights, graphs re-captured at different times)
+            # or leave the epoch loop at different epochs (the others then block in the all-reduce).
+            pack = torch.cat([sums.to(self.device), torch.tensor([float(total), float(n)], dtype=torch.float64,
+                                                                 device=self.device)])
+            dist.all_reduce(pack, op=dist.ReduceOp.SUM)
+            sums, total, n = pack[:5], int(pack[5].item()), int(pack[6].item())
+        n = max(n, 1)
+        f, b, c, um, us = sums.tolist()
         return f / n, b / n, 100.0 * c / max(total, 1), um / n, us / n
 
     def train_epoch(self, dataloader, stage):

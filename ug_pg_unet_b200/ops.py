@@ -19,7 +19,8 @@ bf16 = torch.bfloat16
 
 # ---- instrumentation used by bench.py: kernel-launch counter and per-launch CUDA-event timing ----
 _LAUNCHES = 0
-_PROFILE = None     # list of (name, flops, start_event, end_event) while profiling
+_PROFILE = None     # list of [name, flops, bytes, start_event, end_event] while profiling
+_PROFILE_EXTERNAL = False
 
 
 def _count(n: int = 1) -> None:
@@ -36,35 +37,51 @@ def launch_count() -> int:
     return _LAUNCHES
 
 
-def start_profile() -> None:
-    global _PROFILE
-    _PROFILE = []
+def start_profile(external: bool = False) -> None:
+    """Brackets every launch of the instrumented ops with a pair of CUDA events.  `external=True` creates
+    the events with cudaEventRecordExternal semantics so that, when the step is being CAPTURED into a CUDA
+    graph, they become event-record NODES between the kernel nodes: a replay then timestamps each kernel on
+    the device with no host code between the two records (an eager step is host-bound, so events recorded
+    from Python around an eager launch also time the host's tensor-map encode + ctypes call)."""
+    global _PROFILE, _PROFILE_EXTERNAL
+    _PROFILE, _PROFILE_EXTERNAL = [], external
+
+
+def profile_events():
+    """The live list of [name, flops, bytes, start_event, end_event] (read after a synchronise)."""
+    return _PROFILE or []
 
 
 def stop_profile():
-    """-> list of (kernel name, algorithmic flops, milliseconds) for every tensor-core launch."""
+    """-> list of (kernel name, algorithmic flops, algorithmic bytes, milliseconds) per instrumented launch."""
     global _PROFILE
     torch.cuda.synchronize()
-    out = [(n, f, a.elapsed_time(b)) for (n, f, a, b) in (_PROFILE or [])]
+    out = [(n, f, by, a.elapsed_time(b)) for (n, f, by, a, b) in (_PROFILE or [])]
     _PROFILE = None
     return out
 
 
 class _timed:
-    def __init__(self, name: str, flops: float):
-        self.name, self.flops = name, flops
+    def __init__(self, name: str, flops: float = 0.0, nbytes: float = 0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
 
     def __enter__(self):
         if _PROFILE is not None:
-            self.a = torch.cuda.Event(enable_timing=True)
-            self.b = torch.cuda.Event(enable_timing=True)
+            kw = {"external": True} if _PROFILE_EXTERNAL else {}
+            self.a = torch.cuda.Event(enable_timing=True, **kw)
+            self.b = torch.cuda.Event(enable_timing=True, **kw)
             self.a.record()
 
     def __exit__(self, *exc):
         if _PROFILE is not None:
             self.b.record()
-            _PROFILE.append((self.name, self.flops, self.a, self.b))
+            _PROFILE.append([self.name, self.flops, self.nbytes, self.a, self.b])
         return False
+
+
+def _nb(*ts) -> float:
+    """Bytes of the given tensors (None skipped): the algorithmic traffic of a kernel that touches each once."""
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
 
 
 def check(rc: int, what: str) -> None:
@@ -123,7 +140,7 @@ def conv_gemm(src0: torch.Tensor, src1: Optional[torch.Tensor], wpack: torch.Ten
         _req(out1, bf16, "out1")
     if stats is not None and tuple(stats.shape) != (stat_parts(), 2, cout):
         raise RuntimeError(f"conv_gemm: stats must be a zeroed [{stat_parts()}, 2, {cout}] buffer (ops.new_stats)")
-    with _timed("conv_gemm", 2.0 * B * H * W * cout * taps * (c0 + c1)):
+    with _timed("conv_gemm", 2.0 * B * H * W * cout * taps * (c0 + c1), _nb(src0, src1, wpack, out0, out1)):
         rc = lib().ugp_conv_gemm_bf16(_ptr(src0), c0, _ptr(src1), c1, B, H, W, taps, _ptr(wpack), cout,
                                       _ptr(out0), _ptr(out1), split_n,
                                       _ptr(_opt(bias, torch.float32, "bias")),
@@ -149,7 +166,7 @@ def conv_wgrad(src0, src1, dz, taps: int, dw_packed: torch.Tensor):
     assert dz.shape[:3] == src0.shape[:3]
     assert dw_packed.numel() == taps * (c0 + c1) * cout
     assert dw_packed.data_ptr() % 16 == 0
-    with _timed("conv_wgrad", 2.0 * B * H * W * cout * taps * (c0 + c1)):
+    with _timed("conv_wgrad", 2.0 * B * H * W * cout * taps * (c0 + c1), _nb(src0, src1, dz, dw_packed)):
         rc = lib().ugp_conv_wgrad_bf16(_ptr(src0), c0, _ptr(src1), c1, _ptr(dz), cout, B, H, W, taps,
                                        _ptr(dw_packed), _stream())
     check(rc, "ugp_conv_wgrad_bf16")
@@ -270,7 +287,9 @@ def im2col_first(x: torch.Tensor, H: Optional[int] = None, W: Optional[int] = No
     H = Hin if H is None else H
     W = Win if W is None else W
     out = torch.empty((B, H, W, 64), dtype=bf16, device=x.device)
-    check(lib().ugp_im2col_first(_ptr(x), B, cin, Hin, Win, H, W, _ptr(out), _stream()), "ugp_im2col_first")
+    with _timed("im2col_first", 0.0, _nb(x, out)):
+        rc = lib().ugp_im2col_first(_ptr(x), B, cin, Hin, Win, H, W, _ptr(out), _stream())
+    check(rc, "ugp_im2col_first")
     return out
 
 
@@ -329,8 +348,10 @@ def bn_relu_apply(z, scale, shift, pool: bool = False, out=None, pooled=None):
         out = torch.empty_like(z)
     if pool and pooled is None:
         pooled = torch.empty((B, H // 2, W // 2, Cn), dtype=bf16, device=z.device)
-    check(lib().ugp_bn_relu_apply(_ptr(z), _ptr(scale), _ptr(shift), B, H, W, Cn, _ptr(out),
-                                  _ptr(pooled) if pool else None, _stream()), "ugp_bn_relu_apply")
+    with _timed("bn_relu_apply_pool" if pool else "bn_relu_apply", 0.0, _nb(z, out, pooled if pool else None)):
+        rc = lib().ugp_bn_relu_apply(_ptr(z), _ptr(scale), _ptr(shift), B, H, W, Cn, _ptr(out),
+                                     _ptr(pooled) if pool else None, _stream())
+    check(rc, "ugp_bn_relu_apply")
     return (out, pooled) if pool else out
 
 
@@ -339,11 +360,12 @@ def bn_relu_bwd(z, dA, dP, scale, shift, mean, rstd, gamma, sums, dbias, dz=None
     B, H, W, Cn = z.shape
     if dz is None:
         dz = torch.empty_like(z)
-    check(lib().ugp_bn_relu_bwd(_ptr(z), _ptr(_opt(dA, bf16, "dA")), _ptr(_opt(dP, bf16, "dP")),
-                                _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _ptr(gamma), B, H,
-                                W, Cn, _ptr(_req(sums, torch.float32, "sums")),
-                                _ptr(_opt(dbias, torch.float32, "dbias")), _ptr(dz), _stream()),
-          "ugp_bn_relu_bwd")
+    with _timed("bn_relu_bwd_pool" if dP is not None else "bn_relu_bwd", 0.0, 2 * _nb(z, dA, dP) + _nb(dz)):
+        rc = lib().ugp_bn_relu_bwd(_ptr(z), _ptr(_opt(dA, bf16, "dA")), _ptr(_opt(dP, bf16, "dP")),
+                                   _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _ptr(gamma), B, H,
+                                   W, Cn, _ptr(_req(sums, torch.float32, "sums")),
+                                   _ptr(_opt(dbias, torch.float32, "dbias")), _ptr(dz), _stream())
+    check(rc, "ugp_bn_relu_bwd")
     return dz
 
 
@@ -352,7 +374,9 @@ def maxpool2x2(x, return_indices: bool = False):
     B, H, W, Cn = x.shape
     out = torch.empty((B, H // 2, W // 2, Cn), dtype=bf16, device=x.device)
     idx = torch.empty((B, H // 2, W // 2, Cn), dtype=torch.int32, device=x.device) if return_indices else None
-    check(lib().ugp_maxpool2x2(_ptr(x), B, H, W, Cn, _ptr(out), _ptr(idx), _stream()), "ugp_maxpool2x2")
+    with _timed("maxpool2x2", 0.0, _nb(x, out, idx)):
+        rc = lib().ugp_maxpool2x2(_ptr(x), B, H, W, Cn, _ptr(out), _ptr(idx), _stream())
+    check(rc, "ugp_maxpool2x2")
     return (out, idx) if return_indices else out
 
 
@@ -369,7 +393,9 @@ def upsample2x(x):
     _req(x, bf16, "x")
     B, h, w, Cn = x.shape
     out = torch.empty((B, 2 * h, 2 * w, Cn), dtype=bf16, device=x.device)
-    check(lib().ugp_upsample2x(_ptr(x), B, h, w, Cn, _ptr(out), _stream()), "ugp_upsample2x")
+    with _timed("upsample2x", 0.0, _nb(x, out)):
+        rc = lib().ugp_upsample2x(_ptr(x), B, h, w, Cn, _ptr(out), _stream())
+    check(rc, "ugp_upsample2x")
     return out
 
 
@@ -377,7 +403,9 @@ def upsample2x_bwd(dout):
     _req(dout, bf16, "dout")
     B, H, W, Cn = dout.shape
     dx = torch.empty((B, H // 2, W // 2, Cn), dtype=bf16, device=dout.device)
-    check(lib().ugp_upsample2x_bwd(_ptr(dout), B, H // 2, W // 2, Cn, _ptr(dx), _stream()), "ugp_upsample2x_bwd")
+    with _timed("upsample2x_bwd", 0.0, _nb(dout, dx)):
+        rc = lib().ugp_upsample2x_bwd(_ptr(dout), B, H // 2, W // 2, Cn, _ptr(dx), _stream())
+    check(rc, "ugp_upsample2x_bwd")
     return dx
 
 
@@ -405,8 +433,10 @@ def outconv_fwd(x, w, bias):
     B, h, wd, Cn = x.shape
     nc = w.shape[0]
     out = torch.empty((B, nc, h, wd), dtype=torch.float32, device=x.device)
-    check(lib().ugp_outconv_fwd(_ptr(x), _ptr(_req(w, torch.float32, "w")), _ptr(bias), B, h * wd, Cn, nc,
-                                _ptr(out), _stream()), "ugp_outconv_fwd")
+    with _timed("outconv_fwd", 0.0, _nb(x, out)):
+        rc = lib().ugp_outconv_fwd(_ptr(x), _ptr(_req(w, torch.float32, "w")), _ptr(bias), B, h * wd, Cn, nc,
+                                   _ptr(out), _stream())
+    check(rc, "ugp_outconv_fwd")
     return out
 
 
@@ -415,9 +445,11 @@ def outconv_bwd(x, w, dl, dx, accumulate: bool, dw, db):
     _req(dl, torch.float32, "dl")
     B, h, wd, Cn = x.shape
     nc = w.shape[0]
-    check(lib().ugp_outconv_bwd(_ptr(x), _ptr(w), _ptr(dl), B, h * wd, Cn, nc, int(accumulate),
-                                _ptr(_req(dx, bf16, "dx")), _ptr(_req(dw, torch.float32, "dw")),
-                                _ptr(_req(db, torch.float32, "db")), _stream()), "ugp_outconv_bwd")
+    with _timed("outconv_bwd", 0.0, _nb(x, dl, dx) + (_nb(dx) if accumulate else 0.0)):
+        rc = lib().ugp_outconv_bwd(_ptr(x), _ptr(w), _ptr(dl), B, h * wd, Cn, nc, int(accumulate),
+                                   _ptr(_req(dx, bf16, "dx")), _ptr(_req(dw, torch.float32, "dw")),
+                                   _ptr(_req(db, torch.float32, "db")), _stream())
+    check(rc, "ugp_outconv_bwd")
     return dx
 
 
@@ -449,7 +481,9 @@ def uncertainty_margin(zprev, H: int, W: int):
     _req(zprev, torch.float32, "zprev")
     B, nc, h, w = zprev.shape
     A = torch.empty((B, nc, H, W), dtype=torch.float32, device=zprev.device)
-    check(lib().ugp_uncertainty_margin(_ptr(zprev), B * nc, h, w, H, W, _ptr(A), _stream()), "ugp_uncertainty_margin")
+    with _timed("uncertainty_margin", 0.0, _nb(zprev, A)):
+        rc = lib().ugp_uncertainty_margin(_ptr(zprev), B * nc, h, w, H, W, _ptr(A), _stream())
+    check(rc, "ugp_uncertainty_margin")
     return A
 
 
@@ -473,8 +507,10 @@ def bce_uncertainty_loss(z, t, A, alpha: float, pos_weight: float, want_grad: bo
     out = torch.empty((5 + 3 * B,), dtype=torch.float64, device=z.device)
     dlogits = torch.empty_like(z) if want_grad else None
     fn = lib().ugp_bce_uncertainty_loss_u8 if u8 else lib().ugp_bce_uncertainty_loss
-    check(fn(_ptr(z), _ptr(t), _ptr(_opt(A, torch.float32, "uncertainty")), alpha, pos_weight, B, per_image,
-             grad_scale, _ptr(dlogits), _ptr(out), _stream()), "ugp_bce_uncertainty_loss")
+    with _timed("bce_uncertainty_loss", 0.0, _nb(z, t, A, dlogits)):
+        rc = fn(_ptr(z), _ptr(t), _ptr(_opt(A, torch.float32, "uncertainty")), alpha, pos_weight, B, per_image,
+                grad_scale, _ptr(dlogits), _ptr(out), _stream())
+    check(rc, "ugp_bce_uncertainty_loss")
     return out, dlogits
 
 
@@ -586,5 +622,8 @@ def rmsprop_conv_packed(weights, square_avgs, dw_packed, wfs, wds, lr: float, al
     Dp = (C.c_void_p * n)(*[None if t is None else _req(t, bf16, "wd").data_ptr() for t in wds])
     co = (C.c_int * n)(*[w.shape[0] for w in weights])
     ci = (C.c_int * n)(*[w.shape[1] for w in weights])
-    check(lib().ugp_rmsprop_conv_packed(Wp, Vp, Gp, Fp, Dp, co, ci, n, lr, alpha, eps, weight_decay, grad_scale,
-                                        _stream()), "ugp_rmsprop_conv_packed")
+    # 28 B / parameter: read w, v, g (12), write w, v, zeroed g (12), write both bf16 packs (4)
+    with _timed("rmsprop_conv_packed", 0.0, 28.0 * sum(w.numel() for w in weights)):
+        rc = lib().ugp_rmsprop_conv_packed(Wp, Vp, Gp, Fp, Dp, co, ci, n, lr, alpha, eps, weight_decay, grad_scale,
+                                           _stream())
+    check(rc, "ugp_rmsprop_conv_packed")

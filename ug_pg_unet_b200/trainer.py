@@ -33,7 +33,7 @@ import torch.optim as optim
 from .engine import PackedWeights, WgradOverlap, conv_packs, enable_deferred_wgrad
 from .optim import FusedRMSprop
 from .parallel import GradBucketReducer, broadcast_module_state
-from .unet import PGUNet1, PGUNet2, PGUNet3, PGUNet4, UncertaintyGuidedLoss, transfer_state
+from .unet import PGUNet1, PGUNet2, PGUNet3, PGUNet4, UncertaintyGuidedLoss, _pos_weight_value, transfer_state
 
 
 class UncertaintyGuidedProgressiveTrainer:
@@ -54,7 +54,9 @@ class UncertaintyGuidedProgressiveTrainer:
         self._side_streams = None
         self._capture_stream = None
         self._copy_stream = None
-        self._graph = None
+        self._graphs = {}                 # captured step graphs, keyed by everything a capture bakes in
+        self.max_step_graphs = 4          # each capture owns a memory pool; further shapes run eagerly
+        self._last_step_losses = None
         self._grad_arena = None
 
         # reference uncertainty_guided_trainer.py:42-47
@@ -100,7 +102,10 @@ class UncertaintyGuidedProgressiveTrainer:
         on_cuda = next(self.current_model.parameters()).is_cuda
         # same hyper-parameters and state_dict layout as the reference's optim.RMSprop; on CUDA the
         # update of all 80 tensors is one kernel launch (FusedRMSprop subclasses optim.RMSprop)
-        self._graph = None
+        for g in self._graphs.values():      # graphs of the previous optimiser / model address freed tensors
+            g.pop("out", None)
+            g["graph"] = None
+        self._graphs.clear()
         if self._reducer is not None:
             self._reducer.remove()
             self._reducer = None
@@ -246,7 +251,7 @@ class UncertaintyGuidedProgressiveTrainer:
 
     def _eager_step(self, data, target, stage):
         self.optimizer.zero_grad(set_to_none=True)
-        final_loss, output_current, unc, _ = self._forward_loss(data, target, stage)
+        final_loss, output_current, unc, base = self._forward_loss(data, target, stage)
         if self.overlap_streams and data.is_cuda and self._grad_arena is not None:
             WgradOverlap.begin(self._streams(data)[1])
             try:
@@ -258,6 +263,9 @@ class UncertaintyGuidedProgressiveTrainer:
         if self._reducer is not None:
             self._reducer.wait()
         self.optimizer.step()
+        # a custom criterion has no fused metrics: keep this step's own (detached) losses so that the epoch
+        # loop can log them without a second forward (reference :221-234 logs the step's own numbers)
+        self._last_step_losses = None if self.uncertainty_loss.last_metrics is not None else (final_loss.detach(), base)
         # detached: a caller holding the logits must not keep this step's autograd graph (and its
         # AccumulateGrad nodes, created on the warm-up stream) alive into the CUDA-graph capture
         return self.uncertainty_loss.last_metrics, output_current.detach(), unc
@@ -271,15 +279,23 @@ class UncertaintyGuidedProgressiveTrainer:
         (stage, shapes) and replayed, so the GPU is not left waiting for the host.  Tensors returned
         from a replay are static buffers that the next step overwrites (the metrics are cloned)."""
         crit = self.base_criterion
-        fused = isinstance(crit, nn.BCEWithLogitsLoss) and crit.reduction == "none" and crit.weight is None
+        fused = isinstance(crit, nn.BCEWithLogitsLoss) and crit.reduction == "none" and crit.weight is None \
+            and (crit.pos_weight is None or crit.pos_weight.numel() == 1)
         dp_graph_ok = self._reducer is None or os.environ.get("UGP_DP_CUDA_GRAPH", "1") == "1"
         if not (self.use_cuda_graph and data.is_cuda and dp_graph_ok and fused):
             return self._eager_step(data, target, stage)
-        key = (stage, tuple(data.shape), tuple(target.shape), id(self.current_model), id(self.optimizer),
-               self.current_model.training)
-        g = self._graph
-        if g is None or g["key"] != key:
-            self._graph = g = {"key": key, "warm": 0, "graph": None}
+        # everything a capture bakes in as a constant: shapes / dtypes, the objects whose tensors it addresses,
+        # and the Python floats passed to the kernels by value (alpha, pos_weight, learning rate, momentum mode)
+        pw = 1.0 if crit.pos_weight is None else _pos_weight_value(crit)
+        key = (stage, tuple(data.shape), data.dtype, tuple(target.shape), target.dtype, id(self.current_model),
+               id(self.optimizer), self.current_model.training, float(self.uncertainty_alpha), id(crit), pw,
+               tuple(float(gp["lr"]) for gp in self.optimizer.param_groups))
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= self.max_step_graphs:
+                # e.g. a stream of ragged batch shapes: run them eagerly, keep the captured graphs
+                return self._eager_step(data, target, stage)
+            self._graphs[key] = g = {"key": key, "warm": 0, "graph": None}
         if g["graph"] is None:
             if g["warm"] < 3:
                 g["warm"] += 1
@@ -312,6 +328,31 @@ class UncertaintyGuidedProgressiveTrainer:
             PackedWeights.invalidate_all()
         m, logits, unc = g["out"]
         return m.clone(), logits, unc
+
+    # ------------------------------------------------------------------ teardown
+    def close(self, destroy_process_group: bool = False):
+        """Releases the captured step graphs (and with them the NCCL kernels they reference), then -
+        optionally - tears the process group down.  `dist.destroy_process_group()` does not return while a
+        live CUDA graph still holds captured collectives of the communicator, so a data-parallel run must
+        drop its graphs first: call this (or use the trainer as a context manager) before leaving."""
+        for g in self._graphs.values():
+            g.pop("out", None)
+            g["graph"] = None
+        self._graphs.clear()
+        if self._reducer is not None:
+            self._reducer.remove()
+            self._reducer = None
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        if destroy_process_group and dist.is_initialized():
+            dist.destroy_process_group()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
     def _prefetch(self, dataloader):
         """Yields device batches with the host -> device copy of batch i+1 issued on a copy stream while
@@ -377,15 +418,17 @@ class UncertaintyGuidedProgressiveTrainer:
             if m is not None:
                 pending.append((m, out.numel(), out.shape[0], unc is not None))
             else:
-                # custom criterion: the reference's own metric arithmetic (:221-234)
+                # custom criterion: the reference's own metric arithmetic (:221-234) on THIS step's logits and
+                # losses - one forward per step, as in the reference (BN running statistics advance once)
                 with torch.no_grad():
-                    fl, mt = self.uncertainty_guided_forward_pass(data, target, stage)
+                    fl, bl = self._last_step_losses if train else (final_loss.detach(), base)
                     pred = self.get_predictions(out)
                     tsq = target.squeeze(1)
-                    pending.append((mt["final_loss"], mt["base_loss"],
+                    pending.append((float(fl), float(bl),
                                     self.dice_coefficient(pred.float(), tsq.float()).item(),
                                     self.calculate_accuracy(pred, tsq.long()),
-                                    mt["uncertainty_weight_mean"], mt["uncertainty_weight_std"]))
+                                    torch.mean(unc).item() if unc is not None else 0.0,
+                                    torch.std(unc).item() if unc is not None else 0.0))
             num_batches += 1
             if train and self.log_interval and batch_idx % self.log_interval == 0:
                 f, b, d, a, um, _ = drain()
