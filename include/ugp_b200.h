@@ -263,6 +263,28 @@ int ugp_rmsprop_conv_packed(float* const* w, float* const* square_avgs, float* c
                             int n_tensors, float lr, float alpha, float eps, float weight_decay,
                             float grad_scale, void* stream);
 
+/* Herlev classification head, reference Herlev/train_herlev.py:66-77 (the nn.Sequential
+ * AdaptiveAvgPool2d(1), Flatten, Dropout(.5), Linear(C,H1), ReLU, Dropout(.3), Linear(H1,H2), ReLU,
+ * Dropout(.2), Linear(H2,K)) and :104-110 (forward = classifier(features)) as ONE kernel.
+ * x: NHWC bf16 feature map [B][HW][C] (C % 64 == 0).  w*: fp32 nn.Linear weights [out][in], b*: biases.
+ * u: null (eval: dropout inactive) or fp32 uniforms [B][C+H1+H2]; an element is kept iff u >= p and scaled
+ * by 1/(1-p) (p0, p1, p2 = the three dropout probabilities).  Outputs: pooled [B][C] (the average pool),
+ * h1 [B][H1], h2 [B][H2] (post-ReLU, pre-dropout: what backward needs), logits [B][K].
+ * tickets: B zeroed uint32 counters (left zeroed).  Deterministic. */
+int ugp_gap_mlp_head_fwd(const void* x, int B, int HW, int C, const float* w1, const float* b1, int H1,
+                         const float* w2, const float* b2, int H2, const float* w3, const float* b3, int K,
+                         const float* u, float p0, float p1, float p2, float* pooled, float* h1, float* h2,
+                         float* logits, unsigned int* tickets, void* stream);
+
+/* Backward of the three Linear layers above (autograd of train_herlev.py:104-110) in one launch (a cluster of
+ * 8 CTAs): dw* / db* (overwritten, fp32, nn.Linear layouts) and dpooled [B][C], the gradient of the pooled
+ * vector (feed it to ugp_global_avg_pool_bwd).  pooled / h1 / h2 / u as produced by / passed to the forward;
+ * scratch: B*(H1+H2) floats.  B <= 64. */
+int ugp_mlp_head_bwd(const float* dlogits, int B, int C, const float* w1, int H1, const float* w2, int H2,
+                     const float* w3, int K, const float* u, float p0, float p1, float p2, const float* pooled,
+                     const float* h1, const float* h2, float* dw1, float* db1, float* dw2, float* db2,
+                     float* dw3, float* db3, float* dpooled, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,8 @@ SIGNATURES = {
     "ugp_ce_weighted_loss": [_p, _p, _p, _f, _i, _i, _f, _p, _p, _p],
     "ugp_global_avg_pool": [_p, _i, _i, _i, _p, _p],
     "ugp_global_avg_pool_bwd": [_p, _i, _i, _i, _p, _p],
+    "ugp_gap_mlp_head_fwd": [_p, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p, _p, _i, _p, _f, _f, _f, _p, _p, _p, _p, _p, _p],
+    "ugp_mlp_head_bwd": [_p, _i, _i, _p, _i, _p, _i, _p, _i, _p, _f, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "ugp_rmsprop_step": [_p, _p, _p, _ll, _f, _f, _f, _f, _f, _p],
     "ugp_rmsprop_multi": [_p, _p, _p, _p, _i, _f, _f, _f, _f, _f, _p],
     "ugp_adam_multi": [_p, _p, _p, _p, _p, _i, _d, _d, _d, _d, _d, _ll, _p, _f, _p],

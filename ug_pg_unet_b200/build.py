@@ -18,7 +18,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libugp_b200.so"
 SOURCES = ["tmap.cu", "conv_gemm.cu", "conv_halo.cu", "conv_pair.cu", "conv_wgrad.cu", "conv_wgrad_halo.cu", "conv_transpose.cu", "elementwise.cu", "bn_bwd.cu", "first_layer.cu",
-           "weights.cu", "head_loss.cu", "eval_metrics.cu", "optim.cu", "capi.cu"]
+           "weights.cu", "head_loss.cu", "mlp_head.cu", "eval_metrics.cu", "optim.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

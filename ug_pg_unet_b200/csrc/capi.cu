@@ -49,6 +49,12 @@ int rmsprop_multi(float* const*, const float* const*, float* const*, const long 
                   float, float, float, float, cudaStream_t);
 int global_avg_pool(const void*, int, int, int, float*, cudaStream_t);
 int global_avg_pool_bwd(const float*, int, int, int, void*, cudaStream_t);
+int gap_mlp_head_fwd(const void*, int, int, int, const float*, const float*, int, const float*, const float*, int,
+                     const float*, const float*, int, const float*, float, float, float, float*, float*, float*,
+                     float*, unsigned int*, cudaStream_t);
+int mlp_head_bwd(const float*, int, int, const float*, int, const float*, int, const float*, int, const float*,
+                 float, float, float, const float*, const float*, const float*, float*, float*, float*, float*,
+                 float*, float*, float*, float*, cudaStream_t);
 int conv_transpose2x2_fwd(const void*, int, int, int, int, const void*, int, const float*, void*, cudaStream_t);
 int conv_transpose2x2_dgrad(const void*, int, int, int, int, const void*, int, void*, cudaStream_t);
 int conv_transpose2x2_wgrad(const void*, const void*, int, int, int, int, int, float*, cudaStream_t);
@@ -196,6 +202,20 @@ int ugp_global_avg_pool(const void* x, int B, int HW, int C, float* out, void* s
 }
 int ugp_global_avg_pool_bwd(const float* dy, int B, int HW, int C, void* dx, void* stream) {
   return ugp::global_avg_pool_bwd(dy, B, HW, C, dx, S(stream));
+}
+int ugp_gap_mlp_head_fwd(const void* x, int B, int HW, int C, const float* w1, const float* b1, int H1,
+                         const float* w2, const float* b2, int H2, const float* w3, const float* b3, int K,
+                         const float* u, float p0, float p1, float p2, float* pooled, float* h1, float* h2,
+                         float* logits, unsigned int* tickets, void* stream) {
+  return ugp::gap_mlp_head_fwd(x, B, HW, C, w1, b1, H1, w2, b2, H2, w3, b3, K, u, p0, p1, p2, pooled, h1, h2,
+                               logits, tickets, S(stream));
+}
+int ugp_mlp_head_bwd(const float* dlogits, int B, int C, const float* w1, int H1, const float* w2, int H2,
+                     const float* w3, int K, const float* u, float p0, float p1, float p2, const float* pooled,
+                     const float* h1, const float* h2, float* dw1, float* db1, float* dw2, float* db2,
+                     float* dw3, float* db3, float* dpooled, float* scratch, void* stream) {
+  return ugp::mlp_head_bwd(dlogits, B, C, w1, H1, w2, H2, w3, K, u, p0, p1, p2, pooled, h1, h2, dw1, db1, dw2,
+                           db2, dw3, db3, dpooled, scratch, S(stream));
 }
 int ugp_conv_transpose2x2_fwd(const void* x, int B, int H, int W, int cin, const void* wf, int cout,
                               const float* bias, void* out, void* stream) {

@@ -492,6 +492,30 @@ class GlobalAvgPoolFn(torch.autograd.Function):
         return ops.global_avg_pool_bwd(dy.contiguous().float(), *ctx.hw)
 
 
+class GapMlpHeadFn(torch.autograd.Function):
+    """The Herlev classifier (Herlev/train_herlev.py:66-77: AdaptiveAvgPool2d(1), Flatten, Dropout, Linear,
+    ReLU, Dropout, Linear, ReLU, Dropout, Linear) on an NHWC bf16 feature map: one forward kernel, one
+    backward kernel for the three Linear layers + the pool adjoint (ugp_global_avg_pool_bwd).
+    `u`: [B, C+H1+H2] uniforms for the three Dropout layers in train mode (None = inactive)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3, u, p0: float, p1: float, p2: float):
+        ws = [t.detach().contiguous() for t in (w1, b1, w2, b2, w3, b3)]
+        logits, pooled, h1, h2 = ops.gap_mlp_head_fwd(x, *ws, u=u, p=(p0, p1, p2))
+        ctx.save_for_backward(ws[0], ws[2], ws[4], pooled, h1, h2)
+        ctx.u, ctx.p, ctx.hw = u, (p0, p1, p2), (x.shape[1], x.shape[2])
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        w1, w2, w3, pooled, h1, h2 = ctx.saved_tensors
+        dw1, db1, dw2, db2, dw3, db3, dpooled = ops.mlp_head_bwd(dlogits.contiguous().float(), w1, w2, w3, pooled,
+                                                                 h1, h2, u=ctx.u, p=ctx.p)
+        dx = ops.global_avg_pool_bwd(dpooled, *ctx.hw) if ctx.needs_input_grad[0] else None
+        ctx.u = None
+        return dx, dw1, db1, dw2, db2, dw3, db3, None, None, None, None
+
+
 # ----------------------------------------------------------------------------- losses
 class BCEUncertaintyLossFn(torch.autograd.Function):
     """mean(BCEWithLogits(pos_weight)(z, t) * (1 + alpha*A)) with dlogits produced in the same pass;

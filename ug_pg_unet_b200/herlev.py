@@ -107,13 +107,43 @@ class HerlevClassificationModel(nn.Module):
             p.requires_grad = True
 
     def _head(self, pooled: torch.Tensor) -> torch.Tensor:
+        """Stock-module head on an already pooled vector (kept for classifiers that were edited)."""
         for m in list(self.classifier)[2:]:       # [0] pool and [1] flatten ran in the kernel
             pooled = m(pooled)
         return pooled
 
+    def _fused_head_layout(self):
+        """(fc1, fc2, fc3, (p0, p1, p2)) when `classifier` still is the reference's Sequential (:66-77):
+        the fused kernel then replaces pool + flatten + 3 dropouts + 3 linears + 2 ReLUs; else None."""
+        c = list(self.classifier)
+        kinds = (nn.AdaptiveAvgPool2d, nn.Flatten, nn.Dropout, nn.Linear, nn.ReLU, nn.Dropout, nn.Linear, nn.ReLU,
+                 nn.Dropout, nn.Linear)
+        if len(c) != len(kinds) or not all(isinstance(m, k) for m, k in zip(c, kinds)):
+            return None
+        fcs = (c[3], c[6], c[9])
+        if any(fc.bias is None or not fc.weight.is_cuda or fc.weight.dtype != torch.float32 for fc in fcs):
+            return None
+        if c[0].output_size not in (1, (1, 1)) or fcs[0].in_features % 64 or fcs[0].out_features % 4 or fcs[1].out_features % 4:
+            return None
+        ps = tuple(float(d.p) if d.training else 0.0 for d in (c[2], c[5], c[8]))
+        if any(pp >= 1.0 for pp in ps):
+            return None
+        return fcs[0], fcs[1], fcs[2], ps
+
+    def _classify(self, feats_nhwc: torch.Tensor) -> torch.Tensor:
+        lay = self._fused_head_layout() if os.environ.get("UGP_NO_FUSED_HEAD", "0") != "1" else None
+        if lay is None or feats_nhwc.shape[0] > 64 or feats_nhwc.shape[3] != lay[0].in_features:
+            return self._head(engine.GlobalAvgPoolFn.apply(feats_nhwc))
+        fc1, fc2, fc3, ps = lay
+        u = None
+        if any(pp > 0.0 for pp in ps):      # train mode: one launch of uniforms for all three Dropout layers
+            u = torch.rand((feats_nhwc.shape[0], fc1.in_features + fc1.out_features + fc2.out_features),
+                           dtype=torch.float32, device=feats_nhwc.device)
+        return engine.GapMlpHeadFn.apply(feats_nhwc, fc1.weight, fc1.bias, fc2.weight, fc2.bias, fc3.weight,
+                                         fc3.bias, u, *ps)
+
     def forward(self, x):
-        pooled = engine.GlobalAvgPoolFn.apply(self._features_nhwc(x))
-        return self._head(pooled)
+        return self._classify(self._features_nhwc(x))
 
     @torch.no_grad()
     def forward_resized(self, x, resolution: int):
@@ -122,7 +152,7 @@ class HerlevClassificationModel(nn.Module):
         if x.dtype != torch.uint8 and x.shape[-1] == resolution and x.shape[-2] == resolution:
             return self(x)
         a = _encode_resized(self.unet, x, resolution, self._depth)
-        return self._head(ops.global_avg_pool(a))
+        return self._classify(a)
 
 
 class HerlevTrainer:

@@ -426,6 +426,61 @@ def global_avg_pool_bwd(dy, H: int, W: int):
     return dx
 
 
+# ----------------------------------------------------------------------------- Herlev classification head
+def gap_mlp_head_fwd(x, w1, b1, w2, b2, w3, b3, u=None, p=(0.0, 0.0, 0.0), tickets=None):
+    """AdaptiveAvgPool2d(1) + Flatten + [Dropout, Linear, ReLU] x 2 + Dropout + Linear on an NHWC bf16
+    feature map in ONE launch; see ugp_gap_mlp_head_fwd.  Returns (logits, pooled, h1, h2)."""
+    _req(x, bf16, "x")
+    B, H, W, Cn = x.shape
+    H1, H2, K = w1.shape[0], w2.shape[0], w3.shape[0]
+    for t, shape, name in ((w1, (H1, Cn), "w1"), (b1, (H1,), "b1"), (w2, (H2, H1), "w2"), (b2, (H2,), "b2"),
+                           (w3, (K, H2), "w3"), (b3, (K,), "b3")):
+        _req(t, torch.float32, name)
+        if tuple(t.shape) != shape:
+            raise RuntimeError(f"gap_mlp_head: {name} has shape {tuple(t.shape)}, expected {shape}")
+    if u is not None:
+        _req(u, torch.float32, "u")
+        assert tuple(u.shape) == (B, Cn + H1 + H2), u.shape
+    dev = x.device
+    if tickets is None:
+        tickets = torch.zeros((B,), dtype=torch.int32, device=dev)
+    pooled = torch.empty((B, Cn), dtype=torch.float32, device=dev)
+    h1 = torch.empty((B, H1), dtype=torch.float32, device=dev)
+    h2 = torch.empty((B, H2), dtype=torch.float32, device=dev)
+    logits = torch.empty((B, K), dtype=torch.float32, device=dev)
+    with _timed("gap_mlp_head_fwd", 0.0, _nb(x)):
+        rc = lib().ugp_gap_mlp_head_fwd(_ptr(x), B, H * W, Cn, _ptr(w1), _ptr(b1), H1, _ptr(w2), _ptr(b2), H2,
+                                        _ptr(w3), _ptr(b3), K, _ptr(u), float(p[0]), float(p[1]), float(p[2]),
+                                        _ptr(pooled), _ptr(h1), _ptr(h2), _ptr(logits), _ptr(tickets), _stream())
+    check(rc, "ugp_gap_mlp_head_fwd")
+    return logits, pooled, h1, h2
+
+
+def mlp_head_bwd(dlogits, w1, w2, w3, pooled, h1, h2, u=None, p=(0.0, 0.0, 0.0)):
+    """Gradients of the three Linear layers and of the pooled vector in one launch; see ugp_mlp_head_bwd.
+    Returns (dw1, db1, dw2, db2, dw3, db3, dpooled)."""
+    _req(dlogits, torch.float32, "dlogits")
+    B, K = dlogits.shape
+    Cn, H1, H2 = w1.shape[1], w1.shape[0], w2.shape[0]
+    dev = dlogits.device
+    flat = torch.empty((w1.numel() + H1 + w2.numel() + H2 + w3.numel() + K,), dtype=torch.float32, device=dev)
+    outs, off = [], 0
+    for shape in (w1.shape, (H1,), w2.shape, (H2,), w3.shape, (K,)):
+        n = 1
+        for d in shape:
+            n *= d
+        outs.append(flat[off:off + n].view(shape))
+        off += n
+    dpooled = torch.empty((B, Cn), dtype=torch.float32, device=dev)
+    scratch = torch.empty((B * (H1 + H2),), dtype=torch.float32, device=dev)
+    with _timed("mlp_head_bwd", 0.0, _nb(w1, w2, w3, flat)):
+        rc = lib().ugp_mlp_head_bwd(_ptr(dlogits), B, Cn, _ptr(w1), H1, _ptr(w2), H2, _ptr(w3), K, _ptr(u),
+                                    float(p[0]), float(p[1]), float(p[2]), _ptr(pooled), _ptr(h1), _ptr(h2),
+                                    *[_ptr(t) for t in outs], _ptr(dpooled), _ptr(scratch), _stream())
+    check(rc, "ugp_mlp_head_bwd")
+    return (*outs, dpooled)
+
+
 # ----------------------------------------------------------------------------- head / loss
 def outconv_fwd(x, w, bias):
     """x NHWC bf16 [B,h,w,C], w fp32 [nc,C(,1,1)] -> fp32 NCHW [B,nc,h,w]."""
