@@ -340,6 +340,13 @@ def run_ours(args):
     # launches per step: counted while the instrumented step was captured (the headline graph replays the same)
     launches = ops.launch_count() * args.steps
     roof = None
+    if rank == 0 and args.dump_launches:
+        with open(args.dump_launches, "w") as f:
+            f.write(f"# per-launch device times of one batch-{B} step ({how})\n"
+                    "# idx name us GFLOP MB TFLOP/s GB/s\n")
+            for i, (n, fl, by, t) in enumerate(prof):
+                f.write(f"{i:4d} {n:22s} {t * 1e3:9.1f} {fl / 1e9:9.2f} {by / 1e6:9.1f} "
+                        f"{(fl / (t / 1e3) / 1e12 if t > 0 else 0):8.1f} {(by / (t / 1e3) / 1e9 if t > 0 else 0):8.0f}\n")
     if rank == 0:
         peak = peaks["bf16_tflops_sustained"]
         step_ms = ms / args.steps
@@ -513,6 +520,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stock", action="store_true")
     ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch table of the instrumented step here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

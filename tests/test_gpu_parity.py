@@ -139,7 +139,7 @@ def test_trainer_step_against_reference_goldens(dev, name):
     assert r["final_loss_rel"] <= max(NORTH_STAR_LOSS, 1.5 * r["final_loss_floor_rel"]), r
     assert r["base_loss_rel"] <= max(NORTH_STAR_LOSS, 1.5 * r["base_loss_floor_rel"]), r
     # masks: bit-exact on every pixel whose reference logit is not within bf16 noise of the threshold; the
-    # excluded band is |z_ref| <= max(5 % of max|z_ref|, 5 sigma of the emulation's rms logit error) - its
+    # excluded band is |z_ref| <= max(5 % of max|z_ref|, 6 sigma of the emulation's rms logit error) - its
     # pixel fraction is printed above and tabulated in DESIGN.md; overall flips no more frequent than the
     # emulation's
     assert r["mask_mismatch_safe"] == 0
@@ -522,6 +522,67 @@ def test_fused_gap_mlp_head_against_stock_modules(dev):
             finally:
                 del os.environ["UGP_NO_FUSED_HEAD"]
             assert rel(m(img), stock) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 7, 5, 8), (1, 1, 1, 64), (1, 28, 28, 256), (1, 3, 112, 256),
+                                   (2, 128, 128, 64), (1, 2, 300, 128)])
+def test_separable_upsample_kernels_against_torch(dev, shape):
+    """Bilinear x2 (align_corners=True, UG_unet_parts.py:76-79) and its adjoint: vertical / horizontal passes
+    through shared memory, channel slabs when a row does not fit; odd, tiny, non-square and multi-slab sizes."""
+    import torch.nn.functional as F
+    from ug_pg_unet_b200 import ops
+
+    B, h, w, C = shape
+    g = torch.Generator(device="cuda").manual_seed(h * 1000 + w)
+    x = torch.randn(B, h, w, C, device=dev, generator=g).bfloat16()
+    up = ops.upsample2x(x)
+    xr = x.permute(0, 3, 1, 2).float().requires_grad_(True)
+    ref = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=True)
+    assert up.shape == (B, 2 * h, 2 * w, C)
+    assert rel(up.permute(0, 3, 1, 2), ref) < 4e-3
+    dU = torch.randn(B, 2 * h, 2 * w, C, device=dev, generator=g).bfloat16()
+    ref.backward(dU.permute(0, 3, 1, 2).float())
+    dx = ops.upsample2x_bwd(dU)
+    assert rel(dx.permute(0, 3, 1, 2), xr.grad) < 4e-3
+    # deterministic (no atomics) and exact on constants: a constant image stays constant
+    assert torch.equal(ops.upsample2x_bwd(dU), dx)
+    c = torch.full((B, h, w, C), 1.5, device=dev).bfloat16()
+    assert torch.equal(ops.upsample2x(c), torch.full((B, 2 * h, 2 * w, C), 1.5, device=dev).bfloat16())
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 32, 32, 512), (3, 64, 64, 128), (1, 6, 10, 64)])
+def test_batchnorm_backward_kernels_against_torch(dev, shape):
+    """The software-pipelined BatchNorm/ReLU(/max-pool) backward (plain and pooled variants, ragged grid
+    tails) against autograd of F.batch_norm + relu + max_pool2d on the same bf16 tensors."""
+    import torch.nn.functional as F
+    from ug_pg_unet_b200 import ops
+
+    B, H, W, C = shape
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    z = (torch.randn(B, H, W, C, device=dev, generator=g) * 1.3 + 0.2).bfloat16()
+    gamma = torch.rand(C, device=dev, generator=g) + 0.5
+    beta = torch.randn(C, device=dev, generator=g) * 0.2
+    for pooled in (False, True):
+        zr = z.permute(0, 3, 1, 2).float().requires_grad_(True)
+        gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        a = F.relu(F.batch_norm(zr, None, None, gm, bt, training=True, eps=1e-5))
+        dA = torch.randn(B, H, W, C, device=dev, generator=g).bfloat16()
+        loss = (a * dA.permute(0, 3, 1, 2).float()).sum()
+        dP = None
+        if pooled:
+            dP = torch.randn(B, H // 2, W // 2, C, device=dev, generator=g).bfloat16()
+            # pool the bf16-rounded activation, as the forward kernel does (arg-max ties resolve identically)
+            ar = a.bfloat16().float()
+            loss = loss + (F.max_pool2d(a + (ar - a).detach(), 2) * dP.permute(0, 3, 1, 2).float()).sum()
+        loss.backward()
+        zf = z.float().reshape(-1, C)
+        mean, var = zf.mean(0), zf.var(0, unbiased=False)
+        rstd = (var + 1e-5).rsqrt()
+        scale, shift = gamma * rstd, beta - mean * gamma * rstd
+        small = torch.empty(3, C, device=dev)
+        dz = ops.bn_relu_bwd(z, dA, dP, scale, shift, mean, rstd, gamma, small[:2], small[2])
+        assert rel(dz.permute(0, 3, 1, 2), zr.grad) < 8e-3, (shape, pooled, rel(dz.permute(0, 3, 1, 2), zr.grad))
+        assert rel(small[0], gm.grad) < 2e-3 and rel(small[1], bt.grad) < 2e-3, (shape, pooled)
 
 
 def test_global_avg_pool_kernels(dev):

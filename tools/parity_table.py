@@ -139,10 +139,10 @@ def measure_trainer(name: str, dev) -> dict:
     zr = fx["logits"]
     zc = logits.detach().cpu()
     # A predicted-mask pixel can only be required to match where the reference logit is not within the
-    # logit noise of the threshold.  The excluded band is |z_ref| <= max(5 % of max|z_ref|, 5 sigma) with
+    # logit noise of the threshold.  The excluded band is |z_ref| <= max(5 % of max|z_ref|, 6 sigma) with
     # sigma = the rms logit error of the oracle's bf16-storage emulation (NOT of the kernels under test).
     rms_floor = fl_logits * zr.double().pow(2).mean().sqrt().item()
-    band = max(0.05 * zr.abs().max().item(), 5.0 * rms_floor)
+    band = max(0.05 * zr.abs().max().item(), 6.0 * rms_floor)
     safe = zr.abs() > band
     mism = (zc > 0) != (zr > 0)
     out = {

@@ -17,7 +17,8 @@ namespace ugp {
 
 int g_bn_skip_reduce = 0;   // what-if timing only (results wrong): skip the reduction pass of the plain variant
 int g_bn_bwd_blocks_per_sm = 2;   // persistent blocks per SM of the backward kernels (tuning switch)
-int g_bn_pool_vec4 = 0;   // pooled backward: 1 = 4-channel threads at 3 blocks/SM (measured: same speed; the kernel is issue-bound)
+int g_bn_min_pixels = 8;   // plain variant: pixels per thread below which the grid shrinks (tuning switch)
+int g_bn_pool_vec4 = 1;   // pooled backward: 1 = 4-channel threads, two windows in flight (software pipeline); 0 = 8-channel threads
 
 struct BnBwdArgs {
   const __nv_bfloat16* z;
@@ -40,8 +41,12 @@ constexpr int kBnThreads = 256;
 // pass (which also needs the three per-channel coefficient sets in registers)
 template <bool kApply> struct BnUnroll { static constexpr int v = kApply ? 4 : 8; };
 
-// Block reduction over the rows that share a channel group, then one atomic per
-// channel per block.
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Block reduction over the rows that share a channel group, then one vector
+// reduction per four channels per block.
 template <int kVals>
 __device__ __forceinline__ void block_reduce_channels(float (*red)[kBnThreads][9], const float* acc0,
                                                       const float* acc1, int cg, int my_cg,
@@ -64,10 +69,13 @@ __device__ __forceinline__ void block_reduce_channels(float (*red)[kBnThreads][9
         if (kVals > 1) a1[j] += red[1][r * cg + my_cg][j];
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(out0 + c0 + j, a0[j]);
-      if (kVals > 1) atomicAdd(out1 + c0 + j, a1[j]);
+    // two 16-byte vector reductions per sum instead of eight scalar ones: the L2 atomic unit serialises
+    // same-address operations, and every block of the launch lands on the same 2*C addresses
+    red_add_f32x4(out0 + c0, a0[0], a0[1], a0[2], a0[3]);
+    red_add_f32x4(out0 + c0 + 4, a0[4], a0[5], a0[6], a0[7]);
+    if (kVals > 1) {
+      red_add_f32x4(out1 + c0, a1[0], a1[1], a1[2], a1[3]);
+      red_add_f32x4(out1 + c0 + 4, a1[4], a1[5], a1[6], a1[7]);
     }
   }
 }
@@ -110,21 +118,26 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const 
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
 
-  constexpr int kBnUnroll = BnUnroll<kApply>::v;
+  // Software pipeline: the raw 16-byte words of trip t+1 are requested BEFORE trip t is consumed.  Without
+  // it every warp of the launch sits in the same phase (all loading, then all computing): measured
+  // (ncu, r02) 16 warps/SM at 45 % issue utilisation and 2.4 TB/s on the 67 MB layers, ~7 us per trip.
+  constexpr int kU = BnUnroll<kApply>::v / 2;      // pixels per trip; two trips in flight
   const long long stride = static_cast<long long>(gridDim.x) * rows_per_block;
-  for (long long p = static_cast<long long>(blockIdx.x) * rows_per_block + my_row; p < M;
-       p += stride * kBnUnroll) {
-    uint4 zr[kBnUnroll], gr[kBnUnroll];     // raw bf16x8 keeps the in-flight footprint small
+  const long long step = stride * kU;
+  uint4 zA[kU], gA[kU], zB[kU], gB[kU];
+  auto fetch = [&](uint4* zr, uint4* gr, long long p) {
 #pragma unroll
-    for (int u = 0; u < kBnUnroll; ++u) {
+    for (int u = 0; u < kU; ++u) {
       const long long pp = p + u * stride;
       if (pp < M) {
         zr[u] = *reinterpret_cast<const uint4*>(a.z + pp * a.C + c0);
         gr[u] = *reinterpret_cast<const uint4*>(a.dA + pp * a.C + c0);
       }
     }
+  };
+  auto consume = [&](const uint4* zr, const uint4* gr, long long p) {
 #pragma unroll
-    for (int u = 0; u < kBnUnroll; ++u) {
+    for (int u = 0; u < kU; ++u) {
       const long long pp = p + u * stride;
       if (pp < M) {
         Vec8 o;
@@ -146,6 +159,17 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const 
         if (kApply) store8(a.dz + pp * a.C + c0, o);
       }
     }
+  };
+  long long p = static_cast<long long>(blockIdx.x) * rows_per_block + my_row;
+  fetch(zA, gA, p);
+  while (p < M) {
+    fetch(zB, gB, p + step);
+    consume(zA, gA, p);
+    p += step;
+    if (p >= M) break;
+    fetch(zA, gA, p + step);
+    consume(zB, gB, p);
+    p += step;
   }
   __shared__ float red[2][kBnThreads][9];
   if (!kApply) {
@@ -277,7 +301,11 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_pool_kernel(const B
 // pooled variant, 4 channels per thread (8-byte loads): half the register footprint of the 8-channel
 // version, so 3 blocks (24 warps) per SM hide the DRAM latency of its load -> compute -> store trips.
 // ---------------------------------------------------------------------------
-constexpr int kPoolBlocksPerSM = 3;
+constexpr int kPoolBlocksPerSM = 2;
+
+struct PoolRaw4 {          // the raw words of one 2x2 window x 4 channels
+  uint2 z[4], g[4], p;
+};
 
 template <bool kApply>
 __global__ void __launch_bounds__(kBnThreads, kPoolBlocksPerSM) bn_relu_bwd_pool4_kernel(const BnBwdArgs a) {
@@ -311,30 +339,25 @@ __global__ void __launch_bounds__(kBnThreads, kPoolBlocksPerSM) bn_relu_bwd_pool
   }
   float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
 
-  for (long long win = static_cast<long long>(blockIdx.x) * rows_per_block + my_row;
-       win < windows; win += static_cast<long long>(gridDim.x) * rows_per_block) {
+  auto pixel = [&](long long win, int i) -> long long {
     const int xo = static_cast<int>(win % Wo);
     const long long t2 = win / Wo;
     const int yo = static_cast<int>(t2 % Ho);
     const int b = static_cast<int>(t2 / Ho);
-    uint32_t zr[4][2], gr[4][2], pr[2];
-    long long pix[4];
+    return (static_cast<long long>(b) * a.H + (2 * yo + (i >> 1))) * a.W + 2 * xo + (i & 1);
+  };
+  auto fetch = [&](PoolRaw4& r, long long win) {
+    if (win >= windows) return;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      pix[i] = (static_cast<long long>(b) * a.H + (2 * yo + (i >> 1))) * a.W + 2 * xo + (i & 1);
-      const uint2 zq = *reinterpret_cast<const uint2*>(a.z + pix[i] * a.C + c0);
-      zr[i][0] = zq.x; zr[i][1] = zq.y;
-      if (a.dA) {
-        const uint2 gq = *reinterpret_cast<const uint2*>(a.dA + pix[i] * a.C + c0);
-        gr[i][0] = gq.x; gr[i][1] = gq.y;
-      } else {
-        gr[i][0] = gr[i][1] = 0u;
-      }
+      const long long pix = pixel(win, i);
+      r.z[i] = *reinterpret_cast<const uint2*>(a.z + pix * a.C + c0);
+      r.g[i] = a.dA ? *reinterpret_cast<const uint2*>(a.dA + pix * a.C + c0) : make_uint2(0u, 0u);
     }
-    {
-      const uint2 pq = *reinterpret_cast<const uint2*>(a.dP + win * a.C + c0);
-      pr[0] = pq.x; pr[1] = pq.y;
-    }
+    r.p = *reinterpret_cast<const uint2*>(a.dP + win * a.C + c0);
+  };
+  auto consume = [&](PoolRaw4& r, long long win) {
+    uint32_t out[4][2];
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
       float dlo[4], dhi[4];
@@ -346,14 +369,17 @@ __global__ void __launch_bounds__(kBnThreads, kPoolBlocksPerSM) bn_relu_bwd_pool
         float best = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          zf[i] = hh ? bf16_hi(zr[i][w]) : bf16_lo(zr[i][w]);
+          const uint32_t zw = w ? r.z[i].y : r.z[i].x;
+          zf[i] = hh ? bf16_hi(zw) : bf16_lo(zw);
           const float av = round_bf16(bn_relu_val(zf[i], sc[j], sh[j]));
           if (i == 0 || av > best) { best = av; arg = i; }     // first max wins (MaxPool2d)
         }
-        const float gpv = hh ? bf16_hi(pr[w]) : bf16_lo(pr[w]);
+        const uint32_t pw = w ? r.p.y : r.p.x;
+        const float gpv = hh ? bf16_hi(pw) : bf16_lo(pw);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float g = hh ? bf16_hi(gr[i][w]) : bf16_lo(gr[i][w]);
+          const uint32_t gw = w ? r.g[i].y : r.g[i].x;
+          float g = hh ? bf16_hi(gw) : bf16_lo(gw);
           if (arg == i) g += gpv;
           g = (fmaf(zf[i], sc[j], sh[j]) > 0.f) ? g : 0.f;
           if (!kApply) {
@@ -368,16 +394,32 @@ __global__ void __launch_bounds__(kBnThreads, kPoolBlocksPerSM) bn_relu_bwd_pool
       }
       if (kApply) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gr[i][w] = pack_bf16x2(dlo[i], dhi[i]);
+        for (int i = 0; i < 4; ++i) out[i][w] = pack_bf16x2(dlo[i], dhi[i]);
       }
     }
     if (kApply) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<uint2*>(a.dz + pix[i] * a.C + c0) = make_uint2(gr[i][0], gr[i][1]);
+        *reinterpret_cast<uint2*>(a.dz + pixel(win, i) * a.C + c0) = make_uint2(out[i][0], out[i][1]);
     }
+  };
+
+  // software pipeline, two windows in flight per thread (see the plain kernel)
+  const long long step = static_cast<long long>(gridDim.x) * rows_per_block;
+  long long win = static_cast<long long>(blockIdx.x) * rows_per_block + my_row;
+  PoolRaw4 ra, rb;
+  fetch(ra, win);
+  while (win < windows) {
+    fetch(rb, win + step);
+    consume(ra, win);
+    win += step;
+    if (win >= windows) break;
+    fetch(ra, win + step);
+    consume(rb, win);
+    win += step;
   }
-  // block reduction over the windows that share a channel group, one atomic per channel per block
+
+  // block reduction over the windows that share a channel group, one vector reduction per 4 channels per block
   __shared__ float red[2][kBnThreads][5];
   if (!kApply) {
 #pragma unroll
@@ -393,14 +435,11 @@ __global__ void __launch_bounds__(kBnThreads, kPoolBlocksPerSM) bn_relu_bwd_pool
 #pragma unroll
       for (int j = 0; j < 4; ++j) { acc0[j] += red[0][r * cg + my_cg][j]; acc1[j] += red[1][r * cg + my_cg][j]; }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (!kApply) {
-        atomicAdd(a.sums + c0 + j, acc0[j]);
-        atomicAdd(a.sums + a.C + c0 + j, acc1[j]);
-      } else {
-        atomicAdd(a.dbias + c0 + j, acc0[j]);
-      }
+    if (!kApply) {
+      red_add_f32x4(a.sums + c0, acc0[0], acc0[1], acc0[2], acc0[3]);
+      red_add_f32x4(a.sums + a.C + c0, acc1[0], acc1[1], acc1[2], acc1[3]);
+    } else {
+      red_add_f32x4(a.dbias + c0, acc0[0], acc0[1], acc0[2], acc0[3]);
     }
   }
 }
@@ -436,7 +475,7 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
     UGP_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_bwd: pooled gradient needs even H, W");
     if (g_bn_pool_vec4 != 0 && kBnThreads % (C / 4) == 0) {
       const int rows4 = kBnThreads / (C / 4);
-      long long blocks = (M / 4 + rows4 * 4 - 1) / (rows4 * 4);
+      long long blocks = (M / 4 + rows4 * 2 - 1) / (rows4 * 2);
       const long long cap4 = static_cast<long long>(device_sm_count()) * kPoolBlocksPerSM;
       if (blocks > cap4) blocks = cap4;
       if (blocks < 1) blocks = 1;
@@ -452,9 +491,9 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
       bn_relu_bwd_pool_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
     }
   } else {
-    // at least two trips of kBnUnroll pixels per thread: small tensors get few blocks, which
-    // keeps the per-channel atomic tail short (16 pixels per thread at least)
-    long long blocks = (M + rows_per_block * 16 - 1) / (rows_per_block * 16);
+    // at least g_bn_min_pixels pixels per thread: small tensors get few blocks, which keeps the
+    // per-channel atomic tail short
+    long long blocks = (M + rows_per_block * g_bn_min_pixels - 1) / (rows_per_block * g_bn_min_pixels);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (!g_bn_skip_reduce) bn_relu_bwd_plain_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);

@@ -223,66 +223,94 @@ __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ x,
 // Bilinear x2 upsample (align_corners=True) on NHWC bf16 and its adjoint
 // (F.interpolate / nn.Upsample at UG_unet_parts.py:76-79 and UG_unet.py:296-301).
 // ----------------------------------------------------------------------------
-// One block per output row (b, Y): the row interpolation is block-uniform, index math is 32-bit,
-// and the two source rows are re-read by neighbouring X through L1.
-__global__ void __launch_bounds__(256)
-upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int B, int h, int w, int C,
+// Both kernels were ALU / issue bound in their first form (ncu, r02: 75 % / 68 % issue utilisation at 1.9 /
+// 2.3 TB/s of DRAM traffic): per 16-byte output the forward did four 16-byte loads, 32 bf16 unpacks, two
+// integer divisions and the float arithmetic of two bilinear_src calls; the adjoint gathered 16-25 taps
+// per output.  Now the interpolation is SEPARATED through shared memory (fp32): forward = vertical mix of
+// the two source rows once per source pixel, then a two-tap horizontal lerp per output pixel; adjoint =
+// vertical gather of the <= 5 contributing rows once per high-res column, then the <= 5-tap horizontal
+// gather.  A thread owns one 4-channel group for the whole kernel and walks pixels with a constant stride
+// (no division in the loops); a warp's 16-byte shared-memory accesses cover 512 contiguous bytes (no bank
+// conflicts); index / weight tables are computed once per block with PyTorch's own arithmetic (bilinear_src).
+//
+// One block per output row (b, Y) and channel slab; slab width Cs (a multiple of 4 with 256 % (Cs/4) == 0)
+// is chosen by the launcher so that the staged row fits in shared memory.
+constexpr int kUpThreads = 256;
+
+__device__ __forceinline__ float4 unpack4(const uint2 u) {
+  return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+}
+
+__global__ void __launch_bounds__(kUpThreads)
+upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int B, int h, int w, int C, int Cs, float sy, float sx,
                   __nv_bfloat16* __restrict__ out) {
-  const int cg = C >> 3;
+  extern __shared__ float up_smem[];
+  float* mix = up_smem;                                   // [w][Cs] vertical mix, fp32
+  int* tx0 = reinterpret_cast<int*>(mix + w * Cs);        // [2w] left source column * Cs
+  float* tlx = reinterpret_cast<float*>(tx0 + 2 * w);     // [2w] weight of the right source column
+  const int cg4 = Cs >> 2;
+  const int c = (threadIdx.x % cg4) * 4;                  // this thread's channel group, fixed
+  const int xr = threadIdx.x / cg4, xstep = kUpThreads / cg4;
   const int H = 2 * h, W = 2 * w;
   const int row = blockIdx.x;
+  const int cs0 = blockIdx.y * Cs;
   const int b = row / H, Y = row - b * H;
   int y0, y1;
   float ly;
-  bilinear_src(Y, h, H, &y0, &y1, &ly);
-  const __nv_bfloat16* r0 = x + (static_cast<long long>(b) * h + y0) * w * C;
-  const __nv_bfloat16* r1 = x + (static_cast<long long>(b) * h + y1) * w * C;
-  __nv_bfloat16* o = out + static_cast<long long>(row) * W * C;
-  const int items = W * cg;
-  for (int i = threadIdx.x; i < items; i += 2 * blockDim.x) {
-    // two output items per trip: eight independent 16-byte loads in flight per thread
-    const int i2 = (i + blockDim.x < items) ? i + blockDim.x : i;
-    const int X = i / cg, X2 = i2 / cg;
-    const int c0 = (i - X * cg) * 8, c2 = (i2 - X2 * cg) * 8;
-    int x0, x1, x02, x12;
-    float lx, lx2;
-    bilinear_src(X, w, W, &x0, &x1, &lx);
-    bilinear_src(X2, w, W, &x02, &x12, &lx2);
-    const uint4 a00 = *reinterpret_cast<const uint4*>(r0 + x0 * C + c0);
-    const uint4 a01 = *reinterpret_cast<const uint4*>(r0 + x1 * C + c0);
-    const uint4 a10 = *reinterpret_cast<const uint4*>(r1 + x0 * C + c0);
-    const uint4 a11 = *reinterpret_cast<const uint4*>(r1 + x1 * C + c0);
-    const uint4 b00 = *reinterpret_cast<const uint4*>(r0 + x02 * C + c2);
-    const uint4 b01 = *reinterpret_cast<const uint4*>(r0 + x12 * C + c2);
-    const uint4 b10 = *reinterpret_cast<const uint4*>(r1 + x02 * C + c2);
-    const uint4 b11 = *reinterpret_cast<const uint4*>(r1 + x12 * C + c2);
-    {
-      const Vec8 v00 = unpack8(a00), v01 = unpack8(a01), v10 = unpack8(a10), v11 = unpack8(a11);
-      Vec8 ov;
+  bilinear_src_scaled(Y, h, sy, &y0, &y1, &ly);
+  for (int X = threadIdx.x; X < W; X += kUpThreads) {
+    int x0, x1;
+    float lx;
+    bilinear_src_scaled(X, w, sx, &x0, &x1, &lx);
+    tx0[X] = x0 * Cs;
+    tlx[X] = (x1 == x0) ? 0.f : lx;       // right edge: both taps are the last column
+  }
+  const __nv_bfloat16* r0 = x + (static_cast<long long>(b) * h + y0) * w * C + cs0 + c;
+  const __nv_bfloat16* r1 = x + (static_cast<long long>(b) * h + y1) * w * C + cs0 + c;
+  for (int xs = xr; xs < w; xs += 4 * xstep) {
+    // four source pixels per trip: eight independent 8-byte loads in flight per thread
+    uint2 a0[4], a1[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        ov.v[j] = (1.f - ly) * ((1.f - lx) * v00.v[j] + lx * v01.v[j]) +
-                  ly * ((1.f - lx) * v10.v[j] + lx * v11.v[j]);
-      store8(o + static_cast<long long>(i) * 8, ov);
+    for (int u = 0; u < 4; ++u) {
+      const int xx = xs + u * xstep;
+      if (xx < w) {
+        a0[u] = *reinterpret_cast<const uint2*>(r0 + xx * C);
+        a1[u] = *reinterpret_cast<const uint2*>(r1 + xx * C);
+      }
     }
-    if (i2 != i) {
-      const Vec8 v00 = unpack8(b00), v01 = unpack8(b01), v10 = unpack8(b10), v11 = unpack8(b11);
-      Vec8 ov;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        ov.v[j] = (1.f - ly) * ((1.f - lx2) * v00.v[j] + lx2 * v01.v[j]) +
-                  ly * ((1.f - lx2) * v10.v[j] + lx2 * v11.v[j]);
-      store8(o + static_cast<long long>(i2) * 8, ov);
+    for (int u = 0; u < 4; ++u) {
+      const int xx = xs + u * xstep;
+      if (xx < w) {
+        const float4 v0 = unpack4(a0[u]), v1 = unpack4(a1[u]);
+        *reinterpret_cast<float4*>(mix + xx * Cs + c) =
+            make_float4(fmaf(ly, v1.x - v0.x, v0.x), fmaf(ly, v1.y - v0.y, v0.y), fmaf(ly, v1.z - v0.z, v0.z),
+                        fmaf(ly, v1.w - v0.w, v0.w));
+      }
     }
+  }
+  __syncthreads();
+  __nv_bfloat16* o = out + static_cast<long long>(row) * W * C + cs0 + c;
+  const float* mc = mix + c;
+#pragma unroll 4
+  for (int X = xr; X < W; X += xstep) {
+    const int o0 = tx0[X];
+    const float lx = tlx[X];
+    const float4 p = *reinterpret_cast<const float4*>(mc + o0);
+    const float4 q = *reinterpret_cast<const float4*>(mc + o0 + ((lx != 0.f) ? Cs : 0));
+    uint2 ov;
+    ov.x = pack_bf16x2(fmaf(lx, q.x - p.x, p.x), fmaf(lx, q.y - p.y, p.y));
+    ov.y = pack_bf16x2(fmaf(lx, q.z - p.z, p.z), fmaf(lx, q.w - p.w, p.w));
+    *reinterpret_cast<uint2*>(o + X * C) = ov;
   }
 }
 
 // weight of high-res index I = 2*i - 2 + k (k = 0..4) on low-res index i; 0 outside the image
-__device__ __forceinline__ float up2_adjoint_weight(int I, int i, int n_lo, int n_hi) {
+__device__ __forceinline__ float up2_adjoint_weight(int I, int i, int n_lo, int n_hi, float scale) {
   if (I < 0 || I >= n_hi) return 0.f;
   int i0, i1;
   float l;
-  bilinear_src(I, n_lo, n_hi, &i0, &i1, &l);
+  bilinear_src_scaled(I, n_lo, scale, &i0, &i1, &l);
   float wgt = 0.f;
   if (i0 == i) wgt += 1.f - l;
   if (i1 == i) wgt += l;
@@ -290,43 +318,81 @@ __device__ __forceinline__ float up2_adjoint_weight(int I, int i, int n_lo, int 
 }
 
 // Adjoint in gather form (deterministic, no atomics): every low-res pixel sums the contributions of
-// the (at most 5x5, typically 4x4) high-res pixels that read it.  One block per low-res row.
-__global__ void __launch_bounds__(256)
-upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int B, int h, int w, int C,
+// the (at most 5x5, typically 4x4) high-res pixels that read it.  One block per low-res row and
+// channel slab: vertical gather into shared memory, then the horizontal gather.
+__global__ void __launch_bounds__(kUpThreads)
+upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int B, int h, int w, int C, int Cs, float sy, float sx,
                       __nv_bfloat16* __restrict__ dx) {
-  const int cg = C >> 3;
+  extern __shared__ float up_smem[];
+  float* vs = up_smem;                           // [W][Cs] vertically gathered row, fp32
+  float* twx = vs + 2 * w * Cs;                  // [w][5] horizontal weights of taps 2x-2 .. 2x+2
+  float* twy = twx + w * 5;                      // [5] vertical weights of rows 2y-2 .. 2y+2 (block-uniform)
+  const int cg4 = Cs >> 2;
+  const int c = (threadIdx.x % cg4) * 4;
+  const int xr = threadIdx.x / cg4, xstep = kUpThreads / cg4;
   const int H = 2 * h, W = 2 * w;
   const int row = blockIdx.x;
+  const int cs0 = blockIdx.y * Cs;
   const int b = row / h, y = row - b * h;
+  if (threadIdx.x < 5) twy[threadIdx.x] = up2_adjoint_weight(2 * y - 2 + static_cast<int>(threadIdx.x), y, h, H, sy);
+  for (int t = threadIdx.x; t < w * 5; t += kUpThreads) {
+    const int xx = t / 5, k = t - xx * 5;
+    twx[t] = up2_adjoint_weight(2 * xx - 2 + k, xx, w, W, sx);
+  }
+  __syncthreads();
   float wy[5];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) wy[i] = up2_adjoint_weight(2 * y - 2 + i, y, h, H);
-  const __nv_bfloat16* base = dout + static_cast<long long>(b) * H * W * C;
-  __nv_bfloat16* o = dx + static_cast<long long>(row) * w * C;
-  const int items = w * cg;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int x = it / cg;
-    const int c0 = (it - x * cg) * 8;
-    float wx[5];
+  for (int i = 0; i < 5; ++i) wy[i] = twy[i];
+  // rows 2y-2 .. 2y+2 clamped into the image (a clamped row has weight 0)
+  const __nv_bfloat16* rp[5];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) wx[k] = up2_adjoint_weight(2 * x - 2 + k, x, w, W);
-    Vec8 acc;
+  for (int i = 0; i < 5; ++i) {
+    int Yr = 2 * y - 2 + i;
+    Yr = Yr < 0 ? 0 : (Yr >= H ? H - 1 : Yr);
+    rp[i] = dout + (static_cast<long long>(b) * H + Yr) * W * C + cs0 + c;
+  }
+  constexpr int kCols = 4;
+  for (int X = xr; X < W; X += kCols * xstep) {
+    // four high-res columns per trip: twenty independent 8-byte loads in flight per thread (the kernel is
+    // bound by DRAM latency x bytes in flight: 3 blocks / SM of staging leave only 768 threads per SM)
+    uint2 r[kCols][5];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+    for (int u = 0; u < kCols; ++u) {
+      const int Xu = (X + u * xstep < W) ? X + u * xstep : X;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      if (wy[i] == 0.f) continue;
-      const __nv_bfloat16* rp = base + static_cast<long long>(2 * y - 2 + i) * W * C + c0;
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        if (wx[k] == 0.f) continue;
-        const Vec8 g = load8(rp + (2 * x - 2 + k) * C);
-        const float wgt = wy[i] * wx[k];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc.v[j] = fmaf(wgt, g.v[j], acc.v[j]);
-      }
+      for (int i = 0; i < 5; ++i) r[u][i] = *reinterpret_cast<const uint2*>(rp[i] + Xu * C);
     }
-    store8(o + static_cast<long long>(it) * 8, acc);
+#pragma unroll
+    for (int u = 0; u < kCols; ++u) {
+      float4 sa = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const float4 ga = unpack4(r[u][i]);
+        sa.x = fmaf(wy[i], ga.x, sa.x); sa.y = fmaf(wy[i], ga.y, sa.y);
+        sa.z = fmaf(wy[i], ga.z, sa.z); sa.w = fmaf(wy[i], ga.w, sa.w);
+      }
+      if (X + u * xstep < W) *reinterpret_cast<float4*>(vs + (X + u * xstep) * Cs + c) = sa;
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* o = dx + static_cast<long long>(row) * w * C + cs0 + c;
+  const float* vc = vs + c;
+#pragma unroll 2
+  for (int xx = xr; xx < w; xx += xstep) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float wgt = twx[xx * 5 + k];
+      int Xs = 2 * xx - 2 + k;
+      Xs = Xs < 0 ? 0 : (Xs >= W ? W - 1 : Xs);       // out-of-image taps carry weight 0
+      const float4 p = *reinterpret_cast<const float4*>(vc + Xs * Cs);
+      acc.x = fmaf(wgt, p.x, acc.x); acc.y = fmaf(wgt, p.y, acc.y);
+      acc.z = fmaf(wgt, p.z, acc.z); acc.w = fmaf(wgt, p.w, acc.w);
+    }
+    uint2 ov;
+    ov.x = pack_bf16x2(acc.x, acc.y);
+    ov.y = pack_bf16x2(acc.z, acc.w);
+    *reinterpret_cast<uint2*>(o + xx * C) = ov;
   }
 }
 
@@ -403,14 +469,36 @@ int maxpool2x2_bwd(const void* x, const void* dout, int B, int H, int W, int C, 
   return UGP_OK;
 }
 
+// Channel-slab width of the separable upsample kernels: the widest Cs that divides C, keeps
+// `pixels * Cs * 4` bytes of staging (+ the tables) inside the shared-memory budget and lets a block of
+// kUpThreads threads own whole 4-channel groups (kUpThreads % (Cs / 4) == 0).
+static int upsample_slab(int C, int pixels, int table_bytes, int budget) {
+  for (int Cs = C; Cs >= 4; Cs -= 4) {
+    if (C % Cs != 0 || kUpThreads % (Cs / 4) != 0) continue;
+    if (static_cast<long long>(pixels) * Cs * 4 + table_bytes <= budget) return Cs;
+  }
+  return 0;
+}
+
 int upsample2x(const void* x, int B, int h, int w, int C, void* out, cudaStream_t stream) {
   UGP_REQUIRE(x && out, "upsample2x: null pointer");
-  UGP_REQUIRE(C % 8 == 0, "upsample2x: C must be a multiple of 8");
+  UGP_REQUIRE(C % 4 == 0, "upsample2x: C must be a multiple of 4");
   UGP_REQUIRE(B > 0 && h > 0 && w > 0 && static_cast<long long>(B) * 2 * h < (1LL << 31) &&
                   static_cast<long long>(2 * w) * C < (1LL << 28),
               "upsample2x: shape out of range");
-  upsample2x_kernel<<<B * 2 * h, 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), B, h, w, C, static_cast<__nv_bfloat16*>(out));
+  const int tables = 2 * w * 8;
+  const float sy = (2 * h > 1) ? static_cast<float>(h - 1) / static_cast<float>(2 * h - 1) : 0.f;
+  const float sx = (2 * w > 1) ? static_cast<float>(w - 1) / static_cast<float>(2 * w - 1) : 0.f;
+  const int Cs = upsample_slab(C, w, tables, 64 * 1024);
+  UGP_REQUIRE(Cs > 0 && C / Cs <= 65535, "upsample2x: row of %d pixels does not fit the staging buffer", w);
+  const int smem = w * Cs * 4 + tables;
+  static bool configured = false;
+  if (!configured) {
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(upsample2x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  upsample2x_kernel<<<dim3(B * 2 * h, C / Cs), kUpThreads, smem, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), B, h, w, C, Cs, sy, sx, static_cast<__nv_bfloat16*>(out));
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
@@ -418,17 +506,26 @@ int upsample2x(const void* x, int B, int h, int w, int C, void* out, cudaStream_
 int upsample2x_bwd(const void* dout, int B, int h, int w, int C, void* dx,
                    cudaStream_t stream) {
   UGP_REQUIRE(dout && dx, "upsample2x_bwd: null pointer");
-  UGP_REQUIRE(C % 8 == 0, "upsample2x_bwd: C must be a multiple of 8");
+  UGP_REQUIRE(C % 4 == 0, "upsample2x_bwd: C must be a multiple of 4");
   UGP_REQUIRE(B > 0 && h > 0 && w > 0 && static_cast<long long>(B) * h < (1LL << 31) &&
                   static_cast<long long>(2 * w) * C < (1LL << 28),
               "upsample2x_bwd: shape out of range");
-  upsample2x_bwd_kernel<<<B * h, 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(dout), B, h, w, C, static_cast<__nv_bfloat16*>(dx));
+  const int tables = (w * 5 + 8) * 4;
+  const float sy = (2 * h > 1) ? static_cast<float>(h - 1) / static_cast<float>(2 * h - 1) : 0.f;
+  const float sx = (2 * w > 1) ? static_cast<float>(w - 1) / static_cast<float>(2 * w - 1) : 0.f;
+  const int Cs = upsample_slab(C, 2 * w, tables, 72 * 1024);
+  UGP_REQUIRE(Cs > 0 && C / Cs <= 65535, "upsample2x_bwd: row of %d pixels does not fit the staging buffer", 2 * w);
+  const int smem = 2 * w * Cs * 4 + tables;
+  static bool configured = false;
+  if (!configured) {
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(upsample2x_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    configured = true;
+  }
+  upsample2x_bwd_kernel<<<dim3(B * h, C / Cs), kUpThreads, smem, stream>>>(
+      static_cast<const __nv_bfloat16*>(dout), B, h, w, C, Cs, sy, sx, static_cast<__nv_bfloat16*>(dx));
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
-
-
 
 
 // ----------------------------------------------------------------------------
