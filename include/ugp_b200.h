@@ -263,6 +263,21 @@ int ugp_rmsprop_conv_packed(float* const* w, float* const* square_avgs, float* c
                             int n_tensors, float lr, float alpha, float eps, float weight_decay,
                             float grad_scale, void* stream);
 
+/* BatchNorm + ReLU of a conv output (as ugp_bn_relu_apply) with the 1x1 head fused: the decoder outputs of
+ * PGUNet2..4 each feed an OutConv (UG_unet_parts.py:84-91; UG_unet.py:214-217, 250-252, 294-297).
+ * lmap[b][k][p] = bh[k] + sum_c wh[k][c] * a[p][c], fp32 NCHW [B][nc][H][W], from the fp32 activation while
+ * it is in registers.  C in {64, 128, 256}, nc in {1, 2}; wh fp32 [nc][C], bh fp32 [nc]. */
+int ugp_bn_relu_apply_head(const void* z, const float* scale, const float* shift, int B, int H, int W, int C,
+                           const float* wh, const float* bh, int nc, void* a, float* lmap, void* stream);
+
+/* Backward of the above (autograd of the same reference lines): ugp_bn_relu_bwd whose activation gradient is
+ * dA (nullable) + sum_k head_dl[b][k][p] * head_w[k][c]; head_grads [nc*C + nc] receives the head's weight
+ * gradient (sum_p dl * a) and bias gradient (sum_p dl) from the same pass (zeroed here).  No pooled gradient. */
+int ugp_bn_relu_bwd_head(const void* z, const void* dA, const float* scale, const float* shift, const float* mean,
+                         const float* rstd, const float* gamma, int B, int H, int W, int C, const float* head_dl,
+                         const float* head_w, int nc, float* sums, float* dbias, void* dz, float* head_grads,
+                         void* stream);
+
 /* Herlev classification head, reference Herlev/train_herlev.py:66-77 (the nn.Sequential
  * AdaptiveAvgPool2d(1), Flatten, Dropout(.5), Linear(C,H1), ReLU, Dropout(.3), Linear(H1,H2), ReLU,
  * Dropout(.2), Linear(H2,K)) and :104-110 (forward = classifier(features)) as ONE kernel.

@@ -175,17 +175,24 @@ class tf32_operands:
 _BF16_STORAGE = False
 
 
+# A/B of a kernel design choice: train-mode BatchNorm statistics taken from the fp32
+# accumulators BEFORE the conv output is rounded to bf16 (True) instead of from the stored bf16 values
+# (False = what conv_epilogue.cuh does).  Only meaningful inside bf16_storage(True).
+_BN_STATS_FROM_FP32 = False
+
+
 class bf16_storage:
-    def __init__(self, on: bool = True):
-        self.on = on
+    def __init__(self, on: bool = True, stats_from_fp32: bool = False):
+        self.on, self.stats_from_fp32 = on, stats_from_fp32
 
     def __enter__(self):
-        global _BF16_STORAGE
-        self.prev, _BF16_STORAGE = _BF16_STORAGE, self.on
+        global _BF16_STORAGE, _BN_STATS_FROM_FP32
+        self.prev = (_BF16_STORAGE, _BN_STATS_FROM_FP32)
+        _BF16_STORAGE, _BN_STATS_FROM_FP32 = self.on, self.stats_from_fp32
 
     def __exit__(self, *a):
-        global _BF16_STORAGE
-        _BF16_STORAGE = self.prev
+        global _BF16_STORAGE, _BN_STATS_FROM_FP32
+        _BF16_STORAGE, _BN_STATS_FROM_FP32 = self.prev
 
 
 # --------------------------------------------------------------------------- blocks
@@ -203,12 +210,21 @@ def double_conv(x: Tensor, sd: StateDict, prefix: str, training: bool, bn_out: O
                                              sd[f"{prefix}.conv_op.{conv_i}.bias"], padding=1))
         else:
             x = F.conv2d(x, _q(w, bq), sd[f"{prefix}.conv_op.{conv_i}.bias"], padding=1)
+        x_acc = x
         if bq and training:
             x = _q(x, True)        # train: raw conv output stored in bf16; eval: BN+ReLU fused in the epilogue
         rm = sd[f"{prefix}.conv_op.{bn_i}.running_mean"].clone()
         rv = sd[f"{prefix}.conv_op.{bn_i}.running_var"].clone()
-        x = F.batch_norm(x, rm, rv, sd[f"{prefix}.conv_op.{bn_i}.weight"], sd[f"{prefix}.conv_op.{bn_i}.bias"],
-                         training=training, momentum=momentum, eps=eps)
+        if bq and training and _BN_STATS_FROM_FP32:
+            # design A/B: normalise the STORED (rounded) values with the statistics of the unrounded ones
+            mean = x_acc.mean(dim=(0, 2, 3), keepdim=True)
+            var = x_acc.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
+            g_ = sd[f"{prefix}.conv_op.{bn_i}.weight"].view(1, -1, 1, 1)
+            b_ = sd[f"{prefix}.conv_op.{bn_i}.bias"].view(1, -1, 1, 1)
+            x = (x - mean) * torch.rsqrt(var + eps) * g_ + b_
+        else:
+            x = F.batch_norm(x, rm, rv, sd[f"{prefix}.conv_op.{bn_i}.weight"], sd[f"{prefix}.conv_op.{bn_i}.bias"],
+                             training=training, momentum=momentum, eps=eps)
         if training and bn_out is not None:
             bn_out[f"{prefix}.conv_op.{bn_i}.running_mean"] = rm
             bn_out[f"{prefix}.conv_op.{bn_i}.running_var"] = rv

@@ -585,6 +585,79 @@ def test_batchnorm_backward_kernels_against_torch(dev, shape):
         assert rel(small[0], gm.grad) < 2e-3 and rel(small[1], bt.grad) < 2e-3, (shape, pooled)
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 1), (1, 8, 32, 128, 2), (3, 32, 32, 256, 1), (1, 5, 3, 64, 2)])
+def test_fused_decoder_head_kernels_against_unfused(dev, shape):
+    """ugp_bn_relu_apply_head / ugp_bn_relu_bwd_head (the OutConv of a decoder block riding in the block's
+    BN/ReLU pass and BatchNorm backward) against the separate kernels: bn_relu_apply + outconv_fwd, and
+    outconv_bwd -> bn_relu_bwd."""
+    from ug_pg_unet_b200 import ops
+
+    B, H, W, C, nc = shape
+    g = torch.Generator(device="cuda").manual_seed(C + nc)
+    z = (torch.randn(B, H, W, C, device=dev, generator=g) * 1.2 + 0.1).bfloat16()
+    gamma = torch.rand(C, device=dev, generator=g) + 0.5
+    zf = z.float().reshape(-1, C)
+    mean, var = zf.mean(0), zf.var(0, unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    scale, shift = gamma * rstd, torch.randn(C, device=dev, generator=g) * 0.1 - mean * gamma * rstd
+    wh = torch.randn(nc, C, device=dev, generator=g) / 8
+    bh = torch.randn(nc, device=dev, generator=g)
+    a_f, lmap = ops.bn_relu_apply_head(z, scale, shift, wh, bh)
+    a_u = ops.bn_relu_apply(z, scale, shift)
+    assert torch.equal(a_f, a_u)
+    want = torch.einsum("bhwc,kc->bkhw", torch.relu(z.float() * scale + shift), wh) + bh.view(1, nc, 1, 1)
+    assert rel(lmap, want) < 1e-5
+    assert rel(lmap, ops.outconv_fwd(a_u, wh, bh)) < 4e-3          # the unfused head reads the bf16 activation
+    # backward
+    dl = torch.randn(B, nc, H, W, device=dev, generator=g)
+    for with_dA in (True, False):
+        dA = torch.randn(B, H, W, C, device=dev, generator=g).bfloat16() if with_dA else None
+        small = torch.empty(3, C, device=dev)
+        dz, hg = ops.bn_relu_bwd_head(z, dA, scale, shift, mean, rstd, gamma, small[:2], small[2], dl, wh)
+        # reference: materialise the head's input gradient in fp32, add, then the plain BN backward in torch
+        gin = torch.einsum("bkhw,kc->bhwc", dl, wh) + (dA.float() if with_dA else 0.0)
+        act = z.float() * scale + shift
+        gm = torch.where(act > 0, gin, torch.zeros_like(gin)).reshape(-1, C)
+        xhat = (zf - mean) * rstd
+        dgamma, dbeta = (gm * xhat).sum(0), gm.sum(0)
+        n = gm.shape[0]
+        dz_ref = (gamma * rstd) * (gm - dbeta / n - xhat * dgamma / n)
+        assert rel(dz, dz_ref.view(B, H, W, C)) < 6e-3, (shape, with_dA, rel(dz, dz_ref.view(B, H, W, C)))
+        assert rel(small[0], dgamma) < 1e-3 and rel(small[1], dbeta) < 1e-3
+        dwh = torch.einsum("bkhw,bhwc->kc", dl, torch.relu(act))
+        assert rel(hg[: nc * C].view(nc, C), dwh) < 1e-4 and rel(hg[nc * C:], dl.sum((0, 2, 3))) < 1e-4
+
+
+def test_fused_and_unfused_decoder_heads_train_alike(dev):
+    """PGUNet3 forward + backward with the heads fused into the decoder blocks vs UGP_NO_FUSED_OUTCONV=1."""
+    import ug_oracle as O
+    import ug_pg_unet_b200 as U
+
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(2, 3, 128, 128, generator=g).to(dev)
+    y = torch.randint(0, 2, (2, 1, 128, 128), generator=g).float().to(dev)
+    sd = O.seeded_state_dict(3, 3, 1, seed=3)
+    outs = []
+    for env in ("0", "1"):
+        os.environ["UGP_NO_FUSED_OUTCONV"] = env
+        try:
+            m = U.PGUNet3(3, 1).to(dev)
+            m.load_state_dict(sd)
+            m.train()
+            logits = m(x)
+            torch.nn.functional.binary_cross_entropy_with_logits(logits, y).backward()
+            outs.append((logits.detach(), {k: p.grad.clone() for k, p in m.named_parameters()}))
+        finally:
+            del os.environ["UGP_NO_FUSED_OUTCONV"]
+    assert rel(outs[0][0], outs[1][0]) < 5e-3
+    for k in outs[0][1]:
+        if k.endswith(("conv_op.0.bias", "conv_op.3.bias")):
+            continue
+        # same kernels below the heads; the two paths differ by the bf16 rounding of the head's input /
+        # input gradient, which the deep layers amplify like any other bf16 perturbation
+        assert rel(outs[0][1][k], outs[1][1][k]) < (2e-2 if k.startswith("outc") else 0.5), k
+
+
 def test_global_avg_pool_kernels(dev):
     from ug_pg_unet_b200 import ops
 

@@ -108,7 +108,10 @@ def _arena_worker(rank, world, port, overlap, out_dir):
                 if id(p) not in {id(c.weight) for c in deferred}:
                     p.grad = torch.full_like(p, float(rank + 1))
             if overlap:
-                assert all(ab.work is not None for ab in reducer.arena_buckets)   # launched from the hooks
+                # launched from the hooks - except the light tail bucket, which wait() sends together
+                # with the flat small-tensor bucket
+                assert all(ab.work is not None for ab in reducer.arena_buckets if ab is not reducer._tail_arena)
+                assert reducer._tail_arena is reducer.arena_buckets[-1] and reducer._tail_arena.work is None
             reducer.wait()
             # arena holds the SUM (the optimiser kernel applies 1/world); `.grad`s hold the mean
             for i, pk in enumerate(packs):

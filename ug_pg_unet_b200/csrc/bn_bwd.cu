@@ -34,6 +34,14 @@ struct BnBwdArgs {
   __nv_bfloat16* dz;         // pass 2 output
   int B, H, W, C;
   float inv_count;
+  // fused 1x1 head (OutConv on the activation this BatchNorm produces, UG_unet.py:294-303): the gradient
+  // of the activation gets  + sum_k dl[b][k][p] * wh[k][c]  and the head's weight / bias gradients are
+  // reduced in the same pass - the head's own backward kernel (and its 2 bytes/element of dx) disappear
+  const float* dl;           // [B][nc][H*W] fp32 gradient of the head's output map (nullable)
+  const float* wh;           // [nc][C] head weights
+  float* dwh;                // [nc][C] (+ [nc] bias gradient behind it), zeroed by the launcher
+  int HW;
+  int hw_shift;              // log2(HW) when HW is a power of two, else -1
 };
 
 constexpr int kBnThreads = 256;
@@ -83,7 +91,7 @@ __device__ __forceinline__ void block_reduce_channels(float (*red)[kBnThreads][9
 // ---------------------------------------------------------------------------
 // plain variant: no pooled gradient; one pixel x 8 channels per (thread, slot)
 // ---------------------------------------------------------------------------
-template <bool kApply>
+template <bool kApply, int kNC = 0>
 __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const BnBwdArgs a) {
   const int cg = a.C >> 3;
   const int my_cg = threadIdx.x % cg;
@@ -121,32 +129,72 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const 
   // Software pipeline: the raw 16-byte words of trip t+1 are requested BEFORE trip t is consumed.  Without
   // it every warp of the launch sits in the same phase (all loading, then all computing): measured
   // (ncu, r02) 16 warps/SM at 45 % issue utilisation and 2.4 TB/s on the 67 MB layers, ~7 us per trip.
-  constexpr int kU = BnUnroll<kApply>::v / 2;      // pixels per trip; two trips in flight
+  constexpr int kHead = kNC > 0 ? kNC : 1;
+  // pixels per trip (two trips in flight); the head variant carries 16*kNC more live registers
+  constexpr int kU = kNC > 0 ? 2 : BnUnroll<kApply>::v / 2;
   const long long stride = static_cast<long long>(gridDim.x) * rows_per_block;
   const long long step = stride * kU;
-  uint4 zA[kU], gA[kU], zB[kU], gB[kU];
-  auto fetch = [&](uint4* zr, uint4* gr, long long p) {
+  const bool has_dA = a.dA != nullptr;             // head only (the last decoder block): no tensor gradient
+  float wh[kHead][8], hacc[kHead][8], hb[kHead];
+#pragma unroll
+  for (int k = 0; k < kHead; ++k) {
+    hb[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wh[k][j] = (kNC > 0) ? __ldg(a.wh + k * a.C + c0 + j) : 0.f;
+      hacc[k][j] = 0.f;
+    }
+  }
+  struct Raw {
+    uint4 z[kU], g[kU];
+    float dl[kU][kHead];
+  };
+  Raw rA, rB;
+  auto fetch = [&](Raw& r, long long p) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long pp = p + u * stride;
       if (pp < M) {
-        zr[u] = *reinterpret_cast<const uint4*>(a.z + pp * a.C + c0);
-        gr[u] = *reinterpret_cast<const uint4*>(a.dA + pp * a.C + c0);
+        r.z[u] = *reinterpret_cast<const uint4*>(a.z + pp * a.C + c0);
+        r.g[u] = has_dA ? *reinterpret_cast<const uint4*>(a.dA + pp * a.C + c0) : make_uint4(0u, 0u, 0u, 0u);
+        if (kNC == 1) {
+          r.dl[u][0] = __ldg(a.dl + pp);              // [B][1][HW]: the map is indexed by the pixel itself
+        } else if (kNC > 1) {
+          // [B][nc][HW]: (b*nc + k)*HW + q = pixel + (b*(nc-1) + k)*HW; no division for power-of-two maps
+          const int pix = static_cast<int>(pp);
+          const int b = (a.hw_shift >= 0) ? (pix >> a.hw_shift) : pix / a.HW;
+#pragma unroll
+          for (int k = 0; k < kHead; ++k)
+            r.dl[u][k] = __ldg(a.dl + pp + static_cast<long long>(b * (kNC - 1) + k) * a.HW);
+        }
       }
     }
   };
-  auto consume = [&](const uint4* zr, const uint4* gr, long long p) {
+  auto consume = [&](const Raw& r, long long p) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long pp = p + u * stride;
       if (pp < M) {
         Vec8 o;
-        const Vec8 zv = unpack8(zr[u]);
-        const Vec8 gv = unpack8(gr[u]);
+        const Vec8 zv = unpack8(r.z[u]);
+        const Vec8 gv = unpack8(r.g[u]);
+        if (kNC > 0 && !kApply && my_cg == 0) {
+#pragma unroll
+          for (int k = 0; k < kHead; ++k) hb[k] += r.dl[u][k];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = zv.v[j];
-          const float g = (fmaf(z, sc[j], sh[j]) > 0.f) ? gv.v[j] : 0.f;
+          const float act = fmaf(z, sc[j], sh[j]);          // > 0: the ReLU passes; then also the activation
+          float gin = gv.v[j];
+          if (kNC > 0) {
+#pragma unroll
+            for (int k = 0; k < kHead; ++k) {
+              gin = fmaf(r.dl[u][k], wh[k][j], gin);
+              if (!kApply) hacc[k][j] = fmaf(r.dl[u][k], fmaxf(act, 0.f), hacc[k][j]);
+            }
+          }
+          const float g = (act > 0.f) ? gin : 0.f;
           if (!kApply) {
             acc0[j] = fmaf(g, z - kz[j], acc0[j]);   // sum g*(z-mean); * rstd at the end
             acc1[j] += g;
@@ -161,14 +209,14 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const 
     }
   };
   long long p = static_cast<long long>(blockIdx.x) * rows_per_block + my_row;
-  fetch(zA, gA, p);
+  fetch(rA, p);
   while (p < M) {
-    fetch(zB, gB, p + step);
-    consume(zA, gA, p);
+    fetch(rB, p + step);
+    consume(rA, p);
     p += step;
     if (p >= M) break;
-    fetch(zA, gA, p + step);
-    consume(zB, gB, p);
+    fetch(rA, p + step);
+    consume(rB, p);
     p += step;
   }
   __shared__ float red[2][kBnThreads][9];
@@ -177,6 +225,26 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const 
     for (int j = 0; j < 8; ++j) acc0[j] *= __ldg(a.rstd + c0 + j);
     block_reduce_channels<2>(red, acc0, acc1, cg, my_cg, my_row, rows_per_block, a.sums,
                              a.sums + a.C, c0);
+    if (kNC > 0) {
+      // head weight gradient dwh[k][c] = sum_p dl[k][p] * a[p][c]; bias gradient = sum_p dl[k][p]
+#pragma unroll
+      for (int k = 0; k < kHead; ++k) {
+        __syncthreads();
+        block_reduce_channels<1>(red, hacc[k], hacc[k], cg, my_cg, my_row, rows_per_block, a.dwh + k * a.C,
+                                 nullptr, c0);
+      }
+      __syncthreads();
+      if (my_cg == 0) {
+#pragma unroll
+        for (int k = 0; k < kHead; ++k) red[0][my_row][k] = hb[k];
+      }
+      __syncthreads();
+      if (threadIdx.x < kHead) {
+        float sum = 0.f;
+        for (int r = 0; r < rows_per_block; ++r) sum += red[0][r][threadIdx.x];
+        atomicAdd(a.dwh + kNC * a.C + threadIdx.x, sum);
+      }
+    }
   } else if (a.dbias) {
     block_reduce_channels<1>(red, acc0, acc1, cg, my_cg, my_row, rows_per_block, a.dbias, nullptr, c0);
   }
@@ -444,12 +512,18 @@ __global__ void __launch_bounds__(kBnThreads, kPoolBlocksPerSM) bn_relu_bwd_pool
   }
 }
 
-int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scale,
-                const float* shift, const float* mean, const float* rstd,
-                const float* gamma, int B, int H, int W, int C, float* sums,
-                float* dbias, void* dz, cudaStream_t stream) {
-  UGP_REQUIRE(z && (dA || dP) && scale && shift && mean && rstd && gamma && sums && dz,
+int bn_relu_bwd_ex(const void* z, const void* dA, const void* dP, const float* scale,
+                   const float* shift, const float* mean, const float* rstd,
+                   const float* gamma, int B, int H, int W, int C, float* sums,
+                   float* dbias, void* dz, const float* head_dl, const float* head_w, int nc,
+                   float* head_grads, cudaStream_t stream) {
+  UGP_REQUIRE(z && (dA || dP || head_dl) && scale && shift && mean && rstd && gamma && sums && dz,
               "bn_relu_bwd: null pointer");
+  if (head_dl) {
+    UGP_REQUIRE(head_w && head_grads && (nc == 1 || nc == 2) && dP == nullptr,
+                "bn_relu_bwd: the fused head takes 1 or 2 classes and no pooled gradient (nc = %d)", nc);
+    UGP_REQUIRE(static_cast<long long>(B) * H * W < (1LL << 31), "bn_relu_bwd: too many pixels for the fused head");
+  }
   UGP_REQUIRE(C % 64 == 0 && C <= 2048 && kBnThreads % (C / 8) == 0,
               "bn_relu_bwd: C %d unsupported", C);
   BnBwdArgs a;
@@ -461,6 +535,11 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
   a.B = B; a.H = H; a.W = W; a.C = C;
   const long long M = static_cast<long long>(B) * H * W;
   a.inv_count = 1.f / static_cast<float>(M);
+  a.dl = head_dl; a.wh = head_w; a.dwh = head_grads; a.HW = H * W;
+  a.hw_shift = -1;
+  for (int sft = 0; sft < 31; ++sft)
+    if ((1 << sft) == a.HW) a.hw_shift = sft;
+  if (head_dl) UGP_CHECK_CUDA(cudaMemsetAsync(head_grads, 0, sizeof(float) * (static_cast<size_t>(nc) * C + nc), stream));
   const int rows_per_block = kBnThreads / (C / 8);
   if (dbias == sums + 2 * C) {          // the engine's [3][C] block: one fill instead of two
     UGP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 3 * C, stream));
@@ -496,12 +575,30 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
     long long blocks = (M + rows_per_block * g_bn_min_pixels - 1) / (rows_per_block * g_bn_min_pixels);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (!g_bn_skip_reduce) bn_relu_bwd_plain_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
-    UGP_CHECK_CUDA(cudaGetLastError());
-    bn_relu_bwd_plain_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+    if (head_dl && nc == 1) {
+      bn_relu_bwd_plain_kernel<false, 1><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      UGP_CHECK_CUDA(cudaGetLastError());
+      bn_relu_bwd_plain_kernel<true, 1><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+    } else if (head_dl) {
+      bn_relu_bwd_plain_kernel<false, 2><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      UGP_CHECK_CUDA(cudaGetLastError());
+      bn_relu_bwd_plain_kernel<true, 2><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+    } else {
+      if (!g_bn_skip_reduce) bn_relu_bwd_plain_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      UGP_CHECK_CUDA(cudaGetLastError());
+      bn_relu_bwd_plain_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+    }
   }
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
+}
+
+int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scale,
+                const float* shift, const float* mean, const float* rstd,
+                const float* gamma, int B, int H, int W, int C, float* sums,
+                float* dbias, void* dz, cudaStream_t stream) {
+  return bn_relu_bwd_ex(z, dA, dP, scale, shift, mean, rstd, gamma, B, H, W, C, sums, dbias, dz, nullptr, nullptr,
+                        0, nullptr, stream);
 }
 
 }  // namespace ugp

@@ -20,6 +20,11 @@ int bn_eval_coeffs(int, const float*, const float*, const float*, const float*, 
                    float*, cudaStream_t);
 int bn_relu_apply(const void*, const float*, const float*, int, int, int, int, void*, void*,
                   cudaStream_t);
+int bn_relu_apply_head(const void*, const float*, const float*, int, int, int, int, const float*, const float*, int,
+                       void*, float*, cudaStream_t);
+int bn_relu_bwd_ex(const void*, const void*, const void*, const float*, const float*, const float*, const float*,
+                   const float*, int, int, int, int, float*, float*, void*, const float*, const float*, int, float*,
+                   cudaStream_t);
 int maxpool2x2(const void*, int, int, int, int, void*, int*, cudaStream_t);
 int maxpool2x2_bwd(const void*, const void*, int, int, int, int, void*, cudaStream_t);
 int upsample2x(const void*, int, int, int, int, void*, cudaStream_t);
@@ -120,6 +125,17 @@ int ugp_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float
 int ugp_bn_relu_apply(const void* z, const float* scale, const float* shift, int B, int H, int W,
                       int C, void* a, void* pooled, void* stream) {
   return ugp::bn_relu_apply(z, scale, shift, B, H, W, C, a, pooled, S(stream));
+}
+int ugp_bn_relu_apply_head(const void* z, const float* scale, const float* shift, int B, int H, int W, int C,
+                           const float* wh, const float* bh, int nc, void* a, float* lmap, void* stream) {
+  return ugp::bn_relu_apply_head(z, scale, shift, B, H, W, C, wh, bh, nc, a, lmap, S(stream));
+}
+int ugp_bn_relu_bwd_head(const void* z, const void* dA, const float* scale, const float* shift, const float* mean,
+                         const float* rstd, const float* gamma, int B, int H, int W, int C, const float* head_dl,
+                         const float* head_w, int nc, float* sums, float* dbias, void* dz, float* head_grads,
+                         void* stream) {
+  return ugp::bn_relu_bwd_ex(z, dA, nullptr, scale, shift, mean, rstd, gamma, B, H, W, C, sums, dbias, dz, head_dl,
+                             head_w, nc, head_grads, S(stream));
 }
 int ugp_bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scale,
                     const float* shift, const float* mean, const float* rstd, const float* gamma,

@@ -144,6 +144,78 @@ __global__ void bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ z,
   }
 }
 
+// a = relu(z*scale + shift) AND the 1x1 head on it (OutConv, UG_unet_parts.py:84-91 applied to a decoder
+// output, UG_unet.py:294-297): lmap[b][k][p] = bh[k] + sum_c wh[k][c] * a[p][c] (fp32 NCHW), computed from
+// the fp32 activation while it is in registers - the head no longer re-reads the activation from HBM.
+// One thread = one pixel x 8 channels; the C/8 <= 32 lanes of a pixel are adjacent, the channel sum is a
+// butterfly over them.
+template <int kNC>
+__global__ void __launch_bounds__(256)
+bn_relu_apply_head_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
+                          const float* __restrict__ shift, long long M, int C, int HW,
+                          const float* __restrict__ wh, const float* __restrict__ bh,
+                          __nv_bfloat16* __restrict__ a, float* __restrict__ lmap) {
+  const int cg = C >> 3;                       // power of two, 8..32 (checked by the launcher)
+  const int cg_shift = 31 - __clz(cg);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long total = M * cg;
+  const int lane = threadIdx.x & 31;
+  const int g = lane & (cg - 1);               // blockDim and the grid stride are multiples of 32 >= cg
+  const int c0 = g * 8;
+  float sc[8], sh[8], w[kNC][8], bias[kNC];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + c0 + j); sh[j] = __ldg(shift + c0 + j); }
+#pragma unroll
+  for (int k = 0; k < kNC; ++k) {
+    bias[k] = __ldg(bh + k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[k][j] = __ldg(wh + k * C + c0 + j);
+  }
+  // warp-uniform loop bounds: every lane takes part in the shuffles, out-of-range lanes carry zeros
+  for (long long base = blockIdx.x * static_cast<long long>(blockDim.x) + (threadIdx.x - lane); base < total;
+       base += 2 * stride) {
+    const long long i1 = base + lane, i2 = base + stride + lane;
+    const bool v1 = i1 < total, v2 = i2 < total;
+    Vec8 x1, x2;
+    if (v1) x1 = load8(z + i1 * 8);
+    if (v2) x2 = load8(z + i2 * 8);
+    float d1[kNC], d2[kNC];
+#pragma unroll
+    for (int k = 0; k < kNC; ++k) { d1[k] = 0.f; d2[k] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x1.v[j] = v1 ? bn_relu_val(x1.v[j], sc[j], sh[j]) : 0.f;
+      x2.v[j] = v2 ? bn_relu_val(x2.v[j], sc[j], sh[j]) : 0.f;
+#pragma unroll
+      for (int k = 0; k < kNC; ++k) { d1[k] = fmaf(w[k][j], x1.v[j], d1[k]); d2[k] = fmaf(w[k][j], x2.v[j], d2[k]); }
+    }
+    if (v1) store8(a + i1 * 8, x1);
+    if (v2) store8(a + i2 * 8, x2);
+#pragma unroll
+    for (int k = 0; k < kNC; ++k) {
+      for (int off = cg >> 1; off > 0; off >>= 1) {
+        d1[k] += __shfl_xor_sync(0xffffffffu, d1[k], off);
+        d2[k] += __shfl_xor_sync(0xffffffffu, d2[k], off);
+      }
+    }
+    if (g == 0) {
+      // [B][nc][HW]: (b*nc + k)*HW + q = pixel + (b*(nc-1) + k)*HW; one class needs no image index at all
+      if (v1) {
+        const long long pix = i1 >> cg_shift;
+        const int b = (kNC == 1) ? 0 : static_cast<int>(pix / HW);
+#pragma unroll
+        for (int k = 0; k < kNC; ++k) lmap[pix + static_cast<long long>(b * (kNC - 1) + k) * HW] = d1[k] + bias[k];
+      }
+      if (v2) {
+        const long long pix = i2 >> cg_shift;
+        const int b = (kNC == 1) ? 0 : static_cast<int>(pix / HW);
+#pragma unroll
+        for (int k = 0; k < kNC; ++k) lmap[pix + static_cast<long long>(b * (kNC - 1) + k) * HW] = d2[k] + bias[k];
+      }
+    }
+  }
+}
+
 // Stand-alone 2x2/stride-2 max pool on NHWC bf16 with PyTorch's index
 // convention (plane-local h*W+w, first maximum wins, scan order (0,0),(0,1),
 // (1,0),(1,1)); indices are optional.  Reference: UG_unet_parts.py:49.
@@ -441,6 +513,24 @@ int bn_relu_apply(const void* z, const float* scale, const float* shift, int B, 
         static_cast<const __nv_bfloat16*>(z), scale, shift, B, H, W, C,
         static_cast<__nv_bfloat16*>(a), nullptr);
   }
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
+}
+
+int bn_relu_apply_head(const void* z, const float* scale, const float* shift, int B, int H, int W, int C,
+                       const float* wh, const float* bh, int nc, void* a, float* lmap, cudaStream_t stream) {
+  UGP_REQUIRE(z && scale && shift && wh && bh && a && lmap, "bn_relu_apply_head: null pointer");
+  UGP_REQUIRE(C == 64 || C == 128 || C == 256, "bn_relu_apply_head: C must be 64, 128 or 256 (got %d)", C);
+  UGP_REQUIRE(nc == 1 || nc == 2, "bn_relu_apply_head: 1 or 2 classes (got %d)", nc);
+  const long long M = static_cast<long long>(B) * H * W;
+  const long long total = M * (C / 8);
+  const int grid = grid_for(total, 256);
+  if (nc == 1)
+    bn_relu_apply_head_kernel<1><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z), scale, shift, M, C,
+                                                           H * W, wh, bh, static_cast<__nv_bfloat16*>(a), lmap);
+  else
+    bn_relu_apply_head_kernel<2><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z), scale, shift, M, C,
+                                                           H * W, wh, bh, static_cast<__nv_bfloat16*>(a), lmap);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }

@@ -202,8 +202,10 @@ class CBRSaved:
 
 
 def cbr_forward(srcs: Sequence[torch.Tensor], taps: int, conv: nn.Conv2d, bn: nn.BatchNorm2d,
-                packs: PackedWeights, emit_pool: bool, save: bool):
-    """One Conv -> BN -> ReLU unit.  Returns (a, pooled or None, CBRSaved or None)."""
+                packs: PackedWeights, emit_pool: bool, save: bool, head=None):
+    """One Conv -> BN -> ReLU unit.  Returns (a, pooled or None, CBRSaved or None).
+    `head` = (w [nc, C], b [nc]) fp32: train mode only, the 1x1 head on the activation is computed in the
+    BN/ReLU pass and returned in place of the pooled tensor."""
     src0 = srcs[0]
     src1 = srcs[1] if len(srcs) > 1 else None
     B, H, W, _ = src0.shape
@@ -223,7 +225,9 @@ def cbr_forward(srcs: Sequence[torch.Tensor], taps: int, conv: nn.Conv2d, bn: nn
         ops.bn_finalize(stats, B * H * W, bn.weight.detach(), bn.bias.detach(), float(bn.eps), momentum,
                         bn.running_mean if track else None, bn.running_var if track else None,
                         bn.num_batches_tracked if track else None, coef[0], coef[1], coef[2], coef[3])
-        if emit_pool:
+        if head is not None:
+            a, p = ops.bn_relu_apply_head(z, coef[0], coef[1], head[0], head[1])
+        elif emit_pool:
             a, p = ops.bn_relu_apply(z, coef[0], coef[1], pool=True)
         else:
             a, p = ops.bn_relu_apply(z, coef[0], coef[1]), None
@@ -238,8 +242,10 @@ def cbr_forward(srcs: Sequence[torch.Tensor], taps: int, conv: nn.Conv2d, bn: nn
 
 
 def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch.Tensor], conv: nn.Conv2d,
-                 bn: nn.BatchNorm2d, packs: PackedWeights, need_dgrad: bool):
-    """Backward of one unit.  Returns (d_srcs list or None, (dW, dbias, dgamma, dbeta))."""
+                 bn: nn.BatchNorm2d, packs: PackedWeights, need_dgrad: bool, head=None):
+    """Backward of one unit.  Returns (d_srcs list or None, (dW, dbias, dgamma, dbeta)).
+    `head` = (dl [B, nc, H, W] fp32, w [nc, C]): gradient of the fused 1x1 head's map; its weight / bias
+    gradients are left in `head[2]` (a list the caller reads)."""
     src0 = saved.srcs[0]
     src1 = saved.srcs[1] if len(saved.srcs) > 1 else None
     cout = conv.out_channels
@@ -249,8 +255,13 @@ def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch
     small = torch.empty((3, cout), dtype=torch.float32, device=dev)   # dgamma, dbeta, dbias (kernel-zeroed)
     if _WHATIF_POOL_AS_PLAIN and dA is not None:
         dP = None
-    dz = ops.bn_relu_bwd(saved.z, dA, dP, coef[0], coef[1], coef[2], coef[3], bn.weight.detach(),
-                         small[:2], small[2])
+    if head is not None:
+        dz, hg = ops.bn_relu_bwd_head(saved.z, dA, coef[0], coef[1], coef[2], coef[3], bn.weight.detach(),
+                                      small[:2], small[2], head[0], head[1])
+        head[2].append(hg)
+    else:
+        dz = ops.bn_relu_bwd(saved.z, dA, dP, coef[0], coef[1], coef[2], coef[3], bn.weight.detach(),
+                             small[:2], small[2])
     kdim = sum(s.shape[3] for s in saved.srcs)
     dwp = packs.dwp_buffer(saved.taps * kdim * cout, dev)
     side = WgradOverlap.stream if packs.defer else None
@@ -313,9 +324,16 @@ class DoubleConvFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, mod, kind: str, emit_pool: bool, x, skip, *params):
+    def forward(ctx, mod, kind: str, emit_pool: bool, head_mod, x, skip, *params):
+        """`head_mod`: an nn.Conv2d(C, nc, 1) applied to this block's output (the PGUNet decoder heads,
+        UG_unet.py:294-297) fused into the second BN/ReLU pass (train mode); its weight and bias are the last
+        two entries of `params` and the head's map is returned beside the activation."""
         conv1, bn1, conv2, bn2 = mod.conv_op[0], mod.conv_op[1], mod.conv_op[3], mod.conv_op[4]
         need_grad = any(ctx.needs_input_grad)
+        head = None
+        if head_mod is not None:
+            hw, hb = params[8], params[9]
+            head = (hw.detach().reshape(hw.shape[0], -1).contiguous(), hb.detach().contiguous())
         pre = None
         if kind == "first":
             srcs, taps = [ops.im2col_first(x)], 1
@@ -331,12 +349,14 @@ class DoubleConvFn(torch.autograd.Function):
         else:
             srcs, taps = [x], 9
         a1, _, s1 = cbr_forward(srcs, taps, conv1, bn1, mod._packs[0], False, need_grad)
-        a2, p2, s2 = cbr_forward([a1], 9, conv2, bn2, mod._packs[1], emit_pool, need_grad)
+        a2, p2, s2 = cbr_forward([a1], 9, conv2, bn2, mod._packs[1], emit_pool, need_grad, head=head)
         ctx.mod, ctx.kind, ctx.emit_pool = mod, kind, emit_pool
         ctx.s1, ctx.s2, ctx.pre = s1, s2, pre
-        ctx.x_needs_grad = kind not in ("first", "col") and ctx.needs_input_grad[3]
-        ctx.skip_needs_grad = skip is not None and ctx.needs_input_grad[4]
-        if emit_pool:
+        ctx.head_w = head[0] if head is not None else None
+        ctx.head_shape = tuple(params[8].shape) if head is not None else None
+        ctx.x_needs_grad = kind not in ("first", "col") and ctx.needs_input_grad[4]
+        ctx.skip_needs_grad = skip is not None and ctx.needs_input_grad[5]
+        if emit_pool or head is not None:
             return a2, p2
         return a2
 
@@ -349,7 +369,14 @@ class DoubleConvFn(torch.autograd.Function):
                                "call .train() before a training step or run inference under torch.no_grad()")
         dA = dA.contiguous() if dA is not None else None
         dP = dP.contiguous() if dP is not None else None
-        d1, g2 = cbr_backward(ctx.s2, dA, dP, conv2, bn2, mod._packs[1], True)
+        head = None
+        if ctx.head_w is not None:
+            # the second output is the head's map: its gradient arrives in the pooled-gradient slot
+            dl, dP = dP, None
+            head = (dl.float().contiguous(), ctx.head_w, []) if dl is not None else None
+            if head is None and dA is None:
+                raise RuntimeError("DoubleConvFn.backward: no gradient reached the block")
+        d1, g2 = cbr_backward(ctx.s2, dA, dP, conv2, bn2, mod._packs[1], True, head=head)
         need_in = ctx.x_needs_grad or ctx.skip_needs_grad
         if _WHATIF_SKIP_BN1_REDUCE:
             set_option("bn_skip_reduce", 1)
@@ -368,8 +395,16 @@ class DoubleConvFn(torch.autograd.Function):
             else:
                 dx = d0[0]
         ctx.s1 = ctx.s2 = ctx.pre = None
-        # params order: conv1.weight, conv1.bias, bn1.weight, bn1.bias, conv2.weight, ...
-        return (None, None, None, dx, dskip, g1[0], g1[1], g1[2], g1[3], g2[0], g2[1], g2[2], g2[3])
+        # params order: conv1.weight, conv1.bias, bn1.weight, bn1.bias, conv2.weight, ... (, head.weight, head.bias)
+        grads = (None, None, None, None, dx, dskip, g1[0], g1[1], g1[2], g1[3], g2[0], g2[1], g2[2], g2[3])
+        if ctx.head_w is not None:
+            if head is not None:
+                hg = head[2][0]
+                nw = ctx.head_w.numel()
+                grads = grads + (hg[:nw].view(ctx.head_shape), hg[nw:])
+            else:
+                grads = grads + (None, None)
+        return grads
 
 
 def double_conv_params(mod) -> Tuple[torch.Tensor, ...]:
@@ -377,8 +412,23 @@ def double_conv_params(mod) -> Tuple[torch.Tensor, ...]:
     return (c1.weight, c1.bias, b1.weight, b1.bias, c2.weight, c2.bias, b2.weight, b2.bias)
 
 
-def run_double_conv(mod, kind: str, x, skip=None, emit_pool: bool = False):
-    return DoubleConvFn.apply(mod, kind, emit_pool, x, skip, *double_conv_params(mod))
+def head_is_fusable(mod, head_conv) -> bool:
+    """The 1x1 head of a decoder block can ride in the block's second BN/ReLU pass (forward) and
+    BatchNorm backward: train-mode BatchNorm (in eval mode BN is folded into the conv epilogue and the head
+    runs as ugp_outconv_fwd), a plain nn.Conv2d(C, nc, 1) with bias on CUDA, C / nc the kernels cover."""
+    bn2 = mod.conv_op[4]
+    return (isinstance(head_conv, nn.Conv2d) and tuple(head_conv.kernel_size) == (1, 1) and head_conv.bias is not None
+            and bn2.training and head_conv.weight.is_cuda and head_conv.weight.dtype == torch.float32
+            and head_conv.in_channels == bn2.num_features
+            and ops.head_fusable(bn2.num_features, head_conv.out_channels)
+            and os.environ.get("UGP_NO_FUSED_OUTCONV", "0") != "1")
+
+
+def run_double_conv(mod, kind: str, x, skip=None, emit_pool: bool = False, head=None):
+    """`head`: nn.Conv2d 1x1 fused into the block (see head_is_fusable) -> returns (activation, head map)."""
+    if head is not None:
+        return DoubleConvFn.apply(mod, kind, False, head, x, skip, *double_conv_params(mod), head.weight, head.bias)
+    return DoubleConvFn.apply(mod, kind, emit_pool, None, x, skip, *double_conv_params(mod))
 
 
 # ----------------------------------------------------------------------------- ConvTranspose2d(k=2, s=2)

@@ -86,7 +86,7 @@ def _nb(*ts) -> float:
 
 def check(rc: int, what: str) -> None:
     _check_rc(rc, what)
-    if what not in ("ugp_conv_gemm_bf16", "ugp_conv_wgrad_bf16"):
+    if what not in ("ugp_conv_gemm_bf16", "ugp_conv_wgrad_bf16", "ugp_bn_relu_bwd_head"):
         _count(2 if what == "ugp_bn_relu_bwd" else 1)
 
 
@@ -353,6 +353,49 @@ def bn_relu_apply(z, scale, shift, pool: bool = False, out=None, pooled=None):
                                      _ptr(pooled) if pool else None, _stream())
     check(rc, "ugp_bn_relu_apply")
     return (out, pooled) if pool else out
+
+
+def bn_relu_apply_head(z, scale, shift, head_w, head_b):
+    """bn_relu_apply + the 1x1 head on the activation in one pass; see ugp_bn_relu_apply_head.
+    head_w fp32 [nc, C], head_b fp32 [nc] -> (a NHWC bf16, lmap fp32 NCHW [B, nc, H, W])."""
+    _req(z, bf16, "z")
+    B, H, W, Cn = z.shape
+    nc = head_w.shape[0]
+    out = torch.empty_like(z)
+    lmap = torch.empty((B, nc, H, W), dtype=torch.float32, device=z.device)
+    with _timed("bn_relu_apply_head", 0.0, _nb(z, out, lmap)):
+        rc = lib().ugp_bn_relu_apply_head(_ptr(z), _ptr(scale), _ptr(shift), B, H, W, Cn,
+                                          _ptr(_req(head_w, torch.float32, "head_w")),
+                                          _ptr(_req(head_b, torch.float32, "head_b")), nc, _ptr(out), _ptr(lmap),
+                                          _stream())
+    check(rc, "ugp_bn_relu_apply_head")
+    return out, lmap
+
+
+def head_fusable(C: int, nc: int) -> bool:
+    """Shapes ugp_bn_relu_apply_head / ugp_bn_relu_bwd_head cover."""
+    return C in (64, 128, 256) and nc in (1, 2)
+
+
+def bn_relu_bwd_head(z, dA, scale, shift, mean, rstd, gamma, sums, dbias, head_dl, head_w):
+    """bn_relu_bwd with the fused head gradient; see ugp_bn_relu_bwd_head.
+    Returns (dz, head_grads fp32 [nc*C + nc]: weight gradient then bias gradient)."""
+    _req(z, bf16, "z")
+    B, H, W, Cn = z.shape
+    nc = head_w.shape[0]
+    _req(head_dl, torch.float32, "head_dl")
+    assert tuple(head_dl.shape) == (B, nc, H, W), head_dl.shape
+    dz = torch.empty_like(z)
+    hg = torch.empty((nc * Cn + nc,), dtype=torch.float32, device=z.device)
+    with _timed("bn_relu_bwd_head", 0.0, 2 * _nb(z, dA, head_dl) + _nb(dz)):
+        rc = lib().ugp_bn_relu_bwd_head(_ptr(z), _ptr(_opt(dA, bf16, "dA")), _ptr(scale), _ptr(shift), _ptr(mean),
+                                        _ptr(rstd), _ptr(gamma), B, H, W, Cn, _ptr(head_dl),
+                                        _ptr(_req(head_w, torch.float32, "head_w")), nc,
+                                        _ptr(_req(sums, torch.float32, "sums")),
+                                        _ptr(_opt(dbias, torch.float32, "dbias")), _ptr(dz), _ptr(hg), _stream())
+    check(rc, "ugp_bn_relu_bwd_head")
+    _count(2)
+    return dz, hg
 
 
 def bn_relu_bwd(z, dA, dP, scale, shift, mean, rstd, gamma, sums, dbias, dz=None):

@@ -15,6 +15,7 @@ tests).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -55,7 +56,7 @@ class GradBucketReducer:
 
     def __init__(self, params: Sequence[torch.nn.Parameter], bucket_mb: float = 16.0,
                  process_group=None, overlap: bool = True, conv_packs=None, arena: Optional[torch.Tensor] = None,
-                 average: bool = True):
+                 average: bool = True, tail_mb: Optional[float] = None):
         """`conv_packs` / `arena`: the deferred convolutions and their flat packed-gradient arena, in
         arena order; their weights are skipped in `params` (they get no `.grad`).
         `average=False`: `.grad` is left pointing at the SUM over ranks inside the flat bucket (no
@@ -85,6 +86,7 @@ class GradBucketReducer:
         self._hooks = []
         self._stream = None
         self.arena_buckets: List[_ArenaBucket] = []
+        self._tail_arena: Optional[_ArenaBucket] = None
         self._packs = list(conv_packs or [])
         if self._packs:
             cur_p, start, off = [], 0, 0
@@ -99,6 +101,28 @@ class GradBucketReducer:
                     cur_p, start = [], off
             if cur_p:
                 self.arena_buckets.append(_ArenaBucket(cur_p, arena[start:off]))
+            # Light tail: the LAST bucket cannot start before backward ends and the optimiser waits for it,
+            # so its all-reduce is exposed.  Keep it to the packs that finish last (<= tail_mb of gradients;
+            # the first layers of the network are small) and give the rest to an earlier bucket that still
+            # overlaps the remaining backward.  It is launched from wait() in ONE coalesced NCCL call together
+            # with the flat small-tensor bucket.
+            tail_mb = float(os.environ.get("UGP_DP_TAIL_MB", "2.0")) if tail_mb is None else tail_mb
+            tail_cap = int(tail_mb * 1024 * 1024 / 4)
+            last = self.arena_buckets[-1]
+            if tail_cap > 0 and len(last.packs) > 1 and last.flat.numel() > tail_cap:
+                keep, n_keep = [], 0
+                for pk in reversed(last.packs):
+                    n = pk.conv.weight.numel()
+                    if keep and n_keep + n > tail_cap:
+                        break
+                    keep.insert(0, pk)
+                    n_keep += n
+                if len(keep) < len(last.packs):
+                    head = last.packs[: len(last.packs) - len(keep)]
+                    n_head = last.flat.numel() - n_keep
+                    self.arena_buckets[-1] = _ArenaBucket(head, last.flat[:n_head])
+                    self.arena_buckets.append(_ArenaBucket(keep, last.flat[n_head:]))
+            self._tail_arena = self.arena_buckets[-1] if (tail_cap > 0 and len(self.arena_buckets) > 1) else None
             for ab in self.arena_buckets:
                 for pk in ab.packs:
                     self._owner[id(pk)] = ab
@@ -122,14 +146,14 @@ class GradBucketReducer:
         if dev.type != "cuda":
             return _null()
         if self._stream is None:
-            self._stream = torch.cuda.Stream(device=dev, priority=-1)
+            self._stream = torch.cuda.Stream(device=dev, priority=_comm_priority())
         self._stream.wait_stream(torch.cuda.current_stream(dev))
         return torch.cuda.stream(self._stream)
 
     def _on_pack_ready(self, pk):
         ab = self._owner[id(pk)]
         ab.pending -= 1
-        if ab.pending == 0:
+        if ab.pending == 0 and ab is not self._tail_arena:       # the tail goes out from wait(), coalesced
             self._launch_arena(ab)
 
     def _launch_arena(self, ab: _ArenaBucket):
@@ -140,7 +164,7 @@ class GradBucketReducer:
     def _on_grad_ready(self, p):
         b = self._owner[p]
         b.pending -= 1
-        if b.pending == 0:
+        if b.pending == 0 and not (b is self.buckets[-1] and self._tail_arena is not None):
             self._launch(b)
 
     def _launch(self, b: _Bucket):
@@ -148,7 +172,7 @@ class GradBucketReducer:
         dev = grads[0].device
         if dev.type == "cuda":
             if self._stream is None:
-                self._stream = torch.cuda.Stream(device=dev, priority=-1)
+                self._stream = torch.cuda.Stream(device=dev, priority=_comm_priority())
             self._stream.wait_stream(torch.cuda.current_stream(dev))
             ctx = torch.cuda.stream(self._stream)
         else:
@@ -160,12 +184,28 @@ class GradBucketReducer:
             b.work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             b.flat = flat
 
+    def _launch_tail(self, ab: _ArenaBucket, b: _Bucket):
+        """The exposed end of the exchange as ONE NCCL launch: the light last arena bucket and the flat
+        bucket of the small tensors (biases, BatchNorm affine, heads), coalesced."""
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b.params]
+        with self._side_stream_ctx(ab.flat.device):
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            with dist._coalescing_manager(group=self.group, device=ab.flat.device, async_ops=True) as cm:
+                dist.all_reduce(ab.flat, op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            ab.work = b.work = cm
+            b.flat = flat
+
     # -- after backward --
     def wait(self):
         """Finish every bucket and write the averaged gradients back into `.grad`."""
         if self.world_size == 1:
             self.reset()
             return
+        tail = self._tail_arena
+        if tail is not None and tail.work is None and self.buckets and self.buckets[-1].work is None \
+                and tail.flat.is_cuda:
+            self._launch_tail(tail, self.buckets[-1])
         for ab in self.arena_buckets:
             if ab.work is None:
                 self._launch_arena(ab)
@@ -203,6 +243,13 @@ class GradBucketReducer:
         self._hooks = []
         for pk in self._packs:
             pk.on_grad_ready = None
+
+
+def _comm_priority() -> int:
+    """Priority of the stream the all-reduces are queued on.  High (-1, the default): a bucket's
+    collective starts as soon as SMs free up, so the exchange finishes under the remaining backward;
+    UGP_NCCL_STREAM_PRIORITY=0 lets the compute kernels win the SMs instead (A/B switch)."""
+    return int(os.environ.get("UGP_NCCL_STREAM_PRIORITY", "-1"))
 
 
 class _null:

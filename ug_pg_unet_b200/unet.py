@@ -82,15 +82,24 @@ class _PGUNetBase(nn.Module):
         `resolution` (optional) resizes the input inside the first-layer packer."""
         feats = self.encode(x, resolution=resolution)
         cur = feats[-1]
-        dec = []
         n = len(feats) - 1
-        for j, name in enumerate(self._ups):
-            cur = getattr(self, name).conv._run("up", cur, feats[n - 1 - j])
-            dec.append(cur)
         heads = [getattr(self, h) for h in self._heads]
-        if len(heads) == 1:
-            return heads[0]._run(dec[-1])
-        maps = [h._run(d) for h, d in zip(heads, dec)]
+        # head j reads decoder output j (a single head reads the last one); in train mode it is computed
+        # inside the block's second BN/ReLU pass (forward) and BatchNorm backward (engine.head_is_fusable)
+        head_of = {len(self._ups) - 1: heads[0]} if len(heads) == 1 else dict(enumerate(heads))
+        maps = []
+        for j, name in enumerate(self._ups):
+            dc = getattr(self, name).conv
+            h = head_of.get(j)
+            if h is not None and engine.head_is_fusable(dc, h.conv):
+                cur, lmap = dc._run("up", cur, feats[n - 1 - j], head=h.conv)
+                maps.append(lmap)
+            else:
+                cur = dc._run("up", cur, feats[n - 1 - j])
+                if h is not None:
+                    maps.append(h._run(cur))
+        if len(maps) == 1:
+            return maps[0]
         return engine.HeadCombineFn.apply(*maps)
 
 

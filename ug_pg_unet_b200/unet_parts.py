@@ -67,8 +67,8 @@ class DoubleConv(nn.Module):
                        PackedWeights(self.conv_op[3], need_dgrad=True))
 
     # -- internal entry points used by Down / Up / PGUNet (NHWC bf16 in/out) --
-    def _run(self, kind, x, skip=None, emit_pool=False):
-        return run_double_conv(self, kind, x, skip, emit_pool)
+    def _run(self, kind, x, skip=None, emit_pool=False, head=None):
+        return run_double_conv(self, kind, x, skip, emit_pool, head=head)
 
     def forward(self, x):
         _require_cuda(x, "DoubleConv")
