@@ -263,6 +263,12 @@ int ugp_rmsprop_conv_packed(float* const* w, float* const* square_avgs, float* c
                             int n_tensors, float lr, float alpha, float eps, float weight_decay,
                             float grad_scale, void* stream);
 
+/* Joint flips of loader bytes on the device: TF.hflip / TF.vflip of MoNuSegImprove/monuseg_dataset.py:150-158
+ * (one decision per sample, applied to image and mask alike).  x, out: [B][H][W][C] bytes (out != x);
+ * flags: B device bytes, bit 0 = horizontal flip, bit 1 = vertical flip.  Pure byte moves: bit-exact. */
+int ugp_flip_u8(const unsigned char* x, const unsigned char* flags, int B, int H, int W, int C, unsigned char* out,
+                void* stream);
+
 /* BatchNorm + ReLU of a conv output (as ugp_bn_relu_apply) with the 1x1 head fused: the decoder outputs of
  * PGUNet2..4 each feed an OutConv (UG_unet_parts.py:84-91; UG_unet.py:214-217, 250-252, 294-297).
  * lmap[b][k][p] = bh[k] + sum_c wh[k][c] * a[p][c], fp32 NCHW [B][nc][H][W], from the fp32 activation while

@@ -658,6 +658,37 @@ def test_fused_and_unfused_decoder_heads_train_alike(dev):
         assert rel(outs[0][1][k], outs[1][1][k]) < (2e-2 if k.startswith("outc") else 0.5), k
 
 
+def test_no_kernel_writes_outside_its_output_buffers(dev):
+    """Guard bands around every buffer the op wrappers hand to a kernel (tools/sanitize.py --guards): one
+    small launch of every kernel family - per-tap / pair / halo convolutions, both weight-gradient kernels,
+    transposed convolution, element-wise, reductions, optimisers, the fused heads - and no byte of a 4 KiB
+    margin below or above an output may change.  (compute-sanitizer is closed on the GPU pool.)"""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize.py"), "--guards"], capture_output=True,
+                       text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "sanitize.py --guards: OK" in r.stdout
+
+
+def test_joint_flips_of_loader_bytes_are_bit_exact(dev):
+    """ugp_flip_u8 against torch.flip (= TF.hflip / TF.vflip of monuseg_dataset.py:150-158) per sample."""
+    from ug_pg_unet_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(4)
+    img = torch.randint(0, 256, (8, 37, 53, 3), device=dev, dtype=torch.uint8, generator=g)
+    msk = torch.randint(0, 2, (8, 1, 37, 53), device=dev, dtype=torch.uint8, generator=g)
+    flags = torch.arange(8, device=dev, dtype=torch.uint8) % 4
+    fi = ops.flip_u8(img, flags)
+    fm = ops.flip_u8(msk.reshape(8, 37, 53, 1).contiguous(), flags).reshape(msk.shape)
+    for b in range(8):
+        dims_i = [d for d, bit in ((1, 1), (0, 2)) if int(flags[b]) & bit]          # [H, W, C]: W = dim 1, H = dim 0
+        assert torch.equal(fi[b], torch.flip(img[b], dims_i) if dims_i else img[b])
+        dims_m = [d for d, bit in ((2, 1), (1, 2)) if int(flags[b]) & bit]          # [1, H, W]
+        assert torch.equal(fm[b], torch.flip(msk[b], dims_m) if dims_m else msk[b])
+    a, m2, fl = ops.joint_flip_u8(img, msk, generator=g)
+    assert a.shape == img.shape and m2.shape == msk.shape and fl.shape == (8,)
+
+
 def test_global_avg_pool_kernels(dev):
     from ug_pg_unet_b200 import ops
 

@@ -239,6 +239,99 @@ def measure_herlev(name: str, dev) -> dict:
     return out
 
 
+def measure_stock_gpu(name: str, dev, mode: str) -> dict:
+    """The reference's own step in STOCK PyTorch on the GPU (tools/stock_torch_step.StockPGUNet: nn.Conv2d /
+    nn.BatchNorm2d / F.max_pool2d / F.interpolate, cuDNN kernels) on the fixture's weights and inputs, in
+    `mode` = "fp32" (TF32 off), "tf32" (PyTorch's default on this GPU) or "bf16" (autocast + channels_last):
+    how far the reference's OWN GPU paths land from the fp32 CPU fixture."""
+    import torch.nn.functional as F
+    import ug_oracle as O
+    import stock_torch_step as S
+
+    fx = torch.load(os.path.join(GOLDEN, name + ".pt"))
+    stage, nc = fx["stage"], fx["nc"]
+    x, y = regenerate_inputs(fx)
+    sd = O.seeded_state_dict(stage, 3, nc, seed=stage)
+    sd_prev = O.seeded_state_dict(stage - 1, 3, nc, seed=stage - 1) if stage > 1 else None
+
+    def build(st, state):
+        m = S.StockPGUNet(st, nc)
+        keymap = {"inc.conv.": "inc."}
+        for i, dn in enumerate(O.down_names(st)):
+            keymap[f"{dn}.mpconv.1."] = f"downs.{i}."
+        for j in range(st):
+            keymap[f"up{j + 1}.conv."] = f"ups.{j}."
+        heads = O.head_names(st)
+        for j, hn in enumerate(heads):
+            keymap[f"{hn}.conv."] = f"heads.{j}."
+        new = {}
+        for k, v in state.items():
+            for a, b in keymap.items():
+                if k.startswith(a):
+                    new[b + k[len(a):]] = v
+                    break
+            else:
+                raise KeyError(k)
+        m.load_state_dict(new, strict=True)
+        inv = {b: a for a, b in keymap.items()}
+        return m.to(dev), inv
+
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = (mode == "tf32")
+    try:
+        fmt = torch.channels_last if mode == "bf16" else torch.contiguous_format
+        model, inv = build(stage, sd)
+        model = model.to(memory_format=fmt).train()
+        xd = x.to(dev).contiguous(memory_format=fmt)
+        yd = y.to(dev)
+        cast = torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16"))
+        with cast:
+            out = model(xd)
+            A = None
+            if stage > 1:
+                prev, _ = build(stage - 1, sd_prev)
+                prev = prev.to(memory_format=fmt).eval()
+                with torch.no_grad():
+                    R = x.shape[-1]
+                    xp = F.interpolate(xd, size=(R // 2, R // 2), mode="bilinear", align_corners=True)
+                    pr = torch.sigmoid(prev(xp).float())
+                    pr = F.interpolate(pr, size=(R, R), mode="bilinear", align_corners=True)
+                    A = 1.0 - 2.0 * torch.abs(pr - 0.5)
+        crit = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([5.0], device=dev), reduction="none")
+        pl = crit(out.float(), yd)
+        loss = torch.mean(pl if A is None else pl * (1.0 + A).detach())
+        loss.backward()
+        torch.cuda.synchronize()
+        rows = {}
+        for k, p in model.named_parameters():
+            pref = max((b for b in inv if k.startswith(b)), key=len)
+            rk = inv[pref] + k[len(pref):]
+            if rk.endswith(ZERO_GRAD_SUFFIX) or rk not in fx["grads"]:
+                continue
+            r, c, nr = against_sample(p.grad.float(), fx["grads"][rk])
+            rows[rk] = {"rel": r, "cos": c, "norm_ratio": nr, "floor_rel": 0.0, "floor_cos": 1.0}
+        zc = out.detach().float().cpu()
+        return {"name": name, "mode": mode, "stage": stage, "B": fx["B"], "logits_rel": rel(zc, fx["logits"]),
+                "final_loss_rel": abs(loss.item() - fx["final_loss"]) / abs(fx["final_loss"]),
+                "mask_mismatch": ((zc > 0) != (fx["logits"] > 0)).float().mean().item(),
+                "median_grad_rel": statistics.median(v["rel"] for v in rows.values()),
+                "worst_grad_rel": max(v["rel"] for v in rows.values()),
+                "n_le_2e-2": sum(v["rel"] <= 2e-2 for v in rows.values()), "n": len(rows),
+                "n_le_1e-3": sum(v["rel"] <= 1e-3 for v in rows.values())}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def stock_table(rows) -> str:
+    lines = ["| fixture | stock PyTorch mode | logits rel | final loss rel | mask mismatch | grad tensors <= 2e-2 | "
+             "grad tensors <= 1e-3 | median grad rel | worst grad rel |", "|---|---|---|---|---|---|---|---|---|"]
+    for r in rows:
+        lines.append(f"| {r['name']} | {r['mode']} | {_fmt(r['logits_rel'])} | {_fmt(r['final_loss_rel'])} | "
+                     f"{_fmt(r['mask_mismatch'])} | {r['n_le_2e-2']}/{r['n']} | {r['n_le_1e-3']}/{r['n']} | "
+                     f"{_fmt(r['median_grad_rel'])} | {_fmt(r['worst_grad_rel'])} |")
+    return "\n".join(lines)
+
+
 def _fmt(v):
     return f"{v:.2e}"
 
@@ -288,6 +381,15 @@ def main():
         print(n, "logits", _fmt(r["logits_rel"]), "floor", _fmt(r["logits_floor"]), r["grad_summary"], flush=True)
     txt = table(results)
     print(txt)
+    stock = []
+    if "--no-stock" not in sys.argv:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        for n in ("trainer_stage1_nc1", "trainer_stage2_nc1", "trainer_stage3_nc1_b16", "trainer_stage4_nc1_b16"):
+            for mode in ("fp32", "tf32", "bf16"):
+                stock.append(measure_stock_gpu(n, dev, mode))
+                print(stock[-1], flush=True)
+        txt += ("\n\nThe reference's step in STOCK PyTorch on the same GPU (cuDNN; the reference's own GPU paths) "
+                "against the same fp32 CPU fixtures:\n\n" + stock_table(stock))
     opts = os.environ.get("UGP_OPTIONS", "")
     if out_path:
         with open(out_path, "w") as f:
@@ -298,7 +400,7 @@ def main():
                     f.write(f"  {k:44s} rel {v['rel']:.3e}  floor {v['floor_rel']:.3e}  cos {v['cos']:.5f}  "
                             f"floor cos {v['floor_cos']:.5f}  |g|/|g_ref| {v['norm_ratio']:.4f}\n")
         with open(os.path.splitext(out_path)[0] + ".json", "w") as f:
-            json.dump(results, f, indent=1)
+            json.dump({"cuda_path": results, "stock_pytorch_gpu": stock}, f, indent=1)
 
 
 if __name__ == "__main__":

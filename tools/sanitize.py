@@ -8,6 +8,8 @@ Shapes are the smallest that select each kernel variant (per-tap GEMM at N = 64 
 halo kernels single / pair / resident-weight, both wgrad kernels, ConvTranspose2d views, the element-wise
 and reduction kernels, the fused optimiser and the fused Herlev head).  Summaries are kept under
 profiles/r02_sanitizer_*.txt.  A selection can be given on the command line (family names).
+
+    python tools/sanitize.py --guards          # our own out-of-bounds-write check (guard bands), see below
 """
 import os
 import sys
@@ -181,13 +183,90 @@ def mlp_head():
     ops.mlp_head_bwd(torch.randn_like(logits), w1, w2, w3, pooled, h1, h2, u=u, p=(0.5, 0.3, 0.2))
 
 
+# ----------------------------------------------------------------------------------------------------------
+# Guard bands (`--guards`): compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer_unavailable.txt),
+# so out-of-bounds WRITES are hunted with canaries of our own: every tensor the op wrappers allocate for a
+# kernel to write (torch.empty / empty_like / zeros inside ug_pg_unet_b200.ops) is carved out of a larger
+# buffer whose 4 KiB margins hold a byte pattern; after every family the margins must be untouched.  Covers
+# plain stores, vector reductions and TMA stores (tensor maps are built on the carved-out pointers).
+# ----------------------------------------------------------------------------------------------------------
+GUARD_BYTES = 4096
+_guards = []
+
+
+class _TorchWithGuards:
+    """Stands in for the `torch` module inside ug_pg_unet_b200.ops: allocation functions add guard bands."""
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    @staticmethod
+    def _carve(shape, dtype, device, zero):
+        if isinstance(shape, int):
+            shape = (shape,)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        esz = torch.empty((), dtype=dtype).element_size()
+        g = GUARD_BYTES // esz
+        raw = torch.empty((n + 2 * g,), dtype=torch.uint8 if False else dtype, device=device)
+        raw.view(torch.uint8).fill_(0xA5)
+        body = raw[g:g + n].view(tuple(shape))
+        if zero:
+            body.zero_()
+        _guards.append((raw, g, n))
+        return body
+
+    def empty(self, *shape, dtype=torch.float32, device=None, **kw):
+        shape = shape[0] if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)) else shape
+        return self._carve(tuple(shape), dtype, device, False)
+
+    def zeros(self, *shape, dtype=torch.float32, device=None, **kw):
+        shape = shape[0] if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)) else shape
+        return self._carve(tuple(shape), dtype, device, True)
+
+    def empty_like(self, t, **kw):
+        return self._carve(tuple(t.shape), kw.get("dtype", t.dtype), t.device, False)
+
+
+def check_guards(family: str) -> int:
+    torch.cuda.synchronize()
+    bad = 0
+    for raw, g, n in _guards:
+        b = raw.view(torch.uint8)
+        esz = raw.element_size()
+        lo, hi = b[: g * esz], b[(g + n) * esz:]
+        if not (bool((lo == 0xA5).all()) and bool((hi == 0xA5).all())):
+            bad += 1
+            print(f"[GUARD] {family}: a kernel wrote outside a {n}-element {raw.dtype} buffer "
+                  f"(below: {int((lo != 0xA5).sum())} bytes, above: {int((hi != 0xA5).sum())} bytes)", flush=True)
+    count = len(_guards)
+    _guards.clear()
+    return bad, count
+
+
 def main():
-    names = sys.argv[1:] or list(FAMILIES)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    guards = "--guards" in sys.argv
+    names = args or list(FAMILIES)
+    if guards:
+        ops.torch = _TorchWithGuards()
+    bad = 0
     for n in names:
         FAMILIES[n]()
         torch.cuda.synchronize()
-        print(f"[ran] {n}", flush=True)
-    print("sanitize.py: all families launched", flush=True)
+        if guards:
+            b, count = check_guards(n)
+            bad += b
+            print(f"[ran] {n}: {count} guarded buffers, {b} violated", flush=True)
+        else:
+            print(f"[ran] {n}", flush=True)
+    if guards:
+        print(f"sanitize.py --guards: {'OK' if bad == 0 else 'FAILED'} ({bad} violated guard bands)", flush=True)
+        if bad:
+            raise SystemExit(1)
+    else:
+        print("sanitize.py: all families launched", flush=True)
 
 
 if __name__ == "__main__":

@@ -25,6 +25,7 @@ int bn_relu_apply_head(const void*, const float*, const float*, int, int, int, i
 int bn_relu_bwd_ex(const void*, const void*, const void*, const float*, const float*, const float*, const float*,
                    const float*, int, int, int, int, float*, float*, void*, const float*, const float*, int, float*,
                    cudaStream_t);
+int flip_u8(const unsigned char*, const unsigned char*, int, int, int, int, unsigned char*, cudaStream_t);
 int maxpool2x2(const void*, int, int, int, int, void*, int*, cudaStream_t);
 int maxpool2x2_bwd(const void*, const void*, int, int, int, int, void*, cudaStream_t);
 int upsample2x(const void*, int, int, int, int, void*, cudaStream_t);
@@ -125,6 +126,10 @@ int ugp_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float
 int ugp_bn_relu_apply(const void* z, const float* scale, const float* shift, int B, int H, int W,
                       int C, void* a, void* pooled, void* stream) {
   return ugp::bn_relu_apply(z, scale, shift, B, H, W, C, a, pooled, S(stream));
+}
+int ugp_flip_u8(const unsigned char* x, const unsigned char* flags, int B, int H, int W, int C, unsigned char* out,
+                void* stream) {
+  return ugp::flip_u8(x, flags, B, H, W, C, out, S(stream));
 }
 int ugp_bn_relu_apply_head(const void* z, const float* scale, const float* shift, int B, int H, int W, int C,
                            const float* wh, const float* bh, int nc, void* a, float* lmap, void* stream) {

@@ -41,6 +41,8 @@ struct WgradParams {
   int cout;
   int kchunks_total;      // B * tiles_x * tiles_y
   int kchunks_per_split;
+  int stage_tiles;        // M tiles a stage buffer holds = min(kT, m_tiles)
+  int stages;             // pipeline depth: as many stages of that size as fit (2..8)
   float* dw;              // [boxes*64][cout] fp32, accumulated
   int debug;              // what-if timing only: 1 = skip MMA issue, 2 = skip the reduction stores
 };
@@ -76,11 +78,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Stage ring sized from the tiles this launch really uses (p.stage_tiles <= kT M tiles per CTA): a layer
+  // with one M tile (the im2col'ed first layer: K = 1 M pixels against a 64 x 64 result) gets 8 stages of
+  // 24 KB in flight instead of 2 stages of 88 KB that are mostly empty - it is bound by load latency.
+  const int stages = p.stages;
+  const int a_bytes = 2 * p.stage_tiles * kWgBoxBytes;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + kStages * Cfg::kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kStages * Cfg::kBBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* done_bar = empty_bar + kStages;
+  uint8_t* sB = sA + stages * a_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + stages * Cfg::kBBytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* done_bar = empty_bar + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
 
   const int warp_idx = threadIdx.x >> 5;
@@ -99,7 +106,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
     tma_prefetch_desc(&tmX0);
     tma_prefetch_desc(&tmX1);
     tma_prefetch_desc(&tmDZ);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -111,7 +118,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
     // partial K boxes (general image sizes): TMA only writes the first BWp*BHp rows of each 64-row
     // box, the MMAs read all 64 -> the rest must contribute zero
     uint4* z4 = reinterpret_cast<uint4*>(smem);
-    for (int i = threadIdx.x; i < kStages * Cfg::kStageBytes / 16; i += blockDim.x) z4[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < stages * (a_bytes + Cfg::kBBytes) / 16; i += blockDim.x) z4[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   tc_fence_before_sync();
@@ -134,7 +141,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
         const int y0 = (t2 - b * p.tiles_y) * p.BHp;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-        uint8_t* a_dst = sA + stage * Cfg::kABytes;
+        uint8_t* a_dst = sA + stage * a_bytes;
         for (int i = 0; i < 2 * nt; ++i) {
           // the boxes of this CTA; an odd box count repeats the last box
           int id = tile0 * 2 + i;
@@ -157,7 +164,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
             tma_load_4d(&tmDZ, &full_bar[stage], b_dst + j * kWgBoxBytes,
                         n_tile * kN + j * 64, x0, y0, b);
         }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp_idx == 1) {
@@ -172,7 +179,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after_sync();
       {
-        const uint32_t a_addr = smem_u32(sA + stage * Cfg::kABytes);
+        const uint32_t a_addr = smem_u32(sA + stage * a_bytes);
         const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
         for (int t = 0; t < nt; ++t) {
 #pragma unroll
@@ -190,7 +197,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
         }
       }
       __syncwarp();
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      if (++stage == stages) { stage = 0; phase ^= 1; }
     }
   } else {
     const int q = warp_idx & 3;
@@ -237,6 +244,9 @@ static int launch_wgrad(const CUtensorMap& tmX0, const CUtensorMap& tmX1,
     configured = true;
   }
   p.m_groups = (p.m_tiles + Cfg::kT - 1) / Cfg::kT;
+  p.stage_tiles = p.m_tiles < Cfg::kT ? p.m_tiles : Cfg::kT;
+  p.stages = (Cfg::kSmemBytes - 256 - 1024) / (2 * p.stage_tiles * kWgBoxBytes + Cfg::kBBytes);
+  if (p.stages > 8) p.stages = 8;
   const int items = p.m_groups * p.n_tiles;
   // split K (pixels) so that the grid is ONE full wave of CTAs (one CTA per SM: 512 TMEM columns):
   // more splits only add fp32 reduction traffic and a ragged last wave

@@ -10,6 +10,8 @@
 
 namespace ugp {
 
+int g_upsample_smem_kb = 72;   // shared-memory budget of a bilinear x2 block (tuning switch `upsample_smem_kb`)
+
 // ----------------------------------------------------------------------------
 // BatchNorm statistics -> per-channel scale/shift (+ running stats update).
 // stats = [parts][2][C]: per-CTA partial {sum, sum of squares} of the stored conv outputs, summed here
@@ -579,12 +581,15 @@ int upsample2x(const void* x, int B, int h, int w, int C, void* out, cudaStream_
   const int tables = 2 * w * 8;
   const float sy = (2 * h > 1) ? static_cast<float>(h - 1) / static_cast<float>(2 * h - 1) : 0.f;
   const float sx = (2 * w > 1) ? static_cast<float>(w - 1) / static_cast<float>(2 * w - 1) : 0.f;
-  const int Cs = upsample_slab(C, w, tables, 64 * 1024);
+  // staging budget: small enough that a block can share an SM with a ~200 KB tensor-core CTA of another
+  // stream (the step overlaps these kernels with weight-gradient / uncertainty-forward convolutions whose
+  // persistent CTAs hold every SM: a 64 KB block then waits for a whole convolution to drain)
+  const int Cs = upsample_slab(C, w, tables, g_upsample_smem_kb * 1024);
   UGP_REQUIRE(Cs > 0 && C / Cs <= 65535, "upsample2x: row of %d pixels does not fit the staging buffer", w);
   const int smem = w * Cs * 4 + tables;
   static bool configured = false;
   if (!configured) {
-    UGP_CHECK_CUDA(cudaFuncSetAttribute(upsample2x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(upsample2x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured = true;
   }
   upsample2x_kernel<<<dim3(B * 2 * h, C / Cs), kUpThreads, smem, stream>>>(
@@ -603,12 +608,12 @@ int upsample2x_bwd(const void* dout, int B, int h, int w, int C, void* dx,
   const int tables = (w * 5 + 8) * 4;
   const float sy = (2 * h > 1) ? static_cast<float>(h - 1) / static_cast<float>(2 * h - 1) : 0.f;
   const float sx = (2 * w > 1) ? static_cast<float>(w - 1) / static_cast<float>(2 * w - 1) : 0.f;
-  const int Cs = upsample_slab(C, 2 * w, tables, 72 * 1024);
+  const int Cs = upsample_slab(C, 2 * w, tables, g_upsample_smem_kb * 1024);
   UGP_REQUIRE(Cs > 0 && C / Cs <= 65535, "upsample2x_bwd: row of %d pixels does not fit the staging buffer", 2 * w);
   const int smem = 2 * w * Cs * 4 + tables;
   static bool configured = false;
   if (!configured) {
-    UGP_CHECK_CUDA(cudaFuncSetAttribute(upsample2x_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(upsample2x_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     configured = true;
   }
   upsample2x_bwd_kernel<<<dim3(B * h, C / Cs), kUpThreads, smem, stream>>>(

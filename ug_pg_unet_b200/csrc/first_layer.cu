@@ -165,4 +165,38 @@ int im2col_first_u8(const unsigned char* x, int B, int Cin, int Hin, int Win, in
   return dispatch_im2col<true>(x, B, Cin, Hin, Win, H, W, out, norm, stream);
 }
 
+// ----------------------------------------------------------------------------
+// Joint horizontal / vertical flips of a batch of loader bytes on the device: the geometric part of the
+// reference's train-time augmentation that is exactly reproducible (MoNuSegImprove/monuseg_dataset.py:
+// 150-158: TF.hflip / TF.vflip applied to image AND mask with one decision per sample).  flags[b] bit 0 =
+// horizontal, bit 1 = vertical.  x: [B][H][W][C] bytes (C = 3 image bytes, C = 1 a mask plane).  The
+// arbitrary-angle PIL rotation and colour jitter of :160-178 stay on the host loader.
+// ----------------------------------------------------------------------------
+__global__ void flip_u8_kernel(const unsigned char* __restrict__ x, const unsigned char* __restrict__ flags, int H,
+                               int W, int C, unsigned char* __restrict__ out) {
+  const int b = blockIdx.y;
+  const unsigned char f = flags[b];
+  const long long plane = static_cast<long long>(H) * W * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < plane;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long pix = i / C;
+    const int xx = static_cast<int>(pix % W), yy = static_cast<int>(pix / W);
+    const int sx = (f & 1) ? W - 1 - xx : xx, sy = (f & 2) ? H - 1 - yy : yy;
+    out[b * plane + i] = x[b * plane + (static_cast<long long>(sy) * W + sx) * C + c];
+  }
+}
+
+int flip_u8(const unsigned char* x, const unsigned char* flags, int B, int H, int W, int C, unsigned char* out,
+            cudaStream_t stream) {
+  UGP_REQUIRE(x && flags && out && x != out, "flip_u8: null pointer / in-place not supported");
+  UGP_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && C > 0, "flip_u8: bad shape");
+  const long long plane = static_cast<long long>(H) * W * C;
+  int gx = static_cast<int>((plane + 255) / 256);
+  if (gx > 1024) gx = 1024;
+  flip_u8_kernel<<<dim3(gx, B), 256, 0, stream>>>(x, flags, H, W, C, out);
+  UGP_CHECK_CUDA(cudaGetLastError());
+  return UGP_OK;
+}
+
 }  // namespace ugp

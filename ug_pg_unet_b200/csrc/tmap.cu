@@ -106,6 +106,7 @@ extern int g_conv_halo_prefetch;
 extern int g_bn_pool_vec4;         // bn_bwd.cu
 extern int g_bn_skip_reduce;
 extern int g_bn_min_pixels;
+extern int g_upsample_smem_kb;
 extern int g_bn_bwd_blocks_per_sm;
 int g_wgrad_waves = 1;
 int g_conv_debug = 0;   // what-if timing switches (results are wrong): 1 = skip MMA issue, 2 = skip epilogue body
@@ -125,6 +126,10 @@ int set_option(const char* name, int value) {
   }
   if (strcmp(name, "bn_bwd_blocks_per_sm") == 0) {
     g_bn_bwd_blocks_per_sm = value < 1 ? 1 : (value > 2 ? 2 : value);
+    return UGP_OK;
+  }
+  if (strcmp(name, "upsample_smem_kb") == 0) {
+    g_upsample_smem_kb = value < 4 ? 4 : (value > 96 ? 96 : value);
     return UGP_OK;
   }
   if (strcmp(name, "bn_min_pixels") == 0) {

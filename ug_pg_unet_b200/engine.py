@@ -29,6 +29,26 @@ _WHATIF_SKIP_BN1_REDUCE = os.environ.get("UGP_WHATIF_SKIP_BN1_REDUCE", "0") == "
 _WHATIF_POOL_AS_PLAIN = os.environ.get("UGP_WHATIF_POOL_AS_PLAIN", "0") == "1"
 
 
+# NVTX ranges (UGP_NVTX=1): one range per DoubleConv block and direction, one per trainer-step phase, so a
+# timeline (nsys, or ncu --nvtx) of the ~190-kernel step reads as blocks.  Off by default: the pushes / pops
+# are host calls on a host-bound eager step (they do not exist inside a replayed CUDA graph).
+NVTX = os.environ.get("UGP_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 class PackedWeights:
     """bf16 GEMM operands of one nn.Conv2d weight, refreshed when the fp32 master changes
     (optimizer.step / load_state_dict / .to(device) all bump `_version` or the storage), plus the
@@ -348,8 +368,9 @@ class DoubleConvFn(torch.autograd.Function):
             srcs, taps = [x, skip], 9
         else:
             srcs, taps = [x], 9
-        a1, _, s1 = cbr_forward(srcs, taps, conv1, bn1, mod._packs[0], False, need_grad)
-        a2, p2, s2 = cbr_forward([a1], 9, conv2, bn2, mod._packs[1], emit_pool, need_grad, head=head)
+        with nvtx_range(f"fwd {kind} {conv1.in_channels}->{conv2.out_channels} @{srcs[0].shape[1]}x{srcs[0].shape[2]}"):
+            a1, _, s1 = cbr_forward(srcs, taps, conv1, bn1, mod._packs[0], False, need_grad)
+            a2, p2, s2 = cbr_forward([a1], 9, conv2, bn2, mod._packs[1], emit_pool, need_grad, head=head)
         ctx.mod, ctx.kind, ctx.emit_pool = mod, kind, emit_pool
         ctx.s1, ctx.s2, ctx.pre = s1, s2, pre
         ctx.head_w = head[0] if head is not None else None
@@ -376,13 +397,14 @@ class DoubleConvFn(torch.autograd.Function):
             head = (dl.float().contiguous(), ctx.head_w, []) if dl is not None else None
             if head is None and dA is None:
                 raise RuntimeError("DoubleConvFn.backward: no gradient reached the block")
-        d1, g2 = cbr_backward(ctx.s2, dA, dP, conv2, bn2, mod._packs[1], True, head=head)
-        need_in = ctx.x_needs_grad or ctx.skip_needs_grad
-        if _WHATIF_SKIP_BN1_REDUCE:
-            set_option("bn_skip_reduce", 1)
-        d0, g1 = cbr_backward(ctx.s1, d1[0], None, conv1, bn1, mod._packs[0], need_in)
-        if _WHATIF_SKIP_BN1_REDUCE:
-            set_option("bn_skip_reduce", 0)
+        with nvtx_range(f"bwd {ctx.kind} {conv1.in_channels}->{conv2.out_channels} @{ctx.s2.z.shape[1]}x{ctx.s2.z.shape[2]}"):
+            d1, g2 = cbr_backward(ctx.s2, dA, dP, conv2, bn2, mod._packs[1], True, head=head)
+            need_in = ctx.x_needs_grad or ctx.skip_needs_grad
+            if _WHATIF_SKIP_BN1_REDUCE:
+                set_option("bn_skip_reduce", 1)
+            d0, g1 = cbr_backward(ctx.s1, d1[0], None, conv1, bn1, mod._packs[0], need_in)
+            if _WHATIF_SKIP_BN1_REDUCE:
+                set_option("bn_skip_reduce", 0)
         dx = dskip = None
         if need_in:
             if ctx.kind == "pool":

@@ -308,6 +308,28 @@ def im2col_first_u8(x: torch.Tensor, H: Optional[int] = None, W: Optional[int] =
     return out
 
 
+def flip_u8(x: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
+    """Per-sample horizontal (bit 0) / vertical (bit 1) flips of uint8 [B,H,W,C] loader bytes (or [B,1,H,W]
+    masks, viewed as [B,H,W,1]); see ugp_flip_u8.  `flags`: uint8 [B] on the device."""
+    _req(x, torch.uint8, "x")
+    _req(flags, torch.uint8, "flags")
+    B, H, W, Cn = x.shape
+    assert flags.numel() == B
+    out = torch.empty_like(x)
+    check(lib().ugp_flip_u8(_ptr(x), _ptr(flags), B, H, W, Cn, _ptr(out), _stream()), "ugp_flip_u8")
+    return out
+
+
+def joint_flip_u8(images: torch.Tensor, masks: torch.Tensor, generator=None):
+    """The flip part of the reference's train-time augmentation (monuseg_dataset.py:150-158) on a device
+    batch: one (hflip, vflip) decision per sample with probability 1/2 each, applied to the image bytes
+    [B,H,W,3] and the mask bytes [B,1,H,W] alike.  Returns (images, masks, flags)."""
+    B = images.shape[0]
+    flags = torch.randint(0, 4, (B,), device=images.device, dtype=torch.uint8, generator=generator)
+    m = masks.reshape(B, masks.shape[-2], masks.shape[-1], 1)
+    return flip_u8(images, flags), flip_u8(m.contiguous(), flags).reshape(masks.shape), flags
+
+
 # ----------------------------------------------------------------------------- BN / pool / upsample
 _STAT_PARTS = None
 
@@ -329,10 +351,12 @@ def bn_finalize(stats, count: int, gamma, beta, eps: float, momentum: float, run
                 running_var, num_batches_tracked, scale, shift, save_mean, save_rstd):
     Cn = gamma.numel()
     assert stats.dim() == 3 and stats.shape[1] == 2 and stats.shape[2] == Cn, stats.shape
-    check(lib().ugp_bn_finalize(_ptr(_req(stats, torch.float32, "stats")), stats.shape[0], Cn, count, _ptr(gamma),
-                                _ptr(beta), eps, momentum, _ptr(running_mean), _ptr(running_var),
-                                _ptr(num_batches_tracked), _ptr(scale), _ptr(shift), _ptr(save_mean),
-                                _ptr(save_rstd), _stream()), "ugp_bn_finalize")
+    with _timed("bn_finalize", 0.0, _nb(stats)):
+        rc = lib().ugp_bn_finalize(_ptr(_req(stats, torch.float32, "stats")), stats.shape[0], Cn, count, _ptr(gamma),
+                                   _ptr(beta), eps, momentum, _ptr(running_mean), _ptr(running_var),
+                                   _ptr(num_batches_tracked), _ptr(scale), _ptr(shift), _ptr(save_mean),
+                                   _ptr(save_rstd), _stream())
+    check(rc, "ugp_bn_finalize")
 
 
 def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps: float, scale, shift):
@@ -559,8 +583,9 @@ def head_combine_fwd(maps: Sequence[torch.Tensor]):
     ptrs = (C.c_void_p * n)(*[_req(m, torch.float32, "map").data_ptr() for m in maps])
     hs = (C.c_int * n)(*[m.shape[-2] for m in maps])
     ws = (C.c_int * n)(*[m.shape[-1] for m in maps])
-    check(lib().ugp_head_combine_fwd_hw(ptrs, hs, ws, n, B * nc, RH, RW, _ptr(logits), _stream()),
-          "ugp_head_combine_fwd")
+    with _timed("head_combine_fwd", 0.0, _nb(*maps) + _nb(logits)):
+        rc = lib().ugp_head_combine_fwd_hw(ptrs, hs, ws, n, B * nc, RH, RW, _ptr(logits), _stream())
+    check(rc, "ugp_head_combine_fwd")
     return logits
 
 
@@ -570,8 +595,9 @@ def head_combine_bwd(dlogits, size):
     B, nc, RH, RW = dlogits.shape
     h, w = (size, size) if isinstance(size, int) else size
     dl = torch.empty((B, nc, h, w), dtype=torch.float32, device=dlogits.device)
-    check(lib().ugp_head_combine_bwd_hw(_ptr(dlogits), B * nc, RH, RW, h, w, _ptr(dl), _stream()),
-          "ugp_head_combine_bwd")
+    with _timed("head_combine_bwd", 0.0, _nb(dlogits, dl)):
+        rc = lib().ugp_head_combine_bwd_hw(_ptr(dlogits), B * nc, RH, RW, h, w, _ptr(dl), _stream())
+    check(rc, "ugp_head_combine_bwd")
     return dl
 
 

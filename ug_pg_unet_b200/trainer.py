@@ -30,7 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 import torch.optim as optim
 
-from .engine import PackedWeights, WgradOverlap, conv_packs, enable_deferred_wgrad
+from .engine import PackedWeights, WgradOverlap, conv_packs, enable_deferred_wgrad, nvtx_range
 from .optim import FusedRMSprop
 from .parallel import GradBucketReducer, broadcast_module_state
 from .unet import PGUNet1, PGUNet2, PGUNet3, PGUNet4, UncertaintyGuidedLoss, _pos_weight_value, transfer_state
@@ -251,18 +251,21 @@ class UncertaintyGuidedProgressiveTrainer:
 
     def _eager_step(self, data, target, stage):
         self.optimizer.zero_grad(set_to_none=True)
-        final_loss, output_current, unc, base = self._forward_loss(data, target, stage)
-        if self.overlap_streams and data.is_cuda and self._grad_arena is not None:
-            WgradOverlap.begin(self._streams(data)[1])
-            try:
+        with nvtx_range(f"step stage {stage}: forward + uncertainty + loss"):
+            final_loss, output_current, unc, base = self._forward_loss(data, target, stage)
+        with nvtx_range("step: backward"):
+            if self.overlap_streams and data.is_cuda and self._grad_arena is not None:
+                WgradOverlap.begin(self._streams(data)[1])
+                try:
+                    final_loss.backward()
+                finally:
+                    WgradOverlap.end()
+            else:
                 final_loss.backward()
-            finally:
-                WgradOverlap.end()
-        else:
-            final_loss.backward()
-        if self._reducer is not None:
-            self._reducer.wait()
-        self.optimizer.step()
+        with nvtx_range("step: gradient exchange + optimiser"):
+            if self._reducer is not None:
+                self._reducer.wait()
+            self.optimizer.step()
         # a custom criterion has no fused metrics: keep this step's own (detached) losses so that the epoch
         # loop can log them without a second forward (reference :221-234 logs the step's own numbers)
         self._last_step_losses = None if self.uncertainty_loss.last_metrics is not None else (final_loss.detach(), base)
