@@ -263,6 +263,22 @@ int ugp_rmsprop_conv_packed(float* const* w, float* const* square_avgs, float* c
                             int n_tensors, float lr, float alpha, float eps, float weight_decay,
                             float grad_scale, void* stream);
 
+/* Input gradient of the SECOND convolution of a DoubleConv (autograd of UG_unet_parts.py:12-13) fused with
+ * the reduction pass of the first BatchNorm's backward (autograd of :11-12): dA = conv3x3(dz, wd) exactly as
+ * ugp_conv_gemm_bf16(taps = 9), and in the epilogue, while the tile is in shared memory,
+ *   raw[0][c] = sum_p dA[p][c] * [a[p][c] > 0],   raw[1][c] = sum_p dA[p][c] * [a[p][c] > 0] * z[p][c]
+ * with z the stored conv output of that BatchNorm (NHWC bf16 [B][H][W][cout]) and a = z*scale + shift.
+ * dz: NHWC bf16 [B][H][W][c]; wd: the input-gradient weight pack; raw: fp32 [2][cout] (zeroed here,
+ * accumulated with fp32 atomics).  H, W must give power-of-two tiles (the fast kernels). */
+int ugp_conv_dgrad_bnstats_bf16(const void* dz, int c, int B, int H, int W, const void* wd, int cout, void* dA,
+                                const void* z, const float* scale, const float* shift, float* raw, void* stream);
+
+/* Apply pass of ugp_bn_relu_bwd alone, taking the sums of ugp_conv_dgrad_bnstats_bf16: dz as there;
+ * sums [2][C] receives dgamma = rstd*(raw[1] - mean*raw[0]) and dbeta = raw[0]; dbias accumulates sum dz. */
+int ugp_bn_relu_bwd_apply(const void* z, const void* dA, const float* raw, const float* scale, const float* shift,
+                          const float* mean, const float* rstd, const float* gamma, int B, int H, int W, int C,
+                          float* sums, float* dbias, void* dz, void* stream);
+
 /* Joint flips of loader bytes on the device: TF.hflip / TF.vflip of MoNuSegImprove/monuseg_dataset.py:150-158
  * (one decision per sample, applied to image and mask alike).  x, out: [B][H][W][C] bytes (out != x);
  * flags: B device bytes, bit 0 = horizontal flip, bit 1 = vertical flip.  Pure byte moves: bit-exact. */

@@ -689,6 +689,41 @@ def test_joint_flips_of_loader_bytes_are_bit_exact(dev):
     assert a.shape == img.shape and m2.shape == msk.shape and fl.shape == (8,)
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 64), (2, 16, 16, 256, 256), (1, 32, 32, 128, 128), (1, 4, 128, 64, 64),
+                                   (1, 4, 128, 128, 128), (2, 64, 64, 256, 256), (16, 128, 128, 64, 64)])
+def test_dgrad_with_fused_batchnorm_backward_sums(dev, shape):
+    """ugp_conv_dgrad_bnstats_bf16 + ugp_bn_relu_bwd_apply against ugp_conv_gemm_bf16 + ugp_bn_relu_bwd (the
+    reduction pass as its own kernel), for the per-tap, pair and halo kernels: the input gradient bit for
+    bit, the sums to fp32 summation order, dz / dgamma / dbeta / dbias alike."""
+    from ug_pg_unet_b200 import ops
+
+    B, H, W, c, cin = shape          # dz has c channels, the gradient (and z of the BN below) cin channels
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    dz2 = torch.randn(B, H, W, c, device=dev, generator=g).bfloat16()
+    w = torch.randn(c, cin, 3, 3, device=dev, generator=g) / (3.0 * c ** 0.5)
+    _, wd = ops.pack_weights(w)
+    z1 = (torch.randn(B, H, W, cin, device=dev, generator=g) * 1.1 + 0.2).bfloat16()
+    gamma = torch.rand(cin, device=dev, generator=g) + 0.5
+    zf = z1.float().reshape(-1, cin)
+    mean, var = zf.mean(0), zf.var(0, unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    scale, shift = gamma * rstd, torch.randn(cin, device=dev, generator=g) * 0.1 - mean * gamma * rstd
+    dA_ref = ops.conv_gemm(dz2, None, wd, 9, cin)
+    small_r = torch.empty(3, cin, device=dev)
+    dz_ref = ops.bn_relu_bwd(z1, dA_ref, None, scale, shift, mean, rstd, gamma, small_r[:2], small_r[2])
+    dA, raw = ops.conv_dgrad_bnstats(dz2, wd, cin, z1, scale, shift)
+    assert torch.equal(dA, dA_ref)
+    m = (z1.float() * scale + shift) > 0
+    gm = torch.where(m, dA_ref.float(), torch.zeros((), device=dev)).reshape(-1, cin)
+    assert rel(raw[0], gm.sum(0)) < 1e-4 and rel(raw[1], (gm * zf).sum(0)) < 1e-4
+    small = torch.empty(3, cin, device=dev)
+    dz = ops.bn_relu_bwd_apply(z1, dA, raw, scale, shift, mean, rstd, gamma, small[:2], small[2])
+    assert rel(dz, dz_ref) < 2e-3
+    torch.testing.assert_close(small[0], small_r[0], rtol=2e-3, atol=1e-3 * float(small_r[0].abs().max()))
+    torch.testing.assert_close(small[1], small_r[1], rtol=2e-3, atol=1e-3 * float(small_r[1].abs().max()))
+    torch.testing.assert_close(small[2], small_r[2], rtol=2e-2, atol=2e-3 * float(small_r[1].abs().max()) + 1e-3)
+
+
 def test_global_avg_pool_kernels(dev):
     from ug_pg_unet_b200 import ops
 

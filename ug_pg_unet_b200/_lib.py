@@ -40,6 +40,8 @@ SIGNATURES = {
     "ugp_bn_relu_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
     "ugp_bn_relu_apply_head": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p],
     "ugp_bn_relu_bwd_head": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p],
+    "ugp_conv_dgrad_bnstats_bf16": [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p],
+    "ugp_bn_relu_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
     "ugp_flip_u8": [_p, _p, _i, _i, _i, _i, _p, _p],
     "ugp_maxpool2x2": [_p, _i, _i, _i, _i, _p, _p, _p],
     "ugp_maxpool2x2_bwd": [_p, _p, _i, _i, _i, _i, _p, _p],

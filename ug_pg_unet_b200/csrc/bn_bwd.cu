@@ -42,6 +42,10 @@ struct BnBwdArgs {
   float* dwh;                // [nc][C] (+ [nc] bias gradient behind it), zeroed by the launcher
   int HW;
   int hw_shift;              // log2(HW) when HW is a power of two, else -1
+  // raw != nullptr: the reduction pass already ran inside the convolution that produced dA
+  // (ugp_conv_dgrad_bnstats_bf16): raw[0][c] = sum g*[a > 0], raw[1][c] = sum g*[a > 0]*z.  The apply pass
+  // derives dgamma / dbeta from them and its first block publishes them in `sums`.
+  const float* raw;
 };
 
 constexpr int kBnThreads = 256;
@@ -110,8 +114,17 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const 
     if (kApply) {
       const float rs = __ldg(a.rstd + c0 + j);
       const float gr = __ldg(a.gamma + c0 + j) * rs;
-      const float mg = __ldg(a.sums + a.C + c0 + j) * a.inv_count;     // mean g
-      const float mgx = __ldg(a.sums + c0 + j) * a.inv_count;          // mean g*xhat
+      float dbeta, dgamma;
+      if (a.raw != nullptr) {
+        dbeta = __ldg(a.raw + c0 + j);
+        dgamma = rs * (__ldg(a.raw + a.C + c0 + j) - mu * dbeta);      // sum g*xhat = rstd*(sum g*z - mean*sum g)
+        if (blockIdx.x == 0 && my_row == 0) { a.sums[c0 + j] = dgamma; a.sums[a.C + c0 + j] = dbeta; }
+      } else {
+        dbeta = __ldg(a.sums + a.C + c0 + j);
+        dgamma = __ldg(a.sums + c0 + j);
+      }
+      const float mg = dbeta * a.inv_count;       // mean g
+      const float mgx = dgamma * a.inv_count;     // mean g*xhat
       // dz = gr*(g - mg - (z-mu)*rs*mgx)
       k0[j] = gr;
       kz[j] = -gr * rs * mgx;
@@ -516,7 +529,7 @@ int bn_relu_bwd_ex(const void* z, const void* dA, const void* dP, const float* s
                    const float* shift, const float* mean, const float* rstd,
                    const float* gamma, int B, int H, int W, int C, float* sums,
                    float* dbias, void* dz, const float* head_dl, const float* head_w, int nc,
-                   float* head_grads, cudaStream_t stream) {
+                   float* head_grads, const float* raw, cudaStream_t stream) {
   UGP_REQUIRE(z && (dA || dP || head_dl) && scale && shift && mean && rstd && gamma && sums && dz,
               "bn_relu_bwd: null pointer");
   if (head_dl) {
@@ -536,6 +549,9 @@ int bn_relu_bwd_ex(const void* z, const void* dA, const void* dP, const float* s
   const long long M = static_cast<long long>(B) * H * W;
   a.inv_count = 1.f / static_cast<float>(M);
   a.dl = head_dl; a.wh = head_w; a.dwh = head_grads; a.HW = H * W;
+  a.raw = raw;
+  UGP_REQUIRE(raw == nullptr || (dA != nullptr && dP == nullptr && head_dl == nullptr),
+              "bn_relu_bwd: precomputed sums go with the plain variant only");
   a.hw_shift = -1;
   for (int sft = 0; sft < 31; ++sft)
     if ((1 << sft) == a.HW) a.hw_shift = sft;
@@ -584,7 +600,8 @@ int bn_relu_bwd_ex(const void* z, const void* dA, const void* dP, const float* s
       UGP_CHECK_CUDA(cudaGetLastError());
       bn_relu_bwd_plain_kernel<true, 2><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
     } else {
-      if (!g_bn_skip_reduce) bn_relu_bwd_plain_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      if (!g_bn_skip_reduce && raw == nullptr)
+        bn_relu_bwd_plain_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
       UGP_CHECK_CUDA(cudaGetLastError());
       bn_relu_bwd_plain_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
     }
@@ -598,7 +615,7 @@ int bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scal
                 const float* gamma, int B, int H, int W, int C, float* sums,
                 float* dbias, void* dz, cudaStream_t stream) {
   return bn_relu_bwd_ex(z, dA, dP, scale, shift, mean, rstd, gamma, B, H, W, C, sums, dbias, dz, nullptr, nullptr,
-                        0, nullptr, stream);
+                        0, nullptr, nullptr, stream);
 }
 
 }  // namespace ugp

@@ -24,7 +24,9 @@ int bn_relu_apply_head(const void*, const float*, const float*, int, int, int, i
                        void*, float*, cudaStream_t);
 int bn_relu_bwd_ex(const void*, const void*, const void*, const float*, const float*, const float*, const float*,
                    const float*, int, int, int, int, float*, float*, void*, const float*, const float*, int, float*,
-                   cudaStream_t);
+                   const float*, cudaStream_t);
+int conv_dgrad_bnstats_bf16(const void*, int, int, int, int, const void*, int, void*, const void*, const float*,
+                            const float*, float*, cudaStream_t);
 int flip_u8(const unsigned char*, const unsigned char*, int, int, int, int, unsigned char*, cudaStream_t);
 int maxpool2x2(const void*, int, int, int, int, void*, int*, cudaStream_t);
 int maxpool2x2_bwd(const void*, const void*, int, int, int, int, void*, cudaStream_t);
@@ -140,7 +142,17 @@ int ugp_bn_relu_bwd_head(const void* z, const void* dA, const float* scale, cons
                          const float* head_w, int nc, float* sums, float* dbias, void* dz, float* head_grads,
                          void* stream) {
   return ugp::bn_relu_bwd_ex(z, dA, nullptr, scale, shift, mean, rstd, gamma, B, H, W, C, sums, dbias, dz, head_dl,
-                             head_w, nc, head_grads, S(stream));
+                             head_w, nc, head_grads, nullptr, S(stream));
+}
+int ugp_conv_dgrad_bnstats_bf16(const void* dz, int c, int B, int H, int W, const void* wd, int cout, void* dA,
+                                const void* z, const float* scale, const float* shift, float* raw, void* stream) {
+  return ugp::conv_dgrad_bnstats_bf16(dz, c, B, H, W, wd, cout, dA, z, scale, shift, raw, S(stream));
+}
+int ugp_bn_relu_bwd_apply(const void* z, const void* dA, const float* raw, const float* scale, const float* shift,
+                          const float* mean, const float* rstd, const float* gamma, int B, int H, int W, int C,
+                          float* sums, float* dbias, void* dz, void* stream) {
+  return ugp::bn_relu_bwd_ex(z, dA, nullptr, scale, shift, mean, rstd, gamma, B, H, W, C, sums, dbias, dz, nullptr,
+                             nullptr, 0, nullptr, raw, S(stream));
 }
 int ugp_bn_relu_bwd(const void* z, const void* dA, const void* dP, const float* scale,
                     const float* shift, const float* mean, const float* rstd, const float* gamma,

@@ -42,6 +42,14 @@ struct EpilogueCtx {
   uint32_t scratch_addr; // 2 KB: the four row-quarter partials of one chunk (kStatsScratchBytes)
   bool has_bias, has_affine, relu, do_stats;
   int valid_rows = 128;  // tile rows >= valid_rows hold no pixel (BW*BH < 128 boxes): stored / counted as zero
+  // BatchNorm-backward statistics mode (the input gradient of a DoubleConv's second convolution IS the
+  // activation gradient of its first BatchNorm): instead of sum / sum of squares of the stored values the
+  // statistics pass accumulates  S1 = sum g*[a > 0]  and  S2 = sum g*[a > 0]*z  per channel, with z the
+  // stored conv output of that BatchNorm (read here as bf16x2 words, row-major [pixels][C/2]) and
+  // a = z*scale + shift (scale / shift in the smem arrays, NOT applied to the output).  This is the whole
+  // reduction pass of ugp_bn_relu_bwd: that kernel then only runs its apply pass.
+  const uint32_t* bwd_z = nullptr;
+  int bwd_z_words = 0;   // words per pixel = C / 2
 };
 
 // v: 64 fp32 accumulator values of this thread's row (columns n_base .. n_base+63).
@@ -51,6 +59,14 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint3
                                                uint32_t buf_addr, int row, int et,
                                                const CUtensorMap* tm_out, int out_col, int out_row,
                                                int out_y = -1, int out_b = 0) {
+  // BN-backward statistics: request this thread's 32 z words (one word column over a quarter of the rows)
+  // now, so that they arrive while the accumulator is converted and staged
+  uint32_t zw[32];
+  if (e.bwd_z != nullptr) {
+    const uint32_t* zp = e.bwd_z + (static_cast<size_t>(out_row) + (et >> 5) * 32) * e.bwd_z_words + (n_base >> 1) + (et & 31);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) zw[i] = __ldg(zp + static_cast<size_t>(i) * e.bwd_z_words);
+  }
   uint32_t packed[32];
   const bool live_row = row < e.valid_rows;
 #pragma unroll
@@ -110,13 +126,29 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint3
     const uint32_t colp = buf_addr + ((wcol & 3) << 2);
     const int chunk = wcol >> 2;
     float s0a = 0.f, s1a = 0.f, q0a = 0.f, q1a = 0.f, s0b = 0.f, s1b = 0.f, q0b = 0.f, q1b = 0.f;
+    if (e.bwd_z == nullptr) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {      // r0 is a multiple of 8: (r0 + i) & 7 == i & 7
-      const uint32_t wa = ld_shared_b32(colp + (r0 + i) * 128 + ((chunk ^ (i & 7)) << 4));
-      const uint32_t wb = ld_shared_b32(colp + (r0 + i + 1) * 128 + ((chunk ^ ((i + 1) & 7)) << 4));
-      const float a0 = bf16_lo(wa), a1 = bf16_hi(wa), b0 = bf16_lo(wb), b1 = bf16_hi(wb);
-      s0a += a0; s1a += a1; q0a = fmaf(a0, a0, q0a); q1a = fmaf(a1, a1, q1a);
-      s0b += b0; s1b += b1; q0b = fmaf(b0, b0, q0b); q1b = fmaf(b1, b1, q1b);
+      for (int i = 0; i < 32; i += 2) {      // r0 is a multiple of 8: (r0 + i) & 7 == i & 7
+        const uint32_t wa = ld_shared_b32(colp + (r0 + i) * 128 + ((chunk ^ (i & 7)) << 4));
+        const uint32_t wb = ld_shared_b32(colp + (r0 + i + 1) * 128 + ((chunk ^ ((i + 1) & 7)) << 4));
+        const float a0 = bf16_lo(wa), a1 = bf16_hi(wa), b0 = bf16_lo(wb), b1 = bf16_hi(wb);
+        s0a += a0; s1a += a1; q0a = fmaf(a0, a0, q0a); q1a = fmaf(a1, a1, q1a);
+        s0b += b0; s1b += b1; q0b = fmaf(b0, b0, q0b); q1b = fmaf(b1, b1, q1b);
+      }
+    } else {
+      // BN-backward mode: g = the staged (bf16-rounded) gradient, masked by the ReLU of z*scale + shift
+      float2 sc, sh;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sc.x), "=f"(sc.y) : "r"(e.scale_addr + (n_base + 2 * wcol) * 4) : "memory");
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sh.x), "=f"(sh.y) : "r"(e.shift_addr + (n_base + 2 * wcol) * 4) : "memory");
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const uint32_t wa = ld_shared_b32(colp + (r0 + i) * 128 + ((chunk ^ (i & 7)) << 4));
+        const float z0 = bf16_lo(zw[i]), z1 = bf16_hi(zw[i]);
+        const float g0 = (fmaf(z0, sc.x, sh.x) > 0.f) ? bf16_lo(wa) : 0.f;
+        const float g1 = (fmaf(z1, sc.y, sh.y) > 0.f) ? bf16_hi(wa) : 0.f;
+        if (i & 1) { s0b += g0; s1b += g1; q0b = fmaf(g0, z0, q0b); q1b = fmaf(g1, z1, q1b); }
+        else       { s0a += g0; s1a += g1; q0a = fmaf(g0, z0, q0a); q1a = fmaf(g1, z1, q1a); }
+      }
     }
     // Deterministic reduction (no atomics): the four row quarters meet in scratch and are summed in
     // a fixed order by the first warp, which owns channel pair (c, c+1) of the CTA's running sums.

@@ -208,7 +208,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     ectx.scratch_addr = smem_u32(sScratch);
     ectx.stats_stride = kMaxC;
     ectx.has_bias = p.bias != nullptr;
-    ectx.has_affine = p.scale != nullptr;
+    ectx.has_affine = p.scale != nullptr && p.bwd_z == nullptr;
+    ectx.bwd_z = p.bwd_z;
+    ectx.bwd_z_words = p.cout >> 1;
     ectx.relu = p.relu != 0;
     ectx.do_stats = do_stats;
     ectx.valid_rows = p.valid_rows;
@@ -255,10 +257,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     if (et == 0) tma_store_wait_all();
     if (do_stats) {
       named_bar_sync(1, 128);
-      for (int i = et; i < p.cout; i += 128) {
-        // this CTA's slot of the [SMs][2][C] partial-statistics buffer (bn_finalize sums the slots in order)
-        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 0) * p.cout + i] = sStats[i];
-        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 1) * p.cout + i] = sStats[kMaxC + i];
+      if (p.bwd_z != nullptr) {
+        // BatchNorm-backward sums of this CTA -> the layer's [2][C] totals (fp32 atomics, like the other
+        // gradient reductions of the backward pass)
+        for (int i = et; i < p.cout; i += 128) {
+          atomicAdd(p.stats + i, sStats[i]);
+          atomicAdd(p.stats + p.cout + i, sStats[kMaxC + i]);
+        }
+      } else {
+        for (int i = et; i < p.cout; i += 128) {
+          // this CTA's slot of the [SMs][2][C] partial-statistics buffer (bn_finalize sums the slots in order)
+          p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 0) * p.cout + i] = sStats[i];
+          p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 1) * p.cout + i] = sStats[kMaxC + i];
+        }
       }
     }
   }
@@ -325,7 +336,7 @@ bool conv_halo_eligible(int H, int W, int cout, int split_n, int taps);
 int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
                    const void* wpack, int cout, void* dst0, void* dst1, int split_n,
                    const float* bias, const float* scale, const float* shift, int relu, float* stats,
-                   cudaStream_t stream);
+                   const void* bwd_z, cudaStream_t stream);
 extern int g_conv_halo_mode;   // 0 = per-tap loads everywhere, 1 = halo staging for wide thin layers
 
 // conv_pair.cu
@@ -341,7 +352,7 @@ int conv_gemm_bf16_ex(const void* src0, int c0, const void* src1, int c1, int B,
                       void* dst0, void* dst1, int split_n, const float* bias,
                       const float* scale, const float* shift, int relu,
                       float* stats, const ConvView* src_view, const ConvView* dst_view,
-                      int bias_period, cudaStream_t stream) {
+                      int bias_period, cudaStream_t stream, const void* bwd_z) {
   UGP_REQUIRE(src0 && wpack && dst0, "conv_gemm: null pointer");
   UGP_REQUIRE(taps == 9 || taps == 1, "conv_gemm: taps must be 9 or 1 (got %d)", taps);
   UGP_REQUIRE(c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
@@ -352,11 +363,18 @@ int conv_gemm_bf16_ex(const void* src0, int c0, const void* src1, int c1, int B,
   UGP_REQUIRE(split_n > 0 && split_n <= cout && split_n % 64 == 0,
               "conv_gemm: bad split_n %d", split_n);
   const bool viewed = src_view != nullptr || dst_view != nullptr;
+  if (bwd_z != nullptr) {
+    // BatchNorm-backward statistics mode: [2][cout] fp32 totals accumulated into `stats` (zeroed here)
+    UGP_REQUIRE(stats && scale && shift && !viewed && split_n == cout && !relu,
+                "conv_gemm: BatchNorm-backward statistics need stats / scale / shift and one dense destination");
+    UGP_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * cout, stream));
+  }
   if (!viewed && g_conv_halo_mode != 0 && conv_halo_eligible(H, W, cout, split_n, taps))
     return conv_halo_bf16(src0, c0, src1, c1, B, H, W, wpack, cout, dst0, dst1, split_n, bias, scale,
-                          shift, relu, stats, stream);
+                          shift, relu, stats, bwd_z, stream);
   int BW = 0, BH = 0;
   const bool general = !pick_box(H, W, kBlockM, &BW, &BH);
+  UGP_REQUIRE(bwd_z == nullptr || !general, "conv_gemm: BatchNorm-backward statistics need power-of-two tiles");
   if (general) {
     UGP_REQUIRE(H > 0 && W > 0 && pick_box_general(H, W, kBlockM, &BW, &BH),
                 "conv_gemm: unsupported spatial size %dx%d", H, W);
@@ -383,6 +401,7 @@ int conv_gemm_bf16_ex(const void* src0, int c0, const void* src1, int c1, int B,
   p.out4d = dst_view != nullptr || general;
   p.valid_rows = BW * BH;
   p.bias = bias; p.scale = scale; p.shift = shift; p.stats = stats;
+  p.bwd_z = static_cast<const uint32_t*>(bwd_z);
 
   CUtensorMap tmA0, tmA1, tmW, tmO0, tmO1;
   int rc;
@@ -427,7 +446,18 @@ int conv_gemm_bf16(const void* src0, int c0, const void* src1, int c1, int B,
                    const float* scale, const float* shift, int relu,
                    float* stats, cudaStream_t stream) {
   return conv_gemm_bf16_ex(src0, c0, src1, c1, B, H, W, taps, wpack, cout, dst0, dst1, split_n, bias,
-                           scale, shift, relu, stats, nullptr, nullptr, 0, stream);
+                           scale, shift, relu, stats, nullptr, nullptr, 0, stream, nullptr);
+}
+
+// Input gradient of a 3x3 convolution whose input is relu(BatchNorm(z)) (the second convolution of a
+// DoubleConv, UG_unet_parts.py:12-13): dA = conv(dz, wd) as conv_gemm_bf16, and in the same launch the
+// reduction pass of that BatchNorm's backward - raw[0][c] = sum dA*[a > 0], raw[1][c] = sum dA*[a > 0]*z.
+int conv_dgrad_bnstats_bf16(const void* dz, int c, int B, int H, int W, const void* wd, int cout, void* dA,
+                            const void* z, const float* scale, const float* shift, float* raw,
+                            cudaStream_t stream) {
+  UGP_REQUIRE(z && scale && shift && raw, "conv_dgrad_bnstats: null pointer");
+  return conv_gemm_bf16_ex(dz, c, nullptr, 0, B, H, W, 9, wd, cout, dA, nullptr, cout, nullptr, scale, shift, 0,
+                           raw, nullptr, nullptr, 0, stream, z);
 }
 
 }  // namespace ugp

@@ -22,6 +22,7 @@ struct ConvGemmParams {
   const float* scale;
   const float* shift;
   float* stats;
+  const uint32_t* bwd_z;   // non-null: BatchNorm-backward statistics mode (conv_epilogue.cuh), stats = fp32 [2][cout] accumulated
 };
 
 constexpr int kBlockM = 128;

@@ -37,6 +37,7 @@ struct ConvHaloParams {
   const float* scale;
   const float* shift;
   float* stats;
+  const uint32_t* bwd_z;     // BatchNorm-backward statistics mode (conv_epilogue.cuh)
 };
 
 extern int g_conv_debug;
@@ -341,7 +342,9 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     ectx.scratch_addr = smem_u32(sScratch);
     ectx.stats_stride = kHaloMaxCout;
     ectx.has_bias = p.bias != nullptr;
-    ectx.has_affine = p.scale != nullptr;
+    ectx.has_affine = p.scale != nullptr && p.bwd_z == nullptr;
+    ectx.bwd_z = p.bwd_z;
+    ectx.bwd_z_words = p.cout >> 1;
     ectx.relu = p.relu != 0;
     ectx.do_stats = do_stats;
     const uint32_t tempty_leader0 = kPair ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
@@ -396,10 +399,19 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     if (et == 0) tma_store_wait_all();
     if (do_stats) {
       named_bar_sync(1, 128);
-      for (int i = et; i < p.cout; i += 128) {
-        // this CTA's slot of the [SMs][2][C] partial-statistics buffer (bn_finalize sums the slots in order)
-        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 0) * p.cout + i] = sStats[i];
-        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 1) * p.cout + i] = sStats[kHaloMaxCout + i];
+      if (p.bwd_z != nullptr) {
+        // BatchNorm-backward sums of this CTA -> the layer's [2][C] totals (fp32 atomics, like the other
+        // gradient reductions of the backward pass)
+        for (int i = et; i < p.cout; i += 128) {
+          atomicAdd(p.stats + i, sStats[i]);
+          atomicAdd(p.stats + p.cout + i, sStats[kHaloMaxCout + i]);
+        }
+      } else {
+        for (int i = et; i < p.cout; i += 128) {
+          // this CTA's slot of the [SMs][2][C] partial-statistics buffer (bn_finalize sums the slots in order)
+          p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 0) * p.cout + i] = sStats[i];
+          p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 1) * p.cout + i] = sStats[kHaloMaxCout + i];
+        }
       }
     }
   }
@@ -486,7 +498,7 @@ bool conv_halo_eligible(int H, int W, int cout, int split_n, int taps) {
 int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, int H, int W,
                    const void* wpack, int cout, void* dst0, void* dst1, int split_n,
                    const float* bias, const float* scale, const float* shift, int relu, float* stats,
-                   cudaStream_t stream) {
+                   const void* bwd_z, cudaStream_t stream) {
   if (dst1 == nullptr) split_n = cout;
   int kn = 128;
   while (kn > 64 && cout % kn != 0) kn >>= 1;   // the epilogue routes each 64-column chunk to dst0 / dst1
@@ -504,6 +516,7 @@ int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, in
   p.debug = g_conv_debug;
   p.prefetch = g_conv_halo_prefetch;
   p.bias = bias; p.scale = scale; p.shift = shift; p.stats = stats;
+  p.bwd_z = static_cast<const uint32_t*>(bwd_z);
 
   CUtensorMap tmA0, tmA1, tmW, tmO0, tmO1;
   int rc;

@@ -183,7 +183,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     ectx.scratch_addr = smem_u32(sScratch);
     ectx.stats_stride = kMaxC;
     ectx.has_bias = p.bias != nullptr;
-    ectx.has_affine = p.scale != nullptr;
+    ectx.has_affine = p.scale != nullptr && p.bwd_z == nullptr;
+    ectx.bwd_z = p.bwd_z;
+    ectx.bwd_z_words = p.cout >> 1;
     ectx.relu = p.relu != 0;
     ectx.do_stats = do_stats;
     const uint32_t tempty_leader[2] = {mapa_u32(smem_u32(&tempty_bar[0]), 0),
@@ -224,10 +226,19 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (et == 0) tma_store_wait_all();
     if (do_stats) {
       named_bar_sync(1, 128);
-      for (int i = et; i < p.cout; i += 128) {
-        // this CTA's slot of the [SMs][2][C] partial-statistics buffer (bn_finalize sums the slots in order)
-        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 0) * p.cout + i] = sStats[i];
-        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 1) * p.cout + i] = sStats[kMaxC + i];
+      if (p.bwd_z != nullptr) {
+        // BatchNorm-backward sums of this CTA -> the layer's [2][C] totals (fp32 atomics, like the other
+        // gradient reductions of the backward pass)
+        for (int i = et; i < p.cout; i += 128) {
+          atomicAdd(p.stats + i, sStats[i]);
+          atomicAdd(p.stats + p.cout + i, sStats[kMaxC + i]);
+        }
+      } else {
+        for (int i = et; i < p.cout; i += 128) {
+          // this CTA's slot of the [SMs][2][C] partial-statistics buffer (bn_finalize sums the slots in order)
+          p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 0) * p.cout + i] = sStats[i];
+          p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 1) * p.cout + i] = sStats[kMaxC + i];
+        }
       }
     }
   }

@@ -25,7 +25,7 @@ int conv_gemm_bf16_ex(const void* src0, int c0, const void* src1, int c1, int B,
                       const void* wpack, int cout, void* dst0, void* dst1, int split_n, const float* bias,
                       const float* scale, const float* shift, int relu, float* stats,
                       const ConvView* src_view, const ConvView* dst_view, int bias_period,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const void* bwd_z = nullptr);
 int conv_wgrad_bf16_ex(const void* src0, int c0, const void* src1, int c1, const void* dz, int cout, int B,
                        int H, int W, int taps, float* dw_packed, const ConvView* dz_view,
                        cudaStream_t stream);

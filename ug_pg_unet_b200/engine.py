@@ -27,6 +27,9 @@ bf16 = torch.bfloat16
 #   UGP_WHATIF_POOL_AS_PLAIN:   pooled gradient dropped, so the pooled BatchNorm backward runs the plain kernels
 _WHATIF_SKIP_BN1_REDUCE = os.environ.get("UGP_WHATIF_SKIP_BN1_REDUCE", "0") == "1"
 _WHATIF_POOL_AS_PLAIN = os.environ.get("UGP_WHATIF_POOL_AS_PLAIN", "0") == "1"
+# UGP_NO_FUSED_BN_BWD_REDUCE=1: the reduction pass of every DoubleConv's first BatchNorm backward runs as its
+# own kernel again instead of inside the epilogue of the dgrad that produces its input (A/B switch)
+_FUSED_BN_BWD_REDUCE = os.environ.get("UGP_NO_FUSED_BN_BWD_REDUCE", "0") != "1"
 
 
 # NVTX ranges (UGP_NVTX=1): one range per DoubleConv block and direction, one per trainer-step phase, so a
@@ -262,10 +265,15 @@ def cbr_forward(srcs: Sequence[torch.Tensor], taps: int, conv: nn.Conv2d, bn: nn
 
 
 def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch.Tensor], conv: nn.Conv2d,
-                 bn: nn.BatchNorm2d, packs: PackedWeights, need_dgrad: bool, head=None):
+                 bn: nn.BatchNorm2d, packs: PackedWeights, need_dgrad: bool, head=None, raw=None, below=None):
     """Backward of one unit.  Returns (d_srcs list or None, (dW, dbias, dgamma, dbeta)).
     `head` = (dl [B, nc, H, W] fp32, w [nc, C]): gradient of the fused 1x1 head's map; its weight / bias
-    gradients are left in `head[2]` (a list the caller reads)."""
+    gradients are left in `head[2]` (a list the caller reads).
+    `raw`: the reduction pass of this unit's BatchNorm backward already ran inside the convolution that
+    produced dA (ops.conv_dgrad_bnstats): only the apply pass runs here.
+    `below` = CBRSaved of the unit whose output this unit's single source is (the first unit of the same
+    DoubleConv): the input gradient is then produced together with THAT unit's BatchNorm-backward sums and
+    returned as (d_srcs, grads, raw_below)."""
     src0 = saved.srcs[0]
     src1 = saved.srcs[1] if len(saved.srcs) > 1 else None
     cout = conv.out_channels
@@ -279,6 +287,9 @@ def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch
         dz, hg = ops.bn_relu_bwd_head(saved.z, dA, coef[0], coef[1], coef[2], coef[3], bn.weight.detach(),
                                       small[:2], small[2], head[0], head[1])
         head[2].append(hg)
+    elif raw is not None:
+        dz = ops.bn_relu_bwd_apply(saved.z, dA, raw, coef[0], coef[1], coef[2], coef[3], bn.weight.detach(),
+                                   small[:2], small[2])
     else:
         dz = ops.bn_relu_bwd(saved.z, dA, dP, coef[0], coef[1], coef[2], coef[3], bn.weight.detach(),
                              small[:2], small[2])
@@ -304,13 +315,20 @@ def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch
         else:
             dW = ops.unpack_wgrad(dwp, cout, cin)
     d_srcs = None
+    raw_below = None
     if need_dgrad:
         _, wd = packs.get()
-        if src1 is None:
+        if below is not None and src1 is None and _FUSED_BN_BWD_REDUCE and \
+                ops.dgrad_bnstats_supported(dz.shape[1], dz.shape[2]):
+            d, raw_below = ops.conv_dgrad_bnstats(dz, wd, kdim, below.z, below.coef[0], below.coef[1])
+            d_srcs = [d]
+        elif src1 is None:
             d_srcs = [ops.conv_gemm(dz, None, wd, 9, kdim)]
         else:
             d0, d1 = ops.conv_gemm(dz, None, wd, 9, kdim, split_n=src0.shape[3])
             d_srcs = [d0, d1]
+    if below is not None:
+        return d_srcs, (dW, small[2], small[0], small[1]), raw_below
     return d_srcs, (dW, small[2], small[0], small[1])
 
 
@@ -398,11 +416,13 @@ class DoubleConvFn(torch.autograd.Function):
             if head is None and dA is None:
                 raise RuntimeError("DoubleConvFn.backward: no gradient reached the block")
         with nvtx_range(f"bwd {ctx.kind} {conv1.in_channels}->{conv2.out_channels} @{ctx.s2.z.shape[1]}x{ctx.s2.z.shape[2]}"):
-            d1, g2 = cbr_backward(ctx.s2, dA, dP, conv2, bn2, mod._packs[1], True, head=head)
+            # the input gradient of conv2 IS the activation gradient of bn1: its reduction pass rides in the
+            # dgrad's epilogue (raw1), bn1's backward then only runs the apply pass
+            d1, g2, raw1 = cbr_backward(ctx.s2, dA, dP, conv2, bn2, mod._packs[1], True, head=head, below=ctx.s1)
             need_in = ctx.x_needs_grad or ctx.skip_needs_grad
             if _WHATIF_SKIP_BN1_REDUCE:
                 set_option("bn_skip_reduce", 1)
-            d0, g1 = cbr_backward(ctx.s1, d1[0], None, conv1, bn1, mod._packs[0], need_in)
+            d0, g1 = cbr_backward(ctx.s1, d1[0], None, conv1, bn1, mod._packs[0], need_in, raw=raw1)
             if _WHATIF_SKIP_BN1_REDUCE:
                 set_option("bn_skip_reduce", 0)
         dx = dskip = None

@@ -86,7 +86,7 @@ def _nb(*ts) -> float:
 
 def check(rc: int, what: str) -> None:
     _check_rc(rc, what)
-    if what not in ("ugp_conv_gemm_bf16", "ugp_conv_wgrad_bf16", "ugp_bn_relu_bwd_head"):
+    if what not in ("ugp_conv_gemm_bf16", "ugp_conv_dgrad_bnstats_bf16", "ugp_conv_wgrad_bf16", "ugp_bn_relu_bwd_head"):
         _count(2 if what == "ugp_bn_relu_bwd" else 1)
 
 
@@ -150,6 +150,45 @@ def conv_gemm(src0: torch.Tensor, src1: Optional[torch.Tensor], wpack: torch.Ten
     check(rc, "ugp_conv_gemm_bf16")
     _count()
     return (out0, out1) if out1 is not None else out0
+
+
+def dgrad_bnstats_supported(H: int, W: int) -> bool:
+    """Spatial sizes whose convolution tiles are runs of consecutive pixels (the fused BN-backward
+    statistics address z by pixel index): the power-of-two maps of the model."""
+    bw = W if W < 128 else 128
+    return W % bw == 0 and 128 % bw == 0 and H % (128 // bw) == 0
+
+
+def conv_dgrad_bnstats(dz, wd, cin: int, z, scale, shift):
+    """dA = conv3x3(dz, wd) plus the reduction pass of the BatchNorm backward that consumes dA; see
+    ugp_conv_dgrad_bnstats_bf16.  Returns (dA NHWC bf16 [B,H,W,cin], raw fp32 [2, cin])."""
+    _req(dz, bf16, "dz")
+    _req(z, bf16, "z")
+    B, H, W, c = dz.shape
+    assert tuple(z.shape) == (B, H, W, cin) and wd.numel() == 9 * c * cin
+    dA = torch.empty((B, H, W, cin), dtype=bf16, device=dz.device)
+    raw = torch.empty((2, cin), dtype=torch.float32, device=dz.device)
+    with _timed("conv_gemm", 2.0 * B * H * W * cin * 9 * c, _nb(dz, wd, dA, z)):
+        rc = lib().ugp_conv_dgrad_bnstats_bf16(_ptr(dz), c, B, H, W, _ptr(_req(wd, bf16, "wd")), cin, _ptr(dA), _ptr(z),
+                                               _ptr(_req(scale, torch.float32, "scale")),
+                                               _ptr(_req(shift, torch.float32, "shift")), _ptr(raw), _stream())
+    check(rc, "ugp_conv_dgrad_bnstats_bf16")
+    _count()
+    return dA, raw
+
+
+def bn_relu_bwd_apply(z, dA, raw, scale, shift, mean, rstd, gamma, sums, dbias):
+    """The apply pass of bn_relu_bwd with the sums of conv_dgrad_bnstats; see ugp_bn_relu_bwd_apply."""
+    _req(z, bf16, "z")
+    B, H, W, Cn = z.shape
+    dz = torch.empty_like(z)
+    with _timed("bn_relu_bwd_apply", 0.0, _nb(z, dA, dz)):
+        rc = lib().ugp_bn_relu_bwd_apply(_ptr(z), _ptr(_req(dA, bf16, "dA")), _ptr(_req(raw, torch.float32, "raw")),
+                                         _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _ptr(gamma), B, H, W, Cn,
+                                         _ptr(_req(sums, torch.float32, "sums")),
+                                         _ptr(_opt(dbias, torch.float32, "dbias")), _ptr(dz), _stream())
+    check(rc, "ugp_bn_relu_bwd_apply")
+    return dz
 
 
 def conv_wgrad(src0, src1, dz, taps: int, dw_packed: torch.Tensor):
