@@ -32,6 +32,14 @@ bn_finalize_kernel(float* __restrict__ stats, int parts, int C, float count,
   const int c = blockIdx.x * 32 + cx;
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
   float s = 0.f, s2 = 0.f;
+  // the kernel is one chain of dependent round trips (slots -> sums -> coefficients): everything the last
+  // step needs is requested up front, together with the slots
+  float g_c = 0.f, b_c = 0.f, rm_c = 0.f, rv_c = 0.f;
+  if (g == 0 && c < C) {
+    g_c = gamma[c];
+    b_c = beta[c];
+    if (running_mean) { rm_c = running_mean[c]; rv_c = running_var[c]; }
+  }
   if (c < C) {
 #pragma unroll 5
     for (int q = g; q < parts; q += kFinGroups) {
@@ -56,15 +64,15 @@ bn_finalize_kernel(float* __restrict__ stats, int parts, int C, float count,
   float var = s2 / count - mean * mean;
   var = fmaxf(var, 0.f);
   const float rstd = rsqrtf(var + eps);
-  const float sc = gamma[c] * rstd;
+  const float sc = g_c * rstd;
   scale[c] = sc;
-  shift[c] = beta[c] - mean * sc;
+  shift[c] = b_c - mean * sc;
   save_mean[c] = mean;
   save_rstd[c] = rstd;
   if (running_mean) {
     const float unbiased = (count > 1.f) ? var * count / (count - 1.f) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    running_mean[c] = (1.f - momentum) * rm_c + momentum * mean;
+    running_var[c] = (1.f - momentum) * rv_c + momentum * unbiased;
   }
 }
 
