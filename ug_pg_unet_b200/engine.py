@@ -27,9 +27,13 @@ bf16 = torch.bfloat16
 #   UGP_WHATIF_POOL_AS_PLAIN:   pooled gradient dropped, so the pooled BatchNorm backward runs the plain kernels
 _WHATIF_SKIP_BN1_REDUCE = os.environ.get("UGP_WHATIF_SKIP_BN1_REDUCE", "0") == "1"
 _WHATIF_POOL_AS_PLAIN = os.environ.get("UGP_WHATIF_POOL_AS_PLAIN", "0") == "1"
-# UGP_NO_FUSED_BN_BWD_REDUCE=1: the reduction pass of every DoubleConv's first BatchNorm backward runs as its
-# own kernel again instead of inside the epilogue of the dgrad that produces its input (A/B switch)
-_FUSED_BN_BWD_REDUCE = os.environ.get("UGP_NO_FUSED_BN_BWD_REDUCE", "0") != "1"
+# UGP_FUSED_BN_BWD_REDUCE=1: the reduction pass of every DoubleConv's first BatchNorm backward runs inside the
+# epilogue of the dgrad that produces its input (ugp_conv_dgrad_bnstats_bf16) instead of as its own kernel.
+# Built, parity-tested and measured: the kernels of a step take 0.10 ms less, but the step
+# does not get faster - the stand-alone reduction pass is HBM-bound and hides under the weight-gradient
+# convolutions of the side stream, while the longer, epilogue-bound dgrad (64 -> 64 @256^2: 77 -> 116 us)
+# competes with them for the tensor pipe.  Off by default.
+_FUSED_BN_BWD_REDUCE = os.environ.get("UGP_FUSED_BN_BWD_REDUCE", "0") == "1"
 
 
 # NVTX ranges (UGP_NVTX=1): one range per DoubleConv block and direction, one per trainer-step phase, so a
