@@ -381,7 +381,7 @@ def run_ours(args):
                 "launches_per_step": fd["launches_per_step"],
                 "timing": how,
                 # dram__bytes_read.sum + dram__bytes_write.sum summed over the class's launches at batch 16, from the
-                # ncu metrics pass profiles/r02_conv_dram_bytes.txt (null until that file is refreshed for this build)
+                # ncu metrics pass profiles/r02_ncu_launches_by_kernel.txt (same bench command, 49 launches of one step)
                 "traffic": CONV_CLASS_DRAM_BYTES if B == 16 else None, "traffic_unit": "bytes/step (class)",
                 "algorithmic_bytes": fd["bytes"],
                 "wgrad": {"achieved": tf(wg), "frac": tf(wg) / peak, **{k: wg[k] for k in ("launches_per_step", "ms_per_step_in_kernel")}},
@@ -505,8 +505,9 @@ def run_ours(args):
 
 
 # Sum of dram__bytes_read.sum + dram__bytes_write.sum over the forward + dgrad convolution launches of one
-# batch-16 step (ncu metrics pass, profiles/r02_conv_dram_bytes.txt).  None = not captured for this build.
-CONV_CLASS_DRAM_BYTES = None
+# batch-16 step (ncu metrics pass, profiles/r02_ncu_launches_by_kernel.txt: 3 372.8 MB against 4 744 MB algorithmic - consecutive
+# kernels meet in the 126 MB L2).
+CONV_CLASS_DRAM_BYTES = 3372.8e6
 
 
 def main():
