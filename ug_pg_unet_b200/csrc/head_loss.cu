@@ -24,6 +24,21 @@ __device__ __forceinline__ void bilinear_src_f(int dst, int in, int out, int* i0
   *lambda = src - static_cast<float>(a);
 }
 
+// Same rule with the scale (in-1)/(out-1) computed once on the host (IEEE float division, identical to the
+// device's): the per-pixel kernels below were bound by the float division and the 64-bit index divisions
+// of their address arithmetic, not by memory (21 us for 9 MB).
+__device__ __forceinline__ void bilinear_src_s(int dst, int in, float scale, int* i0, int* i1, float* lambda) {
+  const float src = scale * static_cast<float>(dst);
+  int a = static_cast<int>(src);
+  if (a > in - 1) a = in - 1;
+  *i0 = a;
+  *i1 = a + ((a < in - 1) ? 1 : 0);
+  *lambda = src - static_cast<float>(a);
+}
+static inline float host_bilinear_scale(int in, int out) {
+  return (out > 1) ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f;
+}
+
 // ----------------------------------------------------------------------------
 // 1x1 OutConv forward: x bf16 [M][C] (NHWC) -> l fp32 [B][nc][h*w] (NCHW).
 // C/8 lanes cooperate on one pixel (16-byte loads), shuffle-reduced.
@@ -177,38 +192,36 @@ struct HeadMaps {
   const float* l[4];
   float* dl[4];
   int h[4], w[4];   // map sizes (rectangular images: H != W)
+  float sy[4], sx[4];   // (h-1)/(RH-1), (w-1)/(RW-1), computed on the host
   int n;
 };
 
+// grid = (ceil(RW / 256), RH, planes): no index division per pixel
 __global__ void head_combine_fwd_kernel(const HeadMaps m, int planes, int RH, int RW,
                                         float* __restrict__ logits) {
-  const long long total = static_cast<long long>(planes) * RH * RW;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-       idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int X = static_cast<int>(idx % RW);
-    const int Y = static_cast<int>((idx / RW) % RH);
-    const long long plane = idx / (static_cast<long long>(RH) * RW);
-    // PyTorch evaluates x6_out + x7_out + x8_out + x9_out left to right,
-    // coarsest first (UG_unet.py:303).
-    float acc = 0.f;
-    for (int s = 0; s < m.n; ++s) {
-      const int sh = m.h[s], sw = m.w[s];
-      const float* src = m.l[s] + plane * sh * sw;
-      float v;
-      if (sh == RH && sw == RW) {
-        v = __ldg(src + static_cast<long long>(Y) * RW + X);
-      } else {
-        int y0, y1, x0, x1;
-        float ly, lx;
-        bilinear_src_f(Y, sh, RH, &y0, &y1, &ly);
-        bilinear_src_f(X, sw, RW, &x0, &x1, &lx);
-        v = (1.f - ly) * ((1.f - lx) * __ldg(src + y0 * sw + x0) + lx * __ldg(src + y0 * sw + x1)) +
-            ly * ((1.f - lx) * __ldg(src + y1 * sw + x0) + lx * __ldg(src + y1 * sw + x1));
-      }
-      acc = (s == 0) ? v : acc + v;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int plane = blockIdx.z, Y = blockIdx.y;
+  if (X >= RW) return;
+  // PyTorch evaluates x6_out + x7_out + x8_out + x9_out left to right,
+  // coarsest first (UG_unet.py:303).
+  float acc = 0.f;
+  for (int s = 0; s < m.n; ++s) {
+    const int sh = m.h[s], sw = m.w[s];
+    const float* src = m.l[s] + static_cast<long long>(plane) * sh * sw;
+    float v;
+    if (sh == RH && sw == RW) {
+      v = __ldg(src + static_cast<long long>(Y) * RW + X);
+    } else {
+      int y0, y1, x0, x1;
+      float ly, lx;
+      bilinear_src_s(Y, sh, m.sy[s], &y0, &y1, &ly);
+      bilinear_src_s(X, sw, m.sx[s], &x0, &x1, &lx);
+      v = (1.f - ly) * ((1.f - lx) * __ldg(src + y0 * sw + x0) + lx * __ldg(src + y0 * sw + x1)) +
+          ly * ((1.f - lx) * __ldg(src + y1 * sw + x0) + lx * __ldg(src + y1 * sw + x1));
     }
-    logits[idx] = acc;
+    acc = (s == 0) ? v : acc + v;
   }
+  logits[(static_cast<long long>(plane) * RH + Y) * RW + X] = acc;
 }
 
 // Adjoint of one upsampled scale in gather form: dl[y,x] = sum over the
@@ -259,26 +272,23 @@ __global__ void head_combine_bwd_kernel(const float* __restrict__ dlogits, int p
 // (UG_unet.py:44-57).  z_prev fp32 [planes][h][w] -> A fp32 [planes][H][W].
 // ----------------------------------------------------------------------------
 __global__ void uncertainty_margin_kernel(const float* __restrict__ zprev, int planes,
-                                          int h, int w, int H, int W,
+                                          int h, int w, int H, int W, float sy, float sx,
                                           float* __restrict__ A) {
-  const long long total = static_cast<long long>(planes) * H * W;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-       idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int X = static_cast<int>(idx % W);
-    const int Y = static_cast<int>((idx / W) % H);
-    const long long plane = idx / (static_cast<long long>(W) * H);
-    const float* src = zprev + plane * h * w;
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bilinear_src_f(Y, h, H, &y0, &y1, &ly);
-    bilinear_src_f(X, w, W, &x0, &x1, &lx);
-    const float p00 = 1.f / (1.f + expf(-__ldg(src + y0 * w + x0)));
-    const float p01 = 1.f / (1.f + expf(-__ldg(src + y0 * w + x1)));
-    const float p10 = 1.f / (1.f + expf(-__ldg(src + y1 * w + x0)));
-    const float p11 = 1.f / (1.f + expf(-__ldg(src + y1 * w + x1)));
-    const float p = (1.f - ly) * ((1.f - lx) * p00 + lx * p01) + ly * ((1.f - lx) * p10 + lx * p11);
-    A[idx] = 1.f - 2.f * fabsf(p - 0.5f);
-  }
+  // grid = (ceil(W / 256), H, planes)
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int plane = blockIdx.z, Y = blockIdx.y;
+  if (X >= W) return;
+  const float* src = zprev + static_cast<long long>(plane) * h * w;
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilinear_src_s(Y, h, sy, &y0, &y1, &ly);
+  bilinear_src_s(X, w, sx, &x0, &x1, &lx);
+  const float p00 = 1.f / (1.f + expf(-__ldg(src + y0 * w + x0)));
+  const float p01 = 1.f / (1.f + expf(-__ldg(src + y0 * w + x1)));
+  const float p10 = 1.f / (1.f + expf(-__ldg(src + y1 * w + x0)));
+  const float p11 = 1.f / (1.f + expf(-__ldg(src + y1 * w + x1)));
+  const float p = (1.f - ly) * ((1.f - lx) * p00 + lx * p01) + ly * ((1.f - lx) * p10 + lx * p11);
+  A[(static_cast<long long>(plane) * H + Y) * W + X] = 1.f - 2.f * fabsf(p - 0.5f);
 }
 
 // Softmax-entropy uncertainty per sample: u = H(softmax(z)) / ln K
@@ -472,7 +482,10 @@ int head_combine_fwd_hw(const float* const* maps, const int* heights, const int*
                 "head_combine_fwd: map %d is %dx%d, logits %dx%d", i, m.h[i], m.w[i], RH, RW);
   }
   const long long total = static_cast<long long>(planes) * RH * RW;
-  head_combine_fwd_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, stream>>>(m, planes, RH, RW, logits);
+  for (int i = 0; i < n; ++i) { m.sy[i] = host_bilinear_scale(m.h[i], RH); m.sx[i] = host_bilinear_scale(m.w[i], RW); }
+  UGP_REQUIRE(planes <= 65535 && RH <= 65535, "head_combine_fwd: too many planes / rows");
+  (void)total;
+  head_combine_fwd_kernel<<<dim3((RW + 255) / 256, RH, planes), 256, 0, stream>>>(m, planes, RH, RW, logits);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
@@ -488,13 +501,13 @@ int head_combine_fwd(const float* const* maps, const int* sizes, int n, int plan
 // from the same bilinear_src_f as the forward kernel, so this is its exact adjoint.
 constexpr int kHeadMaxTaps = 64;
 __global__ void __launch_bounds__(256)
-head_combine_bwd_rows_kernel(const float* __restrict__ dlogits, int RH, int RW, int sh, int sw,
-                             float* __restrict__ dl) {
-  extern __shared__ float t[];            // RW floats
+head_combine_bwd_rows_kernel(const float* __restrict__ dlogits, int RH, int RW, int sh, int sw, float sy, float sx,
+                             float invy, float invx, float* __restrict__ dl) {
+  extern __shared__ float t[];            // RW floats folded row + RW (j0, lx) table entries
+  int* tj0 = reinterpret_cast<int*>(t + RW);
+  float* tlx = t + 2 * RW;
   __shared__ float wys[kHeadMaxTaps];
   const int plane = blockIdx.x / sh, y = blockIdx.x - plane * sh;
-  const float invy = (sh > 1) ? static_cast<float>(RH - 1) / static_cast<float>(sh - 1) : 0.f;
-  const float invx = (sw > 1) ? static_cast<float>(RW - 1) / static_cast<float>(sw - 1) : 0.f;
   int Ylo = static_cast<int>(floorf((y - 1) * invy)) - 1, Yhi = static_cast<int>(ceilf((y + 1) * invy)) + 1;
   if (Ylo < 0) Ylo = 0;
   if (Yhi > RH - 1) Yhi = RH - 1;
@@ -502,7 +515,7 @@ head_combine_bwd_rows_kernel(const float* __restrict__ dlogits, int RH, int RW, 
   if (threadIdx.x < ny) {
     int i0, i1;
     float l;
-    bilinear_src_f(Ylo + threadIdx.x, sh, RH, &i0, &i1, &l);
+    bilinear_src_s(Ylo + threadIdx.x, sh, sy, &i0, &i1, &l);
     wys[threadIdx.x] = (i0 == y ? 1.f - l : 0.f) + (i1 == y ? l : 0.f);
   }
   __syncthreads();
@@ -511,6 +524,11 @@ head_combine_bwd_rows_kernel(const float* __restrict__ dlogits, int RH, int RW, 
     float acc = 0.f;
     for (int k = 0; k < ny; ++k) acc = fmaf(wys[k], __ldg(g + static_cast<long long>(k) * RW + X), acc);
     t[X] = acc;
+    int j0, j1;
+    float lx;
+    bilinear_src_s(X, sw, sx, &j0, &j1, &lx);      // source columns / weight of fine column X, once per block
+    tj0[X] = j0;
+    tlx[X] = (j1 == j0) ? 0.f : lx;
   }
   __syncthreads();
   for (int x = threadIdx.x; x < sw; x += blockDim.x) {
@@ -519,10 +537,10 @@ head_combine_bwd_rows_kernel(const float* __restrict__ dlogits, int RH, int RW, 
     if (Xhi > RW - 1) Xhi = RW - 1;
     float acc = 0.f;
     for (int X = Xlo; X <= Xhi; ++X) {
-      int j0, j1;
-      float lx;
-      bilinear_src_f(X, sw, RW, &j0, &j1, &lx);
-      const float wx = (j0 == x ? 1.f - lx : 0.f) + (j1 == x ? lx : 0.f);
+      const int j0 = tj0[X];
+      const float lx = tlx[X];
+      // fine column X reads coarse columns j0 (weight 1 - lx) and j0 + 1 (weight lx; lx = 0 at the right edge)
+      const float wx = (j0 == x ? 1.f - lx : 0.f) + (j0 + 1 == x ? lx : 0.f);
       acc = fmaf(wx, t[X], acc);
     }
     dl[(static_cast<long long>(plane) * sh + y) * sw + x] = acc;
@@ -534,9 +552,12 @@ int head_combine_bwd_hw(const float* dlogits, int planes, int RH, int RW, int sh
   UGP_REQUIRE(dlogits && dl && sh >= 1 && sh <= RH && sw >= 1 && sw <= RW, "head_combine_bwd: bad arguments");
   const long long total = static_cast<long long>(planes) * sh * sw;
   const int taps = (sh > 1) ? 2 * ((RH - 1) / (sh - 1) + 1) + 4 : RH;
-  if ((sh != RH || sw != RW) && taps <= kHeadMaxTaps && RW * 4 <= 48 * 1024 &&
+  if ((sh != RH || sw != RW) && taps <= kHeadMaxTaps && RW * 12 <= 48 * 1024 &&
       static_cast<long long>(planes) * sh < (1LL << 31)) {
-    head_combine_bwd_rows_kernel<<<planes * sh, 256, RW * sizeof(float), stream>>>(dlogits, RH, RW, sh, sw, dl);
+    const float invy = (sh > 1) ? static_cast<float>(RH - 1) / static_cast<float>(sh - 1) : 0.f;
+    const float invx = (sw > 1) ? static_cast<float>(RW - 1) / static_cast<float>(sw - 1) : 0.f;
+    head_combine_bwd_rows_kernel<<<planes * sh, 256, 3 * RW * sizeof(float), stream>>>(
+        dlogits, RH, RW, sh, sw, host_bilinear_scale(sh, RH), host_bilinear_scale(sw, RW), invy, invx, dl);
   } else {
     head_combine_bwd_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, stream>>>(dlogits, planes, RH, RW, sh,
                                                                                  sw, dl);
@@ -554,7 +575,10 @@ int uncertainty_margin(const float* zprev, int planes, int h, int w, int H, int 
                        cudaStream_t stream) {
   UGP_REQUIRE(zprev && A, "uncertainty_margin: null pointer");
   const long long total = static_cast<long long>(planes) * H * W;
-  uncertainty_margin_kernel<<<grid_cap((total + 255) / 256, 16), 256, 0, stream>>>(zprev, planes, h, w, H, W, A);
+  (void)total;
+  UGP_REQUIRE(planes <= 65535 && H <= 65535, "uncertainty_margin: too many planes / rows");
+  uncertainty_margin_kernel<<<dim3((W + 255) / 256, H, planes), 256, 0, stream>>>(
+      zprev, planes, h, w, H, W, host_bilinear_scale(h, H), host_bilinear_scale(w, W), A);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }

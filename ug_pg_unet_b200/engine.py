@@ -572,7 +572,9 @@ class HeadCombineFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         dlogits = dlogits.contiguous()
-        return tuple(ops.head_combine_bwd(dlogits, s) for s in ctx.sizes)
+        full = (dlogits.shape[-2], dlogits.shape[-1])
+        # the finest map is added as is: its gradient is dlogits itself (no launch, no copy)
+        return tuple(dlogits if tuple(s) == full else ops.head_combine_bwd(dlogits, s) for s in ctx.sizes)
 
 
 class GlobalAvgPoolFn(torch.autograd.Function):
