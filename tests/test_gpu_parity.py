@@ -724,6 +724,49 @@ def test_dgrad_with_fused_batchnorm_backward_sums(dev, shape):
     torch.testing.assert_close(small[2], small_r[2], rtol=2e-2, atol=2e-3 * float(small_r[1].abs().max()) + 1e-3)
 
 
+def test_custom_criterion_runs_one_forward_per_step_and_graph_cache_keys(dev):
+    """A base_criterion the fused loss kernel does not cover runs the reference's own arithmetic - ONE
+    train-mode forward per step (BatchNorm counters advance once per step, reference :203-234) - and the
+    step-graph cache keeps one captured graph per (shape, alpha, criterion) instead of evicting."""
+    import contextlib
+    import io
+    import ug_pg_unet_b200 as U
+
+    g = torch.Generator().manual_seed(2)
+    batches = [(torch.randn(2, 3, 64, 64, generator=g), torch.randint(0, 2, (2, 1, 64, 64), generator=g).float())
+               for _ in range(3)]
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = U.UncertaintyGuidedProgressiveTrainer(3, 1, device=dev, log_interval=0)
+        tr.current_stage, tr.current_model = 2, tr.models[2]
+        tr.setup_optimizer(2)
+        tr.base_criterion = lambda z, t: torch.nn.functional.binary_cross_entropy_with_logits(z, t, reduction="none")
+        res = tr.train_epoch(batches, 2)
+    assert all(math.isfinite(v) for v in res) and 0.0 <= res[2] <= 1.0 and 0.0 <= res[3] <= 1.0
+    assert int(tr.models[2].inc.conv.conv_op[1].num_batches_tracked) == 3          # not 6
+    # fused criterion again: graphs keyed by everything a capture bakes in
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr.base_criterion = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([5.0], device=dev), reduction="none")
+        x, y = batches[0][0].to(dev), batches[0][1].to(dev)
+        for _ in range(5):
+            tr.train_step(x, y, 2)
+        assert len(tr._graphs) == 1 and next(iter(tr._graphs.values()))["graph"] is not None
+        tr.uncertainty_alpha = 0.5                       # baked into the capture as a float: a new key
+        for _ in range(5):
+            tr.train_step(x, y, 2)
+        assert len(tr._graphs) == 2
+        m_a = tr.train_step(x, y, 2)[0]
+        tr.uncertainty_alpha = 1.0                       # back to the first graph, still captured
+        k = len(tr._graphs)
+        m_b = tr.train_step(x, y, 2)[0]
+        assert len(tr._graphs) == k and not torch.equal(m_a[:1], m_b[:1])
+        xr, yr = x[:1].contiguous(), y[:1].contiguous()  # ragged batch: own entry, nothing evicted
+        tr.train_step(xr, yr, 2)
+        assert len(tr._graphs) == 3 and sum(g_["graph"] is not None for g_ in tr._graphs.values()) == 2
+        tr.close()
+        assert not tr._graphs
+
+
 def test_global_avg_pool_kernels(dev):
     from ug_pg_unet_b200 import ops
 

@@ -144,3 +144,62 @@ def test_bucketed_gradient_averaging_world2(tmp_path, overlap):
 def test_shard_batch_requires_equal_shards():
     with pytest.raises(ValueError):
         shard_batch(torch.zeros(5, 1), 0, 2)
+
+
+def _herlev_worker(rank, world, port, out_dir):
+    """Data-parallel HerlevTrainer host logic (no kernels): epoch metrics identical on every rank, reducer
+    rebuilt when requires_grad flags change (ranks must not pick different learning rates or
+    leave the epoch loop apart)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import contextlib
+        import io
+        import ug_pg_unet_b200.herlev as H
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr = H.HerlevTrainer({"device": "cpu", "epochs_per_stage": 1, "num_classes": 7, "log_interval": 0,
+                                  "stages": [1]})
+        assert tr.distributed and tr.world_size == world
+        # rank-dependent per-batch numbers, as rank-local BatchNorm buffers produce them in validation
+        calls = {"n": 0}
+
+        def fake_forward_loss(data, target, stage):
+            calls["n"] += 1
+            f = torch.tensor(1.0 + rank + 0.1 * calls["n"])
+            logits = torch.zeros(target.shape[0], 7)
+            logits[:, 0] = 1.0
+            return f, f * 0.5, logits, None, None
+
+        tr._forward_loss = fake_forward_loss
+        loader = [(torch.zeros(4, 3, 32, 32), torch.tensor([0, 0, 1, 2]))] * (2 + rank)   # ragged: 2 vs 3 batches
+        res = tr.validate_epoch(loader, 1)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, res)
+        assert all(g == gathered[0] for g in gathered), gathered          # same numbers everywhere
+        # loss = mean over ALL batches of all ranks; accuracy over all samples
+        per_rank = [[1.0 + r + 0.1 * (i + 1) for i in range(2 + r)] for r in range(world)]
+        want = sum(sum(v) for v in per_rank) / sum(len(v) for v in per_rank)
+        assert abs(res[0] - want) < 1e-6 and abs(res[2] - 50.0) < 1e-6
+        # reducer follows requires_grad
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr.setup_optimizer_scheduler(1)
+        n0 = sum(len(b.params) for b in tr._reducers[1].buckets)
+        tr.models[1]._freeze_encoder()
+        assert tr._reducer_sig[1] != tr._grad_signature(1)
+        tr._build_reducer(1)
+        n1 = sum(len(b.params) for b in tr._reducers[1].buckets)
+        assert n1 < n0 and tr._reducer_sig[1] == tr._grad_signature(1)
+        tr.close()
+        assert not tr._reducers and not tr._graphs
+        open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_herlev_data_parallel_host_logic_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_herlev_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+

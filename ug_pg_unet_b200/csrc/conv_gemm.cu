@@ -338,6 +338,7 @@ int conv_halo_bf16(const void* src0, int c0, const void* src1, int c1, int B, in
                    const float* bias, const float* scale, const float* shift, int relu, float* stats,
                    const void* bwd_z, cudaStream_t stream);
 extern int g_conv_halo_mode;   // 0 = per-tap loads everywhere, 1 = halo staging for wide thin layers
+int g_conv_small_kn = 1;       // 1 = 128-wide tiles when 256-wide ones would fill < 60 % of the SMs (16 x 16 layers: 38 -> 32 us)
 
 // conv_pair.cu
 bool conv_pair_eligible(int m_tiles, int cout, int split_n);
@@ -382,6 +383,11 @@ int conv_gemm_bf16_ex(const void* src0, int c0, const void* src1, int c1, int B,
   }
   int kn = 256;
   while (kn > 64 && cout % kn != 0) kn >>= 1;   // the epilogue routes each 64-column chunk to dst0 / dst1
+  // Few tiles (the 16 x 16 bottleneck at batch 16: 32 m tiles x 2 = 64 tiles on 148 SMs): 128-wide tiles
+  // double the CTAs; each then streams the same K with half the weight bytes (tuning switch conv_small_kn)
+  if (g_conv_small_kn != 0 && kn == 256 && cout <= 512 && !general &&
+      B * (H * W / kBlockM) * (cout / 256) * 10 < device_sm_count() * 6)
+    kn = 128;
 
   UGP_REQUIRE(kn == 256 || cout <= 512, "conv_gemm: cout %d with a %d-wide tile unsupported", cout, kn);
 
