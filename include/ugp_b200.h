@@ -116,6 +116,28 @@ int ugp_im2col_first(const float* x, int B, int Cin, int Hin, int Win, int H,
 int ugp_im2col_first_u8(const unsigned char* x, int B, int Cin, int Hin, int Win, int H, int W,
                         const float* mean, const float* stddev, void* out, void* stream);
 
+/* The first convolution without the packed rows in HBM (replaces ugp_im2col_first[_u8] + ugp_conv_gemm_bf16
+ * with taps = 1, and ugp_conv_wgrad_bf16 on the packed rows): nn.Conv2d(n_channels, 64, 3, padding=1) at
+ * UG_unet_parts.py:10 inside InConv, its autograd weight gradient, and the bilinear align_corners=True
+ * resize of uncertainty_guided_trainer.py:208 / UG_unet.py:36-41 when (Hin,Win) != (H,W).  The 64-wide
+ * rows are built in shared memory, directly as the tcgen05 operand tile.
+ *   x        is_u8 = 0: fp32 NCHW [B,Cin,Hin,Win];  is_u8 = 1: uint8 NHWC [B,Hin,Win,Cin] loader bytes with
+ *            value = (byte / 255 - mean[c]) / std[c]  (mean / std: HOST arrays, nullable, ignored for fp32)
+ *   wpack    the first-layer forward pack of ugp_pack_weights: bf16 [1][cout][64], k = (r*3+s)*Cin + ci
+ *   dst      bf16 NHWC [B,H,W,cout];  bias / scale / shift / relu / stats as ugp_conv_gemm_bf16
+ *   dw_packed  fp32 [64][cout], accumulated (as ugp_conv_wgrad_bf16 with taps = 1, 64 source channels)
+ * Supported (ugp_conv_first_supported != 0): Cin = 3, cout = 64 or 128 (the stage-4 / stage-3 networks),
+ * B*H*W % 128 == 0; the weight gradient (ugp_conv_first_wgrad_supported) additionally needs cout = 64.
+ * Callers keep the packer + GEMM path for everything else.  The forward results are bit-identical to that
+ * path; the weight gradient differs by the order of its fp32 atomics only. */
+int ugp_conv_first_supported(int Cin, int cout, int B, int H, int W);
+int ugp_conv_first_wgrad_supported(int Cin, int cout, int B, int H, int W);
+int ugp_conv_first_fwd(const void* x, int is_u8, int B, int Cin, int Hin, int Win, int H, int W, const float* mean,
+                       const float* stddev, const void* wpack, int cout, void* dst, const float* bias,
+                       const float* scale, const float* shift, int relu, float* stats, void* stream);
+int ugp_conv_first_wgrad(const void* x, int is_u8, int B, int Cin, int Hin, int Win, int H, int W, const float* mean,
+                         const float* stddev, const void* dz, int cout, float* dw_packed, void* stream);
+
 /* ---- BatchNorm2d / ReLU / MaxPool2d / bilinear x2 ------------------------ */
 /* Train-mode statistics -> scale/shift, running-stat update (eps, momentum as
  * nn.BatchNorm2d: biased var to normalise, unbiased into running_var,

@@ -1372,3 +1372,100 @@ def test_herlev_graph_step_tracks_eager_step(dev):
     assert abs(me[0, 0] - mg[0, 0]) <= 1e-3 * abs(me[0, 0])           # identical first step
     assert rel(mg[:, 0], me[:, 0]) < 5e-2                             # bf16 / atomic-order drift afterwards
     assert rel(wg, we) < 5e-2 and mg[-1, 0] < mg[0, 0]
+
+
+@pytest.mark.gpu
+def test_early_optimizer_matches_the_default_order(dev):
+    """UGP_EARLY_OPTIMIZER: the packed-weight RMSprop launched from inside backward (side stream, after the
+    last weight gradient and the last dgrad are queued) ends at the same weights as the default order - up to
+    the run-to-run floor of the atomically accumulated gradients, measured here with two default runs."""
+    import contextlib
+    import io
+    import ug_pg_unet_b200 as U
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 3, 64, 64, generator=g).to(dev)
+    y = torch.randint(0, 2, (4, 1, 64, 64), generator=g).float().to(dev)
+
+    def run(early):
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr = U.UncertaintyGuidedProgressiveTrainer(3, 1, device=dev, log_interval=0)
+            tr.current_stage, tr.current_model = 2, tr.models[2]
+            tr.setup_optimizer(2)
+            tr.early_optimizer = early
+            losses = [float(tr.train_step(x, y, 2)[0][0]) for _ in range(6)]      # eager warm-ups, capture, replays
+        w = torch.cat([p.detach().float().reshape(-1) for p in tr.current_model.parameters()])
+        pending = [pk.grad_pending for pk in tr._arena_packs]
+        tr.close()
+        return w, losses, pending
+
+    w_a, l_a, _ = run(False)
+    w_b, l_b, _ = run(False)
+    w_e, l_e, pend = run(True)
+    assert not any(pend)
+    floor = ((w_a - w_b).norm() / w_a.norm()).item()
+    err = ((w_e - w_a).norm() / w_a.norm()).item()
+    assert err <= 3 * floor + 1e-4, (err, floor)
+    # the losses of a random-init net on random data drift apart run to run (atomically reduced BatchNorm
+    # gradients): the early order must stay within the drift of two default runs
+    drift = max(abs(a - b) / abs(a) for a, b in zip(l_a, l_b))
+    assert all(abs(a - e) <= (3 * drift + 2e-3) * abs(a) for a, e in zip(l_a, l_e)), (l_a, l_b, l_e)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 64, 64, 64, 64), (1, 32, 32, 32, 32), (16, 256, 256, 256, 256),
+                                   (3, 224, 224, 224, 224), (4, 256, 256, 128, 128), (5, 200, 120, 96, 64)])
+@pytest.mark.parametrize("u8", [False, True])
+@pytest.mark.parametrize("cout", [64, 128])
+def test_fused_first_layer_is_bit_identical_to_packer_plus_gemm(dev, shape, u8, cout):
+    """ugp_conv_first_fwd / ugp_conv_first_wgrad (first convolution with its 64-wide rows built in shared memory,
+    UG_unet_parts.py:10 + the resize of uncertainty_guided_trainer.py:208) against the path they replace -
+    ugp_im2col_first[_u8] + ugp_conv_gemm_bf16 / ugp_conv_wgrad_bf16 on the packed rows: the stored bf16 output,
+    the BatchNorm statistics and the eval-mode folded output bit for bit; the weight gradient up to the
+    order of the fp32 atomics."""
+    from ug_pg_unet_b200 import ops
+
+    B, Hin, Win, H, W = shape
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    if u8:
+        x = torch.randint(0, 256, (B, Hin, Win, 3), generator=g, dtype=torch.uint8).to(dev)
+        mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    else:
+        x = torch.randn(B, 3, Hin, Win, generator=g).to(dev)
+        mean = std = None
+    w = (torch.randn(cout, 3, 3, 3, generator=g) * 0.2).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    wf, _ = ops.pack_weights(w, need_dgrad=False)
+    rows = ops.first_rows(x, H, W, mean, std, cout=cout)
+    assert isinstance(rows, ops.FirstRows), "shape must be covered by the fused kernels"
+    col = rows.materialize()
+    # train mode: raw output + per-CTA statistics
+    st_a, st_b = ops.new_stats(cout, dev), ops.new_stats(cout, dev)
+    z_a = ops.conv_gemm(rows, None, wf, 1, cout, bias=bias, stats=st_a)
+    z_b = ops.conv_gemm(col, None, wf, 1, cout, bias=bias, stats=st_b)
+    assert torch.equal(z_a, z_b)
+    sa, sb = st_a.double().sum(0), st_b.double().sum(0)
+    assert torch.allclose(sa, sb, rtol=1e-5, atol=1e-3), (sa - sb).abs().max()
+    st_c = ops.new_stats(cout, dev)                       # run-to-run identical statistics (shared slots commute)
+    ops.conv_gemm(rows, None, wf, 1, cout, bias=bias, stats=st_c)
+    assert torch.equal(st_a, st_c)
+    # eval mode: folded BatchNorm + ReLU in the epilogue
+    sc, sh = torch.rand(cout, generator=g).to(dev) + 0.5, torch.randn(cout, generator=g).to(dev)
+    a_a = ops.conv_gemm(rows, None, wf, 1, cout, bias=bias, scale=sc, shift=sh, relu=True)
+    a_b = ops.conv_gemm(col, None, wf, 1, cout, bias=bias, scale=sc, shift=sh, relu=True)
+    assert torch.equal(a_a, a_b)
+    # weight gradient (cout = 128 falls back to the packed rows inside ops.conv_wgrad)
+    dz = torch.randn(B, H, W, cout, generator=g).to(dev).to(torch.bfloat16)
+    dw_a = torch.zeros(64 * cout, device=dev)
+    dw_b = torch.zeros(64 * cout, device=dev)
+    ops.conv_wgrad(rows, None, dz, 1, dw_a)
+    ops.conv_wgrad(col, None, dz, 1, dw_b)
+    ref = col.double().reshape(-1, 64).t() @ dz.double().reshape(-1, cout)          # [k][cout]
+    err_a = (dw_a.double().view(64, cout) - ref).abs().max().item()
+    err_b = (dw_b.double().view(64, cout) - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err_a <= max(2 * err_b, 1e-5 * scale), (err_a, err_b, scale)
+    # accumulation: a second launch adds
+    ops.conv_wgrad(rows, None, dz, 1, dw_a)
+    assert (dw_a.double().view(64, cout) - 2 * ref).abs().max().item() <= max(4 * err_b, 2e-5 * scale)

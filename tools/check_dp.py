@@ -98,7 +98,11 @@ def main():
             ab.work.wait()
     torch.cuda.current_stream().wait_stream(red._stream)
     torch.cuda.synchronize()
-    assert torch.equal(arena, want), "arena bucket all-reduce is not the element-wise sum over ranks"
+    if world == 2:
+        assert torch.equal(arena, want), "arena bucket all-reduce is not the element-wise sum over ranks"
+    else:       # > 2 ranks: NCCL's summation order depends on the message size, so bucket-wise != whole-arena bit for bit
+        e3 = ((arena - want).norm() / want.norm()).item()
+        assert e3 < 1e-6, ("arena bucket all-reduce vs whole-arena all-reduce", e3)
     arena.zero_()
     tr.optimizer.zero_grad(set_to_none=True)
     tr.setup_optimizer(st)                      # fresh reducer / optimizer / arena
@@ -113,6 +117,13 @@ def main():
     for o in ws[1:]:
         assert torch.equal(ws[0], o), "ranks diverged"
     assert not torch.equal(w, w0)
+    # every parameter (the first block's convolutions are the ones whose all-reduce and update run last)
+    for n, p in tr.current_model.named_parameters():
+        flat = p.detach().float().contiguous()
+        lo, hi = flat.clone(), flat.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), f"ranks diverged on {n}"
     # ---- 3. BN statistics stay rank-local
     rm = tr.current_model.up2.conv.conv_op[4].running_mean
     rms = [torch.empty_like(rm) for _ in range(world)]
@@ -120,7 +131,7 @@ def main():
     assert not torch.equal(rms[0], rms[1])
     if rank == 0:
         print(f"check_dp ok: world {world}, overlapped arena vs local sum {err:.2e} (run-to-run floor {floor:.2e}), "
-              f"frozen-arena all-reduce exact, {len(tr._reducer.arena_buckets)} arena bucket(s), "
+              f"frozen-arena all-reduce {'exact' if world == 2 else 'within 1e-6 of the whole-arena one'}, {len(tr._reducer.arena_buckets)} arena bucket(s), "
               f"weights identical on all ranks after 7 steps")
     torch.cuda.synchronize()
     dist.barrier()

@@ -33,6 +33,10 @@ SIGNATURES = {
     "ugp_cls_eval": [_p, _p, _i, _i, _p, _p, _p, _p],
     "ugp_pack_weights": [_p, _i, _i, _p, _p, _p],
     "ugp_unpack_wgrad": [_p, _i, _i, _p, _i, _p],
+    "ugp_conv_first_supported": [_i, _i, _i, _i, _i],
+    "ugp_conv_first_wgrad_supported": [_i, _i, _i, _i, _i],
+    "ugp_conv_first_fwd": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p],
+    "ugp_conv_first_wgrad": [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p],
     "ugp_im2col_first": [_p, _i, _i, _i, _i, _i, _i, _p, _p],
     "ugp_bn_finalize": [_p, _i, _i, _ll, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "ugp_bn_eval_coeffs": [_i, _p, _p, _p, _p, _f, _p, _p, _p],

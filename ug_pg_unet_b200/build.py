@@ -17,7 +17,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libugp_b200.so"
-SOURCES = ["tmap.cu", "conv_gemm.cu", "conv_halo.cu", "conv_pair.cu", "conv_wgrad.cu", "conv_wgrad_halo.cu", "conv_transpose.cu", "elementwise.cu", "bn_bwd.cu", "first_layer.cu",
+SOURCES = ["tmap.cu", "conv_gemm.cu", "conv_halo.cu", "conv_pair.cu", "conv_wgrad.cu", "conv_wgrad_halo.cu", "conv_transpose.cu", "elementwise.cu", "bn_bwd.cu", "first_layer.cu", "conv_first.cu",
            "weights.cu", "head_loss.cu", "mlp_head.cu", "eval_metrics.cu", "optim.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -36,7 +36,7 @@ def needs_build() -> bool:
     if not LIB_PATH.exists():
         return True
     lib_m = LIB_PATH.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "ugp_common.cuh", CSRC / "ugp_vec.cuh", CSRC / "conv_gemm.cuh", CSRC / "conv_epilogue.cuh",
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "ugp_common.cuh", CSRC / "ugp_vec.cuh", CSRC / "conv_gemm.cuh", CSRC / "conv_epilogue.cuh", CSRC / "first_rows.cuh",
                                          PKG_DIR.parent / "include" / "ugp_b200.h"]
     return any(d.stat().st_mtime > lib_m for d in deps)
 

@@ -72,6 +72,12 @@ int channel_sum(const void*, long long, int, float*, cudaStream_t);
 int adam_multi(float* const*, const float* const*, float* const*, float* const*, const long long*, int, double,
                double, double, double, double, long long, const long long*, float, cudaStream_t);
 int counter_add(long long*, long long, cudaStream_t);
+bool conv_first_supported(int, int, int, int, int);
+bool conv_first_wgrad_supported(int, int, int, int, int);
+int conv_first_fwd(const void*, int, int, int, int, int, int, int, const float*, const float*, const void*, int, void*,
+                   const float*, const float*, const float*, int, float*, cudaStream_t);
+int conv_first_wgrad(const void*, int, int, int, int, int, int, int, const float*, const float*, const void*, int,
+                     float*, cudaStream_t);
 int im2col_first_u8(const unsigned char*, int, int, int, int, int, int, const float*, const float*, void*,
                     cudaStream_t);
 int bce_uncertainty_loss_u8(const float*, const unsigned char*, const float*, float, float, int, long long,
@@ -270,6 +276,22 @@ int ugp_unpack_wgrad_tconv(float* dw_packed, int cin, int cout, float* grad, int
 }
 int ugp_channel_sum(const void* x, long long pixels, int C, float* out, void* stream) {
   return ugp::channel_sum(x, pixels, C, out, S(stream));
+}
+int ugp_conv_first_supported(int Cin, int cout, int B, int H, int W) {
+  return ugp::conv_first_supported(Cin, cout, B, H, W) ? 1 : 0;
+}
+int ugp_conv_first_wgrad_supported(int Cin, int cout, int B, int H, int W) {
+  return ugp::conv_first_wgrad_supported(Cin, cout, B, H, W) ? 1 : 0;
+}
+int ugp_conv_first_fwd(const void* x, int is_u8, int B, int Cin, int Hin, int Win, int H, int W, const float* mean,
+                       const float* stddev, const void* wpack, int cout, void* dst, const float* bias,
+                       const float* scale, const float* shift, int relu, float* stats, void* stream) {
+  return ugp::conv_first_fwd(x, is_u8, B, Cin, Hin, Win, H, W, mean, stddev, wpack, cout, dst, bias, scale, shift,
+                             relu, stats, S(stream));
+}
+int ugp_conv_first_wgrad(const void* x, int is_u8, int B, int Cin, int Hin, int Win, int H, int W, const float* mean,
+                         const float* stddev, const void* dz, int cout, float* dw_packed, void* stream) {
+  return ugp::conv_first_wgrad(x, is_u8, B, Cin, Hin, Win, H, W, mean, stddev, dz, cout, dw_packed, S(stream));
 }
 int ugp_im2col_first_u8(const unsigned char* x, int B, int Cin, int Hin, int Win, int H, int W,
                         const float* mean, const float* stddev, void* out, void* stream) {

@@ -50,19 +50,21 @@ struct EpilogueCtx {
   // reduction pass of ugp_bn_relu_bwd: that kernel then only runs its apply pass.
   const uint32_t* bwd_z = nullptr;
   int bwd_z_words = 0;   // words per pixel = C / 2
+  bool whatif_no_store = false;   // what-if timing only (wrong results): the tile is staged but never stored
 };
 
 // v: 64 fp32 accumulator values of this thread's row (columns n_base .. n_base+63).
 // buf_addr: smem byte address of the 16 KB staging buffer (1024-aligned, SWIZZLE_128B rows).
-template <int kStagingBufs>
+// kBwdZ = false compiles the BatchNorm-backward statistics mode out (kernels that never run it: fewer registers).
+template <int kStagingBufs, bool kBwdZ = true>
 __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint32_t* v, int n_base,
                                                uint32_t buf_addr, int row, int et,
                                                const CUtensorMap* tm_out, int out_col, int out_row,
                                                int out_y = -1, int out_b = 0) {
   // BN-backward statistics: request this thread's 32 z words (one word column over a quarter of the rows)
   // now, so that they arrive while the accumulator is converted and staged
-  uint32_t zw[32];
-  if (e.bwd_z != nullptr) {
+  uint32_t zw[kBwdZ ? 32 : 1];
+  if (kBwdZ && e.bwd_z != nullptr) {
     const uint32_t* zp = e.bwd_z + (static_cast<size_t>(out_row) + (et >> 5) * 32) * e.bwd_z_words + (n_base >> 1) + (et & 31);
 #pragma unroll
     for (int i = 0; i < 32; ++i) zw[i] = __ldg(zp + static_cast<size_t>(i) * e.bwd_z_words);
@@ -102,7 +104,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint3
                  packed[4 * j + 3]);
   fence_proxy_async_smem();
   named_bar_sync(2, 128);
-  if (et == 0) {
+  if (et == 0 && !e.whatif_no_store) {
     if (out_y < 0) {
       asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                        reinterpret_cast<uint64_t>(tm_out)),
@@ -126,7 +128,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint3
     const uint32_t colp = buf_addr + ((wcol & 3) << 2);
     const int chunk = wcol >> 2;
     float s0a = 0.f, s1a = 0.f, q0a = 0.f, q1a = 0.f, s0b = 0.f, s1b = 0.f, q0b = 0.f, q1b = 0.f;
-    if (e.bwd_z == nullptr) {
+    if (!kBwdZ || e.bwd_z == nullptr) {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {      // r0 is a multiple of 8: (r0 + i) & 7 == i & 7
         const uint32_t wa = ld_shared_b32(colp + (r0 + i) * 128 + ((chunk ^ (i & 7)) << 4));
@@ -143,7 +145,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueCtx& e, const uint3
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const uint32_t wa = ld_shared_b32(colp + (r0 + i) * 128 + ((chunk ^ (i & 7)) << 4));
-        const float z0 = bf16_lo(zw[i]), z1 = bf16_hi(zw[i]);
+        const float z0 = bf16_lo(zw[kBwdZ ? i : 0]), z1 = bf16_hi(zw[kBwdZ ? i : 0]);
         const float g0 = (fmaf(z0, sc.x, sh.x) > 0.f) ? bf16_lo(wa) : 0.f;
         const float g1 = (fmaf(z1, sc.y, sh.y) > 0.f) ? bf16_hi(wa) : 0.f;
         if (i & 1) { s0b += g0; s1b += g1; q0b = fmaf(g0, z0, q0b); q1b = fmaf(g1, z1, q1b); }

@@ -14,24 +14,16 @@
 // HBM-bound on the 128 B/pixel output.  One thread = one pixel: neighbours are
 // read through L1 (adjacent threads share them), the row is written as eight
 // 16-byte stores.
-#include "ugp_common.cuh"
-#include "ugp_vec.cuh"
+#include "first_rows.cuh"
 
 namespace ugp {
-
-struct ByteNorm {
-  float scale[8], bias[8];   // value = byte * scale[c] + bias[c]
-};
 
 template <int kCin, bool kResize, bool kU8>
 __global__ void __launch_bounds__(256)
 im2col_first_kernel(const void* __restrict__ xin, int B, int Hin, int Win, int H, int W,
                     __nv_bfloat16* __restrict__ out, const ByteNorm norm) {
-  const float* x = static_cast<const float*>(xin);
-  const uint8_t* xb = static_cast<const uint8_t*>(xin);
   __shared__ uint4 stage[256 * 8];
   const long long total = static_cast<long long>(B) * H * W;
-  const long long plane = static_cast<long long>(Hin) * Win;
   // block-uniform trip count: every thread reaches the barriers, tail pixels are clamped and not stored
   for (long long pix0 = blockIdx.x * static_cast<long long>(blockDim.x); pix0 < total;
        pix0 += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -40,67 +32,14 @@ im2col_first_kernel(const void* __restrict__ xin, int B, int Hin, int Win, int H
     const int xo = static_cast<int>(pc % W);
     const int yo = static_cast<int>((pc / W) % H);
     const int b = static_cast<int>(pc / (static_cast<long long>(W) * H));
-    const float* img = x + static_cast<long long>(b) * kCin * plane;           // fp32 NCHW
-    const uint8_t* imgb = xb + static_cast<long long>(b) * kCin * plane;      // uint8 NHWC
-    float vals[64];
-#pragma unroll
-    for (int k = 9 * kCin; k < 64; ++k) vals[k] = 0.f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int yy = yo + r - 1;
-      int y0 = 0, y1 = 0;
-      float ly = 0.f;
-      if (kResize) bilinear_src(yy < 0 ? 0 : (yy >= H ? H - 1 : yy), Hin, H, &y0, &y1, &ly);
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int xx = xo + s - 1;
-        const bool inside = yy >= 0 && yy < H && xx >= 0 && xx < W;
-        int x0 = 0, x1 = 0;
-        float lx = 0.f;
-        if (kResize) bilinear_src(xx < 0 ? 0 : (xx >= W ? W - 1 : xx), Win, W, &x0, &x1, &lx);
-#pragma unroll
-        for (int ci = 0; ci < kCin; ++ci) {
-          float v = 0.f;
-          if (inside && kU8) {
-            const float sc = norm.scale[ci], bi = norm.bias[ci];
-            if (!kResize) {
-              v = fmaf(static_cast<float>(imgb[(static_cast<long long>(yy) * Win + xx) * kCin + ci]), sc, bi);
-            } else {
-              const float v00 = fmaf(static_cast<float>(imgb[(static_cast<long long>(y0) * Win + x0) * kCin + ci]), sc, bi);
-              const float v01 = fmaf(static_cast<float>(imgb[(static_cast<long long>(y0) * Win + x1) * kCin + ci]), sc, bi);
-              const float v10 = fmaf(static_cast<float>(imgb[(static_cast<long long>(y1) * Win + x0) * kCin + ci]), sc, bi);
-              const float v11 = fmaf(static_cast<float>(imgb[(static_cast<long long>(y1) * Win + x1) * kCin + ci]), sc, bi);
-              v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-            }
-          } else if (inside) {
-            const float* p = img + ci * plane;
-            if (!kResize) {
-              v = __ldg(p + static_cast<long long>(yy) * Win + xx);
-            } else {
-              const float v00 = __ldg(p + static_cast<long long>(y0) * Win + x0);
-              const float v01 = __ldg(p + static_cast<long long>(y0) * Win + x1);
-              const float v10 = __ldg(p + static_cast<long long>(y1) * Win + x0);
-              const float v11 = __ldg(p + static_cast<long long>(y1) * Win + x1);
-              v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-            }
-          }
-          vals[(r * 3 + s) * kCin + ci] = v;
-        }
-      }
-    }
+    uint4 u[8];
+    first_layer_row<kCin, kResize, kU8>(xin, Hin, Win, H, W, b, yo, xo, norm, u);
     // Stage the 256 rows of this block through shared memory (16-byte chunks, XOR-swizzled by the row)
     // so that the global stores are fully coalesced: lane l writes chunk l of a contiguous 32 KB run
     // instead of eight 16-byte pieces 128 bytes apart.
     uint4* srow = stage + threadIdx.x * 8;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      uint4 u;
-      u.x = pack_bf16x2(vals[g * 8 + 0], vals[g * 8 + 1]);
-      u.y = pack_bf16x2(vals[g * 8 + 2], vals[g * 8 + 3]);
-      u.z = pack_bf16x2(vals[g * 8 + 4], vals[g * 8 + 5]);
-      u.w = pack_bf16x2(vals[g * 8 + 6], vals[g * 8 + 7]);
-      srow[g ^ (threadIdx.x & 7)] = u;
-    }
+    for (int g = 0; g < 8; ++g) srow[g ^ (threadIdx.x & 7)] = u[g];
     __syncthreads();
     const long long base_pix = pix - threadIdx.x;            // first pixel of this block's trip
     uint4* dst = reinterpret_cast<uint4*>(out + base_pix * 64);
@@ -145,6 +84,17 @@ static int dispatch_im2col(const void* x, int B, int Cin, int Hin, int Win, int 
   return UGP_OK;
 }
 
+int make_byte_norm(ByteNorm* out, int Cin, const float* mean, const float* stddev, const char* who) {
+  UGP_REQUIRE(Cin >= 1 && Cin <= 7, "%s: Cin %d unsupported (1..7)", who, Cin);
+  for (int c = 0; c < Cin; ++c) {   // HOST arrays (nullable): (byte/255 - mean) / std
+    const float m = mean ? mean[c] : 0.f, sd = stddev ? stddev[c] : 1.f;
+    UGP_REQUIRE(sd > 0.f, "%s: std[%d] must be positive", who, c);
+    out->scale[c] = 1.f / (255.f * sd);
+    out->bias[c] = -m / sd;
+  }
+  return UGP_OK;
+}
+
 int im2col_first(const float* x, int B, int Cin, int Hin, int Win, int H, int W, void* out,
                  cudaStream_t stream) {
   UGP_REQUIRE(x && out, "im2col_first: null pointer");
@@ -156,12 +106,7 @@ int im2col_first_u8(const unsigned char* x, int B, int Cin, int Hin, int Win, in
   UGP_REQUIRE(x && out, "im2col_first_u8: null pointer");
   UGP_REQUIRE(Cin >= 1 && Cin <= 7, "im2col_first_u8: Cin %d unsupported (1..7)", Cin);
   ByteNorm norm{};
-  for (int c = 0; c < Cin; ++c) {   // HOST arrays (nullable): (byte/255 - mean) / std
-    const float m = mean ? mean[c] : 0.f, sd = stddev ? stddev[c] : 1.f;
-    UGP_REQUIRE(sd > 0.f, "im2col_first_u8: std[%d] must be positive", c);
-    norm.scale[c] = 1.f / (255.f * sd);
-    norm.bias[c] = -m / sd;
-  }
+  if (int rc = make_byte_norm(&norm, Cin, mean, stddev, "im2col_first_u8")) return rc;
   return dispatch_im2col<true>(x, B, Cin, Hin, Win, H, W, out, norm, stream);
 }
 

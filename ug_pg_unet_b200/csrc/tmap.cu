@@ -107,6 +107,7 @@ extern int g_bn_pool_vec4;         // bn_bwd.cu
 extern int g_bn_skip_reduce;
 extern int g_bn_min_pixels;
 extern int g_conv_small_kn;
+extern int g_conv_first_fused;
 extern int g_upsample_smem_kb;
 extern int g_bn_bwd_blocks_per_sm;
 int g_wgrad_waves = 1;
@@ -131,6 +132,10 @@ int set_option(const char* name, int value) {
   }
   if (strcmp(name, "upsample_smem_kb") == 0) {
     g_upsample_smem_kb = value < 4 ? 4 : (value > 96 ? 96 : value);
+    return UGP_OK;
+  }
+  if (strcmp(name, "conv_first_fused") == 0) {
+    g_conv_first_fused = value;
     return UGP_OK;
   }
   if (strcmp(name, "conv_small_kn") == 0) {

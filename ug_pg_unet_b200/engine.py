@@ -202,16 +202,23 @@ class WgradOverlap:
     kept alive in `keep` until the trainer has joined the streams."""
     stream: Optional[torch.cuda.Stream] = None
     keep: list = []
+    # the pack whose weight gradient is produced LAST (the first deferred layer of the network) and what to
+    # do once it and its input gradient are queued: the trainer starts the packed-weight optimiser there, on
+    # the side stream, beside the tail of the backward pass (trainer._early_optimizer_step)
+    last_pack = None
+    on_last = None
 
     @classmethod
-    def begin(cls, stream):
+    def begin(cls, stream, last_pack=None, on_last=None):
         cls.stream, cls.keep = stream, []
+        cls.last_pack, cls.on_last = last_pack, on_last
 
     @classmethod
     def end(cls):
         """Joins the side stream into the current one and releases the kept tensors."""
         st = cls.stream
         cls.stream = None
+        cls.last_pack = cls.on_last = None
         if st is not None:
             torch.cuda.current_stream().wait_stream(st)
         cls.keep = []
@@ -331,6 +338,8 @@ def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch
         else:
             d0, d1 = ops.conv_gemm(dz, None, wd, 9, kdim, split_n=src0.shape[3])
             d_srcs = [d0, d1]
+    if side is not None and packs is WgradOverlap.last_pack and WgradOverlap.on_last is not None:
+        WgradOverlap.on_last()          # every packed weight gradient and every dgrad is queued now
     if below is not None:
         return d_srcs, (dW, small[2], small[0], small[1]), raw_below
     return d_srcs, (dW, small[2], small[0], small[1])
@@ -358,7 +367,7 @@ class DoubleConvFn(torch.autograd.Function):
 
     kind: 'plain'  x NHWC bf16
           'first'  x fp32 NCHW image, first conv runs through im2col (9*Cin <= 64)
-          'col'    x already packed first-layer rows [B,H,W,64] (uint8 loader bytes -> ops.im2col_first_u8)
+          'col'    x already packed first-layer rows [B,H,W,64] (ops.im2col_first[_u8]) or an ops.FirstRows handle
           'pool'   MaxPool2d(2) then DoubleConv  (Down, UG_unet_parts.py:44-54)
           'up'     bilinear x2 of x, concat [skip, up], DoubleConv (Up, UG_unet_parts.py:70-81)
           'cat'    concat [x, skip] walked as two sources (UpSample, UG_unet_parts.py:64-67)
@@ -378,7 +387,7 @@ class DoubleConvFn(torch.autograd.Function):
             head = (hw.detach().reshape(hw.shape[0], -1).contiguous(), hb.detach().contiguous())
         pre = None
         if kind == "first":
-            srcs, taps = [ops.im2col_first(x)], 1
+            srcs, taps = [ops.first_rows(x, cout=conv1.out_channels)], 1      # fused first layer: no packed rows in HBM
         elif kind == "col":
             srcs, taps = [x], 1
         elif kind == "pool":

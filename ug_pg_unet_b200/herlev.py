@@ -36,12 +36,7 @@ _RES = {1: 32, 2: 64, 3: 128, 4: 256}
 def _encode_resized(unet: _PGUNetBase, x: torch.Tensor, resolution: int, depth: int) -> torch.Tensor:
     """Inference-only encoder forward of `F.interpolate(x, resolution, bilinear, align_corners=True)`
     with the resize folded into the first-layer packer; returns the deepest NHWC bf16 feature map."""
-    if x.dtype == torch.uint8:        # loader bytes [B,H,W,3]: /255 + Normalize folded into the packer
-        col = unet.pack_bytes(x, resolution)
-    else:
-        if x.dtype != torch.float32:
-            x = x.float()
-        col = ops.im2col_first(x.contiguous(), resolution, resolution)
+    col = unet.first_rows(x, resolution)     # loader bytes [B,H,W,3]: /255 + Normalize folded into the row builder
     dc = unet.inc.conv
     downs = [getattr(unet, n).mpconv[1] for n in unet._downs][:depth]
     a, _, _ = engine.cbr_forward([col], 1, dc.conv_op[0], dc.conv_op[1], dc._packs[0], False, False)

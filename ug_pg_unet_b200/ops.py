@@ -117,6 +117,9 @@ def conv_gemm(src0: torch.Tensor, src1: Optional[torch.Tensor], wpack: torch.Ten
               cout: int, *, bias=None, scale=None, shift=None, relu: bool = False, stats=None,
               split_n: Optional[int] = None, out0=None, out1=None):
     """D = conv(src0 ++ src1, wpack) (+bias, *scale+shift, relu); see ugp_conv_gemm_bf16."""
+    if isinstance(src0, FirstRows):
+        assert src1 is None and taps == 1 and split_n is None and out0 is None
+        return _conv_first_fwd(src0, wpack, cout, bias, scale, shift, relu, stats)
     _req(src0, bf16, "src0")
     B, H, W, c0 = src0.shape
     c1 = 0
@@ -193,6 +196,14 @@ def bn_relu_bwd_apply(z, dA, raw, scale, shift, mean, rstd, gamma, sums, dbias):
 
 def conv_wgrad(src0, src1, dz, taps: int, dw_packed: torch.Tensor):
     """dw_packed[tap][ci][co] += sum_p src[p+shift, ci] * dz[p, co]."""
+    if isinstance(src0, FirstRows):
+        assert src1 is None and taps == 1
+        _req(dz, bf16, "dz")
+        _req(dw_packed, torch.float32, "dw_packed")
+        B, H, W, _ = src0.shape
+        if lib().ugp_conv_first_wgrad_supported(src0.cin, dz.shape[3], B, H, W):
+            return _conv_first_wgrad(src0, dz, dw_packed)
+        src0 = src0.materialize()          # e.g. the stage-3 network's 128-wide first layer: packed rows
     _req(src0, bf16, "src0")
     _req(dz, bf16, "dz")
     _req(dw_packed, torch.float32, "dw_packed")
@@ -317,6 +328,82 @@ def channel_sum(x, out=None):
     check(lib().ugp_channel_sum(_ptr(x), x.numel() // Cn, Cn, _ptr(_req(out, torch.float32, "out")), _stream()),
           "ugp_channel_sum")
     return out
+
+
+class FirstRows:
+    """The first layer's GEMM rows [B,H,W,64] (3x3 neighbourhoods of the - optionally resized - image) NOT
+    written to HBM: `conv_gemm` / `conv_wgrad` given this object as their source run the fused first-layer
+    kernels (ugp_conv_first_fwd / ugp_conv_first_wgrad), which build the rows in shared memory.  Quacks
+    like the packed tensor where the engine looks at it (`shape`, `device`); `materialize()` packs for real."""
+    __slots__ = ("x", "u8", "cin", "Hin", "Win", "H", "W", "mean", "std", "shape", "device", "_mean_c", "_std_c")
+
+    def __init__(self, x, H, W, mean=None, std=None):
+        self.x = x
+        self.u8 = x.dtype == torch.uint8
+        if self.u8:
+            B, self.Hin, self.Win, self.cin = x.shape
+        else:
+            B, self.cin, self.Hin, self.Win = x.shape
+        self.H, self.W = H, W
+        self.mean = None if mean is None else tuple(float(v) for v in mean)
+        self.std = None if std is None else tuple(float(v) for v in std)
+        self._mean_c = None if self.mean is None else (C.c_float * self.cin)(*self.mean)
+        self._std_c = None if self.std is None else (C.c_float * self.cin)(*self.std)
+        self.shape = (B, H, W, 64)
+        self.device = x.device
+
+    def materialize(self) -> torch.Tensor:
+        if self.u8:
+            return im2col_first_u8(self.x, self.H, self.W, self.mean, self.std)
+        return im2col_first(self.x, self.H, self.W)
+
+
+def conv_first_supported(cin: int, cout: int, B: int, H: int, W: int) -> bool:
+    return bool(lib().ugp_conv_first_supported(cin, cout, B, H, W))
+
+
+def first_rows(x: torch.Tensor, H: Optional[int] = None, W: Optional[int] = None, mean=None, std=None, cout: int = 64):
+    """The first layer's source: a `FirstRows` handle when the fused first-layer kernels cover the shape
+    (Cin = 3, 64 or 128 output channels, B*H*W % 128 == 0), else the packed bf16 [B,H,W,64] tensor.
+    x: fp32 NCHW image, or uint8 NHWC loader bytes (mean / std: ToTensor + Normalize folded in)."""
+    if x.dtype == torch.uint8:
+        B, Hin, Win, cin = x.shape
+    else:
+        _req(x, torch.float32, "x")
+        B, cin, Hin, Win = x.shape
+    H = Hin if H is None else H
+    W = Win if W is None else W
+    rows = FirstRows(x, H, W, mean, std)
+    if conv_first_supported(cin, cout, B, H, W):
+        return rows
+    return rows.materialize()
+
+
+def _conv_first_fwd(rows: "FirstRows", wpack, cout, bias, scale, shift, relu, stats):
+    B, H, W, _ = rows.shape
+    assert wpack.numel() == cout * 64, (wpack.shape, cout)
+    out = torch.empty((B, H, W, cout), dtype=bf16, device=rows.device)
+    if stats is not None and tuple(stats.shape) != (stat_parts(), 2, cout):
+        raise RuntimeError(f"conv_first: stats must be a zeroed [{stat_parts()}, 2, {cout}] buffer (ops.new_stats)")
+    with _timed("conv_first", 2.0 * B * H * W * cout * 9 * rows.cin, _nb(rows.x, wpack, out)):
+        rc = lib().ugp_conv_first_fwd(_ptr(rows.x), int(rows.u8), B, rows.cin, rows.Hin, rows.Win, H, W, rows._mean_c,
+                                      rows._std_c, _ptr(_req(wpack, bf16, "wpack")), cout, _ptr(out),
+                                      _ptr(_opt(bias, torch.float32, "bias")), _ptr(_opt(scale, torch.float32, "scale")),
+                                      _ptr(_opt(shift, torch.float32, "shift")), int(relu),
+                                      _ptr(_opt(stats, torch.float32, "stats")), _stream())
+    check(rc, "ugp_conv_first_fwd")
+    return out
+
+
+def _conv_first_wgrad(rows: "FirstRows", dz, dw_packed):
+    B, H, W, _ = rows.shape
+    cout = dz.shape[3]
+    assert tuple(dz.shape[:3]) == (B, H, W) and dw_packed.numel() == 64 * cout
+    with _timed("conv_first_wgrad", 2.0 * B * H * W * cout * 9 * rows.cin, _nb(rows.x, dz, dw_packed)):
+        rc = lib().ugp_conv_first_wgrad(_ptr(rows.x), int(rows.u8), B, rows.cin, rows.Hin, rows.Win, H, W, rows._mean_c,
+                                        rows._std_c, _ptr(dz), cout, _ptr(dw_packed), _stream())
+    check(rc, "ugp_conv_first_wgrad")
+    return dw_packed
 
 
 def im2col_first(x: torch.Tensor, H: Optional[int] = None, W: Optional[int] = None):

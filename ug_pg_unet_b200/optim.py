@@ -64,6 +64,40 @@ class FusedRMSprop(torch.optim.RMSprop):
         return super().state_dict()
 
     @torch.no_grad()
+    def step_deferred(self) -> int:
+        """The packed-gradient part of `step()` alone: RMSprop + bf16 operand repack + gradient zeroing of every
+        convolution whose packed weight gradient is pending, in one launch on the CURRENT stream.  The trainer
+        calls it on its side stream as soon as the last weight gradient and the last input gradient of the
+        backward pass are queued, so the 375 MB update runs beside the tail of backward instead of after it;
+        the `step()` that follows skips these tensors.  Returns the number of tensors updated."""
+        n = 0
+        for group in self.param_groups:
+            if group["momentum"] != 0 or group["centered"] or group.get("maximize", False):
+                return 0
+            dw, dv, dg, dwf, dwd, dpk = [], [], [], [], [], []
+            for p in group["params"]:
+                pk = self._packs.get(id(p))
+                if pk is None or not (pk.defer and pk.grad_pending and p.grad is None):
+                    continue
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.zeros((), dtype=torch.float32)
+                    st["square_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                wf, wd = pk.get()
+                dw.append(p.data); dv.append(st["square_avg"]); dg.append(pk._dwp)
+                dwf.append(wf); dwd.append(wd); dpk.append(pk)
+            if dw:
+                ops.rmsprop_conv_packed(dw, dv, dg, dwf, dwd, float(group["lr"]), float(group["alpha"]),
+                                        float(group["eps"]), float(group["weight_decay"]),
+                                        float(self.deferred_grad_scale))
+                for pk in dpk:
+                    pk.grad_pending = False
+                    pk.mark_fresh()
+                n += len(dw)
+        return n
+
+    @torch.no_grad()
     def step(self, closure=None):
         loss = None
         if closure is not None:

@@ -184,6 +184,20 @@ class GradBucketReducer:
             b.work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             b.flat = flat
 
+    def flush_arena(self):
+        """Launches the all-reduce of every arena bucket that has not gone out yet (the light tail): called
+        when the last packed weight gradient is queued, so that the packed-weight optimiser can start beside
+        the end of backward.  The flat small-tensor bucket then goes out alone from wait()."""
+        if self.world_size == 1:
+            return
+        for ab in self.arena_buckets:
+            if ab.work is None and ab.flat.is_cuda:
+                self._launch_arena(ab)
+        # async_op collectives run on NCCL's own stream: work.wait() is what orders a stream after them
+        for ab in self.arena_buckets:
+            if ab.work is not None:
+                ab.work.wait()                       # the CURRENT stream waits; wait() may wait again later
+
     def _launch_tail(self, ab: _ArenaBucket, b: _Bucket):
         """The exposed end of the exchange as ONE NCCL launch: the light last arena bucket and the flat
         bucket of the small tensors (biases, BatchNorm affine, heads), coalesced."""

@@ -58,6 +58,11 @@ class UncertaintyGuidedProgressiveTrainer:
         self.max_step_graphs = 4          # each capture owns a memory pool; further shapes run eagerly
         self._last_step_losses = None
         self._grad_arena = None
+        self._arena_packs = []
+        # UGP_EARLY_OPTIMIZER=1: packed-weight optimiser launched from inside backward, beside its tail, instead
+        # of after it.  Off by default: same-box A/B at N = 1, 2 and 8 GPUs showed no step-time change (the tail
+        # of backward is HBM-bound like the update itself), so the simpler order stays.
+        self.early_optimizer = os.environ.get("UGP_EARLY_OPTIMIZER", "0") == "1"
 
         # reference uncertainty_guided_trainer.py:42-47
         self.stage_configs = {
@@ -116,6 +121,7 @@ class UncertaintyGuidedProgressiveTrainer:
             enable_deferred_wgrad(m, False)
         packs, arena = enable_deferred_wgrad(self.current_model, on_cuda and self.defer_conv_grads)
         self._grad_arena = arena
+        self._arena_packs = packs            # arena order = the order backward produces the weight gradients
         if on_cuda:
             self.optimizer = FusedRMSprop(self.current_model.parameters(), lr=lr, weight_decay=1e-4,
                                           conv_packs=conv_packs(self.current_model))
@@ -249,13 +255,32 @@ class UncertaintyGuidedProgressiveTrainer:
             self._side_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
         return self._side_streams
 
+    def _early_optimizer_step(self):
+        """Called from backward once the LAST packed weight gradient (the network's first deferred layer) and
+        its input gradient are queued: starts the packed-weight optimiser on the weight-gradient side stream,
+        beside the tail of the backward pass (the first BatchNorm's backward and the image layer's weight
+        gradient on the main stream), instead of after it.  The update rewrites the bf16 input-gradient packs,
+        so the side stream first waits for everything queued on the main stream (every dgrad) and - data
+        parallel - for the all-reduce of every arena bucket."""
+        side = WgradOverlap.stream
+        main = torch.cuda.current_stream()
+        if self._reducer is not None:
+            with torch.cuda.stream(side):            # the reducer forks from the stream the wgrads run on,
+                self._reducer.flush_arena()          # and makes it wait for every arena bucket's all-reduce
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.optimizer.step_deferred()
+
     def _eager_step(self, data, target, stage):
         self.optimizer.zero_grad(set_to_none=True)
         with nvtx_range(f"step stage {stage}: forward + uncertainty + loss"):
             final_loss, output_current, unc, base = self._forward_loss(data, target, stage)
         with nvtx_range("step: backward"):
             if self.overlap_streams and data.is_cuda and self._grad_arena is not None:
-                WgradOverlap.begin(self._streams(data)[1])
+                early = self._arena_packs[-1] if (self._arena_packs and self.early_optimizer
+                                                  and isinstance(self.optimizer, FusedRMSprop)) else None
+                WgradOverlap.begin(self._streams(data)[1], last_pack=early,
+                                   on_last=self._early_optimizer_step if early is not None else None)
                 try:
                     final_loss.backward()
                 finally:

@@ -45,6 +45,20 @@ class _PGUNetBase(nn.Module):
                              f"{self.inc.conv.conv_op[0].in_channels}] image bytes, got {tuple(x.shape)}")
         return ops.im2col_first_u8(x.contiguous(), resolution, resolution, self.input_mean, self.input_std)
 
+    def first_rows(self, x: torch.Tensor, resolution: Optional[int] = None):
+        """The first convolution's source for an fp32 NCHW image or uint8 HWC loader bytes at `resolution`:
+        an `ops.FirstRows` handle (rows built inside the fused first-layer kernels) where those cover the
+        shape, else the packed rows of `pack_bytes` / `ops.im2col_first`."""
+        c1 = self.inc.conv.conv_op[0]
+        if x.dtype == torch.uint8:
+            if x.dim() != 4 or x.shape[-1] != c1.in_channels:
+                return self.pack_bytes(x, resolution)          # raises the shape error
+            return ops.first_rows(x.contiguous(), resolution, resolution, self.input_mean, self.input_std,
+                                  cout=c1.out_channels)
+        if x.dtype != torch.float32:
+            x = x.float()
+        return ops.first_rows(x.contiguous(), resolution, resolution, cout=c1.out_channels)
+
     def encode(self, x: torch.Tensor, depth: Optional[int] = None, resolution: Optional[int] = None):
         """Runs `inc` and the first `depth` Down blocks (all by default) on an fp32 NCHW image - or on
         uint8 HWC image bytes, see `pack_bytes` - and returns the list of NHWC bf16 feature maps.  The
@@ -54,14 +68,15 @@ class _PGUNetBase(nn.Module):
         if depth is not None:
             downs = downs[:depth]
         if x.dtype == torch.uint8:
-            kind, x = "col", self.pack_bytes(x, resolution)
+            kind, x = "col", self.first_rows(x, resolution)
         else:
             kind = "first"
             if x.dtype != torch.float32:
                 x = x.float()
             if resolution is not None and tuple(x.shape[-2:]) != (resolution, resolution):
-                kind, x = "col", ops.im2col_first(x.contiguous(), resolution, resolution)
-            x = x.contiguous()
+                kind, x = "col", self.first_rows(x, resolution)
+            else:
+                x = x.contiguous()
         feats = []
         if downs:
             a, p = self.inc.conv._run(kind, x, emit_pool=True)
@@ -326,17 +341,14 @@ def _forward_resized(model: _PGUNetBase, x: torch.Tensor, resolution: int) -> to
     """model(F.interpolate(x, resolution, bilinear, align_corners=True)) with the resize folded into the
     first-layer packer (UG_unet.py:36-43)."""
     if x.dtype == torch.uint8:
-        return _forward_from_col(model, model.pack_bytes(x, resolution))
+        return _forward_from_col(model, model.first_rows(x, resolution))
     if x.shape[-1] == resolution and x.shape[-2] == resolution:
         return model(x)
-    if x.dtype != torch.float32:
-        x = x.float()
-    col = ops.im2col_first(x.contiguous(), resolution, resolution)
-    return _forward_from_col(model, col)
+    return _forward_from_col(model, model.first_rows(x, resolution))
 
 
-def _forward_from_col(model: _PGUNetBase, col: torch.Tensor) -> torch.Tensor:
-    """Inference forward starting from an already packed first-layer input (no autograd)."""
+def _forward_from_col(model: _PGUNetBase, col) -> torch.Tensor:
+    """Inference forward starting from the first layer's rows - packed, or an ops.FirstRows handle (no autograd)."""
     dc = model.inc.conv
     c1, b1, c2, b2 = dc.conv_op[0], dc.conv_op[1], dc.conv_op[3], dc.conv_op[4]
     downs = [getattr(model, n).mpconv[1] for n in model._downs]
