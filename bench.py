@@ -317,16 +317,23 @@ def run_ours(args):
         with contextlib.redirect_stdout(io.StringIO()):
             trainer.train_epoch(OneBatchLoader(max(4, min(6, args.warmup + 1)), batch), STAGE)   # warm-up / capture
             sync_all()
-            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e2.record()
-            res = trainer.train_epoch(OneBatchLoader(args.steps, batch), STAGE)     # reads metrics back (D2H)
-            e3.record()
-            sync_all()
-        return e2.elapsed_time(e3), res
+            # K steps, three times: the host side of this region (pinned copies, allocator, the box's other
+            # tenants) shows a stall of tens of ms in about one epoch out of ten, which is not the path's
+            # throughput - the MEDIAN epoch is reported and all three are kept in the line (`epochs_ms`)
+            runs = []
+            for _ in range(3):
+                e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e2.record()
+                res = trainer.train_epoch(OneBatchLoader(args.steps, batch), STAGE)     # reads metrics back (D2H)
+                e3.record()
+                sync_all()
+                runs.append((e2.elapsed_time(e3), res))
+        runs.sort(key=lambda r: r[0])
+        return runs[1][0], runs[1][1], [r[0] for r in runs]
 
-    ms_e2e, res = e2e_epochs((hx, hy))
+    ms_e2e, res, all_e2e = e2e_epochs((hx, hy))
     ux, uy = synth_batch_u8(B, 4321 + rank)
-    ms_u8, res_u8 = e2e_epochs((ux, uy))
+    ms_u8, res_u8, all_u8 = e2e_epochs((ux, uy))
 
     ms, ms_e2e, ms_u8 = allmax(ms, ms_e2e, ms_u8)
     ips = world * B * args.steps / (ms / 1e3)
@@ -469,10 +476,12 @@ def run_ours(args):
             "e2e": {"value": ips_e2e, "unit": "images/s",
                     "h2d_bytes_per_step": int(hx.numel() * 4 + hy.numel() * 4),
                     "d2h_bytes_per_step": int((5 + 3 * B) * 8), "ms_per_step": ms_e2e / args.steps,
-                    "final_loss": res[0], "input": "pinned fp32 NCHW images + fp32 masks (what the reference's loaders yield)"},
+                    "final_loss": res[0], "input": "pinned fp32 NCHW images + fp32 masks (what the reference's loaders yield)",
+                    "stat": f"median of 3 epochs of {args.steps} steps", "epochs_ms": all_e2e},
             "e2e_u8": {"value": ips_u8, "unit": "images/s", "h2d_bytes_per_step": int(ux.numel() + uy.numel()),
                        "d2h_bytes_per_step": int((5 + 3 * B) * 8), "ms_per_step": ms_u8 / args.steps,
-                       "final_loss": res_u8[0], "input": "pinned uint8 HWC image bytes + uint8 masks (loader-byte path)"},
+                       "final_loss": res_u8[0], "input": "pinned uint8 HWC image bytes + uint8 masks (loader-byte path)",
+                       "stat": f"median of 3 epochs of {args.steps} steps", "epochs_ms": all_u8},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

@@ -50,3 +50,6 @@ print(f"# conv forward + dgrad class: {sum(v[0] for v in fd)} launches, {sum(v[1
       f"DRAM {sum(v[2] for v in fd) / 1e6:.1f} MB per step")
 print(f"# conv wgrad class: {sum(v[0] for v in wg)} launches, {sum(v[1] for v in wg):.1f} us, "
       f"DRAM {sum(v[2] for v in wg) / 1e6:.1f} MB per step")
+fl = [v for n, v in agg.items() if n.startswith(("conv_first_", "im2col_first"))]
+print(f"# first layer (fused row building, HBM-bound; outside both classes): {sum(v[0] for v in fl)} launches, "
+      f"{sum(v[1] for v in fl):.1f} us, DRAM {sum(v[2] for v in fl) / 1e6:.1f} MB per step")

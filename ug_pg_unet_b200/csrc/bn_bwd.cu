@@ -97,6 +97,7 @@ __device__ __forceinline__ void block_reduce_channels(float (*red)[kBnThreads][9
 // ---------------------------------------------------------------------------
 template <bool kApply, int kNC = 0>
 __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const BnBwdArgs a) {
+  pdl_wait();      // the apply pass is launched while the reduction pass drains (programmatic dependent launch)
   const int cg = a.C >> 3;
   const int my_cg = threadIdx.x % cg;
   const int my_row = threadIdx.x / cg;
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_plain_kernel(const 
 // ---------------------------------------------------------------------------
 template <bool kApply>
 __global__ void __launch_bounds__(kBnThreads, 2) bn_relu_bwd_pool_kernel(const BnBwdArgs a) {
+  pdl_wait();      // the apply pass is launched while the reduction pass drains (programmatic dependent launch)
   const int cg = a.C >> 3;
   const int Ho = a.H >> 1, Wo = a.W >> 1;
   const long long windows = static_cast<long long>(a.B) * Ho * Wo;
@@ -390,6 +392,7 @@ struct PoolRaw4 {          // the raw words of one 2x2 window x 4 channels
 
 template <bool kApply>
 __global__ void __launch_bounds__(kBnThreads, kPoolBlocksPerSM) bn_relu_bwd_pool4_kernel(const BnBwdArgs a) {
+  pdl_wait();      // the apply pass is launched while the reduction pass drains (programmatic dependent launch)
   const int cg = a.C >> 2;
   const int Ho = a.H >> 1, Wo = a.W >> 1;
   const long long windows = static_cast<long long>(a.B) * Ho * Wo;
@@ -576,14 +579,14 @@ int bn_relu_bwd_ex(const void* z, const void* dA, const void* dP, const float* s
       if (blocks < 1) blocks = 1;
       bn_relu_bwd_pool4_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
       UGP_CHECK_CUDA(cudaGetLastError());
-      bn_relu_bwd_pool4_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      UGP_CHECK_CUDA(launch_k(bn_relu_bwd_pool4_kernel<true>, dim3(static_cast<int>(blocks)), dim3(kBnThreads), 0, stream, a));
     } else {
       long long blocks = (M / 4 + rows_per_block * 4 - 1) / (rows_per_block * 4);
       if (blocks > cap) blocks = cap;
       if (blocks < 1) blocks = 1;
       bn_relu_bwd_pool_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
       UGP_CHECK_CUDA(cudaGetLastError());
-      bn_relu_bwd_pool_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      UGP_CHECK_CUDA(launch_k(bn_relu_bwd_pool_kernel<true>, dim3(static_cast<int>(blocks)), dim3(kBnThreads), 0, stream, a));
     }
   } else {
     // at least g_bn_min_pixels pixels per thread: small tensors get few blocks, which keeps the
@@ -594,16 +597,16 @@ int bn_relu_bwd_ex(const void* z, const void* dA, const void* dP, const float* s
     if (head_dl && nc == 1) {
       bn_relu_bwd_plain_kernel<false, 1><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
       UGP_CHECK_CUDA(cudaGetLastError());
-      bn_relu_bwd_plain_kernel<true, 1><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      UGP_CHECK_CUDA(launch_k(bn_relu_bwd_plain_kernel<true, 1>, dim3(static_cast<int>(blocks)), dim3(kBnThreads), 0, stream, a));
     } else if (head_dl) {
       bn_relu_bwd_plain_kernel<false, 2><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
       UGP_CHECK_CUDA(cudaGetLastError());
-      bn_relu_bwd_plain_kernel<true, 2><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      UGP_CHECK_CUDA(launch_k(bn_relu_bwd_plain_kernel<true, 2>, dim3(static_cast<int>(blocks)), dim3(kBnThreads), 0, stream, a));
     } else {
       if (!g_bn_skip_reduce && raw == nullptr)
         bn_relu_bwd_plain_kernel<false><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
       UGP_CHECK_CUDA(cudaGetLastError());
-      bn_relu_bwd_plain_kernel<true><<<static_cast<int>(blocks), kBnThreads, 0, stream>>>(a);
+      UGP_CHECK_CUDA(launch_k(bn_relu_bwd_plain_kernel<true>, dim3(static_cast<int>(blocks)), dim3(kBnThreads), 0, stream, a));
     }
   }
   UGP_CHECK_CUDA(cudaGetLastError());

@@ -101,6 +101,7 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc(tmem_slot, 2 * kN);
+  pdl_wait();      // everything above overlaps the previous kernel's tail (programmatic dependent launch)
   if (warp_idx >= 2 && warp_idx < 6) {
     for (int i = threadIdx.x - 64; i < kN; i += 128) {
       sStats[i] = 0.f;
@@ -454,8 +455,8 @@ static int launch_first_fwd(const CUtensorMap& tmW, const CUtensorMap& tmO, cons
   }
   const int cap = 2 * device_sm_count();
   const int grid = p.m_tiles < cap ? p.m_tiles : cap;
-  conv_first_fwd_kernel<kN, 3, kResize, kU8><<<grid, kFirstThreads, FirstCfg<kN>::kSmemBytes, stream>>>(tmW, tmO, p);
-  UGP_CHECK_CUDA(cudaGetLastError());
+  UGP_CHECK_CUDA(launch_k(conv_first_fwd_kernel<kN, 3, kResize, kU8>, dim3(grid), dim3(kFirstThreads),
+                          FirstCfg<kN>::kSmemBytes, stream, tmW, tmO, p));
   return UGP_OK;
 }
 

@@ -96,6 +96,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  pdl_wait();      // everything above overlaps the previous kernel's tail (programmatic dependent launch)
   if (warp_idx >= 2) {
     const int et = threadIdx.x - 64;
     for (int i = et; i < p.cout; i += 128) {
@@ -165,6 +166,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      if (tile + static_cast<int>(gridDim.x) >= num_tiles) pdl_trigger();   // last tile of this CTA: the next kernel may be scheduled
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + as * kN;
@@ -297,9 +299,7 @@ static int launch_conv(const CUtensorMap& tmA0, const CUtensorMap& tmA1,
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  conv_gemm_kernel<kN><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA0, tmA1, tmW,
-                                                               tmO0, tmO1, p);
-  UGP_CHECK_CUDA(cudaGetLastError());
+  UGP_CHECK_CUDA(launch_k(conv_gemm_kernel<kN>, dim3(grid), dim3(192), Cfg::kSmemBytes, stream, tmA0, tmA1, tmW, tmO0, tmO1, p));
   return UGP_OK;
 }
 

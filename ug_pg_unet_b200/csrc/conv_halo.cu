@@ -142,6 +142,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     if (kPair) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
     else tmem_alloc(tmem_slot, Cfg::kTmemCols);
   }
+  pdl_wait();      // everything above overlaps the previous kernel's tail (programmatic dependent launch)
   if (warp_idx >= 2 && warp_idx < 6) {
     const int et = threadIdx.x - 64;
     for (int i = et; i < p.cout; i += 128) {
@@ -359,6 +360,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tmA0, const CU
     uint32_t chunk_counter = 0;
     int it = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+      if (tile + num_workers >= num_tiles && et == 0) pdl_trigger();   // last tile of this CTA: the next kernel may be scheduled
       const int m_tile = kPair ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles;
       const int n_tile = tile % p.n_tiles;
       const int tx = m_tile % p.tiles_x;
@@ -462,7 +464,7 @@ static int launch_halo_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, co
   const int tiles = (p.m_tiles / 2) * p.n_tiles;
   const int max_pairs = device_sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  conv_halo_pair_kernel<kN><<<2 * pairs, 224, Cfg::smem_bytes(p), stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+  UGP_CHECK_CUDA(launch_k(conv_halo_pair_kernel<kN>, dim3(2 * pairs), dim3(224), Cfg::smem_bytes(p), stream, tmA0, tmA1, tmW, tmO0, tmO1, p));
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
@@ -482,7 +484,7 @@ static int launch_halo(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const C
   if (g_conv_halo_resident == 0) { p.resident = 0; p.b_region_bytes = Cfg::kBStages * Cfg::kBBytes; p.staging_bufs = 2; }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  conv_halo_kernel<kN><<<grid, 224, Cfg::smem_bytes(p), stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+  UGP_CHECK_CUDA(launch_k(conv_halo_kernel<kN>, dim3(grid), dim3(224), Cfg::smem_bytes(p), stream, tmA0, tmA1, tmW, tmO0, tmO1, p));
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }

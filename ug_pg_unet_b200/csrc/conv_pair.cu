@@ -80,6 +80,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc_pair(tmem_slot, kPairTmemCols);
+  pdl_wait();      // everything above overlaps the previous kernel's tail (programmatic dependent launch)
   if (warp_idx >= 2) {
     const int et = threadIdx.x - 64;
     for (int i = et; i < p.cout; i += 128) {
@@ -193,6 +194,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     uint32_t chunk_counter = 0;
     int it = 0;
     for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
+      if (tile + num_pairs >= num_tiles && et == 0) pdl_trigger();   // last tile of this CTA: the next kernel may be scheduled
       const int pm = tile / p.n_tiles;
       const int n_tile = tile - pm * p.n_tiles;
       const int m_tile = 2 * pm + static_cast<int>(rank);
@@ -272,7 +274,7 @@ int launch_conv_pair(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUt
   const int tiles = (p.m_tiles / 2) * p.n_tiles;
   const int max_pairs = device_sm_count() / 2;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  conv_pair_kernel<<<2 * pairs, 192, kPairSmemBytes, stream>>>(tmA0, tmA1, tmW, tmO0, tmO1, p);
+  UGP_CHECK_CUDA(launch_k(conv_pair_kernel, dim3(2 * pairs), dim3(192), kPairSmemBytes, stream, tmA0, tmA1, tmW, tmO0, tmO1, p));
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }

@@ -28,6 +28,7 @@ bn_finalize_kernel(float* __restrict__ stats, int parts, int C, float count,
                    float* __restrict__ shift, float* __restrict__ save_mean,
                    float* __restrict__ save_rstd) {
   __shared__ float red[2][kFinGroups][33];
+  pdl_wait();      // launched while the convolution that writes `stats` drains (programmatic dependent launch)
   const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
@@ -100,6 +101,7 @@ __global__ void bn_relu_apply_kernel(const __nv_bfloat16* __restrict__ z,
                                      const float* __restrict__ shift, int B, int H,
                                      int W, int C, __nv_bfloat16* __restrict__ a,
                                      __nv_bfloat16* __restrict__ pooled) {
+  pdl_wait();      // scale / shift come from bn_finalize, launched just before (programmatic dependent launch)
   const int cg = C >> 3;
   // the grid stride (gridDim.x * 256) is a multiple of cg (256 % cg == 0, checked by the launcher), so
   // a thread keeps its 8-channel group for the whole loop: scale / shift live in registers
@@ -165,6 +167,7 @@ bn_relu_apply_head_kernel(const __nv_bfloat16* __restrict__ z, const float* __re
                           const float* __restrict__ shift, long long M, int C, int HW,
                           const float* __restrict__ wh, const float* __restrict__ bh,
                           __nv_bfloat16* __restrict__ a, float* __restrict__ lmap) {
+  pdl_wait();      // scale / shift come from bn_finalize, launched just before (programmatic dependent launch)
   const int cg = C >> 3;                       // power of two, 8..32 (checked by the launcher)
   const int cg_shift = 31 - __clz(cg);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -490,10 +493,9 @@ int bn_finalize(float* stats, int parts, int C, long long count, const float* ga
   UGP_REQUIRE(stats && gamma && beta && scale && shift && save_mean && save_rstd,
               "bn_finalize: null pointer");
   UGP_REQUIRE(parts >= 1, "bn_finalize: parts must be >= 1");
-  bn_finalize_kernel<<<(C + 31) / 32, 32 * kFinGroups, 0, stream>>>(
-      stats, parts, C, static_cast<float>(count), gamma, beta, eps, momentum, running_mean,
-      running_var, nbt, scale, shift, save_mean, save_rstd);
-  UGP_CHECK_CUDA(cudaGetLastError());
+  UGP_CHECK_CUDA(launch_k(bn_finalize_kernel, dim3((C + 31) / 32), dim3(32 * kFinGroups), 0, stream,
+                          stats, parts, C, static_cast<float>(count), gamma, beta, eps, momentum, running_mean,
+                          running_var, nbt, scale, shift, save_mean, save_rstd));
   return UGP_OK;
 }
 
@@ -514,14 +516,14 @@ int bn_relu_apply(const void* z, const float* scale, const float* shift, int B, 
   if (pooled) {
     UGP_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_relu_apply: pooling needs even H, W");
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
-    bn_relu_apply_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(z), scale, shift, B, H, W, C,
-        static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(pooled));
+    UGP_CHECK_CUDA(launch_k(bn_relu_apply_kernel<true>, dim3(grid_for(total, 256)), dim3(256), 0, stream,
+                            static_cast<const __nv_bfloat16*>(z), scale, shift, B, H, W, C,
+                            static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(pooled)));
   } else {
     const long long total = static_cast<long long>(B) * H * W * (C / 8);
-    bn_relu_apply_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(z), scale, shift, B, H, W, C,
-        static_cast<__nv_bfloat16*>(a), nullptr);
+    UGP_CHECK_CUDA(launch_k(bn_relu_apply_kernel<false>, dim3(grid_for(total, 256)), dim3(256), 0, stream,
+                            static_cast<const __nv_bfloat16*>(z), scale, shift, B, H, W, C,
+                            static_cast<__nv_bfloat16*>(a), static_cast<__nv_bfloat16*>(nullptr)));
   }
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
@@ -536,11 +538,13 @@ int bn_relu_apply_head(const void* z, const float* scale, const float* shift, in
   const long long total = M * (C / 8);
   const int grid = grid_for(total, 256);
   if (nc == 1)
-    bn_relu_apply_head_kernel<1><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z), scale, shift, M, C,
-                                                           H * W, wh, bh, static_cast<__nv_bfloat16*>(a), lmap);
+    UGP_CHECK_CUDA(launch_k(bn_relu_apply_head_kernel<1>, dim3(grid), dim3(256), 0, stream,
+                            static_cast<const __nv_bfloat16*>(z), scale, shift, M, C, H * W, wh, bh,
+                            static_cast<__nv_bfloat16*>(a), lmap));
   else
-    bn_relu_apply_head_kernel<2><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z), scale, shift, M, C,
-                                                           H * W, wh, bh, static_cast<__nv_bfloat16*>(a), lmap);
+    UGP_CHECK_CUDA(launch_k(bn_relu_apply_head_kernel<2>, dim3(grid), dim3(256), 0, stream,
+                            static_cast<const __nv_bfloat16*>(z), scale, shift, M, C, H * W, wh, bh,
+                            static_cast<__nv_bfloat16*>(a), lmap));
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }

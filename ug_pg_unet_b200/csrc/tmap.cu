@@ -108,6 +108,10 @@ extern int g_bn_skip_reduce;
 extern int g_bn_min_pixels;
 extern int g_conv_small_kn;
 extern int g_conv_first_fused;
+// Programmatic dependent launch of the chains conv -> bn_finalize -> BN/ReLU pass -> conv and BN-backward reduce ->
+// apply -> dgrad conv (launch_k / pdl_wait, ugp_common.cuh): the next kernel's launch and prologue overlap the tail
+// of the previous one.  Same box A/B at batch 16: 5.363 -> 5.329 ms/step (4 pairs); 0 = plain launches.
+int g_pdl = 1;
 extern int g_upsample_smem_kb;
 extern int g_bn_bwd_blocks_per_sm;
 int g_wgrad_waves = 1;
@@ -132,6 +136,10 @@ int set_option(const char* name, int value) {
   }
   if (strcmp(name, "upsample_smem_kb") == 0) {
     g_upsample_smem_kb = value < 4 ? 4 : (value > 96 ? 96 : value);
+    return UGP_OK;
+  }
+  if (strcmp(name, "pdl") == 0) {
+    g_pdl = value;
     return UGP_OK;
   }
   if (strcmp(name, "conv_first_fused") == 0) {

@@ -57,7 +57,32 @@ struct ConvView {
 };
 int device_sm_count();
 
+// Programmatic dependent launch (ugp_set_option("pdl", 1)): a kernel launched through launch_k may be
+// scheduled while its predecessor on the stream is still draining - its CTAs run their prologue (barrier
+// init, TMEM allocation, descriptor prefetch) and then block in pdl_wait() until the predecessor has
+// completed and its writes are visible.  Every kernel launched this way executes pdl_wait() on ALL threads
+// before its first access to global memory another kernel may have written, and before any global write.
+extern int g_pdl;
+
 #ifdef __CUDACC__
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl != 0 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------
 // Small PTX wrappers
