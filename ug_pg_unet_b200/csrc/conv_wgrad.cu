@@ -26,6 +26,7 @@ namespace ugp {
 bool pick_box_general(int H, int W, int pixels, int* BW, int* BH);   // conv_gemm.cu
 extern int g_conv_debug;
 extern int g_wgrad_waves;   // CTA waves the split-K grid is sized for (default 1)
+extern int g_wgrad_max_ctas;
 
 struct WgradParams {
   int taps;
@@ -250,7 +251,8 @@ static int launch_wgrad(const CUtensorMap& tmX0, const CUtensorMap& tmX1,
   const int items = p.m_groups * p.n_tiles;
   // split K (pixels) so that the grid is ONE full wave of CTAs (one CTA per SM: 512 TMEM columns):
   // more splits only add fp32 reduction traffic and a ragged last wave
-  const int sms = device_sm_count();
+  int sms = device_sm_count();
+  if (g_wgrad_max_ctas > 0 && g_wgrad_max_ctas < sms) sms = g_wgrad_max_ctas;
   int splits = g_wgrad_waves * sms / items;
   if (splits < 1) splits = 1;
   // keep at least 8 K chunks (512 pixels) per split

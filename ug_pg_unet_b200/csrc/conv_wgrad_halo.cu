@@ -19,6 +19,7 @@ namespace ugp {
 
 extern int g_conv_debug;
 extern int g_wgrad_waves;
+extern int g_wgrad_max_ctas;
 
 struct WgradHaloParams {
   int chunks0, chunks1;
@@ -215,7 +216,9 @@ int conv_wgrad_halo_bf16(const void* src0, int c0, const void* src1, int c1, con
   p.dw = dw_packed;
   p.debug = g_conv_debug;
   const int items = (p.chunks0 + p.chunks1) * p.n_tiles;
-  int splits = g_wgrad_waves * device_sm_count() / items;
+  int wave = device_sm_count();
+  if (g_wgrad_max_ctas > 0 && g_wgrad_max_ctas < wave) wave = g_wgrad_max_ctas;
+  int splits = g_wgrad_waves * wave / items;
   int max_splits = p.kchunks_total / 4;
   if (max_splits < 1) max_splits = 1;
   if (splits > max_splits) splits = max_splits;

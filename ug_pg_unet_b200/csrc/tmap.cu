@@ -115,6 +115,7 @@ int g_pdl = 1;
 extern int g_upsample_smem_kb;
 extern int g_bn_bwd_blocks_per_sm;
 int g_wgrad_waves = 1;
+int g_wgrad_max_ctas = 0;   // > 0: the split-K grids of the weight-gradient kernels are sized for this many CTAs instead of all SMs
 int g_conv_debug = 0;   // what-if timing switches (results are wrong): 1 = skip MMA issue, 2 = skip epilogue body
 
 int set_option(const char* name, int value) {
@@ -168,6 +169,10 @@ int set_option(const char* name, int value) {
   }
   if (strcmp(name, "conv_pair") == 0) {
     g_conv_pair_mode = value;
+    return UGP_OK;
+  }
+  if (strcmp(name, "wgrad_max_ctas") == 0) {
+    g_wgrad_max_ctas = value < 0 ? 0 : value;
     return UGP_OK;
   }
   if (strcmp(name, "wgrad_waves") == 0) {

@@ -207,19 +207,36 @@ class WgradOverlap:
     # the side stream, beside the tail of the backward pass (trainer._early_optimizer_step)
     last_pack = None
     on_last = None
+    # optional second side stream: consecutive weight gradients alternate between the two, so that the
+    # split-K reduction tail of one overlaps the main loop of the next (UGP_WGRAD_STREAMS=2)
+    stream2: Optional[torch.cuda.Stream] = None
+    _turn = 0
 
     @classmethod
-    def begin(cls, stream, last_pack=None, on_last=None):
+    def begin(cls, stream, last_pack=None, on_last=None, stream2=None):
         cls.stream, cls.keep = stream, []
         cls.last_pack, cls.on_last = last_pack, on_last
+        cls.stream2, cls._turn = stream2, 0
+
+    @classmethod
+    def pick(cls):
+        """The side stream of the next weight gradient."""
+        if cls.stream is None or cls.stream2 is None:
+            return cls.stream
+        cls._turn ^= 1
+        return cls.stream if cls._turn else cls.stream2
+
+    @classmethod
+    def streams(cls):
+        return [s for s in (cls.stream, cls.stream2) if s is not None]
 
     @classmethod
     def end(cls):
-        """Joins the side stream into the current one and releases the kept tensors."""
-        st = cls.stream
-        cls.stream = None
+        """Joins the side stream(s) into the current one and releases the kept tensors."""
+        sts = cls.streams()
+        cls.stream = cls.stream2 = None
         cls.last_pack = cls.on_last = None
-        if st is not None:
+        for st in sts:
             torch.cuda.current_stream().wait_stream(st)
         cls.keep = []
 
@@ -306,7 +323,7 @@ def cbr_backward(saved: CBRSaved, dA: Optional[torch.Tensor], dP: Optional[torch
                              small[:2], small[2])
     kdim = sum(s.shape[3] for s in saved.srcs)
     dwp = packs.dwp_buffer(saved.taps * kdim * cout, dev)
-    side = WgradOverlap.stream if packs.defer else None
+    side = WgradOverlap.pick() if packs.defer else None
     if side is not None:
         side.wait_stream(torch.cuda.current_stream())
         WgradOverlap.keep.append((src0, src1, dz))

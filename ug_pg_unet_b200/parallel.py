@@ -148,6 +148,9 @@ class GradBucketReducer:
         if self._stream is None:
             self._stream = torch.cuda.Stream(device=dev, priority=_comm_priority())
         self._stream.wait_stream(torch.cuda.current_stream(dev))
+        from .engine import WgradOverlap
+        for st in WgradOverlap.streams():            # a bucket's packs may come from either weight-gradient stream
+            self._stream.wait_stream(st)
         return torch.cuda.stream(self._stream)
 
     def _on_pack_ready(self, pk):

@@ -63,6 +63,8 @@ class UncertaintyGuidedProgressiveTrainer:
         # of after it.  Off by default: same-box A/B at N = 1, 2 and 8 GPUs showed no step-time change (the tail
         # of backward is HBM-bound like the update itself), so the simpler order stays.
         self.early_optimizer = os.environ.get("UGP_EARLY_OPTIMIZER", "0") == "1"
+        # weight gradients of consecutive layers on ONE side stream (1) or alternating between two (2)
+        self.wgrad_streams = int(os.environ.get("UGP_WGRAD_STREAMS", "1"))
 
         # reference uncertainty_guided_trainer.py:42-47
         self.stage_configs = {
@@ -252,7 +254,8 @@ class UncertaintyGuidedProgressiveTrainer:
     def _streams(self, like):
         if self._side_streams is None:
             dev = like.device
-            self._side_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            self._side_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev),
+                                  torch.cuda.Stream(device=dev))
         return self._side_streams
 
     def _early_optimizer_step(self):
@@ -264,6 +267,8 @@ class UncertaintyGuidedProgressiveTrainer:
         parallel - for the all-reduce of every arena bucket."""
         side = WgradOverlap.stream
         main = torch.cuda.current_stream()
+        if WgradOverlap.stream2 is not None:
+            side.wait_stream(WgradOverlap.stream2)
         if self._reducer is not None:
             with torch.cuda.stream(side):            # the reducer forks from the stream the wgrads run on,
                 self._reducer.flush_arena()          # and makes it wait for every arena bucket's all-reduce
@@ -280,7 +285,8 @@ class UncertaintyGuidedProgressiveTrainer:
                 early = self._arena_packs[-1] if (self._arena_packs and self.early_optimizer
                                                   and isinstance(self.optimizer, FusedRMSprop)) else None
                 WgradOverlap.begin(self._streams(data)[1], last_pack=early,
-                                   on_last=self._early_optimizer_step if early is not None else None)
+                                   on_last=self._early_optimizer_step if early is not None else None,
+                                   stream2=self._streams(data)[2] if self.wgrad_streams == 2 else None)
                 try:
                     final_loss.backward()
                 finally:
