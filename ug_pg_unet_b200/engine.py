@@ -33,6 +33,7 @@ _WHATIF_POOL_AS_PLAIN = os.environ.get("UGP_WHATIF_POOL_AS_PLAIN", "0") == "1"
 # does not get faster - the stand-alone reduction pass is HBM-bound and hides under the weight-gradient
 # convolutions of the side stream, while the longer, epilogue-bound dgrad (64 -> 64 @256^2: 77 -> 116 us)
 # competes with them for the tensor pipe.  Off by default.
+_MATERIALIZE_GRADS = os.environ.get("UGP_MATERIALIZE_GRADS", "0") == "1"     # autograd's default (A/B only)
 _FUSED_BN_BWD_REDUCE = os.environ.get("UGP_FUSED_BN_BWD_REDUCE", "0") == "1"
 
 
@@ -398,6 +399,10 @@ class DoubleConvFn(torch.autograd.Function):
         two entries of `params` and the head's map is returned beside the activation."""
         conv1, bn1, conv2, bn2 = mod.conv_op[0], mod.conv_op[1], mod.conv_op[3], mod.conv_op[4]
         need_grad = any(ctx.needs_input_grad)
+        # an output nobody differentiates (the last decoder block's activation: only its fused head map is
+        # used) arrives in backward as None, not as a materialised tensor of zeros - the BatchNorm-backward
+        # kernels take a null activation gradient (saves a 134 MB fill and two 134 MB reads per step)
+        ctx.set_materialize_grads(_MATERIALIZE_GRADS)
         head = None
         if head_mod is not None:
             hw, hb = params[8], params[9]
