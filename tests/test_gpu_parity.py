@@ -1469,3 +1469,36 @@ def test_fused_first_layer_is_bit_identical_to_packer_plus_gemm(dev, shape, u8, 
     # accumulation: a second launch adds
     ops.conv_wgrad(rows, None, dz, 1, dw_a)
     assert (dw_a.double().view(64, cout) - 2 * ref).abs().max().item() <= max(4 * err_b, 2e-5 * scale)
+
+
+@pytest.mark.gpu
+def test_prefetch_ring_delivers_every_batch_in_order(dev):
+    """trainer._prefetch: host batches copied on the copy stream into a ring of reused device buffers
+    (slot reuse ordered by GPU events after the consuming step) arrive bit-exact and in order - more batches
+    than slots, a slow consumer on the main stream, a ragged last batch and a dtype change."""
+    import contextlib
+    import io
+    import ug_pg_unet_b200 as U
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = U.UncertaintyGuidedProgressiveTrainer(3, 1, device=dev, log_interval=0)
+    g = torch.Generator().manual_seed(11)
+    batches = [(torch.randn(4, 3, 32, 32, generator=g).pin_memory(), torch.randint(0, 2, (4, 1, 32, 32), generator=g).float().pin_memory())
+               for _ in range(8)]
+    batches.append((torch.randn(2, 3, 32, 32, generator=g), torch.randint(0, 2, (2, 1, 32, 32), generator=g).float()))   # ragged
+    batches.append((torch.randint(0, 256, (4, 32, 32, 3), generator=g, dtype=torch.uint8),
+                    torch.randint(0, 2, (4, 1, 32, 32), generator=g, dtype=torch.uint8)))                              # loader bytes
+    batches += batches[:3]
+    got = []
+    busy = torch.empty(64 << 20, device=dev)
+    for d, t in tr._prefetch(batches):
+        assert d.device.type == "cuda" and t.device.type == "cuda"
+        for _ in range(3):
+            busy.add_(1.0)                       # the consumer keeps the main stream busy: copies run ahead of it
+        got.append((d.clone(), t.clone()))       # what the step would read, on the main stream
+    torch.cuda.synchronize()
+    assert len(got) == len(batches)
+    for (d, t), (hd, ht) in zip(got, batches):
+        assert d.dtype == hd.dtype and torch.equal(d.cpu(), hd) and torch.equal(t.cpu(), ht)
+    assert sum(s is not None for s in tr._stage_ring) == 3
+    tr.close()
