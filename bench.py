@@ -516,7 +516,7 @@ def run_ours(args):
 # Sum of dram__bytes_read.sum + dram__bytes_write.sum over the forward + dgrad convolution launches of one
 # batch-16 step (ncu metrics pass, profiles/r02_ncu_launches_by_kernel.txt: 3 372.8 MB against 4 744 MB algorithmic - consecutive
 # kernels meet in the 126 MB L2).
-CONV_CLASS_DRAM_BYTES = 3372.8e6
+CONV_CLASS_DRAM_BYTES = 3117.7e6
 
 
 def main():
