@@ -33,6 +33,7 @@ _WHATIF_POOL_AS_PLAIN = os.environ.get("UGP_WHATIF_POOL_AS_PLAIN", "0") == "1"
 # does not get faster - the stand-alone reduction pass is HBM-bound and hides under the weight-gradient
 # convolutions of the side stream, while the longer, epilogue-bound dgrad (64 -> 64 @256^2: 77 -> 116 us)
 # competes with them for the tensor pipe.  Off by default.
+_HEAD_ADJOINT_ON_SIDE_STREAM = os.environ.get("UGP_HEAD_ADJOINT_MAIN", "0") != "1"      # =1: on the main stream (A/B)
 _MATERIALIZE_GRADS = os.environ.get("UGP_MATERIALIZE_GRADS", "0") == "1"     # autograd's default (A/B only)
 _FUSED_BN_BWD_REDUCE = os.environ.get("UGP_FUSED_BN_BWD_REDUCE", "0") == "1"
 
@@ -212,12 +213,14 @@ class WgradOverlap:
     # split-K reduction tail of one overlaps the main loop of the next (UGP_WGRAD_STREAMS=2)
     stream2: Optional[torch.cuda.Stream] = None
     _turn = 0
+    head_event = None       # recorded after the coarse head-map adjoints launched on the side stream (HeadCombineFn)
+    head_direct_ptr = 0     # data_ptr of dlogits, the finest map's gradient (never on the side stream)
 
     @classmethod
     def begin(cls, stream, last_pack=None, on_last=None, stream2=None):
         cls.stream, cls.keep = stream, []
         cls.last_pack, cls.on_last = last_pack, on_last
-        cls.stream2, cls._turn = stream2, 0
+        cls.stream2, cls._turn, cls.head_event = stream2, 0, None
 
     @classmethod
     def pick(cls):
@@ -236,7 +239,7 @@ class WgradOverlap:
         """Joins the side stream(s) into the current one and releases the kept tensors."""
         sts = cls.streams()
         cls.stream = cls.stream2 = None
-        cls.last_pack = cls.on_last = None
+        cls.last_pack = cls.on_last = cls.head_event = None
         for st in sts:
             torch.cuda.current_stream().wait_stream(st)
         cls.keep = []
@@ -446,6 +449,7 @@ class DoubleConvFn(torch.autograd.Function):
         head = None
         if ctx.head_w is not None:
             # the second output is the head's map: its gradient arrives in the pooled-gradient slot
+            wait_head_grads(dP)
             dl, dP = dP, None
             head = (dl.float().contiguous(), ctx.head_w, []) if dl is not None else None
             if head is None and dA is None:
@@ -569,6 +573,14 @@ class ConvTranspose2x2Fn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------- OutConv / head
+def wait_head_grads(dl):
+    """Orders the current stream after the head-map adjoints HeadCombineFn.backward put on the side stream -
+    unless `dl` is the finest map's gradient, which is dlogits itself and was never on the side stream."""
+    ev = WgradOverlap.head_event
+    if ev is not None and dl is not None and dl.data_ptr() != WgradOverlap.head_direct_ptr:
+        torch.cuda.current_stream().wait_event(ev)
+
+
 class OutConvFn(torch.autograd.Function):
     """1x1 conv C -> num_classes on an NHWC bf16 activation; fp32 NCHW logits out
     (OutConv, UG_unet_parts.py:84-91)."""
@@ -582,6 +594,7 @@ class OutConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dl):
+        wait_head_grads(dl)
         x, weight = ctx.saved_tensors
         nc = weight.shape[0]
         w2 = weight.detach().reshape(nc, -1).contiguous()
@@ -604,8 +617,28 @@ class HeadCombineFn(torch.autograd.Function):
     def backward(ctx, dlogits):
         dlogits = dlogits.contiguous()
         full = (dlogits.shape[-2], dlogits.shape[-1])
-        # the finest map is added as is: its gradient is dlogits itself (no launch, no copy)
-        return tuple(dlogits if tuple(s) == full else ops.head_combine_bwd(dlogits, s) for s in ctx.sizes)
+        side = WgradOverlap.stream
+        if side is None or not _HEAD_ADJOINT_ON_SIDE_STREAM:
+            # the finest map is added as is: its gradient is dlogits itself (no launch, no copy)
+            return tuple(dlogits if tuple(s) == full else ops.head_combine_bwd(dlogits, s) for s in ctx.sizes)
+        # Inside a trainer step: the coarse maps' adjoints are first needed one decoder block later (the finest
+        # block's backward, ~0.6 ms, runs first on dlogits itself), so their launches go to the weight-gradient
+        # side stream, idle at this point, instead of delaying the main stream; the consumers wait for
+        # WgradOverlap.head_event (wait_head_grads).
+        main = torch.cuda.current_stream()
+        B, nc = dlogits.shape[0], dlogits.shape[1]
+        outs = [None if tuple(s) == full else torch.empty((B, nc, s[0], s[1]), dtype=torch.float32, device=dlogits.device)
+                for s in ctx.sizes]
+        side.wait_stream(main)
+        WgradOverlap.keep.append(dlogits)
+        with torch.cuda.stream(side):
+            for s, o in zip(ctx.sizes, outs):
+                if o is not None:
+                    ops.head_combine_bwd(dlogits, s, out=o)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        WgradOverlap.head_event, WgradOverlap.head_direct_ptr = ev, dlogits.data_ptr()
+        return tuple(dlogits if o is None else o for o in outs)
 
 
 class GlobalAvgPoolFn(torch.autograd.Function):

@@ -715,12 +715,13 @@ def head_combine_fwd(maps: Sequence[torch.Tensor]):
     return logits
 
 
-def head_combine_bwd(dlogits, size):
-    """`size`: side of a square map or (h, w)."""
+def head_combine_bwd(dlogits, size, out=None):
+    """`size`: side of a square map or (h, w); `out`: preallocated fp32 [B, nc, h, w] result."""
     _req(dlogits, torch.float32, "dlogits")
     B, nc, RH, RW = dlogits.shape
     h, w = (size, size) if isinstance(size, int) else size
-    dl = torch.empty((B, nc, h, w), dtype=torch.float32, device=dlogits.device)
+    dl = torch.empty((B, nc, h, w), dtype=torch.float32, device=dlogits.device) if out is None else out
+    assert tuple(dl.shape) == (B, nc, h, w) and dl.dtype == torch.float32 and dl.is_contiguous()
     with _timed("head_combine_bwd", 0.0, _nb(dlogits, dl)):
         rc = lib().ugp_head_combine_bwd_hw(_ptr(dlogits), B * nc, RH, RW, h, w, _ptr(dl), _stream())
     check(rc, "ugp_head_combine_bwd")
