@@ -285,3 +285,22 @@ def test_classification_metrics_from_confusion_match_the_reference_golden(golden
             assert abs(got[name][m] - fx[name][key]) < 1e-12
     assert {k: round(v, 12) for k, v in got["per_class_accuracy"].items()} == \
         {k: round(v, 12) for k, v in fx["per_class_accuracy"].items()}
+
+
+def test_fused_first_layer_shape_rule_and_options():
+    """Host-only entry points of the C ABI (no GPU touched): which first-layer shapes the fused kernels take
+    (ugp_conv_first_supported / _wgrad_supported, include/ugp_b200.h) - everything else keeps the packer +
+    GEMM path - and the tuning switches this round added are known to ugp_set_option."""
+    from ug_pg_unet_b200 import _lib
+    handle = _lib.lib()
+    fwd, wg = handle.ugp_conv_first_supported, handle.ugp_conv_first_wgrad_supported
+    assert fwd(3, 64, 16, 256, 256) == 1 and wg(3, 64, 16, 256, 256) == 1          # configs[1]
+    assert fwd(3, 128, 16, 128, 128) == 1 and wg(3, 128, 16, 128, 128) == 0        # the stage-3 network: forward only
+    assert fwd(3, 64, 16, 224, 224) == 1                                           # Herlev at the reference's 224 x 224
+    assert fwd(3, 256, 16, 64, 64) == 0 and fwd(3, 512, 16, 32, 32) == 0           # stage-2 / stage-1 widths: packer + GEMM
+    assert fwd(1, 64, 16, 256, 256) == 0 and fwd(4, 64, 16, 256, 256) == 0         # other channel counts
+    assert fwd(3, 64, 1, 28, 28) == 0                                              # 784 pixels: not a multiple of 128
+    for name in (b"pdl", b"conv_first_fused", b"wgrad_max_ctas", b"conv_small_kn"):
+        assert handle.ugp_set_option(name, 1 if name != b"wgrad_max_ctas" else 0) == 0
+    assert handle.ugp_set_option(b"conv_first_fused", 0) == 0 and fwd(3, 64, 16, 256, 256) == 0
+    assert handle.ugp_set_option(b"conv_first_fused", 1) == 0 and fwd(3, 64, 16, 256, 256) == 1
