@@ -300,7 +300,7 @@ def test_fused_first_layer_shape_rule_and_options():
     assert fwd(3, 256, 16, 64, 64) == 0 and fwd(3, 512, 16, 32, 32) == 0           # stage-2 / stage-1 widths: packer + GEMM
     assert fwd(1, 64, 16, 256, 256) == 0 and fwd(4, 64, 16, 256, 256) == 0         # other channel counts
     assert fwd(3, 64, 1, 28, 28) == 0                                              # 784 pixels: not a multiple of 128
-    for name in (b"pdl", b"conv_first_fused", b"wgrad_max_ctas", b"conv_small_kn"):
+    for name in (b"pdl", b"conv_first_fused", b"conv_first_patch", b"wgrad_max_ctas", b"conv_small_kn"):
         assert handle.ugp_set_option(name, 1 if name != b"wgrad_max_ctas" else 0) == 0
     assert handle.ugp_set_option(b"conv_first_fused", 0) == 0 and fwd(3, 64, 16, 256, 256) == 0
     assert handle.ugp_set_option(b"conv_first_fused", 1) == 0 and fwd(3, 64, 16, 256, 256) == 1

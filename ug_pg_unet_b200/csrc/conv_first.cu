@@ -33,12 +33,22 @@ int g_conv_first_fused = 1;   // ugp_set_option("conv_first_fused", 0): callers 
 // epilogues and two tiles' worth of row building overlap on every SM; 96 registers per thread.
 constexpr int kFirstThreads = 64 + 128 + 128;
 constexpr int kFirstStages = 3;
+// Image patches (kPatch mode: fp32 NCHW input at the layer's resolution, power-of-two tile boxes): instead of
+// 27 global loads with their address arithmetic per row, warp 0 brings the tile's (BW + 8) x (BH + 2) x 3
+// fp32 neighbourhood (4 pixels of margin left and right: aligned box start) in with ONE TMA box per tile (out-of-image coordinates read as zero = the padding) and
+// the producers read their 27 values with constant-offset shared loads: ~70 instead of ~600 instructions per
+// row on a kernel that is instruction-issue bound.
+constexpr int kFirstPatchBytes = 4992;     // >= 136 x 3 x 3 x 4 (W >= 128), 72 x 4 x 3 x 4, 40 x 6 x 3 x 4, 24 x 10 x 3 x 4
+constexpr int kPatchLeft = 4;              // the box starts 4 pixels (16 bytes) left of the tile: TMA needs a 16-byte aligned
+                                           // start in the innermost dimension (x0 - 1 faults with an illegal instruction)
 
 template <int kN>
 struct FirstCfg {
   static constexpr int kBBytes = kN * 128;
-  static constexpr int kSmemBytes = kFirstStages * kATileBytes + kBBytes + 2 * kOutChunkBytes + 5 * kN * 4 +
-                                    kStatsScratchBytes + 256 + 1024;
+  static constexpr int kPatchStages = (kN == 64) ? 3 : 2;     // two CTAs of <= 113 KB must fit one SM
+  static constexpr int kSmemBytes = kFirstStages * kATileBytes + kBBytes + 2 * kOutChunkBytes +
+                                    kPatchStages * kFirstPatchBytes + 5 * kN * 4 + kStatsScratchBytes + 256 + 1024;
+  static_assert(2 * (kSmemBytes + 1024) <= 227 * 1024, "two CTAs per SM");
 };
 
 struct FirstParams {
@@ -49,6 +59,8 @@ struct FirstParams {
   int relu;
   int stat_parts;         // slots of the partial-statistics buffer (= SM count)
   int debug;              // what-if timing only (conv_debug): 1 = no TMA store, 4 = producers skip the image loads
+  int BW, bw_shift, BH, PW;   // kPatch: tile box BW x BH pixels (BW = 1 << bw_shift), patch row pitch PW floats
+  int patch_bytes;            // PW * (BH + 2) * Cin * 4
   const float* bias;
   const float* scale;
   const float* shift;
@@ -61,17 +73,42 @@ __device__ __forceinline__ void store_row_sw128(uint32_t rowp, int prow, const u
   for (int g = 0; g < 8; ++g) st_shared_v4(rowp + ((g ^ (prow & 7)) << 4), u[g].x, u[g].y, u[g].z, u[g].w);
 }
 
-template <int kN, int kCin, bool kResize, bool kU8>
+template <int kCin>
+__device__ __forceinline__ void patch_row(uint32_t pa, int plane, int pw, uint4 (&u)[8]) {
+  // pa: shared address of this pixel's top-left neighbour in channel 0; plane / pw: channel / row pitch in floats
+  float vals[64];
+#pragma unroll
+  for (int k = 9 * kCin; k < 64; ++k) vals[k] = 0.f;
+#pragma unroll
+  for (int ci = 0; ci < kCin; ++ci)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const uint32_t ra = pa + static_cast<uint32_t>((ci * plane + r * pw) << 2);
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) vals[(r * 3 + sx) * kCin + ci] = __uint_as_float(ld_shared_b32(ra + sx * 4));
+    }
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    u[g].x = pack_bf16x2(vals[g * 8 + 0], vals[g * 8 + 1]);
+    u[g].y = pack_bf16x2(vals[g * 8 + 2], vals[g * 8 + 3]);
+    u[g].z = pack_bf16x2(vals[g * 8 + 4], vals[g * 8 + 5]);
+    u[g].w = pack_bf16x2(vals[g * 8 + 6], vals[g * 8 + 7]);
+  }
+}
+
+template <int kN, int kCin, bool kResize, bool kU8, bool kPatch>
 __global__ void __launch_bounds__(kFirstThreads, 2)
 conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
-                      const FirstParams p) {
+                      const __grid_constant__ CUtensorMap tmX, const FirstParams p) {
+  static_assert(!kPatch || (!kResize && !kU8), "patch mode: fp32 input at the layer's resolution");
   using Cfg = FirstCfg<kN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                     // [stage] 128 rows x 128 B
   uint8_t* sB = sA + kFirstStages * kATileBytes;          // kN rows (cout) x 128 B
   uint8_t* sOut = sB + Cfg::kBBytes;
-  float* sStats = reinterpret_cast<float*>(sOut + 2 * kOutChunkBytes);   // [2][kN]
+  uint8_t* sPatch = sOut + 2 * kOutChunkBytes;            // [patch stage] fp32 [c][row][x]
+  float* sStats = reinterpret_cast<float*>(sPatch + Cfg::kPatchStages * kFirstPatchBytes);   // [2][kN]
   float* sBias = sStats + 2 * kN;
   float* sScale = sBias + kN;
   float* sShift = sScale + kN;
@@ -81,7 +118,9 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   uint64_t* tfull_bar = a_empty + kFirstStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* w_full = tempty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint64_t* p_full = w_full + 1;
+  uint64_t* p_empty = p_full + Cfg::kPatchStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + Cfg::kPatchStages);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,6 +137,11 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       mbar_init(&tempty_bar[i], 4);
     }
     mbar_init(w_full, 1);
+    for (int i = 0; i < Cfg::kPatchStages; ++i) {
+      mbar_init(&p_full[i], 1);
+      mbar_init(&p_empty[i], 4);       // lane 0 of each producer warp, after its 27 shared loads
+    }
+    if (kPatch) tma_prefetch_desc(&tmX);
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc(tmem_slot, 2 * kN);
@@ -117,10 +161,29 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp_idx == 0) {
-    // ===================== weight tile: loaded once, resident =====================
-    if (elect_one()) {
+    // ===================== weight tile: loaded once, resident; image patches: one TMA box per tile ==========
+    const bool leader = elect_one() != 0;
+    if (leader) {
       mbar_arrive_expect_tx(w_full, Cfg::kBBytes);
       tma_load_2d(&tmW, w_full, sB, 0, 0);
+    }
+    if constexpr (kPatch) {
+      const int hw = p.H * p.W;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+        const int ps = it % Cfg::kPatchStages;
+        mbar_wait(&p_empty[ps], ((it / Cfg::kPatchStages) & 1) ^ 1);
+        if (leader) {
+          const int pix0 = tile * kBlockM;
+          const int b = pix0 / hw;
+          const int rem = pix0 - b * hw;
+          const int y0 = rem / p.W;
+          const int x0 = rem - y0 * p.W;
+          mbar_arrive_expect_tx(&p_full[ps], p.patch_bytes);
+          tma_load_4d(&tmX, &p_full[ps], sPatch + ps * kFirstPatchBytes, x0 - kPatchLeft, y0 - 1, 0, b);
+        }
+        __syncwarp();
+      }
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
@@ -210,7 +273,21 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[stage]);
     };
-    if constexpr (kResize) {
+    if constexpr (kPatch) {
+      const int tx = prow & (p.BW - 1), ty = prow >> p.bw_shift;
+      const int plane = (p.BH + 2) * p.PW;
+      const uint32_t base = smem_u32(sPatch) + static_cast<uint32_t>((ty * p.PW + tx + kPatchLeft - 1) << 2);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+        const int ps = it % Cfg::kPatchStages;
+        mbar_wait(&p_full[ps], (it / Cfg::kPatchStages) & 1);
+        uint4 u[8];
+        patch_row<kCin>(base + ps * kFirstPatchBytes, plane, p.PW, u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_empty[ps]);        // the patch stage may be refilled
+        emit(u, it);
+      }
+    } else if constexpr (kResize) {
       int it = 0;
       for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
         const int pix = tile * kBlockM + prow;
@@ -271,7 +348,8 @@ conv_first_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 constexpr int kFwStages = 4;
 constexpr int kFwBox = 64 * 128;                                  // 64 pixels x 64 values bf16
 constexpr int kFwStageBytes = 3 * kFwBox;                         // A box twice (M = 128) + dZ box
-constexpr int kFwSmemBytes = kFwStages * kFwStageBytes + 256 + 1024;
+constexpr int kFwPatchBytes = 2688;                               // >= 72 x 3 x 3 x 4 (W >= 64), 40 x 4 x 3 x 4, 24 x 6 x 3 x 4
+constexpr int kFwSmemBytes = kFwStages * (kFwStageBytes + kFwPatchBytes) + 256 + 1024;
 constexpr int kFwThreads = 64 + 256;                              // warp 0 dZ loads, warp 1 MMA, 8 producer warps
 
 struct FirstWgradParams {
@@ -281,6 +359,8 @@ struct FirstWgradParams {
   int kchunks_per_split;
   float* dw;              // [64 (k)][64 (cout)] fp32, accumulated
   ByteNorm norm;
+  int BW, bw_shift, BH, PW;   // kPatch: chunk box BW x BH = 64 pixels, patch row pitch PW floats
+  int patch_bytes;
 };
 
 __device__ __forceinline__ void red_add_f32x4_first(float* addr, float a, float b, float c, float d) {
@@ -288,15 +368,20 @@ __device__ __forceinline__ void red_add_f32x4_first(float* addr, float a, float 
                : "memory");
 }
 
-template <int kCin, bool kResize, bool kU8>
+template <int kCin, bool kResize, bool kU8, bool kPatch>
 __global__ void __launch_bounds__(kFwThreads, 2)
-conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const FirstWgradParams p) {
+conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmX,
+                        const FirstWgradParams p) {
+  static_assert(!kPatch || (!kResize && !kU8), "patch mode: fp32 input at the layer's resolution");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kFwStages * kFwStageBytes);
+  uint8_t* sPatch = smem + kFwStages * kFwStageBytes;     // [stage] fp32 [c][row][x]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sPatch + kFwStages * kFwPatchBytes);
   uint64_t* empty_bar = full_bar + kFwStages;
   uint64_t* done_bar = empty_bar + kFwStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  uint64_t* p_full = done_bar + 1;
+  uint64_t* p_empty = p_full + kFwStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + kFwStages);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -310,8 +395,11 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const FirstWgr
     for (int i = 0; i < kFwStages; ++i) {
       mbar_init(&full_bar[i], 3);      // the dZ box (expect_tx arrival) + the 2 producer warps of the chunk
       mbar_init(&empty_bar[i], 1);
+      mbar_init(&p_full[i], 1);
+      mbar_init(&p_empty[i], 2);       // lane 0 of the chunk's 2 producer warps, after their shared loads
     }
     mbar_init(done_bar, 1);
+    if (kPatch) tma_prefetch_desc(&tmX);
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc(tmem_slot, kFirstN);
@@ -329,6 +417,19 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const FirstWgr
       if (leader) {
         mbar_arrive_expect_tx(&full_bar[stage], kFwBox);
         tma_load_2d(&tmDZ, &full_bar[stage], smem + stage * kFwStageBytes + 2 * kFwBox, 0, (kc_begin + i) * 64);
+      }
+      if constexpr (kPatch) {
+        mbar_wait(&p_empty[stage], ((i / kFwStages) & 1) ^ 1);
+        if (leader) {
+          const int hw = p.H * p.W;
+          const int pix0 = (kc_begin + i) * 64;
+          const int b = pix0 / hw;
+          const int rem = pix0 - b * hw;
+          const int y0 = rem / p.W;
+          const int x0 = rem - y0 * p.W;
+          mbar_arrive_expect_tx(&p_full[stage], p.patch_bytes);
+          tma_load_4d(&tmX, &p_full[stage], sPatch + stage * kFwPatchBytes, x0 - kPatchLeft, y0 - 1, 0, b);
+        }
       }
       __syncwarp();
     }
@@ -371,7 +472,20 @@ conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const FirstWgr
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
     };
-    if constexpr (kResize) {
+    if constexpr (kPatch) {
+      const int tx = prow & (p.BW - 1), ty = prow >> p.bw_shift;
+      const int plane = (p.BH + 2) * p.PW;
+      const uint32_t base = smem_u32(sPatch) + static_cast<uint32_t>((ty * p.PW + tx + kPatchLeft - 1) << 2);
+      for (int i = pair; i < n_k; i += 4) {
+        const int stage = i % kFwStages;
+        mbar_wait(&p_full[stage], (i / kFwStages) & 1);
+        uint4 u[8];
+        patch_row<kCin>(base + stage * kFwPatchBytes, plane, p.PW, u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_empty[stage]);
+        emit(u, i);
+      }
+    } else if constexpr (kResize) {
       for (int i = pair; i < n_k; i += 4) {
         const int pix = (kc_begin + i) * 64 + prow;
         const int b = pix / hw;
@@ -445,26 +559,49 @@ bool conv_first_wgrad_supported(int Cin, int cout, int B, int H, int W) {
   return cout == kFirstN && conv_first_supported(Cin, cout, B, H, W);
 }
 
-template <int kN, bool kResize, bool kU8>
-static int launch_first_fwd(const CUtensorMap& tmW, const CUtensorMap& tmO, const FirstParams& p, cudaStream_t stream) {
+int g_conv_first_patch = 1;   // ugp_set_option("conv_first_patch", 0): per-row global loads instead of TMA image patches
+
+// Patch mode applies to fp32 images at the layer's resolution whose `pixels`-pixel tiles are power-of-two
+// boxes inside one image (W >= pixels: pieces of a row; W < pixels: whole rows); fills the box geometry.
+static bool patch_geometry(const void* x, bool u8, bool resize, int Cin, int H, int W, int pixels, int* BW, int* shift,
+                           int* BH, int* PW, int* bytes) {
+  if (g_conv_first_patch == 0 || u8 || resize || Cin != 3) return false;
+  if (reinterpret_cast<uintptr_t>(x) % 16 != 0 || W % 4 != 0 || W < 16) return false;
+  const int bw = W < pixels ? W : pixels;
+  if ((bw & (bw - 1)) != 0 || W % bw != 0) return false;
+  const int bh = pixels / bw;
+  if (H % bh != 0) return false;
+  int sh = 0;
+  while ((1 << sh) < bw) ++sh;
+  *BW = bw; *shift = sh; *BH = bh; *PW = bw + 2 * kPatchLeft;
+  *bytes = (*PW) * (bh + 2) * Cin * 4;
+  return true;
+}
+
+template <int kN, bool kResize, bool kU8, bool kPatch>
+static int launch_first_fwd(const CUtensorMap& tmW, const CUtensorMap& tmO, const CUtensorMap& tmX, const FirstParams& p,
+                            cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    UGP_CHECK_CUDA(cudaFuncSetAttribute(conv_first_fwd_kernel<kN, 3, kResize, kU8>,
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(conv_first_fwd_kernel<kN, 3, kResize, kU8, kPatch>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, FirstCfg<kN>::kSmemBytes));
     configured = true;
   }
   const int cap = 2 * device_sm_count();
   const int grid = p.m_tiles < cap ? p.m_tiles : cap;
-  UGP_CHECK_CUDA(launch_k(conv_first_fwd_kernel<kN, 3, kResize, kU8>, dim3(grid), dim3(kFirstThreads),
-                          FirstCfg<kN>::kSmemBytes, stream, tmW, tmO, p));
+  UGP_CHECK_CUDA(launch_k(conv_first_fwd_kernel<kN, 3, kResize, kU8, kPatch>, dim3(grid), dim3(kFirstThreads),
+                          FirstCfg<kN>::kSmemBytes, stream, tmW, tmO, tmX, p));
   return UGP_OK;
 }
 
 template <int kN>
-static int dispatch_first_fwd(bool resize, bool u8, const CUtensorMap& tmW, const CUtensorMap& tmO, const FirstParams& p,
-                              cudaStream_t stream) {
-  if (u8) return resize ? launch_first_fwd<kN, true, true>(tmW, tmO, p, stream) : launch_first_fwd<kN, false, true>(tmW, tmO, p, stream);
-  return resize ? launch_first_fwd<kN, true, false>(tmW, tmO, p, stream) : launch_first_fwd<kN, false, false>(tmW, tmO, p, stream);
+static int dispatch_first_fwd(bool resize, bool u8, bool patch, const CUtensorMap& tmW, const CUtensorMap& tmO,
+                              const CUtensorMap& tmX, const FirstParams& p, cudaStream_t stream) {
+  if (patch) return launch_first_fwd<kN, false, false, true>(tmW, tmO, tmX, p, stream);
+  if (u8) return resize ? launch_first_fwd<kN, true, true, false>(tmW, tmO, tmX, p, stream)
+                        : launch_first_fwd<kN, false, true, false>(tmW, tmO, tmX, p, stream);
+  return resize ? launch_first_fwd<kN, true, false, false>(tmW, tmO, tmX, p, stream)
+                : launch_first_fwd<kN, false, false, false>(tmW, tmO, tmX, p, stream);
 }
 
 int conv_first_fwd(const void* x, int is_u8, int B, int Cin, int Hin, int Win, int H, int W, const float* mean,
@@ -490,19 +627,27 @@ int conv_first_fwd(const void* x, int is_u8, int B, int Cin, int Hin, int Win, i
   if ((rc = make_tmap_2d_bf16(&tmW, wpack, cout, 64, 64, cout))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmO, dst, total, cout, 64, kBlockM))) return rc;
   const bool resize = Hin != H || Win != W;
-  return cout == 64 ? dispatch_first_fwd<64>(resize, is_u8 != 0, tmW, tmO, p, stream)
-                    : dispatch_first_fwd<128>(resize, is_u8 != 0, tmW, tmO, p, stream);
+  CUtensorMap tmX = tmW;    // unused outside patch mode
+  const bool patch = patch_geometry(x, is_u8 != 0, resize, Cin, H, W, kBlockM, &p.BW, &p.bw_shift, &p.BH, &p.PW,
+                                    &p.patch_bytes);
+  if (patch) {
+    UGP_REQUIRE(p.patch_bytes <= kFirstPatchBytes, "conv_first_fwd: patch of %d bytes does not fit", p.patch_bytes);
+    if ((rc = make_tmap_nchw_f32(&tmX, x, B, Cin, H, W, p.PW, p.BH + 2, Cin))) return rc;
+  }
+  return cout == 64 ? dispatch_first_fwd<64>(resize, is_u8 != 0, patch, tmW, tmO, tmX, p, stream)
+                    : dispatch_first_fwd<128>(resize, is_u8 != 0, patch, tmW, tmO, tmX, p, stream);
 }
 
-template <bool kResize, bool kU8>
-static int launch_first_wgrad(const CUtensorMap& tmDZ, const FirstWgradParams& p, int grid, cudaStream_t stream) {
+template <bool kResize, bool kU8, bool kPatch>
+static int launch_first_wgrad(const CUtensorMap& tmDZ, const CUtensorMap& tmX, const FirstWgradParams& p, int grid,
+                              cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    UGP_CHECK_CUDA(cudaFuncSetAttribute(conv_first_wgrad_kernel<3, kResize, kU8>,
+    UGP_CHECK_CUDA(cudaFuncSetAttribute(conv_first_wgrad_kernel<3, kResize, kU8, kPatch>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kFwSmemBytes));
     configured = true;
   }
-  conv_first_wgrad_kernel<3, kResize, kU8><<<grid, kFwThreads, kFwSmemBytes, stream>>>(tmDZ, p);
+  conv_first_wgrad_kernel<3, kResize, kU8, kPatch><<<grid, kFwThreads, kFwSmemBytes, stream>>>(tmDZ, tmX, p);
   UGP_CHECK_CUDA(cudaGetLastError());
   return UGP_OK;
 }
@@ -531,8 +676,16 @@ int conv_first_wgrad(const void* x, int is_u8, int B, int Cin, int Hin, int Win,
   CUtensorMap tmDZ;
   if (int rc = make_tmap_2d_bf16(&tmDZ, dz, total, cout, 64, 64)) return rc;
   const bool resize = Hin != H || Win != W;
-  if (is_u8) return resize ? launch_first_wgrad<true, true>(tmDZ, p, splits, stream) : launch_first_wgrad<false, true>(tmDZ, p, splits, stream);
-  return resize ? launch_first_wgrad<true, false>(tmDZ, p, splits, stream) : launch_first_wgrad<false, false>(tmDZ, p, splits, stream);
+  CUtensorMap tmX = tmDZ;   // unused outside patch mode
+  if (patch_geometry(x, is_u8 != 0, resize, Cin, H, W, 64, &p.BW, &p.bw_shift, &p.BH, &p.PW, &p.patch_bytes)) {
+    UGP_REQUIRE(p.patch_bytes <= kFwPatchBytes, "conv_first_wgrad: patch of %d bytes does not fit", p.patch_bytes);
+    if (int rc = make_tmap_nchw_f32(&tmX, x, B, Cin, H, W, p.PW, p.BH + 2, Cin)) return rc;
+    return launch_first_wgrad<false, false, true>(tmDZ, tmX, p, splits, stream);
+  }
+  if (is_u8) return resize ? launch_first_wgrad<true, true, false>(tmDZ, tmX, p, splits, stream)
+                           : launch_first_wgrad<false, true, false>(tmDZ, tmX, p, splits, stream);
+  return resize ? launch_first_wgrad<true, false, false>(tmDZ, tmX, p, splits, stream)
+                : launch_first_wgrad<false, false, false>(tmDZ, tmX, p, splits, stream);
 }
 
 }  // namespace ugp

@@ -89,6 +89,29 @@ int make_tmap_nhwc_view_bf16(CUtensorMap* out, const void* ptr, int B, int H, in
   return encode(out, ptr, 4, dims, strides, box);
 }
 
+// fp32 NCHW image viewed as a 4-D tensor (W, H, C, B), W innermost, NO swizzle: a (boxW x boxH x boxC) patch
+// lands in shared memory as plain [c][row][x] floats; coordinates outside the image read as zero (= the
+// convolution's zero padding).  W must be a multiple of 4 and the base 16-byte aligned (TMA stride rules).
+int make_tmap_nchw_f32(CUtensorMap* out, const void* ptr, int B, int C, int H, int W, int boxW, int boxH, int boxC) {
+  EncodeTiledFn fn = resolve_encoder();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled not available from the driver");
+    return UGP_ERR_DRIVER;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+  cuuint32_t box[4] = {(cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxC, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (fp32 image) failed with CUresult %d", (int)r);
+    return UGP_ERR_DRIVER;
+  }
+  return UGP_OK;
+}
+
 // Row-major bf16 matrix [rows][cols]; cols innermost.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, long long rows,
                       int cols, int boxCols, int boxRows) {
@@ -108,6 +131,7 @@ extern int g_bn_skip_reduce;
 extern int g_bn_min_pixels;
 extern int g_conv_small_kn;
 extern int g_conv_first_fused;
+extern int g_conv_first_patch;
 // Programmatic dependent launch of the chains conv -> bn_finalize -> BN/ReLU pass -> conv and BN-backward reduce ->
 // apply -> dgrad conv (launch_k / pdl_wait, ugp_common.cuh): the next kernel's launch and prologue overlap the tail
 // of the previous one.  Same box A/B at batch 16: 5.363 -> 5.329 ms/step (4 pairs); 0 = plain launches.
@@ -141,6 +165,10 @@ int set_option(const char* name, int value) {
   }
   if (strcmp(name, "pdl") == 0) {
     g_pdl = value;
+    return UGP_OK;
+  }
+  if (strcmp(name, "conv_first_patch") == 0) {
+    g_conv_first_patch = value;
     return UGP_OK;
   }
   if (strcmp(name, "conv_first_fused") == 0) {

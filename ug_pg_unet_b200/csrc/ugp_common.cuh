@@ -48,6 +48,7 @@ int make_tmap_nhwc_bf16(CUtensorMap* out, const void* ptr, int B, int H, int W,
                         int C, int boxC, int boxW, int boxH);
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, long long rows,
                       int cols, int boxCols, int boxRows);
+int make_tmap_nchw_f32(CUtensorMap* out, const void* ptr, int B, int C, int H, int W, int boxW, int boxH, int boxC);
 int make_tmap_nhwc_view_bf16(CUtensorMap* out, const void* ptr, int B, int H, int W, int C,
                              long long pix_stride, long long row_stride, long long img_stride,
                              int boxC, int boxW, int boxH);
