@@ -12,7 +12,8 @@ Prints ONE JSON line (rank 0):
   value      images/s with inputs resident in HBM (CUDA events around K graph replays, max over ranks)
   e2e        the same through the public trainer API (`train_epoch`) from pinned HOST fp32 buffers - H2D of
              every batch and D2H of the step metrics inside the timed region; `e2e_u8` = the loader-byte
-             path (uint8 HWC images + uint8 masks, 4x fewer bytes)
+             path (uint8 HWC images + uint8 masks, 4x fewer bytes).  Both run three epochs of K steps and
+             report the median epoch (`epochs_ms` keeps all three)
   roofline   the dominant kernel CLASS (tcgen05 implicit-GEMM convolution, forward + dgrad launches):
              algorithmic FLOP / device time.  Device time per launch comes from a CUDA-graph replay of the
              step on ONE stream with event-record nodes between the kernel nodes (no host code between the
